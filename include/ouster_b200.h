@@ -1,0 +1,207 @@
+/*
+ * ouster_b200.h -- C ABI of the B200-native scan->pointcloud path.
+ *
+ * Drop-in boundary for the hot path of ouster_core (ouster-sdk 1.0.1):
+ *   packet field decode (PacketFormat) -> LidarFrame/LidarScan -> destagger() -> XYZLut/cartesian().
+ * The reference reaches this path through C++ symbols in namespace ouster::sdk::core (there is
+ * no plugin ABI); the replacement headers under include/ouster/core/ keep those C++
+ * signatures and call the entry points below.  Each entry point cites the reference interface
+ * it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - every function returns an ob_status; on failure ob_last_error() holds the exact message text
+ *    of the exception the reference would have thrown (thread-local).  No exception crosses the ABI.
+ *  - every data pointer may be device memory, pinned host memory or pageable host memory; the kind
+ *    is detected with cudaPointerGetAttributes.  Host buffers are staged through the ob_stream's
+ *    device arena (H2D before the kernel, D2H after it, all on the stream).
+ *  - calls are asynchronous on the ob_stream; ob_stream_sync() makes host-visible results final.
+ *  - handles (ob_lut, ob_decoder) are immutable after creation and may be shared by threads;
+ *    an ob_stream belongs to one caller thread at a time (one per sensor stream, like FrameBatcher).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with OB_NO_DEVICE.
+ */
+#ifndef OUSTER_B200_H
+#define OUSTER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OB_ABI_VERSION 1
+#define OB_MAX_FIELDS 24  /* decoded channel fields per packet format */
+#define OB_MAX_RETURNS 2
+
+typedef enum ob_status {
+    OB_OK = 0,
+    OB_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference */
+    OB_RUNTIME_ERROR = 2,    /* std::runtime_error in the reference */
+    OB_CUDA_ERROR = 3,
+    OB_NO_DEVICE = 4
+} ob_status;
+
+typedef enum ob_dtype { OB_F32 = 0, OB_F64 = 1 } ob_dtype;
+
+typedef struct ob_stream ob_stream;   /* CUDA stream + device arena + pinned staging */
+typedef struct ob_lut ob_lut;         /* device-resident XYZLutT<T> (direction/offset tables) */
+typedef struct ob_decoder ob_decoder; /* device-resident PacketFormat decode table */
+
+/* ---- library ---- */
+int ob_abi_version(void);
+const char* ob_last_error(void);
+/* number of visible CUDA devices (0 without a driver/GPU); never fails */
+int ob_device_count(void);
+/* kernels launched by this library since load (all threads); the bench's gpu_launches claim */
+uint64_t ob_kernel_launch_count(void);
+/* tuning hook (launch geometry only, never results): cloud_tw, cloud_stages, cloud_threads,
+ * cloud_ctas_per_sm, decode_stages, decode_threads, decode_ctas_per_sm, force_fallback.
+ * Defaults come from OB_* environment variables of the same (upper-case) names. */
+ob_status ob_set_tunable(int device, const char* name, int value);
+
+/* ---- streams ---- */
+ob_status ob_stream_create(int device, ob_stream** out);
+/* wrap a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) */
+ob_status ob_stream_wrap(int device, void* cuda_stream, ob_stream** out);
+ob_status ob_stream_sync(ob_stream* s);
+void* ob_stream_cuda_handle(ob_stream* s);
+ob_status ob_stream_destroy(ob_stream* s);
+
+/* pinned host allocations for callers that want full-rate H2D/D2H */
+ob_status ob_host_alloc(size_t bytes, void** out);
+ob_status ob_host_free(void* p);
+
+/* ---- XYZ lookup table ----
+ * replaces XYZLutT<T>(direction, offset, h, w)            ouster_core/include/ouster/core/xyzlut.h:135
+ *          impl::make_xyz_lut(w,h,range_unit,b2l,tf,az,alt) ouster_core/src/xyzlut.cpp:11-89
+ * direction/offset: row-major (h*w) x 3 of dtype (ArrayX3R<T>, typedefs.h:71).
+ * ob_lut_from_intrinsics builds the table on the GPU in double and casts to dtype (xyzlut.h:119-124).
+ * errors: "lut dimensions must be greater than zero", "unexpected frame dimensions" (xyzlut.cpp:15,20)
+ */
+ob_status ob_lut_create(ob_dtype dtype, const void* direction, const void* offset, size_t h,
+                        size_t w, int device, ob_lut** out);
+ob_status ob_lut_from_intrinsics(ob_dtype dtype, size_t w, size_t h, double range_unit,
+                                 const double* beam_to_lidar_transform /* 4x4 row-major */,
+                                 const double* transform /* 4x4 row-major */,
+                                 const double* azimuth_angles_deg, size_t n_azimuth,
+                                 const double* altitude_angles_deg, size_t n_altitude, int device,
+                                 ob_lut** out);
+/* copy the tables back to host arrays of the LUT's dtype (XYZLutT::direction / ::offset members) */
+ob_status ob_lut_download(const ob_lut* lut, void* direction, void* offset);
+ob_status ob_lut_info(const ob_lut* lut, size_t* h, size_t* w, int* dtype, int* device);
+/* device pointers of the tables (for zero-copy consumers such as torch tensors) */
+ob_status ob_lut_device_ptrs(const ob_lut* lut, void** direction, void** offset);
+ob_status ob_lut_destroy(ob_lut* lut);
+
+/* ---- range -> XYZ ----
+ * replaces XYZLutT<T>::operator()(range)     xyzlut.h:139-143
+ *          impl::cartesianT<T>(points, ...)   ouster_core/include/ouster/core/impl/cartesian.h:36-66
+ *          cartesian(range, lut)              ouster_core/src/xyzlut.cpp:116-124
+ * range: n_pixels uint32 (staggered H x W), xyz: n_pixels x 3 of the LUT dtype.
+ * error: "unexpected image dimensions" when n_pixels != h*w (xyzlut.cpp:117-119)
+ */
+ob_status ob_cartesian(const ob_lut* lut, const uint32_t* range, size_t n_pixels, void* xyz,
+                       ob_stream* s);
+
+/* ---- destagger / stagger ----
+ * replaces destagger_into<T>/destagger<T>/stagger<T> (2-D and N-D forms)
+ *          ouster_core/include/ouster/core/impl/lidar_frame_impl.h:733-811, 825-989
+ * img/out: row-major h x w x k elements of elem_size bytes (k = product of trailing dims, 1 for 2-D).
+ * d[u][j] = g[u][(j - s_u) mod w]; inverse negates s_u.
+ * errors: "image height does not match shifts size" (:741)
+ */
+ob_status ob_destagger(size_t elem_size, size_t k, const void* img, const int32_t* pixel_shift_by_row,
+                       size_t n_shifts, size_t h, size_t w, int inverse, void* out, ob_stream* s);
+
+/* ---- fused range -> (XYZ, destaggered range, destaggered XYZ), batched over frames ----
+ * One launch performs, for every frame f and return r of the batch, what the reference does as
+ * separate passes: lut(range) (xyzlut.h:139-150) and destagger<uint32_t>(range, shifts)
+ * (impl/lidar_frame_impl.h:825-834), optionally destagger<T,3>(xyz) (:849-860).
+ * Layout: element (f, r, ...) of an array lives at base + f*frame_stride + r*return_stride
+ * (strides in ELEMENTS of that array's scalar type).  NULL outputs are skipped.
+ */
+typedef struct ob_cloud_io {
+    uint32_t n_frames;
+    uint32_t n_returns; /* 1 or 2 (RANGE, RANGE2) */
+    const uint32_t* range;
+    size_t range_frame_stride, range_return_stride;
+    void* xyz; /* staggered order, as cartesian() defines: point i = row*w + col */
+    size_t xyz_frame_stride, xyz_return_stride;
+    uint32_t* range_destaggered;
+    size_t rd_frame_stride, rd_return_stride;
+    void* xyz_destaggered;
+    size_t xd_frame_stride, xd_return_stride;
+} ob_cloud_io;
+
+ob_status ob_scan_to_cloud(const ob_lut* lut, const int32_t* pixel_shift_by_row /* h, host */,
+                           size_t n_shifts, const ob_cloud_io* io, ob_stream* s);
+
+/* ---- packet field decode (PacketFormat / FrameBatcher pixel work) ----
+ * replaces PacketFormat::block_field<T,BlockDim> / col_field<T>  ouster_core/src/parsing.cpp:628-675
+ *          FieldDecodeInfo::get<T>                ouster_core/include/ouster/core/field_decode_info.h:41-54
+ *          FrameBatcher::parse_by_block / parse_by_col + zero_fields  ouster_core/src/lidar_frame.cpp:1371-1528
+ * The host keeps the FrameBatcher state machine (lidar_frame.cpp:1698-1959) and hands the GPU a
+ * frame's packets plus a column map; the GPU writes every pixel field of the frame in one pass.
+ */
+typedef struct ob_field_desc {
+    uint32_t offset;    /* FieldDecodeInfo::offset, bytes from the start of a pixel's channel data */
+    uint32_t elem_size; /* sizeof(T) of the destination LidarFrame field (1,2,4,8; 6 = 3 x float16) */
+    uint64_t mask;      /* FieldDecodeInfo::mask, applied literally (add_custom_profile replaces 0 by the type
+                           mask on the host, profile_extension.cpp:147-150) */
+    int32_t shift;      /* FieldDecodeInfo::shift (>0 right, <0 left) */
+    int32_t range_return; /* r >= 0: this field is the range image of return r (feeds fused XYZ); else -1 */
+    uint32_t zero_pattern; /* 16-bit pattern replicated over missing columns: 0, or 0x7e00 for FLOAT16
+                              fields (lidar_frame.cpp:1396-1402) */
+    uint32_t reserved;
+} ob_field_desc;
+
+typedef struct ob_packet_layout {
+    uint32_t packet_header_size; /* 32, legacy 0   (parsing.cpp:459) */
+    uint32_t col_header_size;    /* 12, legacy 16  (parsing.cpp:460) */
+    uint32_t channel_data_size;  /* profile table  (parsing.cpp:327-356) */
+    uint32_t col_size;           /* col_header + h*channel_data + col_footer (parsing.cpp:465-466) */
+    uint32_t packet_size;        /* lidar_packet_size (parsing.cpp:467-469) */
+    uint32_t columns_per_packet;
+    uint32_t pixels_per_column;  /* h */
+    uint32_t columns_per_frame;  /* w */
+    /* column header decode infos (parsing.cpp:499-538): offsets relative to the column start */
+    ob_field_desc col_timestamp, col_measurement_id, col_status;
+} ob_packet_layout;
+
+ob_status ob_decoder_create(const ob_packet_layout* layout, const ob_field_desc* fields,
+                            size_t n_fields, int device, ob_decoder** out);
+ob_status ob_decoder_destroy(ob_decoder* dec);
+
+/* One frame worth of work for ob_decode_frames.
+ * packets: n_slots buffers of layout.packet_size bytes, packet_stride apart, in ARRIVAL order.
+ * col_src[j] (host, w entries) = slot*columns_per_packet + column index of the packet column whose
+ *   pixel data lands in frame column j, or -1: column j is zero-filled (missing / invalid / dropped).
+ *   NULL means the identity map (slot j/cpp, column j%cpp): a complete in-order frame.
+ * hdr_src: same for the per-column headers (timestamp/measurement_id/status); NULL = col_src.
+ *   (They differ only when block parsing meets non-consecutive measurement ids, parsing.cpp:647-653.)
+ * fields[i]: h x w row-major image of fields[i].elem_size bytes for decoder field i; NULL = skip.
+ * Fused consumers (all optional): with lut != NULL, xyz[r] / range_destaggered[r] receive the same
+ * products as ob_scan_to_cloud for the range field(s) tagged with range_return = r.
+ */
+typedef struct ob_decode_io {
+    const uint8_t* packets;
+    size_t n_slots, packet_stride;
+    const int32_t* col_src;
+    const int32_t* hdr_src;
+    void* fields[OB_MAX_FIELDS];
+    uint64_t* timestamp;      /* w */
+    uint16_t* measurement_id; /* w */
+    uint32_t* status;         /* w */
+    void* xyz[OB_MAX_RETURNS];
+    uint32_t* range_destaggered[OB_MAX_RETURNS];
+} ob_decode_io;
+
+ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, size_t n_frames,
+                           const ob_lut* lut /* nullable */,
+                           const int32_t* pixel_shift_by_row /* nullable, h, host */, size_t n_shifts,
+                           ob_stream* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OUSTER_B200_H */

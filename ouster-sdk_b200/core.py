@@ -1,0 +1,295 @@
+"""Host-side Python mirror of the reference's hot-path API over the C ABI.
+
+Reference interfaces mirrored (python binding python/src/cpp/client/processing.cpp):
+  XYZLut / XYZLutFloat .__call__(range|frame)   :340-357, 640-700
+  destagger(info|shifts, field, inverse)         :527-638
+Arrays may be numpy arrays (host) or torch tensors (host or CUDA); CUDA tensors are used
+in place (zero copy), host arrays are staged by the C library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import CloudIO, check, lib
+
+
+def device_count():
+    return lib.ob_device_count()
+
+
+def kernel_launch_count():
+    return lib.ob_kernel_launch_count()
+
+
+def set_tunable(name, value, device=0):
+    check(lib.ob_set_tunable(device, name.encode(), int(value)))
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        assert x.is_contiguous(), "tensors must be contiguous"
+        return x.data_ptr()
+    assert x.flags["C_CONTIGUOUS"], "arrays must be C-contiguous"
+    return x.ctypes.data
+
+
+def _itemsize(x):
+    return x.element_size() if _is_torch(x) else x.dtype.itemsize
+
+
+def _np_dtype(x):
+    if _is_torch(x):
+        import torch
+        return {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64),
+                torch.uint8: np.dtype(np.uint8), torch.int32: np.dtype(np.int32),
+                torch.uint32: np.dtype(np.uint32), torch.int64: np.dtype(np.int64),
+                torch.uint16: np.dtype(np.uint16), torch.int16: np.dtype(np.int16),
+                torch.uint64: np.dtype(np.uint64), torch.int8: np.dtype(np.int8)}[x.dtype]
+    return x.dtype
+
+
+class PinnedBuffer:
+    """numpy view over cudaHostAlloc'd memory (ob_host_alloc)."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        check(lib.ob_host_alloc(nbytes, C.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+        self.raw = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib.ob_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype):
+    """Pinned host array; keeps its allocation alive through the `.base` chain."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    buf = PinnedBuffer(max(n, 1))
+    arr = buf.raw[:n].view(dtype).reshape(shape)
+    arr_holder = _Holder(arr, buf)
+    return arr_holder.arr
+
+
+class _Holder:
+    _keep = []
+
+    def __init__(self, arr, buf):
+        self.arr = arr
+        _Holder._keep.append(buf)  # pinned buffers live for the process (few, large)
+
+
+class Stream:
+    """ob_stream: CUDA stream + staging; one per caller thread / sensor stream."""
+
+    def __init__(self, device=0, cuda_stream=None):
+        h = C.c_void_p()
+        if cuda_stream is None:
+            check(lib.ob_stream_create(device, C.byref(h)))
+        else:
+            check(lib.ob_stream_wrap(device, C.c_void_p(cuda_stream), C.byref(h)))
+        self.h, self.device = h, device
+
+    @property
+    def cuda_stream(self):
+        return lib.ob_stream_cuda_handle(self.h)
+
+    def sync(self):
+        check(lib.ob_stream_sync(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.ob_stream_destroy(self.h)
+            self.h = None
+
+
+_default_streams = {}
+
+
+def _stream(stream, device=0):
+    if stream is not None:
+        return stream
+    if device not in _default_streams:
+        _default_streams[device] = Stream(device)
+    return _default_streams[device]
+
+
+class XYZLutT:
+    """XYZLutT<T> (ouster_core/include/ouster/core/xyzlut.h:76-158) with device-resident tables.
+
+    `direction`/`offset` are fetched lazily from the device (the reference keeps host copies)."""
+
+    def __init__(self, handle, h, w, dtype, device):
+        self._h, self.h, self.w, self.dtype, self.device = handle, h, w, np.dtype(dtype), device
+        self._host = None
+
+    # -- constructors ----------------------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, direction, offset, h, w, device=0):
+        """XYZLutT(direction, offset, h, w)  (xyzlut.h:135)."""
+        dt = _np_dtype(direction)
+        if dt not in (np.dtype(np.float32), np.dtype(np.float64)) or _np_dtype(offset) != dt:
+            raise ValueError("direction/offset must both be float32 or float64")
+        n = h * w * 3
+        dn = direction.numel() if _is_torch(direction) else direction.size
+        on = offset.numel() if _is_torch(offset) else offset.size
+        if dn != n or on != n:
+            raise ValueError("unexpected image dimensions")
+        hd = C.c_void_p()
+        check(lib.ob_lut_create(_capi.OB_F64 if dt == np.float64 else _capi.OB_F32, _ptr(direction),
+                                _ptr(offset), h, w, device, C.byref(hd)))
+        return cls(hd, h, w, dt, device)
+
+    @classmethod
+    def from_intrinsics(cls, w, h, range_unit, beam_to_lidar_transform, transform,
+                        azimuth_angles_deg, altitude_angles_deg, dtype=np.float64, device=0):
+        """impl::make_xyz_lut(w, h, range_unit, ...)  (ouster_core/src/xyzlut.cpp:11-89)."""
+        b2l = np.ascontiguousarray(beam_to_lidar_transform, np.float64).reshape(16)
+        tr = np.ascontiguousarray(transform, np.float64).reshape(16)
+        az = np.ascontiguousarray(azimuth_angles_deg, np.float64)
+        alt = np.ascontiguousarray(altitude_angles_deg, np.float64)
+        dt = np.dtype(dtype)
+        hd = C.c_void_p()
+        check(lib.ob_lut_from_intrinsics(_capi.OB_F64 if dt == np.float64 else _capi.OB_F32, w, h,
+                                         range_unit, b2l.ctypes.data, tr.ctypes.data,
+                                         az.ctypes.data, az.size, alt.ctypes.data, alt.size,
+                                         device, C.byref(hd)))
+        return cls(hd, h, w, dt, device)
+
+    @classmethod
+    def from_sensor_info(cls, info, use_extrinsics=True, dtype=np.float64, device=0):
+        """XYZLutT(const SensorInfo&, bool use_extrinsics) (xyzlut.h:111-112, xyzlut.cpp:91-106).
+        `info`: mapping/obj with w, h, beam_to_lidar_transform, lidar_to_sensor_transform,
+        sensor_to_body (optional), beam_azimuth_angles, beam_altitude_angles."""
+        g = (lambda k, d=None: info.get(k, d)) if isinstance(info, dict) else \
+            (lambda k, d=None: getattr(info, k, d))
+        RANGE_UNIT = 0.001  # types.h:46
+        tr = np.array(g("lidar_to_sensor_transform"), np.float64).reshape(4, 4)
+        ext = g("sensor_to_body")
+        if use_extrinsics and ext is not None:
+            ext = np.array(ext, np.float64).reshape(4, 4).copy()
+            ext[:3, 3] /= RANGE_UNIT
+            tr = ext @ tr
+        return cls.from_intrinsics(g("w"), g("h"), RANGE_UNIT, g("beam_to_lidar_transform"), tr,
+                                   g("beam_azimuth_angles"), g("beam_altitude_angles"), dtype, device)
+
+    # -- members ---------------------------------------------------------------------------
+    def _download(self):
+        if self._host is None:
+            d = np.empty((self.h * self.w, 3), self.dtype)
+            o = np.empty((self.h * self.w, 3), self.dtype)
+            check(lib.ob_lut_download(self._h, d.ctypes.data, o.ctypes.data))
+            self._host = (d, o)
+        return self._host
+
+    @property
+    def direction(self):
+        return self._download()[0]
+
+    @property
+    def offset(self):
+        return self._download()[1]
+
+    def __call__(self, rng, out=None, stream=None):
+        """lut(range) -> (h*w, 3) points, staggered order (xyzlut.h:139-150)."""
+        return cartesian(self, rng, out=out, stream=stream)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib.ob_lut_destroy(self._h)
+            self._h = None
+
+
+def XYZLut(info, use_extrinsics=True, device=0):
+    """Python `XYZLut` (double), python/src/cpp/client/processing.cpp:640-700."""
+    return XYZLutT.from_sensor_info(info, use_extrinsics, np.float64, device)
+
+
+def XYZLutFloat(info, use_extrinsics=True, device=0):
+    """Python `XYZLutFloat`."""
+    return XYZLutT.from_sensor_info(info, use_extrinsics, np.float32, device)
+
+
+def _numel(x):
+    return x.numel() if _is_torch(x) else x.size
+
+
+def cartesian(lut, rng, out=None, stream=None):
+    """cartesian(range, lut) / lut(range).  Raises ValueError("unexpected image dimensions")
+    on size mismatch (ouster_core/src/xyzlut.cpp:117-119)."""
+    st = _stream(stream, lut.device)
+    if _np_dtype(rng) != np.dtype(np.uint32):
+        if _is_torch(rng):
+            raise ValueError("range must be uint32")
+        rng = np.ascontiguousarray(rng, np.uint32)
+    n = _numel(rng)
+    own = out is None
+    if own:
+        if _is_torch(rng) and rng.is_cuda:
+            import torch
+            out = torch.empty((n, 3), dtype=torch.float64 if lut.dtype == np.float64 else torch.float32,
+                              device=rng.device)
+        else:
+            out = np.empty((n, 3), lut.dtype)
+    check(lib.ob_cartesian(lut._h, _ptr(rng), n, _ptr(out), st.h))
+    if own and not (_is_torch(out) and out.is_cuda):
+        st.sync()
+    return out
+
+
+def destagger(img, pixel_shift_by_row, inverse=False, out=None, stream=None, device=0):
+    """destagger<T>(img, pixel_shift_by_row, inverse) for (H,W) or (H,W,...) images
+    (ouster_core/include/ouster/core/impl/lidar_frame_impl.h:733-860)."""
+    st = _stream(stream, device)
+    shape = tuple(img.shape)
+    if len(shape) < 2:
+        raise ValueError("image must be at least 2-dimensional")
+    h, w = shape[0], shape[1]
+    k = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+    sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
+    own = out is None
+    if own:
+        if _is_torch(img):
+            import torch
+            out = torch.empty_like(img)
+        else:
+            img = np.ascontiguousarray(img)
+            out = np.empty_like(img)
+    check(lib.ob_destagger(_itemsize(img), k, _ptr(img), sh.ctypes.data, sh.size, h, w,
+                           int(bool(inverse)), _ptr(out), st.h))
+    if own and not (_is_torch(out) and out.is_cuda):
+        st.sync()
+    return out
+
+
+def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None,
+                  xyz_destaggered=None, stream=None):
+    """Fused batch: rng is [F, R, H, W] uint32; outputs [F, R, H*W, 3] (xyz), [F, R, H, W]
+    (range_destaggered), [F, R, H, W, 3] (xyz_destaggered).  Asynchronous on `stream`."""
+    st = _stream(stream, lut.device)
+    F, R, H, W = tuple(rng.shape)
+    io = CloudIO()
+    io.n_frames, io.n_returns = F, R
+    n = H * W
+    io.range, io.range_frame_stride, io.range_return_stride = _ptr(rng), R * n, n
+    if xyz is not None:
+        io.xyz, io.xyz_frame_stride, io.xyz_return_stride = _ptr(xyz), R * n * 3, n * 3
+    if range_destaggered is not None:
+        io.range_destaggered, io.rd_frame_stride, io.rd_return_stride = _ptr(range_destaggered), R * n, n
+    if xyz_destaggered is not None:
+        io.xyz_destaggered, io.xd_frame_stride, io.xd_return_stride = _ptr(xyz_destaggered), R * n * 3, n * 3
+    sh, nsh = None, 0
+    if pixel_shift_by_row is not None:
+        sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
+        nsh = sh.size
+    check(lib.ob_scan_to_cloud(lut._h, sh.ctypes.data if sh is not None else None, nsh,
+                               C.byref(io), st.h))

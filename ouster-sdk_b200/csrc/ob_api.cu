@@ -1,0 +1,560 @@
+// ob_api.cu -- C-ABI glue: error state, streams, staging of host buffers, LUT handles and the
+// entry points declared in include/ouster_b200.h (everything except the decode path, which
+// lives in ob_decode.cu).
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ob_api_common.h"
+
+namespace ob {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+ob_status fail(ob_status st, const std::string& msg) {
+    g_last_error = msg;
+    return st;
+}
+ob_status fail_cuda(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear sticky-less error state
+    return OB_CUDA_ERROR;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+static std::mutex g_tun_mx;
+static Tunables g_tun[64];
+static char g_tun_have[64];
+
+static Tunables& tunables_mut(int device) {
+    if (device < 0 || device >= 64) device = 0;
+    if (!g_tun_have[device]) {
+        Tunables t;
+        t.cloud_tw = env_int("OB_CLOUD_TW", 512);
+        t.cloud_stages = std::max(2, env_int("OB_CLOUD_STAGES", 4));
+        t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 128)));
+        t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
+        t.decode_stages = std::max(2, env_int("OB_DECODE_STAGES", 2));
+        t.decode_threads = std::min(1024, std::max(64, env_int("OB_DECODE_THREADS", 512)));
+        t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 1));
+        t.force_fallback = env_int("OB_FORCE_FALLBACK", 0);
+        int sm = 148;
+        if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+            cudaGetLastError();
+            sm = 148;
+        }
+        t.sm_count = sm > 0 ? sm : 148;
+        g_tun[device] = t;
+        g_tun_have[device] = 1;
+    }
+    return g_tun[device];
+}
+
+const Tunables& tunables(int device) {
+    std::lock_guard<std::mutex> lk(g_tun_mx);
+    return tunables_mut(device);
+}
+
+bool set_tunable(int device, const char* name, int value) {
+    std::lock_guard<std::mutex> lk(g_tun_mx);
+    Tunables& t = tunables_mut(device);
+    const std::string n(name);
+    if (n == "cloud_tw") t.cloud_tw = std::max(4, value / 4 * 4);
+    else if (n == "cloud_stages") t.cloud_stages = std::max(2, value);
+    else if (n == "cloud_threads") t.cloud_threads = std::min(256, std::max(32, value / 32 * 32));
+    else if (n == "cloud_ctas_per_sm") t.cloud_ctas_per_sm = std::max(1, value);
+    else if (n == "decode_stages") t.decode_stages = std::max(2, value);
+    else if (n == "decode_threads") t.decode_threads = std::min(1024, std::max(64, value / 32 * 32));
+    else if (n == "decode_ctas_per_sm") t.decode_ctas_per_sm = std::max(1, value);
+    else if (n == "force_fallback") t.force_fallback = value;
+    else return false;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pointer classification and staging
+// ---------------------------------------------------------------------------------------------
+bool is_device_ptr(const void* p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+Staging::~Staging() {
+    // scratch is released in stream order; host-visible results are final after ob_stream_sync
+    for (void* p : scratch_) cudaFreeAsync(p, st_);
+}
+
+cudaError_t Staging::in(const void* p, size_t bytes, const void** dev) {
+    if (bytes == 0 || p == nullptr) {
+        *dev = p;
+        return cudaSuccess;
+    }
+    if (is_device_ptr(p)) {
+        *dev = p;
+        return cudaSuccess;
+    }
+    void* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, bytes, st_);
+    if (e != cudaSuccess) return e;
+    scratch_.push_back(d);
+    e = cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st_);
+    *dev = d;
+    return e;
+}
+
+cudaError_t Staging::out(void* p, size_t bytes, void** dev) {
+    if (bytes == 0 || p == nullptr) {
+        *dev = p;
+        return cudaSuccess;
+    }
+    if (is_device_ptr(p)) {
+        *dev = p;
+        return cudaSuccess;
+    }
+    void* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, bytes, st_);
+    if (e != cudaSuccess) return e;
+    scratch_.push_back(d);
+    pending_.push_back({p, d, bytes});
+    *dev = d;
+    return cudaSuccess;
+}
+
+cudaError_t Staging::scratch(size_t bytes, void** dev) {
+    void* d = nullptr;
+    cudaError_t e = cudaMallocAsync(&d, bytes ? bytes : 16, st_);
+    if (e != cudaSuccess) return e;
+    scratch_.push_back(d);
+    *dev = d;
+    return cudaSuccess;
+}
+
+cudaError_t Staging::flush() {
+    for (const Pending& q : pending_) {
+        cudaError_t e = cudaMemcpyAsync(q.host, q.dev, q.bytes, cudaMemcpyDeviceToHost, st_);
+        if (e != cudaSuccess) return e;
+    }
+    pending_.clear();
+    return cudaSuccess;
+}
+
+ob_status require_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(OB_NO_DEVICE,
+                    "no CUDA device available: the ouster_b200 compute path has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(OB_INVALID_ARGUMENT, "invalid CUDA device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+    return OB_OK;
+}
+
+// reduce pixel_shift_by_row to rotation offsets in [0, w): d[u][j] = g[u][(j - off) mod w]
+// (impl/lidar_frame_impl.h:756; true mathematical modulo -- identical to the reference's
+// size_t expression for every power-of-two width, see DESIGN.md for other widths)
+void reduce_shifts(const int32_t* shifts, size_t h, size_t w, int inverse, std::vector<uint16_t>& out) {
+    out.resize(h);
+    const long long W = static_cast<long long>(w);
+    for (size_t u = 0; u < h; ++u) {
+        long long s = inverse ? -static_cast<long long>(shifts[u]) : static_cast<long long>(shifts[u]);
+        long long m = s % W;
+        if (m < 0) m += W;
+        out[u] = static_cast<uint16_t>(m);
+    }
+}
+
+}  // namespace ob
+
+using namespace ob;
+
+struct ob_stream {
+    int device;
+    cudaStream_t st;
+    bool owned;
+};
+
+struct ob_lut {
+    int device;
+    int dtype;
+    size_t h, w;
+    void* dir;
+    void* off;
+};
+
+// used by ob_decode.cu
+namespace ob {
+void lut_view(const ob_lut* lut, const void** dir, const void** off, int* dtype, size_t* h,
+              size_t* w, int* device) {
+    *dir = lut->dir;
+    *off = lut->off;
+    *dtype = lut->dtype;
+    *h = lut->h;
+    *w = lut->w;
+    *device = lut->device;
+}
+cudaStream_t stream_handle(ob_stream* s) { return s->st; }
+int stream_device(ob_stream* s) { return s->device; }
+}  // namespace ob
+
+extern "C" {
+
+int ob_abi_version(void) { return OB_ABI_VERSION; }
+
+const char* ob_last_error(void) { return g_last_error.c_str(); }
+
+int ob_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint64_t ob_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+ob_status ob_set_tunable(int device, const char* name, int value) {
+    if (!name || !set_tunable(device, name, value)) return fail(OB_INVALID_ARGUMENT, "unknown tunable");
+    return OB_OK;
+}
+
+ob_status ob_stream_create(int device, ob_stream** out) {
+    if (!out) return fail(OB_INVALID_ARGUMENT, "null output pointer");
+    ob_status rs = require_device(device);
+    if (rs != OB_OK) return rs;
+    cudaStream_t st;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamCreate");
+    // keep the stream-ordered pool from trimming between calls
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = new ob_stream{device, st, true};
+    return OB_OK;
+}
+
+ob_status ob_stream_wrap(int device, void* cuda_stream, ob_stream** out) {
+    if (!out) return fail(OB_INVALID_ARGUMENT, "null output pointer");
+    ob_status rs = require_device(device);
+    if (rs != OB_OK) return rs;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = new ob_stream{device, static_cast<cudaStream_t>(cuda_stream), false};
+    return OB_OK;
+}
+
+ob_status ob_stream_sync(ob_stream* s) {
+    if (!s) return fail(OB_INVALID_ARGUMENT, "null stream");
+    cudaError_t e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaStreamSynchronize");
+    return OB_OK;
+}
+
+void* ob_stream_cuda_handle(ob_stream* s) { return s ? static_cast<void*>(s->st) : nullptr; }
+
+ob_status ob_stream_destroy(ob_stream* s) {
+    if (!s) return OB_OK;
+    if (s->owned) {
+        cudaStreamSynchronize(s->st);
+        cudaStreamDestroy(s->st);
+    }
+    delete s;
+    return OB_OK;
+}
+
+ob_status ob_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(OB_INVALID_ARGUMENT, "null output pointer");
+    if (ob_device_count() <= 0) return fail(OB_NO_DEVICE, "no CUDA device available");
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaHostAlloc");
+    return OB_OK;
+}
+
+ob_status ob_host_free(void* p) {
+    if (!p) return OB_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFreeHost");
+    return OB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LUT
+// ---------------------------------------------------------------------------------------------
+static size_t dtype_size(int dtype) { return dtype == OB_F64 ? 8 : 4; }
+
+ob_status ob_lut_create(ob_dtype dtype, const void* direction, const void* offset, size_t h,
+                        size_t w, int device, ob_lut** out) {
+    if (!out || !direction || !offset) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (dtype != OB_F32 && dtype != OB_F64) return fail(OB_INVALID_ARGUMENT, "unknown dtype");
+    if (w == 0 || h == 0)
+        return fail(OB_INVALID_ARGUMENT, "lut dimensions must be greater than zero");
+    ob_status rs = require_device(device);
+    if (rs != OB_OK) return rs;
+    const size_t bytes = h * w * 3 * dtype_size(dtype);
+    void *d = nullptr, *o = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc(lut)");
+    e = cudaMalloc(&o, bytes);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail_cuda(e, "cudaMalloc(lut)");
+    }
+    e = cudaMemcpy(d, direction, bytes, cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(o, offset, bytes, cudaMemcpyDefault);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        cudaFree(o);
+        return fail_cuda(e, "cudaMemcpy(lut)");
+    }
+    *out = new ob_lut{device, static_cast<int>(dtype), h, w, d, o};
+    return OB_OK;
+}
+
+ob_status ob_lut_from_intrinsics(ob_dtype dtype, size_t w, size_t h, double range_unit,
+                                 const double* b2l, const double* transform, const double* az,
+                                 size_t n_az, const double* alt, size_t n_alt, int device,
+                                 ob_lut** out) {
+    if (!out) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (dtype != OB_F32 && dtype != OB_F64) return fail(OB_INVALID_ARGUMENT, "unknown dtype");
+    // validation order and texts of make_xyz_lut, ouster_core/src/xyzlut.cpp:14-21
+    if (w == 0 || h == 0)
+        return fail(OB_INVALID_ARGUMENT, "lut dimensions must be greater than zero");
+    if ((n_az != h || n_alt != h) && (n_az != w * h || n_alt != w * h))
+        return fail(OB_INVALID_ARGUMENT, "unexpected frame dimensions");
+    if (!b2l || !transform || !az || !alt) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    ob_status rs = require_device(device);
+    if (rs != OB_OK) return rs;
+
+    const size_t n3 = w * h * 3;
+    double *daz = nullptr, *dalt = nullptr, *dd = nullptr, *doff = nullptr;
+    cudaError_t e = cudaMalloc(&daz, n_az * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dalt, n_alt * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dd, n3 * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&doff, n3 * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(daz, az, n_az * 8, cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(dalt, alt, n_alt * 8, cudaMemcpyDefault);
+    if (e == cudaSuccess)
+        e = launch_make_lut(w, h, range_unit, b2l, transform, daz, n_az, dalt, n_alt, dd, doff, 0);
+    void *rd = dd, *ro = doff;
+    if (e == cudaSuccess && dtype == OB_F32) {
+        float *fd = nullptr, *fo = nullptr;
+        e = cudaMalloc(&fd, n3 * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&fo, n3 * 4);
+        if (e == cudaSuccess) e = launch_cast_f64_f32(dd, fd, n3, 0);
+        if (e == cudaSuccess) e = launch_cast_f64_f32(doff, fo, n3, 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) {
+            cudaFree(dd);
+            cudaFree(doff);
+            dd = doff = nullptr;
+            rd = fd;
+            ro = fo;
+        } else {
+            cudaFree(fd);
+            cudaFree(fo);
+        }
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(daz);
+    cudaFree(dalt);
+    if (e != cudaSuccess) {
+        cudaFree(dd);
+        cudaFree(doff);
+        return fail_cuda(e, "ob_lut_from_intrinsics");
+    }
+    *out = new ob_lut{device, static_cast<int>(dtype), h, w, rd, ro};
+    return OB_OK;
+}
+
+ob_status ob_lut_download(const ob_lut* lut, void* direction, void* offset) {
+    if (!lut || !direction || !offset) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    const size_t bytes = lut->h * lut->w * 3 * dtype_size(lut->dtype);
+    cudaSetDevice(lut->device);
+    cudaError_t e = cudaMemcpy(direction, lut->dir, bytes, cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(offset, lut->off, bytes, cudaMemcpyDefault);
+    if (e != cudaSuccess) return fail_cuda(e, "ob_lut_download");
+    return OB_OK;
+}
+
+ob_status ob_lut_info(const ob_lut* lut, size_t* h, size_t* w, int* dtype, int* device) {
+    if (!lut) return fail(OB_INVALID_ARGUMENT, "null lut");
+    if (h) *h = lut->h;
+    if (w) *w = lut->w;
+    if (dtype) *dtype = lut->dtype;
+    if (device) *device = lut->device;
+    return OB_OK;
+}
+
+ob_status ob_lut_device_ptrs(const ob_lut* lut, void** direction, void** offset) {
+    if (!lut) return fail(OB_INVALID_ARGUMENT, "null lut");
+    if (direction) *direction = lut->dir;
+    if (offset) *offset = lut->off;
+    return OB_OK;
+}
+
+ob_status ob_lut_destroy(ob_lut* lut) {
+    if (!lut) return OB_OK;
+    cudaSetDevice(lut->device);
+    cudaFree(lut->dir);
+    cudaFree(lut->off);
+    delete lut;
+    return OB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// scan -> cloud
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+
+template <typename T>
+static ob_status scan_to_cloud_t(const ob_lut* lut, const uint16_t* shift, const ob_cloud_io* io,
+                                 ob_stream* s) {
+    const size_t n_px = lut->h * lut->w;
+    const uint32_t F = io->n_frames, R = io->n_returns;
+    Staging stg(s->st);
+    // extent (in elements) spanned by a strided [F][R][n] array
+    auto extent = [&](size_t fs, size_t rs, size_t n) {
+        return (F - 1) * fs + (R - 1) * rs + n;
+    };
+    CloudArgs<T> a;
+    a.dir = static_cast<const T*>(lut->dir);
+    a.off = static_cast<const T*>(lut->off);
+    a.range_fs = io->range_frame_stride;
+    a.range_rs = io->range_return_stride;
+    a.xyz_fs = io->xyz_frame_stride;
+    a.xyz_rs = io->xyz_return_stride;
+    a.rd_fs = io->rd_frame_stride;
+    a.rd_rs = io->rd_return_stride;
+    a.xd_fs = io->xd_frame_stride;
+    a.xd_rs = io->xd_return_stride;
+    a.H = static_cast<int>(lut->h);
+    a.W = static_cast<int>(lut->w);
+    a.n_returns = static_cast<int>(R);
+    a.n_frames = F;
+    a.shift = shift;
+    const void* din = nullptr;
+    void* dout = nullptr;
+    cudaError_t e = stg.in(io->range, extent(a.range_fs, a.range_rs, n_px) * 4, &din);
+    if (e != cudaSuccess) return fail_cuda(e, "stage range");
+    a.range = static_cast<const uint32_t*>(din);
+    a.xyz = nullptr;
+    a.rd = nullptr;
+    a.xd = nullptr;
+    if (io->xyz) {
+        e = stg.out(io->xyz, extent(a.xyz_fs, a.xyz_rs, n_px * 3) * sizeof(T), &dout);
+        if (e != cudaSuccess) return fail_cuda(e, "stage xyz");
+        a.xyz = static_cast<T*>(dout);
+    }
+    if (io->range_destaggered) {
+        e = stg.out(io->range_destaggered, extent(a.rd_fs, a.rd_rs, n_px) * 4, &dout);
+        if (e != cudaSuccess) return fail_cuda(e, "stage range_destaggered");
+        a.rd = static_cast<uint32_t*>(dout);
+    }
+    if (io->xyz_destaggered) {
+        e = stg.out(io->xyz_destaggered, extent(a.xd_fs, a.xd_rs, n_px * 3) * sizeof(T), &dout);
+        if (e != cudaSuccess) return fail_cuda(e, "stage xyz_destaggered");
+        a.xd = static_cast<T*>(dout);
+    }
+    e = launch_cloud<T>(a, s->device, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "scan_to_cloud launch");
+    e = stg.flush();
+    if (e != cudaSuccess) return fail_cuda(e, "scan_to_cloud D2H");
+    return OB_OK;
+}
+
+extern "C" {
+
+ob_status ob_scan_to_cloud(const ob_lut* lut, const int32_t* shifts, size_t n_shifts,
+                           const ob_cloud_io* io, ob_stream* s) {
+    if (!lut || !io || !s) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (!io->range) return fail(OB_INVALID_ARGUMENT, "null range image");
+    if (io->n_returns < 1 || io->n_returns > OB_MAX_RETURNS)
+        return fail(OB_INVALID_ARGUMENT, "n_returns must be 1 or 2");
+    if (io->n_frames == 0) return OB_OK;
+    const bool needs_shift = io->range_destaggered || io->xyz_destaggered;
+    if (needs_shift) {
+        if (!shifts || n_shifts != lut->h)
+            return fail(OB_INVALID_ARGUMENT, "image height does not match shifts size");
+        if (lut->h > static_cast<size_t>(kMaxRows))
+            return fail(OB_INVALID_ARGUMENT, "fused destagger supports at most 512 rows");
+    }
+    if (lut->w > 65535) return fail(OB_INVALID_ARGUMENT, "frame width exceeds 65535 columns");
+    ob_status rs = require_device(s->device);
+    if (rs != OB_OK) return rs;
+    if (lut->device != s->device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
+    std::vector<uint16_t> sh;
+    if (needs_shift) reduce_shifts(shifts, lut->h, lut->w, 0, sh);
+    if (lut->dtype == OB_F64) return scan_to_cloud_t<double>(lut, needs_shift ? sh.data() : nullptr, io, s);
+    return scan_to_cloud_t<float>(lut, needs_shift ? sh.data() : nullptr, io, s);
+}
+
+ob_status ob_cartesian(const ob_lut* lut, const uint32_t* range, size_t n_pixels, void* xyz,
+                       ob_stream* s) {
+    if (!lut || !s) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (n_pixels != lut->h * lut->w) return fail(OB_INVALID_ARGUMENT, "unexpected image dimensions");
+    if (!range || !xyz) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    ob_cloud_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.n_frames = 1;
+    io.n_returns = 1;
+    io.range = range;
+    io.xyz = xyz;
+    return ob_scan_to_cloud(lut, nullptr, 0, &io, s);
+}
+
+ob_status ob_destagger(size_t elem_size, size_t k, const void* img, const int32_t* shifts,
+                       size_t n_shifts, size_t h, size_t w, int inverse, void* out, ob_stream* s) {
+    if (!s) return fail(OB_INVALID_ARGUMENT, "null stream");
+    // checks and texts of destagger_into, impl/lidar_frame_impl.h:740-747
+    if (n_shifts != h) return fail(OB_INVALID_ARGUMENT, "image height does not match shifts size");
+    if (h == 0 || w == 0) return OB_OK;
+    if (!img || !out || !shifts) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (elem_size == 0 || k == 0) return fail(OB_INVALID_ARGUMENT, "element size must be positive");
+    if (w > 65535) return fail(OB_INVALID_ARGUMENT, "frame width exceeds 65535 columns");
+    ob_status rs = require_device(s->device);
+    if (rs != OB_OK) return rs;
+    std::vector<uint16_t> sh;
+    reduce_shifts(shifts, h, w, inverse, sh);
+    const size_t bytes = h * w * k * elem_size;
+    Staging stg(s->st);
+    const void* din = nullptr;
+    void* dout = nullptr;
+    cudaError_t e = stg.in(img, bytes, &din);
+    if (e != cudaSuccess) return fail_cuda(e, "stage image");
+    e = stg.out(out, bytes, &dout);
+    if (e != cudaSuccess) return fail_cuda(e, "stage output");
+    if (din == dout) return fail(OB_INVALID_ARGUMENT, "image and destaggered must not alias");
+    e = launch_destagger(elem_size, k, din, sh.data(), h, w, dout, s->device, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "destagger launch");
+    e = stg.flush();
+    if (e != cudaSuccess) return fail_cuda(e, "destagger D2H");
+    return OB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,634 @@
+// ob_cloud.cu -- K1: fused range -> XYZ (LUT projection) + per-row destagger rotation,
+// batched over frames and returns.  sm_100a.
+//
+// What it replaces (reference paths relative to /root/reference):
+//   impl::cartesianT<T>        ouster_core/include/ouster/core/impl/cartesian.h:36-66
+//   destagger_into<T> (2-D/N-D) ouster_core/include/ouster/core/impl/lidar_frame_impl.h:733-811
+//
+// Design (HBM-bound streaming kernel, no tensor cores -- there is no contraction here):
+//   * persistent CTAs, interleaved tile schedule; a tile = TW consecutive pixels of one row of
+//     one frame, all returns.
+//   * a ring of S shared-memory stages filled by TMA bulk copies (cp.async.bulk, SASS UBLKCP)
+//     tracked by mbarriers: the LUT direction/offset slices and the range slices of the tile.
+//     The LUT slices carry an L2 evict_last policy (re-read by every frame), the per-frame
+//     streams evict_first.
+//   * each thread turns 4 pixels (3 x 128-bit LDS of direction, 3 of offset, one 128-bit LDS
+//     of range per return) into 12 coordinates per return and writes them IN PLACE over the
+//     direction (return 0) / offset (return 1) slice; __fmul_rn/__fadd_rn keep the reference's
+//     un-fused multiply-add rounding so float/double results are bit-identical to the CPU build.
+//   * results leave through TMA bulk stores (cp.async.bulk.global.shared::cta): staggered XYZ
+//     straight from the in-place buffers; the destaggered range straight from the *input*
+//     range slice when the row shift is a multiple of 4 pixels (16-byte aligned rotation),
+//     otherwise through a warp-shuffle realignment (lane L takes lane L-1's uint4) and aligned
+//     128-bit stores.
+#include <algorithm>
+#include <cstdio>
+
+#include "ob_internal.h"
+#include "ob_ptx.cuh"
+
+namespace ob {
+
+template <typename T>
+struct CloudParams {
+    const T* dir;
+    const T* off;
+    const uint32_t* range;
+    T* xyz;
+    uint32_t* rd;
+    T* xd;
+    unsigned long long range_fs, range_rs, xyz_fs, xyz_rs, rd_fs, rd_rs, xd_fs, xd_rs;
+    int H, W, TW, tiles_per_row, stages;
+    unsigned n_frames, n_tiles, stage_bytes;
+    unsigned short shift[kMaxRows];
+};
+
+template <typename T>
+struct Vec;  // 16-byte vector of T
+template <>
+struct Vec<float> {
+    using type = float4;
+    static constexpr int N = 4;
+};
+template <>
+struct Vec<double> {
+    using type = double2;
+    static constexpr int N = 2;
+};
+
+__device__ __forceinline__ float project(uint32_t r, float d, float o) {
+    // r * dir + ofs with the int->float conversion and two roundings of the reference loop
+    return r == 0 ? 0.0f : __fadd_rn(__fmul_rn(static_cast<float>(r), d), o);
+}
+__device__ __forceinline__ double project(uint32_t r, double d, double o) {
+    return r == 0 ? 0.0 : __dadd_rn(__dmul_rn(static_cast<double>(r), d), o);
+}
+
+// 12 consecutive T values (4 pixels x 3) via 16-byte shared-memory accesses
+template <typename T>
+__device__ __forceinline__ void lds12(const T* s, T (&v)[12]) {
+    using V = typename Vec<T>::type;
+    constexpr int NV = 12 / Vec<T>::N;
+    const V* p = reinterpret_cast<const V*>(s);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        V x = p[i];
+        const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+        for (int j = 0; j < Vec<T>::N; ++j) v[i * Vec<T>::N + j] = e[j];
+    }
+}
+template <typename T>
+__device__ __forceinline__ void sts12(T* s, const T (&v)[12]) {
+    using V = typename Vec<T>::type;
+    constexpr int NV = 12 / Vec<T>::N;
+    V* p = reinterpret_cast<V*>(s);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        V x;
+        T* e = reinterpret_cast<T*>(&x);
+#pragma unroll
+        for (int j = 0; j < Vec<T>::N; ++j) e[j] = v[i * Vec<T>::N + j];
+        p[i] = x;
+    }
+}
+
+struct TileCoord {
+    unsigned f;
+    int row, c0, tw;
+};
+
+template <typename T>
+__device__ __forceinline__ TileCoord tile_coord(const CloudParams<T>& p, unsigned t) {
+    TileCoord tc;
+    const unsigned per_frame = static_cast<unsigned>(p.H) * p.tiles_per_row;
+    tc.f = t / per_frame;
+    const unsigned rem = t - tc.f * per_frame;
+    tc.row = rem / p.tiles_per_row;
+    tc.c0 = (rem - tc.row * p.tiles_per_row) * p.TW;
+    tc.tw = min(p.TW, p.W - tc.c0);
+    return tc;
+}
+
+template <typename T, int R>
+__global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ CloudParams<T> p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint8_t* stage0 = smem + 128;
+
+    const int tid = threadIdx.x;
+    const int S = p.stages;
+    const bool need_lut = (p.xyz != nullptr) || (p.xd != nullptr);
+    const unsigned lut_bytes_full = 3u * p.TW * sizeof(T);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const unsigned first = blockIdx.x;
+    const unsigned n_my = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (tid == 0) {
+        pol_keep = policy_evict_last();
+        pol_stream = policy_evict_first();
+    }
+
+    auto issue_load = [&](unsigned k) {  // thread 0 only
+        const TileCoord tc = tile_coord(p, first + k * gridDim.x);
+        const int s = k % S;
+        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+        const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
+        const unsigned lut_b = 3u * tc.tw * sizeof(T);
+        const unsigned rng_b = 4u * tc.tw;
+        mbar_expect_tx(&full[s], (need_lut ? 2u * lut_b : 0u) + R * rng_b);
+        if (need_lut) {
+            bulk_g2s_hint(st, p.dir + px * 3, lut_b, &full[s], pol_keep);
+            bulk_g2s_hint(st + lut_bytes_full, p.off + px * 3, lut_b, &full[s], pol_keep);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            bulk_g2s_hint(st + 2 * lut_bytes_full + r * 4u * p.TW,
+                          p.range + tc.f * p.range_fs + r * p.range_rs + px, rng_b, &full[s],
+                          pol_stream);
+        }
+    };
+
+    if (tid == 0) {
+        const unsigned pre = min(n_my, static_cast<unsigned>(S));
+        for (unsigned k = 0; k < pre; ++k) issue_load(k);
+    }
+
+    for (unsigned k = 0; k < n_my; ++k) {
+        const int s = k % S;
+        // refill the stage tile k-1 used: its bulk stores must have finished READING smem
+        if (tid == 0 && k >= 1 && (k - 1 + S) < n_my) {
+            bulk_wait_read<0>();
+            issue_load(k - 1 + S);
+        }
+        const TileCoord tc = tile_coord(p, first + k * gridDim.x);
+        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+        T* dir_s = reinterpret_cast<T*>(st);
+        T* off_s = reinterpret_cast<T*>(st + lut_bytes_full);
+        uint32_t* rng_s = reinterpret_cast<uint32_t*>(st + 2 * lut_bytes_full);
+
+        mbar_wait(&full[s], (k / S) & 1);
+
+        const int sh = (p.rd != nullptr || p.xd != nullptr) ? p.shift[tc.row] : 0;
+        const int q = sh & 3;
+        const int n_groups = tc.tw >> 2;
+
+        // ---- destaggered range, unaligned row shift: warp-shuffle realignment ----
+        if (p.rd != nullptr && q != 0) {
+            const int lane = tid & 31;
+            const int nv = n_groups;  // source vectors; dest vectors m = 0..nv (edges partial)
+            const int base_col = tc.c0 + sh - q;  // multiple of 4
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(rng_s + r * p.TW);
+                uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + static_cast<size_t>(tc.row) * p.W;
+                for (int m0 = (tid >> 5) * 32; m0 <= nv; m0 += blockDim.x) {
+                    const int m = m0 + lane;
+                    uint4 b = make_uint4(0, 0, 0, 0);
+                    if (m < nv) b = s4[m];
+                    uint4 a;
+                    a.x = __shfl_up_sync(0xffffffffu, b.x, 1);
+                    a.y = __shfl_up_sync(0xffffffffu, b.y, 1);
+                    a.z = __shfl_up_sync(0xffffffffu, b.z, 1);
+                    a.w = __shfl_up_sync(0xffffffffu, b.w, 1);
+                    if (lane == 0) a = (m > 0 && m <= nv) ? s4[m - 1] : make_uint4(0, 0, 0, 0);
+                    if (m > nv) continue;
+                    uint4 o;
+                    if (q == 1) o = make_uint4(a.w, b.x, b.y, b.z);
+                    else if (q == 2) o = make_uint4(a.z, a.w, b.x, b.y);
+                    else o = make_uint4(a.y, a.z, a.w, b.x);
+                    int col = base_col + 4 * m;
+                    col = col >= p.W ? col - p.W : col;
+                    col = col >= p.W ? col - p.W : col;
+                    uint32_t* dst = drow + col;
+                    if (m == 0) {  // elements e >= q come from this tile
+                        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+                        for (int e = q; e < 4; ++e) stg_stream(dst + e, ov[e]);
+                    } else if (m == nv) {  // elements e < q
+                        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+                        for (int e = 0; e < q; ++e) stg_stream(dst + e, ov[e]);
+                    } else {
+                        stg_stream(reinterpret_cast<uint4*>(dst), o);
+                    }
+                }
+            }
+        }
+
+        // ---- projection, in place ----
+        if (need_lut) {
+            for (int g = tid; g < n_groups; g += blockDim.x) {
+                T d[12], o[12];
+                lds12(dir_s + 12 * g, d);
+                lds12(off_s + 12 * g, o);
+                uint4 rr[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    rr[r] = reinterpret_cast<const uint4*>(rng_s + r * p.TW)[g];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t rv[4] = {rr[r].x, rr[r].y, rr[r].z, rr[r].w};
+                    T out[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) out[i] = project(rv[i / 3], d[i], o[i]);
+                    sts12((r == 0 ? dir_s : off_s) + 12 * g, out);
+                }
+            }
+            fence_proxy_async();
+        }
+        __syncthreads();
+
+        bool thread_path_xd = false;
+        if (tid == 0) {
+            const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
+            if (p.xyz != nullptr) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    bulk_s2g(p.xyz + tc.f * p.xyz_fs + r * p.xyz_rs + px * 3,
+                             r == 0 ? dir_s : off_s, 3u * tc.tw * sizeof(T));
+            }
+            if (q == 0 && (p.rd != nullptr || p.xd != nullptr)) {
+                int d0 = tc.c0 + sh;
+                d0 = d0 >= p.W ? d0 - p.W : d0;
+                const int n1 = min(tc.tw, p.W - d0);
+                const size_t rowpx = static_cast<size_t>(tc.row) * p.W;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (p.rd != nullptr) {
+                        uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + rowpx;
+                        const uint32_t* src = rng_s + r * p.TW;
+                        bulk_s2g(drow + d0, src, 4u * n1);
+                        if (n1 < tc.tw) bulk_s2g(drow, src + n1, 4u * (tc.tw - n1));
+                    }
+                    if (p.xd != nullptr) {
+                        T* drow = p.xd + tc.f * p.xd_fs + r * p.xd_rs + rowpx * 3;
+                        const T* src = r == 0 ? dir_s : off_s;
+                        bulk_s2g(drow + static_cast<size_t>(d0) * 3, src, 3u * n1 * sizeof(T));
+                        if (n1 < tc.tw)
+                            bulk_s2g(drow, src + static_cast<size_t>(n1) * 3,
+                                     3u * (tc.tw - n1) * sizeof(T));
+                    }
+                }
+            }
+            bulk_commit();
+        }
+        // ---- destaggered XYZ, unaligned row shift: coalesced 32-bit word copies ----
+        if (p.xd != nullptr && q != 0) {
+            thread_path_xd = true;
+            constexpr int WPE = sizeof(T) / 4;  // 32-bit words per scalar
+            const int row_words = p.W * 3 * WPE;
+            const int n_words = tc.tw * 3 * WPE;
+            int d0 = tc.c0 + sh;
+            d0 = d0 >= p.W ? d0 - p.W : d0;
+            const int dst0 = d0 * 3 * WPE;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                uint32_t* drow = reinterpret_cast<uint32_t*>(
+                    p.xd + tc.f * p.xd_fs + r * p.xd_rs + static_cast<size_t>(tc.row) * p.W * 3);
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(r == 0 ? dir_s : off_s);
+                for (int i = tid; i < n_words; i += blockDim.x) {
+                    int dw = dst0 + i;
+                    dw = dw >= row_words ? dw - row_words : dw;
+                    stg_stream(drow + dw, src[i]);
+                }
+            }
+        }
+        if (thread_path_xd) __syncthreads();  // stage may be refilled next iteration
+    }
+    if (tid == 0) bulk_wait<0>();
+}
+
+// Generic kernel: any width / alignment / stride.  One pixel per thread, grid-stride.
+template <typename T>
+__global__ void cloud_generic_kernel(const __grid_constant__ CloudParams<T> p, int n_returns) {
+    const size_t n_px = static_cast<size_t>(p.H) * p.W;
+    const size_t total = n_px * p.n_frames;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t f = i / n_px;
+        const size_t px = i - f * n_px;
+        const int row = static_cast<int>(px / p.W);
+        const int col = static_cast<int>(px - static_cast<size_t>(row) * p.W);
+        int dcol = col;
+        if (p.rd != nullptr || p.xd != nullptr) {
+            dcol = col + p.shift[row];
+            dcol = dcol >= p.W ? dcol - p.W : dcol;
+        }
+        const size_t dpx = static_cast<size_t>(row) * p.W + dcol;
+        T d[3] = {0, 0, 0}, o[3] = {0, 0, 0};
+        if (p.xyz != nullptr || p.xd != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                d[c] = p.dir[px * 3 + c];
+                o[c] = p.off[px * 3 + c];
+            }
+        }
+        for (int r = 0; r < n_returns; ++r) {
+            const uint32_t rv = p.range[f * p.range_fs + r * p.range_rs + px];
+            if (p.rd != nullptr) p.rd[f * p.rd_fs + r * p.rd_rs + dpx] = rv;
+            if (p.xyz != nullptr || p.xd != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const T v = project(rv, d[c], o[c]);
+                    if (p.xyz != nullptr) p.xyz[f * p.xyz_fs + r * p.xyz_rs + px * 3 + c] = v;
+                    if (p.xd != nullptr) p.xd[f * p.xd_fs + r * p.xd_rs + dpx * 3 + c] = v;
+                }
+            }
+        }
+    }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
+    const Tunables& tn = tunables(device);
+    CloudParams<T> p;
+    p.dir = a.dir;
+    p.off = a.off;
+    p.range = a.range;
+    p.xyz = a.xyz;
+    p.rd = a.rd;
+    p.xd = a.xd;
+    p.range_fs = a.range_fs;
+    p.range_rs = a.range_rs;
+    p.xyz_fs = a.xyz_fs;
+    p.xyz_rs = a.xyz_rs;
+    p.rd_fs = a.rd_fs;
+    p.rd_rs = a.rd_rs;
+    p.xd_fs = a.xd_fs;
+    p.xd_rs = a.xd_rs;
+    p.H = a.H;
+    p.W = a.W;
+    p.n_frames = a.n_frames;
+    for (int i = 0; i < kMaxRows; ++i) p.shift[i] = 0;
+    if (a.shift != nullptr)
+        for (int i = 0; i < a.H && i < kMaxRows; ++i) p.shift[i] = a.shift[i];
+
+    const bool need_lut = a.xyz != nullptr || a.xd != nullptr;
+    // element-stride alignment so that every tile slice is 16-byte aligned
+    const size_t t4 = 16 / sizeof(T);  // T elements per 16 bytes
+    bool fast = !tn.force_fallback && (a.W % 4 == 0) && a.H <= kMaxRows && aligned16(a.range) &&
+                a.range_fs % 4 == 0 && a.range_rs % 4 == 0;
+    if (need_lut) fast = fast && aligned16(a.dir) && aligned16(a.off);
+    if (a.xyz) fast = fast && aligned16(a.xyz) && a.xyz_fs % t4 == 0 && a.xyz_rs % t4 == 0;
+    if (a.rd) fast = fast && aligned16(a.rd) && a.rd_fs % 4 == 0 && a.rd_rs % 4 == 0;
+    if (a.xd) fast = fast && aligned16(a.xd) && a.xd_fs % t4 == 0 && a.xd_rs % t4 == 0;
+    if (a.n_returns < 1 || a.n_returns > 2) return cudaErrorInvalidValue;
+    if ((a.rd != nullptr || a.xd != nullptr) && a.H > kMaxRows) return cudaErrorInvalidValue;
+
+    if (!fast) {
+        p.TW = 0;
+        p.tiles_per_row = 0;
+        p.stages = 0;
+        p.n_tiles = 0;
+        p.stage_bytes = 0;
+        const size_t total = static_cast<size_t>(a.H) * a.W * a.n_frames;
+        const int threads = 256;
+        const size_t want = (total + threads - 1) / threads;
+        const int blocks = static_cast<int>(std::min<size_t>(want, static_cast<size_t>(tn.sm_count) * 16));
+        cloud_generic_kernel<T><<<std::max(blocks, 1), threads, 0, st>>>(p, a.n_returns);
+        count_launch();
+        return cudaGetLastError();
+    }
+
+    int TW = tn.cloud_tw;
+    if (sizeof(T) == 8) TW = std::max(4, TW / 2 / 4 * 4);
+    TW = std::min(TW, a.W);
+    TW = std::max(4, TW / 4 * 4);
+    // small launches: shrink tiles until every SM has work for a few CTAs
+    const unsigned want_tiles = static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm * 2;
+    while (TW > 128 && static_cast<unsigned>(a.H) * ((a.W + TW - 1) / TW) * a.n_frames < want_tiles)
+        TW = std::max(128, TW / 2 / 4 * 4);
+    p.TW = TW;
+    p.tiles_per_row = (a.W + TW - 1) / TW;
+    p.stages = tn.cloud_stages;
+    p.n_tiles = static_cast<unsigned>(a.H) * p.tiles_per_row * a.n_frames;
+    p.stage_bytes = 2u * 3u * TW * sizeof(T) + static_cast<unsigned>(a.n_returns) * 4u * TW;
+    p.stage_bytes = (p.stage_bytes + 127u) & ~127u;
+    const size_t smem = 128 + static_cast<size_t>(p.stages) * p.stage_bytes;
+    const int grid = static_cast<int>(
+        std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm));
+    auto kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2> : cloud_tma_kernel<T, 1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<std::max(grid, 1), tn.cloud_threads, smem, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_cloud<float>(const CloudArgs<float>&, int, cudaStream_t);
+template cudaError_t launch_cloud<double>(const CloudArgs<double>&, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// Generic destagger (any element size / trailing dims): byte rotation of every row.
+// out_row[b] = in_row[(b - shift_bytes) mod row_bytes]; 16-byte aligned stores on the destination,
+// source words realigned with a byte funnel shift.
+// replaces destagger_into<T> / <T,ndim>  impl/lidar_frame_impl.h:733-811
+// ---------------------------------------------------------------------------------------------
+struct DestaggerParams {
+    const uint8_t* in;
+    uint8_t* out;
+    unsigned long long row_bytes;
+    unsigned px_bytes;
+    int H;
+    unsigned short shift[kMaxRows];
+};
+
+__global__ void destagger_words_kernel(const __grid_constant__ DestaggerParams p) {
+    // row_bytes % 4 == 0, base pointers 4-byte aligned
+    const unsigned row_words = static_cast<unsigned>(p.row_bytes >> 2);
+    const int row = blockIdx.y;
+    const unsigned sb = static_cast<unsigned>(p.shift[row]) * p.px_bytes;  // < row_bytes
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(p.in + row * p.row_bytes);
+    uint32_t* out = reinterpret_cast<uint32_t*>(p.out + row * p.row_bytes);
+    const unsigned bsh = (sb & 3u) * 8u;
+    for (unsigned dw = blockIdx.x * blockDim.x + threadIdx.x; dw < row_words;
+         dw += gridDim.x * blockDim.x) {
+        // source byte address of destination byte 4*dw
+        long long src = static_cast<long long>(dw) * 4 - sb;
+        if (src < 0) src += static_cast<long long>(p.row_bytes);
+        unsigned sw = static_cast<unsigned>(src >> 2);
+        if (bsh == 0) {
+            out[dw] = in[sw];
+        } else {
+            // src is not word aligned: bytes come from words sw and sw+1 (mod row)
+            const unsigned sw1 = (sw + 1 == row_words) ? 0u : sw + 1;
+            out[dw] = __funnelshift_r(in[sw], in[sw1], (static_cast<unsigned>(src) & 3u) * 8u);
+        }
+    }
+}
+
+__global__ void destagger_bytes_kernel(const __grid_constant__ DestaggerParams p) {
+    const int row = blockIdx.y;
+    const unsigned long long sb = static_cast<unsigned long long>(p.shift[row]) * p.px_bytes;
+    const uint8_t* in = p.in + row * p.row_bytes;
+    uint8_t* out = p.out + row * p.row_bytes;
+    for (unsigned long long b = blockIdx.x * blockDim.x + threadIdx.x; b < p.row_bytes;
+         b += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        unsigned long long src = b >= sb ? b - sb : b + p.row_bytes - sb;
+        out[b] = in[src];
+    }
+}
+
+// rows beyond kMaxRows: shifts fetched from device memory
+__global__ void destagger_bytes_dev_kernel(const uint8_t* in_, uint8_t* out_,
+                                           unsigned long long row_bytes, unsigned px_bytes,
+                                           const unsigned short* shift) {
+    const int row = blockIdx.y;
+    const unsigned long long sb = static_cast<unsigned long long>(shift[row]) * px_bytes;
+    const uint8_t* in = in_ + row * row_bytes;
+    uint8_t* out = out_ + row * row_bytes;
+    for (unsigned long long b = blockIdx.x * blockDim.x + threadIdx.x; b < row_bytes;
+         b += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        unsigned long long src = b >= sb ? b - sb : b + row_bytes - sb;
+        out[b] = in[src];
+    }
+}
+
+cudaError_t launch_destagger(size_t elem_size, size_t k, const void* img, const uint16_t* shift_host,
+                             size_t h, size_t w, void* out, int device, cudaStream_t st) {
+    (void)device;
+    if (h == 0 || w == 0) return cudaSuccess;
+    const size_t px_bytes = elem_size * k;
+    const size_t row_bytes = px_bytes * w;
+    if (h > 65535) return cudaErrorInvalidValue;
+    if (h > static_cast<size_t>(kMaxRows)) {
+        unsigned short* dsh = nullptr;
+        cudaError_t e = cudaMallocAsync(&dsh, h * sizeof(unsigned short), st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(dsh, shift_host, h * sizeof(unsigned short), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return e;
+        dim3 grid(static_cast<unsigned>(std::min<size_t>((row_bytes + 255) / 256, 64)),
+                  static_cast<unsigned>(h));
+        destagger_bytes_dev_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(img),
+                                                         static_cast<uint8_t*>(out), row_bytes,
+                                                         static_cast<unsigned>(px_bytes), dsh);
+        count_launch();
+        e = cudaGetLastError();
+        cudaFreeAsync(dsh, st);
+        return e;
+    }
+    DestaggerParams p;
+    p.in = static_cast<const uint8_t*>(img);
+    p.out = static_cast<uint8_t*>(out);
+    p.row_bytes = row_bytes;
+    p.px_bytes = static_cast<unsigned>(px_bytes);
+    p.H = static_cast<int>(h);
+    for (int i = 0; i < kMaxRows; ++i) p.shift[i] = i < static_cast<int>(h) ? shift_host[i] : 0;
+    const bool words = (row_bytes % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 3u) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(out) & 3u) == 0) && row_bytes < (1ull << 31);
+    if (words) {
+        const size_t row_words = row_bytes / 4;
+        dim3 grid(static_cast<unsigned>(std::min<size_t>((row_words + 255) / 256, 64)),
+                  static_cast<unsigned>(h));
+        destagger_words_kernel<<<grid, 256, 0, st>>>(p);
+    } else {
+        dim3 grid(static_cast<unsigned>(std::min<size_t>((row_bytes + 255) / 256, 64)),
+                  static_cast<unsigned>(h));
+        destagger_bytes_kernel<<<grid, 256, 0, st>>>(p);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// LUT construction on the device, in double.
+// replaces impl::make_xyz_lut  ouster_core/src/xyzlut.cpp:11-89 (same operation order)
+// ---------------------------------------------------------------------------------------------
+struct LutParams {
+    double b2l[16];
+    double tr[16];
+    double range_unit;
+    unsigned long long w, h;
+    int per_beam;
+};
+
+__global__ void make_lut_kernel(const __grid_constant__ LutParams p, const double* az_deg,
+                                const double* alt_deg, double* dir, double* off) {
+    const double kPi = 3.14159265358979323846;
+    const unsigned long long n = p.w * p.h;
+    const double b03 = p.b2l[3], b23 = p.b2l[11];
+    double dist = b03;
+    if (b23 != 0) dist = sqrt(__dadd_rn(__dmul_rn(b03, b03), __dmul_rn(b23, b23)));
+    const double azimuth_radians = kPi * 2.0 / static_cast<double>(p.w);
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x;
+         i < n; i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+        const unsigned long long row = i / p.w, col = i - row * p.w;
+        double enc, az, alt;
+        if (p.per_beam) {
+            enc = __dsub_rn(2.0 * kPi, __dmul_rn(static_cast<double>(col), azimuth_radians));
+            az = __ddiv_rn(__dmul_rn(-az_deg[row], kPi), 180.0);
+            alt = __ddiv_rn(__dmul_rn(alt_deg[row], kPi), 180.0);
+        } else {
+            enc = 0;
+            az = __ddiv_rn(__dmul_rn(az_deg[i], kPi), 180.0);
+            alt = __ddiv_rn(__dmul_rn(alt_deg[i], kPi), 180.0);
+        }
+        const double ea = __dadd_rn(enc, az);
+        double d[3], o[3];
+        const double ca = cos(alt);
+        d[0] = __dmul_rn(cos(ea), ca);
+        d[1] = __dmul_rn(sin(ea), ca);
+        d[2] = sin(alt);
+        o[0] = __dsub_rn(__dmul_rn(cos(enc), b03), __dmul_rn(d[0], dist));
+        o[1] = __dsub_rn(__dmul_rn(sin(enc), b03), __dmul_rn(d[1], dist));
+        o[2] = __dadd_rn(__dmul_rn(-d[2], dist), b23);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double dj = __dadd_rn(__dadd_rn(__dmul_rn(d[0], p.tr[j * 4 + 0]),
+                                            __dmul_rn(d[1], p.tr[j * 4 + 1])),
+                                  __dmul_rn(d[2], p.tr[j * 4 + 2]));
+            double oj = __dadd_rn(__dadd_rn(__dmul_rn(o[0], p.tr[j * 4 + 0]),
+                                            __dmul_rn(o[1], p.tr[j * 4 + 1])),
+                                  __dmul_rn(o[2], p.tr[j * 4 + 2]));
+            oj = __dadd_rn(oj, p.tr[j * 4 + 3]);
+            dir[i * 3 + j] = __dmul_rn(dj, p.range_unit);
+            off[i * 3 + j] = __dmul_rn(oj, p.range_unit);
+        }
+    }
+}
+
+cudaError_t launch_make_lut(size_t w, size_t h, double range_unit, const double* b2l16,
+                            const double* tr16, const double* az_dev, size_t n_az,
+                            const double* alt_dev, size_t n_alt, double* dir_dev, double* off_dev,
+                            cudaStream_t st) {
+    LutParams p;
+    for (int i = 0; i < 16; ++i) {
+        p.b2l[i] = b2l16[i];
+        p.tr[i] = tr16[i];
+    }
+    p.range_unit = range_unit;
+    p.w = w;
+    p.h = h;
+    p.per_beam = (n_az == h && n_alt == h) ? 1 : 0;
+    const size_t n = w * h;
+    const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 1184));
+    make_lut_kernel<<<std::max(blocks, 1), 256, 0, st>>>(p, az_dev, alt_dev, dir_dev, off_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void cast_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst,
+                                    size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = static_cast<float>(src[i]);  // round-to-nearest, as Eigen's cast<float>()
+}
+
+cudaError_t launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t st) {
+    const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 1184));
+    cast_f64_f32_kernel<<<std::max(blocks, 1), 256, 0, st>>>(src, dst, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace ob

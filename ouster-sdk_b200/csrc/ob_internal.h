@@ -1,0 +1,104 @@
+// ob_internal.h -- internal declarations shared by the kernels and the C-ABI glue.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../../include/ouster_b200.h"
+
+namespace ob {
+
+constexpr int kMaxRows = 512;  // rows (beams) whose shifts travel as kernel parameters
+
+struct Tunables {
+    int cloud_tw;          // pixels per tile (multiple of 4)
+    int cloud_stages;      // TMA ring depth
+    int cloud_threads;     // threads per CTA
+    int cloud_ctas_per_sm; // persistent CTAs per SM
+    int decode_stages;
+    int decode_threads;
+    int decode_ctas_per_sm;
+    int force_fallback;    // 1: use the generic (non-TMA) kernels
+    int sm_count;
+};
+const Tunables& tunables(int device);
+bool set_tunable(int device, const char* name, int value);
+
+// ---- launchers implemented in the .cu files; all return cudaError_t ----
+template <typename T>
+struct CloudArgs {
+    const T* dir;
+    const T* off;
+    const uint32_t* range;
+    T* xyz;
+    uint32_t* rd;
+    T* xd;
+    size_t range_fs, range_rs, xyz_fs, xyz_rs, rd_fs, rd_rs, xd_fs, xd_rs;
+    int H, W, n_returns;
+    uint32_t n_frames;
+    const uint16_t* shift;  // H entries, already reduced to [0, W) (host memory); may be null if no rd/xd
+};
+
+template <typename T>
+cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st);
+
+cudaError_t launch_destagger(size_t elem_size, size_t k, const void* img, const uint16_t* shift_host,
+                             size_t h, size_t w, void* out, int device, cudaStream_t st);
+
+cudaError_t launch_make_lut(size_t w, size_t h, double range_unit, const double* b2l16,
+                            const double* tr16, const double* az_dev, size_t n_az,
+                            const double* alt_dev, size_t n_alt, double* dir_dev, double* off_dev,
+                            cudaStream_t st);
+cudaError_t launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t st);
+
+// ---- decode ----
+struct DecodeField {  // device-side copy of ob_field_desc, pre-digested
+    uint32_t offset;
+    uint32_t elem_size;
+    uint64_t mask;
+    int32_t shift;
+    int32_t range_return;
+    uint32_t zero_pattern;
+    uint32_t pad;
+};
+
+struct DecodeLayout {
+    uint32_t packet_header_size, col_header_size, channel_data_size, col_size, packet_size;
+    uint32_t cpp, H, W;
+    DecodeField ts, mid, status;
+    uint32_t n_fields;
+    DecodeField fields[OB_MAX_FIELDS];
+};
+
+struct DecodeFrame {  // one per frame of a batched launch, lives in device memory
+    const uint8_t* packets;
+    unsigned long long packet_stride;
+    uint32_t n_slots;
+    uint32_t flags;          // bit0: identity column map
+    const int32_t* col_src;  // device, W entries (unused when identity)
+    const int32_t* hdr_src;  // device, W entries
+    void* fields[OB_MAX_FIELDS];
+    uint64_t* timestamp;
+    uint16_t* measurement_id;
+    uint32_t* status;
+    void* xyz[OB_MAX_RETURNS];
+    uint32_t* rd[OB_MAX_RETURNS];
+};
+
+struct DecodeLaunch {
+    const DecodeLayout* layout_host;  // host copy (for launch geometry)
+    const DecodeLayout* layout_dev;   // device copy
+    const DecodeFrame* frames_dev;
+    uint32_t n_frames;
+    const void* lut_dir;  // nullable
+    const void* lut_off;
+    int lut_dtype;
+    const uint16_t* shift_host;  // nullable (H entries reduced to [0,W))
+};
+cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st);
+
+void count_launch(uint64_t n = 1);
+
+}  // namespace ob
