@@ -65,8 +65,11 @@ class PinnedBuffer:
         self.raw = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
 
     def __del__(self):
-        if getattr(self, "ptr", None):
-            lib.ob_host_free(self.ptr)
+        if getattr(self, "ptr", None) and lib is not None:
+            try:
+                lib.ob_host_free(self.ptr)
+            except Exception:
+                pass
             self.ptr = None
 
 
@@ -107,8 +110,11 @@ class Stream:
         check(lib.ob_stream_sync(self.h))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib.ob_stream_destroy(self.h)
+        if getattr(self, "h", None) and lib is not None:
+            try:
+                lib.ob_stream_destroy(self.h)
+            except Exception:
+                pass
             self.h = None
 
 
@@ -204,8 +210,11 @@ class XYZLutT:
         return cartesian(self, rng, out=out, stream=stream)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib.ob_lut_destroy(self._h)
+        if getattr(self, "_h", None) and lib is not None:
+            try:
+                lib.ob_lut_destroy(self._h)
+            except Exception:
+                pass
             self._h = None
 
 
@@ -293,3 +302,80 @@ def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None
         nsh = sh.size
     check(lib.ob_scan_to_cloud(lut._h, sh.ctypes.data if sh is not None else None, nsh,
                                C.byref(io), st.h))
+
+
+class Decoder:
+    """ob_decoder: device-side PacketFormat decode table.
+
+    layout: dict with packet_header_size, col_header_size, channel_data_size, col_size,
+            packet_size, columns_per_packet, pixels_per_column, columns_per_frame and the three
+            column-header infos col_timestamp / col_measurement_id / col_status as
+            (offset, mask, shift) tuples.
+    fields: list of dicts {name, offset, mask, shift, elem_size, range_return, zero_pattern}.
+    """
+
+    def __init__(self, layout, fields, device=0):
+        from ._capi import FieldDesc, PacketLayout
+        L = PacketLayout()
+        for k in ("packet_header_size", "col_header_size", "channel_data_size", "col_size",
+                  "packet_size", "columns_per_packet", "pixels_per_column", "columns_per_frame"):
+            setattr(L, k, int(layout[k]))
+        for k in ("col_timestamp", "col_measurement_id", "col_status"):
+            o, m, sft = layout[k]
+            setattr(L, k, FieldDesc(int(o), 8, int(m), int(sft), -1, 0, 0))
+        arr = (FieldDesc * max(len(fields), 1))()
+        for i, f in enumerate(fields):
+            arr[i] = FieldDesc(int(f["offset"]), int(f["elem_size"]), int(f["mask"]), int(f["shift"]),
+                               int(f.get("range_return", -1)), int(f.get("zero_pattern", 0)), 0)
+        h = C.c_void_p()
+        check(lib.ob_decoder_create(C.byref(L), arr, len(fields), device, C.byref(h)))
+        self._h, self.device = h, device
+        self.layout, self.fields = dict(layout), [dict(f) for f in fields]
+        self.h_px, self.w_px = int(layout["pixels_per_column"]), int(layout["columns_per_frame"])
+
+    def decode(self, frames, lut=None, pixel_shift_by_row=None, stream=None):
+        """frames: list of dicts {packets, n_slots, packet_stride, col_src (np.int32 [W] or None),
+        fields: {name: array}, timestamp, measurement_id, status, xyz: [a0, a1],
+        range_destaggered: [a0, a1]}.  Asynchronous on `stream`."""
+        from ._capi import DecodeIO
+        st = _stream(stream, self.device)
+        ios = (DecodeIO * len(frames))()
+        keep = []
+        for i, fr in enumerate(frames):
+            io = ios[i]
+            io.packets = _ptr(fr["packets"])
+            io.n_slots = int(fr["n_slots"])
+            io.packet_stride = int(fr["packet_stride"])
+            cs = fr.get("col_src")
+            if cs is not None:
+                cs = np.ascontiguousarray(cs, np.int32)
+                keep.append(cs)
+                io.col_src = cs.ctypes.data
+            outs = fr.get("fields", {})
+            for k, f in enumerate(self.fields):
+                a = outs.get(f["name"])
+                if a is not None:
+                    io.fields[k] = _ptr(a)
+            for k in ("timestamp", "measurement_id", "status"):
+                if fr.get(k) is not None:
+                    setattr(io, k, _ptr(fr[k]))
+            for r, a in enumerate(fr.get("xyz", []) or []):
+                if a is not None:
+                    io.xyz[r] = _ptr(a)
+            for r, a in enumerate(fr.get("range_destaggered", []) or []):
+                if a is not None:
+                    io.range_destaggered[r] = _ptr(a)
+        sh, nsh = None, 0
+        if pixel_shift_by_row is not None:
+            sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
+            nsh = sh.size
+        check(lib.ob_decode_frames(self._h, ios, len(frames), lut._h if lut is not None else None,
+                                   sh.ctypes.data if sh is not None else None, nsh, st.h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            try:
+                lib.ob_decoder_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None

@@ -43,7 +43,7 @@ static Tunables& tunables_mut(int device) {
         Tunables t;
         t.cloud_tw = env_int("OB_CLOUD_TW", 512);
         t.cloud_stages = std::max(2, env_int("OB_CLOUD_STAGES", 4));
-        t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 128)));
+        t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 256)));
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
         t.decode_stages = std::max(2, env_int("OB_DECODE_STAGES", 2));
         t.decode_threads = std::min(1024, std::max(64, env_int("OB_DECODE_THREADS", 512)));

@@ -1,0 +1,446 @@
+// ob_decode.cu -- K2: fused lidar-packet field decode -> row-major LidarFrame fields, with the
+// per-row destagger of the range image(s) and the XYZ LUT projection done in the same pass.
+//
+// What it replaces (reference paths relative to /root/reference):
+//   FieldDecodeInfo::get<T>                      ouster_core/include/ouster/core/field_decode_info.h:41-54
+//   PacketFormat::block_field / col_field        ouster_core/src/parsing.cpp:628-675
+//   FrameBatcher::parse_by_block / parse_by_col  ouster_core/src/lidar_frame.cpp:1422-1528
+//   zero_fields / zero_header_cols               ouster_core/src/lidar_frame.cpp:1274-1278, 1371-1418
+//   + cartesianT / destagger of the decoded range (impl/cartesian.h:36-66, impl/lidar_frame_impl.h:733-760)
+//
+// The reference walks every packet once per field (10 passes for dual return) with a transposing
+// scatter; here a tile of TC frame columns (the columns of P whole packets) is brought into shared
+// memory once by TMA bulk copies (one cp.async.bulk per packet, mbarrier-tracked, S-deep ring),
+// every pixel is decoded once for all fields from registers, and the outputs leave as row-major
+// coalesced stores (lane = frame column).  Decoded ranges are kept in a shared-memory tile so that
+// the XYZ projection can run on 16-byte LUT loads / XYZ stores (lane = 16-byte chunk of a row).
+//
+// Column map: frame column j takes its pixels from packet column col_src[j] (slot*cpp + c), or is
+// zero-filled when col_src[j] < 0.  With the identity map (complete in-order frame) whole packets
+// are bulk-copied; irregular groups are gathered column by column by the threads.
+#include <algorithm>
+#include <type_traits>
+
+#include "ob_internal.h"
+#include "ob_ptx.cuh"
+
+namespace ob {
+
+constexpr int kMaxTileCols = 64;
+constexpr int kMaxStages = 8;
+
+struct DecodeParams {
+    DecodeLayout L;
+    const DecodeFrame* frames;
+    const void* lut_dir;
+    const void* lut_off;
+    uint32_t n_frames, tiles_per_frame, n_tiles;
+    uint32_t TC, P;             // tile columns (= P * cpp), packets per tile
+    uint32_t pkt_stride_s;      // bytes reserved per packet in a stage (multiple of 16)
+    uint32_t stage_bytes, stages;
+    uint32_t n_words;           // 32-bit words of a pixel kept in registers (0: per-field smem reads)
+    uint32_t word_aligned;      // wire layout is 4-byte aligned everywhere
+    uint32_t n_returns;         // returns with a range field tagged
+    uint32_t vec_ok;            // XYZ rows are 16-byte aligned (W % 4 == 0, aligned pointers)
+    uint32_t has_shift;
+    unsigned short shift[kMaxRows];
+};
+
+struct TileCtl {  // per-stage bookkeeping written by the producer thread
+    int col_src[kMaxTileCols];  // source packet column (slot*cpp + c) or -1
+    unsigned char group_fast[kMaxTileCols];
+};
+
+__device__ __forceinline__ uint32_t lds_u32_any(const uint8_t* p, bool aligned) {
+    if (aligned) return *reinterpret_cast<const uint32_t*>(p);
+    return static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) |
+           (static_cast<uint32_t>(p[2]) << 16) | (static_cast<uint32_t>(p[3]) << 24);
+}
+
+__device__ __forceinline__ uint32_t pick(const uint32_t (&w)[8], uint32_t i) {
+    switch (i) {  // i is warp-uniform: a uniform branch, no divergence
+        case 0: return w[0];
+        case 1: return w[1];
+        case 2: return w[2];
+        case 3: return w[3];
+        case 4: return w[4];
+        case 5: return w[5];
+        case 6: return w[6];
+        default: return w[7];
+    }
+}
+
+// FieldDecodeInfo::get: 8-byte little-endian load at `offset`, mask, shift (caller truncates)
+__device__ __forceinline__ uint64_t apply_mask_shift(uint32_t lo, uint32_t hi, const DecodeField& f) {
+    uint64_t word = (static_cast<uint64_t>(hi) << 32) | lo;
+    word &= f.mask;
+    if (f.shift > 0) word >>= f.shift;
+    else if (f.shift < 0) word <<= -f.shift;
+    return word;
+}
+
+__device__ __forceinline__ uint64_t extract_regs(const uint32_t (&w)[8], const DecodeField& f) {
+    const uint32_t wo = f.offset >> 2, bo = (f.offset & 3u) * 8u;
+    const uint32_t w0 = pick(w, wo), w1 = pick(w, wo + 1);
+    uint32_t lo = w0, hi = w1;
+    if (bo) {
+        const uint32_t w2 = pick(w, wo + 2);
+        lo = __funnelshift_r(w0, w1, bo);
+        hi = __funnelshift_r(w1, w2, bo);
+    }
+    return apply_mask_shift(lo, hi, f);
+}
+
+__device__ __forceinline__ uint64_t extract_smem(const uint8_t* px, const DecodeField& f, bool aligned) {
+    const uint8_t* p = px + f.offset;
+    if (aligned && (f.offset & 3u) == 0)
+        return apply_mask_shift(*reinterpret_cast<const uint32_t*>(p),
+                                *reinterpret_cast<const uint32_t*>(p + 4), f);
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        lo |= static_cast<uint32_t>(p[i]) << (8 * i);
+        hi |= static_cast<uint32_t>(p[4 + i]) << (8 * i);
+    }
+    return apply_mask_shift(lo, hi, f);
+}
+
+__device__ __forceinline__ void store_elem(void* base, size_t idx, uint32_t es, uint64_t v) {
+    switch (es) {
+        case 1: static_cast<uint8_t*>(base)[idx] = static_cast<uint8_t>(v); break;
+        case 2: static_cast<uint16_t*>(base)[idx] = static_cast<uint16_t>(v); break;
+        case 4: static_cast<uint32_t*>(base)[idx] = static_cast<uint32_t>(v); break;
+        case 8: static_cast<uint64_t*>(base)[idx] = v; break;
+        default: {  // 6 bytes: 3 x 16 bit (float3x16_t, RGB)
+            uint16_t* q = static_cast<uint16_t*>(base) + idx * 3;
+            q[0] = static_cast<uint16_t>(v);
+            q[1] = static_cast<uint16_t>(v >> 16);
+            q[2] = static_cast<uint16_t>(v >> 32);
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t zero_value(const DecodeField& f) {
+    const uint64_t z = f.zero_pattern & 0xffffu;
+    return z | (z << 16) | (z << 32) | (z << 48);
+}
+
+__device__ __forceinline__ float project1(uint32_t r, float d, float o) {
+    return r == 0 ? 0.0f : __fadd_rn(__fmul_rn(static_cast<float>(r), d), o);
+}
+__device__ __forceinline__ double project1(uint32_t r, double d, double o) {
+    return r == 0 ? 0.0 : __dadd_rn(__dmul_rn(static_cast<double>(r), d), o);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ DecodeParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const DecodeLayout& L = p.L;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int S = p.stages;
+
+    // ---- shared memory carve-up ----
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                       // kMaxStages
+    TileCtl* ctl = reinterpret_cast<TileCtl*>(smem + 64);                      // S entries
+    size_t off = 64 + static_cast<size_t>(kMaxStages) * sizeof(TileCtl);
+    off = (off + 127) & ~static_cast<size_t>(127);
+    uint8_t* stage0 = smem + off;
+    uint32_t* rtile = reinterpret_cast<uint32_t*>(stage0 + static_cast<size_t>(S) * p.stage_bytes);
+    // rtile[r][row][TC]
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    const unsigned first = blockIdx.x;
+    const unsigned n_my = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    uint64_t pol_stream = 0;
+    if (tid == 0) pol_stream = policy_evict_first();
+
+    auto tile_of = [&](unsigned k, unsigned& f, unsigned& j0, unsigned& tc) {
+        const unsigned t = first + k * gridDim.x;
+        f = t / p.tiles_per_frame;
+        j0 = (t - f * p.tiles_per_frame) * p.TC;
+        tc = min(p.TC, L.W - j0);
+    };
+
+    auto issue = [&](unsigned k) {  // producer: thread 0
+        unsigned f, j0, tc;
+        tile_of(k, f, j0, tc);
+        const int s = k % S;
+        const DecodeFrame& fr = p.frames[f];
+        TileCtl& c = ctl[s];
+        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+        const bool identity = (fr.flags & 1u) != 0;
+        const bool bulk_ok = (fr.flags & 2u) != 0;
+        uint32_t tx = 0;
+        const unsigned n_groups = (tc + L.cpp - 1) / L.cpp;
+        // pass 1: classify
+        for (unsigned g = 0; g < n_groups; ++g) {
+            const unsigned jg = j0 + g * L.cpp;
+            const unsigned ncol = min(L.cpp, L.W - jg);
+            bool fast = bulk_ok && ncol == L.cpp;
+            int slot = -1;
+            for (unsigned i = 0; i < ncol; ++i) {
+                int src;
+                if (identity) {
+                    const unsigned sl = (jg + i) / L.cpp;
+                    src = sl < fr.n_slots ? static_cast<int>(jg + i) : -1;
+                } else {
+                    src = fr.col_src[jg + i];
+                }
+                c.col_src[g * L.cpp + i] = src;
+                if (src < 0) {
+                    fast = false;
+                } else {
+                    const int sl = src / static_cast<int>(L.cpp), ci = src - sl * static_cast<int>(L.cpp);
+                    if (ci != static_cast<int>(i) || (i > 0 && sl != slot)) fast = false;
+                    slot = sl;
+                }
+            }
+            c.group_fast[g] = fast ? 1 : 0;
+            if (fast) tx += L.packet_size;
+        }
+        mbar_expect_tx(&full[s], tx);
+        for (unsigned g = 0; g < n_groups; ++g) {
+            if (!c.group_fast[g]) continue;
+            const int slot = c.col_src[g * L.cpp] / static_cast<int>(L.cpp);
+            bulk_g2s_hint(st + static_cast<size_t>(g) * p.pkt_stride_s,
+                          fr.packets + static_cast<size_t>(slot) * fr.packet_stride, L.packet_size,
+                          &full[s], pol_stream);
+        }
+    };
+
+    if (tid == 0) {
+        const unsigned pre = min(n_my, static_cast<unsigned>(S));
+        for (unsigned k = 0; k < pre; ++k) issue(k);
+    }
+    __syncthreads();
+
+    const bool aligned = p.word_aligned != 0;
+    const unsigned n_ret = p.n_returns;
+
+    for (unsigned k = 0; k < n_my; ++k) {
+        const int s = k % S;
+        unsigned f, j0, tc;
+        tile_of(k, f, j0, tc);
+        const DecodeFrame& fr = p.frames[f];
+        TileCtl& c = ctl[s];
+        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+
+        mbar_wait(&full[s], (k / S) & 1);
+
+        // ---- irregular groups: gather the columns with ordinary loads ----
+        {
+            const unsigned n_groups = (tc + L.cpp - 1) / L.cpp;
+            bool any_slow = false;
+            for (unsigned g = 0; g < n_groups; ++g) any_slow |= (c.group_fast[g] == 0);
+            if (any_slow) {
+                for (unsigned t = warp; t < tc; t += nwarps) {
+                    const unsigned g = t / L.cpp;
+                    if (c.group_fast[g]) continue;
+                    const int src = c.col_src[t];
+                    if (src < 0) continue;
+                    const int sl = src / static_cast<int>(L.cpp), ci = src - sl * static_cast<int>(L.cpp);
+                    const uint8_t* gsrc = fr.packets + static_cast<size_t>(sl) * fr.packet_stride +
+                                          L.packet_header_size + static_cast<size_t>(ci) * L.col_size;
+                    uint8_t* dst = st + static_cast<size_t>(g) * p.pkt_stride_s + L.packet_header_size +
+                                   static_cast<size_t>(t - g * L.cpp) * L.col_size;
+                    // copy the column plus the 8 bytes a trailing field read may touch,
+                    // clamped to the end of the source packet
+                    const size_t col_end = L.packet_header_size + static_cast<size_t>(ci + 1) * L.col_size;
+                    const size_t extra = min(static_cast<size_t>(8), L.packet_size - col_end);
+                    const unsigned nbytes = L.col_size + static_cast<unsigned>(extra);
+                    if (aligned && ((reinterpret_cast<uintptr_t>(gsrc) & 3u) == 0)) {
+                        for (unsigned b = lane * 4; b + 4 <= nbytes; b += 128)
+                            *reinterpret_cast<uint32_t*>(dst + b) =
+                                *reinterpret_cast<const uint32_t*>(gsrc + b);
+                        for (unsigned b = (nbytes & ~3u) + lane; b < nbytes; b += 32) dst[b] = gsrc[b];
+                    } else {
+                        for (unsigned b = lane; b < nbytes; b += 32) dst[b] = gsrc[b];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- column headers (timestamp / measurement_id / status) ----
+        if (fr.timestamp != nullptr || fr.measurement_id != nullptr || fr.status != nullptr) {
+            for (unsigned t = tid; t < tc; t += nthreads) {
+                const int src = c.col_src[t];
+                uint64_t ts = 0, mid = 0, stt = 0;
+                if (src >= 0) {
+                    const unsigned g = t / L.cpp;
+                    const uint8_t* colp = st + static_cast<size_t>(g) * p.pkt_stride_s +
+                                          L.packet_header_size + static_cast<size_t>(t - g * L.cpp) * L.col_size;
+                    ts = extract_smem(colp, L.ts, aligned);
+                    mid = extract_smem(colp, L.mid, aligned);
+                    stt = extract_smem(colp, L.status, aligned);
+                }
+                if (fr.timestamp) fr.timestamp[j0 + t] = ts;
+                if (fr.measurement_id) fr.measurement_id[j0 + t] = static_cast<uint16_t>(mid);
+                if (fr.status) fr.status[j0 + t] = static_cast<uint32_t>(stt);
+            }
+        }
+
+        // ---- phase A: decode every pixel once, all fields; lane = frame column ----
+        const unsigned col_groups = (tc + 31) / 32;  // 32-column lane groups per row
+        for (unsigned item = warp; item < L.H * col_groups; item += nwarps) {
+            const unsigned row = item / col_groups;
+            const unsigned t = (item - row * col_groups) * 32 + lane;
+            if (t >= tc) continue;
+            const int src = c.col_src[t];
+            const unsigned g = t / L.cpp;
+            const uint8_t* px = st + static_cast<size_t>(g) * p.pkt_stride_s + L.packet_header_size +
+                                static_cast<size_t>(t - g * L.cpp) * L.col_size + L.col_header_size +
+                                static_cast<size_t>(row) * L.channel_data_size;
+            uint32_t w[8];
+            if (p.n_words && src >= 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    w[i] = (static_cast<uint32_t>(i) < p.n_words) ? lds_u32_any(px + 4 * i, aligned) : 0u;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = 0u;
+            }
+            const size_t pix = static_cast<size_t>(row) * L.W + j0 + t;
+            int dcol = static_cast<int>(j0 + t);
+            if (p.has_shift) {
+                dcol += p.shift[row];
+                dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
+            }
+            const size_t dpix = static_cast<size_t>(row) * L.W + dcol;
+            for (unsigned fi = 0; fi < L.n_fields; ++fi) {
+                const DecodeField& fd = L.fields[fi];
+                void* out = fr.fields[fi];
+                if (out == nullptr && fd.range_return < 0) continue;
+                uint64_t v;
+                if (src < 0) v = zero_value(fd);
+                else if (p.n_words) v = extract_regs(w, fd);
+                else v = extract_smem(px, fd, aligned);
+                if (out != nullptr) store_elem(out, pix, fd.elem_size, v);
+                if (fd.range_return >= 0) {
+                    const uint32_t rv = static_cast<uint32_t>(v);
+                    const int r = fd.range_return;
+                    rtile[(static_cast<size_t>(r) * L.H + row) * p.TC + t] = rv;
+                    if (fr.rd[r] != nullptr) fr.rd[r][dpix] = rv;
+                }
+            }
+        }
+        __syncthreads();  // rtile complete; packet stage no longer read
+
+        // refill this stage as early as possible
+        if (tid == 0 && (k + S) < n_my) issue(k + S);
+
+        // ---- phase B: XYZ from the range tile ----
+        if (p.lut_dir != nullptr) {
+            const T* dir = static_cast<const T*>(p.lut_dir);
+            const T* offs = static_cast<const T*>(p.lut_off);
+            constexpr int VN = 16 / sizeof(T);  // scalars per 16-byte chunk
+            if (p.vec_ok && (tc % 4u) == 0) {
+                using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+                const unsigned nvr = 3u * tc / VN;  // chunks per row segment
+                for (unsigned idx = tid; idx < L.H * nvr; idx += nthreads) {
+                    const unsigned row = idx / nvr, q = idx - row * nvr;
+                    const size_t ebase = (static_cast<size_t>(row) * L.W + j0) * 3 + static_cast<size_t>(q) * VN;
+                    const V dv = *reinterpret_cast<const V*>(dir + ebase);
+                    const V ov = *reinterpret_cast<const V*>(offs + ebase);
+                    const T* de = reinterpret_cast<const T*>(&dv);
+                    const T* oe = reinterpret_cast<const T*>(&ov);
+                    for (unsigned r = 0; r < n_ret; ++r) {
+                        T* xo = static_cast<T*>(fr.xyz[r]);
+                        if (xo == nullptr) continue;
+                        const uint32_t* rrow = rtile + (static_cast<size_t>(r) * L.H + row) * p.TC;
+                        V outv;
+                        T* oe2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) {
+                            const unsigned el = q * VN + e;
+                            oe2[e] = project1(rrow[el / 3u], de[e], oe[e]);
+                        }
+                        *reinterpret_cast<V*>(xo + ebase) = outv;
+                    }
+                }
+            } else {
+                for (unsigned idx = tid; idx < L.H * tc; idx += nthreads) {
+                    const unsigned row = idx / tc, t = idx - row * tc;
+                    const size_t ebase = (static_cast<size_t>(row) * L.W + j0 + t) * 3;
+                    for (unsigned r = 0; r < n_ret; ++r) {
+                        T* xo = static_cast<T*>(fr.xyz[r]);
+                        if (xo == nullptr) continue;
+                        const uint32_t rv = rtile[(static_cast<size_t>(r) * L.H + row) * p.TC + t];
+#pragma unroll
+                        for (int cidx = 0; cidx < 3; ++cidx)
+                            xo[ebase + cidx] = project1(rv, dir[ebase + cidx], offs[ebase + cidx]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // rtile free for the next tile
+    }
+}
+
+cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
+    const Tunables& tn = tunables(device);
+    const DecodeLayout& L = *a.layout_host;
+    if (L.cpp == 0 || L.H == 0 || L.W == 0 || L.cpp > static_cast<uint32_t>(kMaxTileCols))
+        return cudaErrorInvalidValue;
+    DecodeParams p;
+    p.L = L;
+    p.frames = a.frames_dev;
+    p.lut_dir = a.lut_dir;
+    p.lut_off = a.lut_off;
+    p.n_frames = a.n_frames;
+    p.P = std::max<uint32_t>(1, 32 / L.cpp);
+    p.TC = p.P * L.cpp;
+    p.tiles_per_frame = (L.W + p.TC - 1) / p.TC;
+    p.n_tiles = p.tiles_per_frame * a.n_frames;
+    p.pkt_stride_s = (L.packet_size + 16 + 15) & ~15u;  // +16: slack for trailing 8-byte field reads
+    p.stage_bytes = (p.P * p.pkt_stride_s + 127) & ~127u;
+    p.stages = std::min(std::max(tn.decode_stages, 1), kMaxStages);
+    const bool word_aligned = (L.packet_header_size % 4 == 0) && (L.col_header_size % 4 == 0) &&
+                              (L.channel_data_size % 4 == 0) && (L.col_size % 4 == 0);
+    p.word_aligned = word_aligned ? 1 : 0;
+    // pixel words kept in registers: a field read touches bytes [offset, offset+8)
+    uint32_t max_end = 0;
+    p.n_returns = 0;
+    for (uint32_t i = 0; i < L.n_fields; ++i) {
+        max_end = std::max(max_end, L.fields[i].offset + 8);
+        if (L.fields[i].range_return >= 0)
+            p.n_returns = std::max<uint32_t>(p.n_returns, L.fields[i].range_return + 1);
+    }
+    const uint32_t need_words = (max_end + 3) / 4;
+    p.n_words = (word_aligned && need_words <= 8) ? need_words : 0;
+    p.vec_ok = (L.W % 4 == 0) ? 1 : 0;  // caller (ob_decode_frames) also checks pointer alignment
+    p.has_shift = a.shift_host != nullptr ? 1 : 0;
+    for (int i = 0; i < kMaxRows; ++i)
+        p.shift[i] = (a.shift_host != nullptr && i < static_cast<int>(L.H)) ? a.shift_host[i] : 0;
+    if (a.shift_host != nullptr && L.H > static_cast<uint32_t>(kMaxRows)) return cudaErrorInvalidValue;
+    if (!a.vec_ok) p.vec_ok = 0;
+
+    const size_t rtile_bytes = static_cast<size_t>(std::max<uint32_t>(p.n_returns, 1)) * L.H * p.TC * 4;
+    size_t ctl_off = 64 + static_cast<size_t>(kMaxStages) * sizeof(TileCtl);
+    ctl_off = (ctl_off + 127) & ~static_cast<size_t>(127);
+    size_t smem = ctl_off + static_cast<size_t>(p.stages) * p.stage_bytes + rtile_bytes;
+    while (smem > 227 * 1024 && p.stages > 1) {
+        p.stages--;
+        smem = ctl_off + static_cast<size_t>(p.stages) * p.stage_bytes + rtile_bytes;
+    }
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    int threads = tn.decode_threads;
+    const int grid = static_cast<int>(
+        std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count) * tn.decode_ctas_per_sm));
+    auto kern = a.lut_dtype == OB_F64 ? decode_kernel<double> : decode_kernel<float>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<std::max(grid, 1), threads, smem, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace ob

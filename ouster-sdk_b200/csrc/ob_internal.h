@@ -88,14 +88,14 @@ struct DecodeFrame {  // one per frame of a batched launch, lives in device memo
 };
 
 struct DecodeLaunch {
-    const DecodeLayout* layout_host;  // host copy (for launch geometry)
-    const DecodeLayout* layout_dev;   // device copy
+    const DecodeLayout* layout_host;  // travels as a kernel parameter
     const DecodeFrame* frames_dev;
     uint32_t n_frames;
     const void* lut_dir;  // nullable
     const void* lut_off;
     int lut_dtype;
     const uint16_t* shift_host;  // nullable (H entries reduced to [0,W))
+    bool vec_ok;                 // LUT / XYZ pointers are 16-byte aligned
 };
 cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st);
 

@@ -44,3 +44,87 @@ def random_lut(n, seed, dtype=np.float32):
     d = (rng.random((n, 3)) + 0.5).astype(dtype)
     o = (rng.random((n, 3)) * 0.01).astype(dtype)
     return d, o
+
+
+# ------------------------------------------------------------------------------------------------
+# decode helpers (test infrastructure: descriptors and column maps derived from the ORACLE tables,
+# so the kernel is checked independently of the product's own host-side PacketFormat)
+# ------------------------------------------------------------------------------------------------
+def oracle_pf(meta_or_profile, h=None, w=None, cpp=16, header="STANDARD"):
+    from oracle import oracle as orc
+    if isinstance(meta_or_profile, dict):
+        m = meta_or_profile
+        return orc.PacketFormat(m["profile"], m["h"], m["w"], m["columns_per_packet"],
+                                orc.HEADER_FUSA if m["header_type"] == "FUSA" else orc.HEADER_STANDARD)
+    return orc.PacketFormat(meta_or_profile, h, w, cpp,
+                            orc.HEADER_FUSA if header == "FUSA" else orc.HEADER_STANDARD)
+
+
+def decoder_desc_from_oracle(pf, frame):
+    """(layout, fields) for ob.Decoder from an oracle PacketFormat and an oracle Frame."""
+    fi = lambda i: (i.offset, i.mask, i.shift)
+    layout = {
+        "packet_header_size": pf.packet_header_size, "col_header_size": pf.col_header_size,
+        "channel_data_size": pf.channel_data_size, "col_size": pf.col_size,
+        "packet_size": pf.lidar_packet_size, "columns_per_packet": pf.columns_per_packet,
+        "pixels_per_column": pf.pixels_per_column, "columns_per_frame": pf.columns_per_frame,
+        "col_timestamp": fi(pf.c.col_timestamp_info),
+        "col_measurement_id": fi(pf.c.col_measurement_id_info),
+        "col_status": fi(pf.c.col_status_info),
+    }
+    fields = []
+    for name in pf.field_names:          # std::map order
+        if not frame.has_field(name):
+            continue
+        info = pf.field_info(name)
+        a = frame.field(name)
+        es = a.dtype.itemsize * (3 if name == "RGB" else 1)
+        fields.append({"name": name, "offset": info.offset, "mask": info.mask, "shift": info.shift,
+                       "elem_size": es,
+                       "range_return": {"RANGE": 0, "RANGE2": 1}.get(name, -1),
+                       "zero_pattern": 0x7e00 if name == "RGB" else 0})
+    return layout, fields
+
+
+def col_map_from_packets(pf, packets):
+    """Final-state rule of FrameBatcher (SURVEY 8a'-3): frame column m_id takes the LAST arriving
+    valid (status & 1) packet column with that measurement id; everything else is zero-filled."""
+    w, cpp = pf.columns_per_frame, pf.columns_per_packet
+    col_src = np.full(w, -1, np.int32)
+    for slot, buf in enumerate(packets):
+        for c in range(cpp):
+            base = pf.packet_header_size + c * pf.col_size
+            col = np.concatenate([buf[base: base + pf.col_size], np.zeros(8, np.uint8)])
+            from oracle import oracle as orc
+            import ctypes as C
+            m_id = orc.lib().orc_field_get(C.byref(pf.c.col_measurement_id_info), col.ctypes.data) & 0xffff
+            status = orc.lib().orc_field_get(C.byref(pf.c.col_status_info), col.ctypes.data) & 0xffffffff
+            if (status & 1) and m_id < w:
+                col_src[m_id] = slot * cpp + c
+    return col_src
+
+
+def random_frame(pf, seed, with_window=True, frame_id=700):
+    """Random LidarFrame as tests/packet_format_test.cpp:246-266 builds it: every profile field
+    drawn within its value mask, headers iota, status 1."""
+    from oracle import oracle as orc
+    f = orc.Frame(pf, with_window=with_window)
+    rs = np.random.default_rng(seed)
+    w = pf.columns_per_frame
+    f.measurement_id[:] = np.arange(w)
+    f.timestamp[:] = 1000 + np.arange(w)
+    f.status[:] = 1
+    f.packet_timestamp[:] = 10 + np.arange(f.c.n_packets)
+    f.alert_flags[:] = rs.integers(0, 256, f.c.n_packets)
+    f.frame_id = frame_id
+    for name in pf.field_names:
+        if not f.has_field(name):
+            continue
+        a = f.field(name)
+        mask = pf.value_mask(name)
+        if name == "RGB":
+            a[...] = rs.integers(0, 1 << 16, size=a.shape, dtype=np.uint64).astype(np.uint16)
+        else:
+            vals = rs.integers(0, mask + 1 if mask < (1 << 63) else (1 << 63), size=a.shape, dtype=np.uint64) & np.uint64(mask)
+            a[...] = vals.astype(a.dtype)
+    return f
