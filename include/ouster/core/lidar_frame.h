@@ -1,0 +1,284 @@
+// lidar_frame.h -- LidarFrame (a.k.a. LidarScan), Field, FrameBatcher (a.k.a. ScanBatcher) and the
+// destagger entry points (mirrors ouster_core/include/ouster/core/lidar_frame.h:36-1160 and
+// field.h for the hot path).
+//
+// LidarFrame stays a host container with the reference's layout (one dense row-major buffer per
+// named field).  FrameBatcher keeps the reference's per-packet state machine on the host
+// (ordering by frame id, cache, init-id changes, header bookkeeping) and moves the per-pixel
+// work -- field decode, zero fill, and optionally destagger + XYZ -- to one fused GPU launch
+// when a frame completes.  Pixel fields are therefore materialised when batch() returns true
+// (the moment the reference declares the frame "ready to use"), or on flush().
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <deque>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ouster/core/chanfield.h"
+#include "ouster/core/packet.h"
+#include "ouster/core/sensor_info.h"
+#include "ouster/core/typedefs.h"
+#include "ouster/core/types.h"
+#include "ouster/core/visibility.h"
+
+struct ob_decoder;
+struct ob_stream;
+struct ob_lut;
+
+namespace ouster {
+namespace sdk {
+namespace core {
+
+enum class FieldClass { NONE = 0, PIXEL_FIELD = 1, COLUMN_FIELD = 2, PACKET_FIELD = 3, FRAME_FIELD = 4 };
+
+/// Describes one field of a LidarFrame (lidar_frame.h:76-122).
+struct OUSTER_API_CLASS FieldType {
+    std::string name;
+    ChanFieldType element_type{ChanFieldType::VOID};
+    std::vector<size_t> extra_dims;
+    FieldClass field_class{FieldClass::PIXEL_FIELD};
+    FieldType() = default;
+    FieldType(const std::string& name_, ChanFieldType element_type_,
+              const std::vector<size_t>& extra_dims_ = {}, FieldClass field_class_ = FieldClass::PIXEL_FIELD)
+        : name(name_), element_type(element_type_), extra_dims(extra_dims_), field_class(field_class_) {}
+    bool operator==(const FieldType& o) const {
+        return name == o.name && element_type == o.element_type && extra_dims == o.extra_dims &&
+               field_class == o.field_class;
+    }
+};
+using LidarFrameFieldTypes = std::vector<FieldType>;
+
+/// Typed dense buffer (field.h:828+).  Zero-initialised like the reference's calloc (field.cpp:254).
+class OUSTER_API_CLASS Field {
+   public:
+    Field() = default;
+    Field(ChanFieldType tag, const std::vector<size_t>& shape);
+    ChanFieldType tag() const { return tag_; }
+    const std::vector<size_t>& shape() const { return shape_; }
+    size_t element_size() const { return field_type_size(tag_); }
+    size_t bytes() const { return buf_.size(); }
+    size_t size() const { return element_size() ? buf_.size() / element_size() : 0; }
+    void* get() { return buf_.data(); }
+    const void* get() const { return buf_.data(); }
+    template <typename T>
+    T* get() { return reinterpret_cast<T*>(buf_.data()); }
+    template <typename T>
+    const T* get() const { return reinterpret_cast<const T*>(buf_.data()); }
+    void set_zero();
+    bool operator==(const Field& o) const { return tag_ == o.tag_ && shape_ == o.shape_ && buf_ == o.buf_; }
+    bool operator!=(const Field& o) const { return !(*this == o); }
+
+   private:
+    ChanFieldType tag_{ChanFieldType::VOID};
+    std::vector<size_t> shape_;
+    std::vector<uint8_t> buf_;
+};
+
+/// 1-D header view with Eigen-like element access.
+template <typename T>
+class HeaderRef {
+   public:
+    HeaderRef(T* d, size_t n) : d_(d), n_(n) {}
+    T* data() const { return d_; }
+    size_t rows() const { return n_; }
+    size_t size() const { return n_; }
+    T& operator[](size_t i) const { return d_[i]; }
+    T& operator()(size_t i) const { return d_[i]; }
+    void setZero() const { for (size_t i = 0; i < n_; ++i) d_[i] = T{}; }
+    size_t count() const {  ///< number of non-zero entries (Eigen's .count())
+        size_t c = 0;
+        for (size_t i = 0; i < n_; ++i) c += (d_[i] != T{});
+        return c;
+    }
+
+   private:
+    T* d_;
+    size_t n_;
+};
+
+class OUSTER_API_CLASS LidarFrame {
+   public:
+    template <typename T>
+    using Header = HeaderRef<T>;
+
+    size_t w{0};
+    size_t h{0};
+    uint64_t frame_status{0};
+    uint8_t shutdown_countdown{0};
+    uint8_t shot_limiting_countdown{0};
+    int64_t frame_id{-1};
+    std::shared_ptr<SensorInfo> sensor_info;
+
+    OUSTER_API_FUNCTION LidarFrame();
+    OUSTER_API_FUNCTION explicit LidarFrame(std::shared_ptr<SensorInfo> sensor_info);
+    OUSTER_API_FUNCTION explicit LidarFrame(const SensorInfo& sensor_info);
+    OUSTER_API_FUNCTION LidarFrame(std::shared_ptr<SensorInfo> sensor_info,
+                                   const std::vector<FieldType>& field_types);
+    OUSTER_API_FUNCTION LidarFrame(size_t h, size_t w, UDPProfileLidar profile,
+                                   size_t columns_per_packet = DEFAULT_COLUMNS_PER_PACKET);
+    OUSTER_API_FUNCTION LidarFrame(size_t h, size_t w, const LidarFrameFieldTypes& field_types,
+                                   size_t columns_per_packet = DEFAULT_COLUMNS_PER_PACKET);
+
+    OUSTER_API_FUNCTION ThermalShutdownStatus thermal_shutdown() const;
+    OUSTER_API_FUNCTION ShotLimitingStatus shot_limiting() const;
+
+    /// Typed 2-D view of a pixel field.  Throws std::invalid_argument on unknown field or
+    /// mismatched element type.
+    template <typename T>
+    ArrayRef<T> field(const std::string& name) {
+        Field& f = checked(name, FieldTag<T>::tag);
+        return ArrayRef<T>(f.get<T>(), h, f.shape().size() > 1 ? f.size() / h : 1);
+    }
+    template <typename T>
+    ArrayRef<const T> field(const std::string& name) const {
+        const Field& f = const_cast<LidarFrame*>(this)->checked(name, FieldTag<T>::tag);
+        return ArrayRef<const T>(f.get<T>(), h, f.shape().size() > 1 ? f.size() / h : 1);
+    }
+    OUSTER_API_FUNCTION Field& field(const std::string& name);
+    OUSTER_API_FUNCTION const Field& field(const std::string& name) const;
+    OUSTER_API_FUNCTION bool has_field(const std::string& name) const;
+    OUSTER_API_FUNCTION Field& add_field(const std::string& name, ChanFieldType type,
+                                         const std::vector<size_t>& extra_dims = {},
+                                         FieldClass field_class = FieldClass::PIXEL_FIELD);
+    OUSTER_API_FUNCTION Field& add_field(const FieldType& type);
+    OUSTER_API_FUNCTION Field del_field(const std::string& name);
+    OUSTER_API_FUNCTION ChanFieldType field_type(const std::string& name) const;
+    OUSTER_API_FUNCTION LidarFrameFieldTypes field_types() const;
+    const std::map<std::string, Field>& fields() const { return fields_; }
+    std::map<std::string, Field>& fields() { return fields_; }
+
+    Header<uint64_t> timestamp() { return {timestamp_.data(), timestamp_.size()}; }
+    Header<const uint64_t> timestamp() const { return {timestamp_.data(), timestamp_.size()}; }
+    Header<uint16_t> measurement_id() { return {measurement_id_.data(), measurement_id_.size()}; }
+    Header<const uint16_t> measurement_id() const { return {measurement_id_.data(), measurement_id_.size()}; }
+    Header<uint32_t> status() { return {status_.data(), status_.size()}; }
+    Header<const uint32_t> status() const { return {status_.data(), status_.size()}; }
+    Header<uint64_t> packet_timestamp() { return {packet_timestamp_.data(), packet_timestamp_.size()}; }
+    Header<const uint64_t> packet_timestamp() const { return {packet_timestamp_.data(), packet_timestamp_.size()}; }
+    Header<uint8_t> alert_flags() { return {alert_flags_.data(), alert_flags_.size()}; }
+    Header<const uint8_t> alert_flags() const { return {alert_flags_.data(), alert_flags_.size()}; }
+
+    /// true when every column inside the window carries status & 1 (lidar_frame.cpp:421-446)
+    OUSTER_API_FUNCTION bool complete(ColumnWindow window) const;
+    OUSTER_API_FUNCTION bool complete() const;
+
+    OUSTER_API_FUNCTION bool equals(const LidarFrame& other) const;
+
+   private:
+    Field& checked(const std::string& name, ChanFieldType tag);
+    void init_headers(size_t columns_per_packet);
+    std::map<std::string, Field> fields_;
+    std::map<std::string, FieldClass> field_class_;
+    std::vector<uint64_t> timestamp_;
+    std::vector<uint16_t> measurement_id_;
+    std::vector<uint32_t> status_;
+    std::vector<uint64_t> packet_timestamp_;
+    std::vector<uint8_t> alert_flags_;
+};
+
+OUSTER_API_FUNCTION bool operator==(const LidarFrame& a, const LidarFrame& b);
+inline bool operator!=(const LidarFrame& a, const LidarFrame& b) { return !(a == b); }
+
+/// Default field set of a profile / sensor (lidar_frame.cpp:228-256, 1038-1117): WINDOW is
+/// dropped for firmware older than 3.2.0.
+OUSTER_API_FUNCTION LidarFrameFieldTypes get_field_types(UDPProfileLidar profile);
+OUSTER_API_FUNCTION LidarFrameFieldTypes get_field_types(const DataFormat& format, const Version& fw);
+OUSTER_API_FUNCTION LidarFrameFieldTypes get_field_types(const SensorInfo& info);
+
+/// Optional fused products of FrameBatcher's GPU pass (an extension over the reference API):
+/// when attached, the same launch that decodes the frame also writes the XYZ of every return
+/// (lut(frame), xyzlut.h:145-150) and the destaggered range images
+/// (destagger<uint32_t>(info, range), impl/lidar_frame_impl.h:875-884).
+struct OUSTER_API_CLASS FusedCloud {
+    std::shared_ptr<ob_lut> lut;           ///< float or double device LUT (see XYZLutT::device_lut())
+    bool lut_is_f64{false};
+    std::vector<int> pixel_shift_by_row;   ///< empty: no destaggered range
+    std::vector<float> xyz_f32[2];         ///< (h*w) x 3 per return, staggered order
+    std::vector<double> xyz_f64[2];
+    std::vector<uint32_t> range_destaggered[2];
+};
+
+class OUSTER_API_CLASS FrameBatcher {
+   public:
+    PacketFormat pf;  ///< The packet format object used for decoding
+
+    OUSTER_API_FUNCTION explicit FrameBatcher(const SensorInfo& info);
+    OUSTER_API_FUNCTION explicit FrameBatcher(const std::shared_ptr<SensorInfo>& info);
+    OUSTER_API_FUNCTION ~FrameBatcher();
+    FrameBatcher(const FrameBatcher&) = delete;
+    FrameBatcher& operator=(const FrameBatcher&) = delete;
+
+    /// Add a packet to the frame; returns true when the frame is ready to use.
+    /// Throws std::invalid_argument("unexpected frame dimensions"),
+    /// std::invalid_argument("unexpected frame columns_per_packet: N"),
+    /// std::runtime_error("32-bit frame id did not increase since the last frame").
+    OUSTER_API_FUNCTION bool batch(const Packet& packet, LidarFrame& lidar_frame);
+    OUSTER_API_FUNCTION bool operator()(const Packet& packet, LidarFrame& lidar_frame);
+    /// Raw-buffer form of batch() (no Packet copy): buf holds one lidar packet.
+    OUSTER_API_FUNCTION bool batch(const uint8_t* buf, size_t size, uint64_t host_timestamp,
+                                   LidarFrame& lidar_frame);
+    OUSTER_API_FUNCTION void reset();
+    OUSTER_API_FUNCTION size_t batched_packets() const;
+    OUSTER_API_FUNCTION size_t dropped_packets() const;
+    OUSTER_API_FUNCTION void set_max_cache_size(size_t max_cache_size);
+    OUSTER_API_FUNCTION size_t get_max_cache_size() const;
+
+    // ---- B200 extensions ----
+    /// Decode whatever has been staged for the current (incomplete) frame into lidar_frame.
+    OUSTER_API_FUNCTION void flush(LidarFrame& lidar_frame);
+    /// Attach fused XYZ / destaggered-range outputs (nullptr detaches).
+    OUSTER_API_FUNCTION void set_fused_cloud(FusedCloud* cloud);
+    /// Kernel launches issued by this batcher.
+    OUSTER_API_FUNCTION size_t gpu_launches() const;
+
+   private:
+    struct CachedPacket {
+        std::vector<uint8_t> buf;
+        uint64_t host_timestamp;
+        uint64_t seq;
+    };
+    size_t max_cache_size_{4};
+    uint16_t next_valid_m_id_{0};
+    std::deque<CachedPacket> cache_;
+    uint64_t cache_seq_{0};
+    int64_t finished_frame_id_{-1};
+    int64_t last_frame_id_{-1};
+    int64_t last_init_id_;
+    std::shared_ptr<SensorInfo> sensor_info_;
+    bool reset_frame_{true};
+    size_t expected_lidar_packets_;
+    size_t batched_lidar_packets_{0};
+    size_t dropped_packets_{0};
+
+    // staging of the frame in flight
+    struct Staging;
+    std::unique_ptr<Staging> stg_;
+    FusedCloud* fused_{nullptr};
+    size_t launches_{0};
+
+    bool batch_impl(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f);
+    void cache_packet(const uint8_t* buf, size_t size, uint64_t host_ts);
+    size_t cache_top() const;
+    void batch_lidar_packet(const uint8_t* buf, uint64_t host_ts, LidarFrame& f);
+    void start_frame(int64_t f_id, const uint8_t* packet_buf, LidarFrame& f);
+    void finalize_frame(LidarFrame& f);
+    bool handle_init_id_change(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f);
+    bool batch_with_caching(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f);
+    bool check_frame_complete(const LidarFrame& f) const;
+    void decode_staged(LidarFrame& f);
+};
+
+/// Deprecated spellings kept by the reference (lidar_frame.h:1157-1160).
+using LidarScan = LidarFrame;
+using LidarScanFieldTypes = LidarFrameFieldTypes;
+using ScanBatcher = FrameBatcher;
+
+}  // namespace core
+}  // namespace sdk
+}  // namespace ouster
+
+#include "ouster/core/impl/lidar_frame_impl.h"
