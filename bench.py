@@ -195,7 +195,7 @@ def main():
 
     if args.workload == "k2":
         from bench_k2 import run_k2
-        run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measured_peaks)
+        run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measured_peaks, ROOT)
         return
 
     F = args.frames

@@ -1,0 +1,247 @@
+"""K2 workload of bench.py (BASELINE configs[2]): synthetic RNG19 dual-return packet stream ->
+ScanBatcher decode -> LidarScan fields -> fused destagger + cartesian, 128x2048, 1xB200.
+
+  value : device-resident packets, one fused decode launch per step over `frames` frames
+          (ob_decode_batch_run): all 10 channel fields + column headers + XYZ x2 + destaggered range x2.
+  e2e   : host packets through the product FrameBatcher (per-packet host state machine, pinned
+          staging, H2D of the wire bytes, fused launch, D2H of every decoded field + XYZ + rd).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+H, W, R, CPP = 128, 2048, 2, 16
+POINTS_PER_FRAME = H * W * R
+K2_BYTES_PER_FRAME_F32 = 23_917_696
+SHIFTS = np.tile(np.array([48, 32, 16, 0], np.int32), H // 4)
+PROFILE = "RNG19_RFL8_SIG16_NIR16_DUAL"
+
+
+def synth_packets(ob, n_distinct, seed=0xdeadbeef):
+    """Random frames encoded with the product's frame_to_packets, the way the reference's tests
+    synthesise packet streams (tests/packet_format_test.cpp:246-266): every profile field drawn
+    within its value mask, headers iota, status 1."""
+    si = ob.SensorInfo(PROFILE, H, W, CPP, fw_rev="v3.2.1", pixel_shift_by_row=SHIFTS)
+    masks = {f[0]: f[6] for f in si.fields()}
+    out, frames = [], []
+    for k in range(n_distinct):
+        rs = np.random.default_rng((seed + k) % (1 << 32))
+        fr = ob.LidarFrame(si)
+        for name in fr.fields:
+            a = fr.field(name)
+            a[...] = (rs.integers(0, 1 << 32, size=a.shape, dtype=np.uint64) & np.uint64(masks[name])).astype(a.dtype)
+        # ~50 % / 80 % empty returns like the reference's benchmark inputs (benchmark_utils.h:102-107)
+        fr.field("RANGE")[rs.random((H, W)) < 0.5] = 0
+        fr.field("RANGE2")[rs.random((H, W)) < 0.8] = 0
+        fr.measurement_id[:] = np.arange(W)
+        fr.timestamp[:] = 1000 + np.arange(W)
+        fr.status[:] = 1
+        fr.packet_timestamp[:] = 10 + np.arange(W // CPP)
+        fr.frame_id = 700 + k
+        pk, ts = ob.frame_to_packets(fr, si, init_id=0, prod_sn=0)
+        assert pk.shape == (W // CPP, 33024)
+        out.append(pk)
+        frames.append(fr)
+    return si, np.stack(out), frames
+
+
+def cpu_reference_decode(orc, opf, packets_frames, threads):
+    """Reference path on the CPU (oracle port): FrameBatcher block-parse decode + destagger<u32> +
+    cartesianT<float> per return; one thread per frame (independent streams)."""
+    from concurrent.futures import ThreadPoolExecutor
+    d = np.zeros((H * W, 3), np.float32)
+    o = np.zeros((H * W, 3), np.float32)
+
+    def one(i):
+        fr = orc.Frame(opf, with_window=True)
+        b = orc.Batcher(opf)
+        for k, p in enumerate(packets_frames[i]):
+            b.batch(p, 10 + k, fr)
+        for name in ("RANGE", "RANGE2"):
+            orc.destagger(fr.field(name), SHIFTS)
+            orc.cartesian(fr.field(name), d, o)
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        for i in range(len(packets_frames)):
+            one(i)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, range(len(packets_frames))))
+    return time.perf_counter() - t0
+
+
+def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measured_peaks, root):
+    dev = torch.device("cuda", local_rank)
+    F = min(args.frames, 32) if args.frames else 32
+    ND = 4
+    si, pk, src_frames = synth_packets(ob, ND, seed=0xdeadbeef ^ rank)
+    n_slots, psz = pk.shape[1], pk.shape[2]
+    pool = np.stack([pk[i % ND] for i in range(F)])            # [F, 128, 33024]
+    t_pk = torch.from_numpy(pool).to(dev)
+    rs = np.random.default_rng(43)
+    d = (rs.random((H * W, 3)) + 0.5).astype(np.float32)
+    o = (rs.random((H * W, 3)) * 0.01).astype(np.float32)
+    t_dir, t_off = torch.from_numpy(d).to(dev), torch.from_numpy(o).to(dev)
+    if dist is not None:
+        dist.broadcast(t_dir, 0)
+        dist.broadcast(t_off, 0)
+    lut = ob.XYZLutT.from_arrays(t_dir, t_off, H, W, device=local_rank)
+    dec = ob.Decoder.from_sensor(si, src_frames[0], device=local_rank)
+    tdt = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
+    fields = {f["name"]: torch.empty((F, H, W), dtype=tdt[f["elem_size"]], device=dev) for f in dec.fields}
+    xyz = [torch.empty((F, H * W, 3), dtype=torch.float32, device=dev) for _ in range(R)]
+    rd = [torch.empty((F, H, W), dtype=torch.int32, device=dev) for _ in range(R)]
+    t_ts = torch.empty((F, W), dtype=torch.int64, device=dev)
+    t_mid = torch.empty((F, W), dtype=torch.int16, device=dev)
+    t_st = torch.empty((F, W), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    obs = ob.Stream(local_rank, cuda_stream=stream.cuda_stream)
+
+    def step():
+        dec.decode_batch(F, t_pk, n_slots, psz, n_slots * psz, fields, lut=lut, pixel_shift_by_row=SHIFTS,
+                         xyz=xyz, range_destaggered=rd, timestamp=t_ts, measurement_id=t_mid,
+                         status=t_st, stream=obs)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = ob.kernel_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    launches = ob.kernel_launch_count() - l0
+    clocks = sampler.stop()
+    ms_total = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * F * POINTS_PER_FRAME * args.steps / (ms_max * 1e-3) / 1e6
+    peak, peak_kind = measured_peaks()
+    avg = float(np.median(per_launch_ms)) * 1e-3
+    achieved = K2_BYTES_PER_FRAME_F32 * F / avg / 1e9
+
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"workload": "k2", "value": value, "ms_per_step": ms_max / args.steps,
+                              "gbps": achieved, "frac": achieved / peak, "clocks": clocks}))
+        return
+
+    # ---- parity of the timed configuration (frame 0): decoded fields == source frame ----
+    parity = None
+    if rank == 0:
+        from oracle import oracle as orc
+        ok = True
+        for f in dec.fields:
+            got = fields[f["name"]][0].cpu().numpy().view(src_frames[0].field(f["name"]).dtype)
+            ok &= bool(np.array_equal(got, src_frames[0].field(f["name"])))
+        for r, nm in enumerate(("RANGE", "RANGE2")):
+            ok &= bool(np.array_equal(xyz[r][0].cpu().numpy(), orc.cartesian(src_frames[0].field(nm), d, o)))
+            ok &= bool(np.array_equal(rd[r][0].cpu().numpy().view(np.uint32),
+                                      orc.destagger(src_frames[0].field(nm), SHIFTS)))
+        ok &= bool(np.array_equal(t_ts[0].cpu().numpy().view(np.uint64), src_frames[0].timestamp))
+        parity = ok
+
+    # ---- e2e: host packets -> product FrameBatcher -> host LidarFrame + fused cloud ----
+    batcher = ob.FrameBatcher(si)
+    batcher.set_fused_cloud(lut, SHIFTS)
+    frame = ob.LidarFrame(si)
+    e2e_frames = min(F, 16)
+
+    host_ts = 10 + np.arange(n_slots, dtype=np.uint64)
+
+    def e2e_step():
+        n_done = 0
+        for i in range(e2e_frames):
+            used, done = batcher.batch_burst(pool[i % F], host_ts, frame)   # 128 packets -> 1 frame
+            n_done += int(done and used == n_slots)
+        return n_done
+
+    # distinct, increasing frame ids so that no packet is dropped as "old frame"
+    for i in range(F):
+        fid = 1000 + i
+        pool[i, :, 2] = fid & 0xff
+        pool[i, :, 3] = (fid >> 8) & 0xff
+    e2e_step()
+    for i in range(F):  # fresh ids for the timed pass
+        fid = 3000 + i
+        pool[i, :, 2] = fid & 0xff
+        pool[i, :, 3] = (fid >> 8) & 0xff
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    done = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * e2e_frames * POINTS_PER_FRAME / float(e2e_t.item()) / 1e6
+    field_bytes = sum(f["elem_size"] for f in dec.fields) * H * W
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle as orc
+        from tests.helpers import oracle_pf
+        opf = oracle_pf(PROFILE, H, W)
+        cores = os.cpu_count() or 1
+        nf = max(8, min(cores, 64))
+        sample = [pool[i % F] for i in range(nf)]
+        cpu_reference_decode(orc, opf, sample[:1], 1)
+        t1 = cpu_reference_decode(orc, opf, sample[:2], 1)
+        tN = min(cpu_reference_decode(orc, opf, sample, cores) for _ in range(2))
+        cpu = {"value": nf * POINTS_PER_FRAME / tN / 1e6, "unit": "Mpoints/s", "cores": cores, "kind": "port",
+               "sample": f"{nf} frames: FrameBatcher block decode + destagger<u32> + cartesianT<float>, "
+                         f"one thread per frame, best of 2",
+               "single_thread_value": 2 * POINTS_PER_FRAME / t1 / 1e6}
+
+    traffic = None
+    tp = os.path.join(root, "profiles", "k2_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    line = {
+        "metric": "Mpoints/s 128x2048 dual-return packets->fields+destagger+XYZ", "value": value,
+        "unit": "Mpoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/u32 decode + f32 xyz", "data": "synthetic",
+        "config": {"workload": "synthetic RNG19 dual-return packet stream -> ScanBatcher decode -> "
+                               "LidarScan -> fused cartesian (K2), 128x2048",
+                   "frames_per_step_per_gpu": F, "points_per_frame": POINTS_PER_FRAME,
+                   "l2_policy": f"{F * K2_BYTES_PER_FRAME_F32 / 1e6:.0f} MB touched per step > 126 MB L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                     "kernel": "decode_kernel<float>",
+                     "algorithmic_bytes_per_launch": K2_BYTES_PER_FRAME_F32 * F,
+                     "avg_launch_ms": avg * 1e3},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_val, "unit": "Mpoints/s",
+                "h2d_bytes_per_step": int(e2e_frames * n_slots * psz),
+                "d2h_bytes_per_step": int(e2e_frames * (field_bytes + R * H * W * 16)),
+                "frames": e2e_frames, "frames_completed": int(done),
+                "path": "FrameBatcher.batch() per packet (host state machine) + fused GPU launch per frame"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "parity_vs_oracle": parity,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()

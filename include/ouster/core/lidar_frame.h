@@ -232,6 +232,9 @@ class OUSTER_API_CLASS FrameBatcher {
     OUSTER_API_FUNCTION void flush(LidarFrame& lidar_frame);
     /// Attach fused XYZ / destaggered-range outputs (nullptr detaches).
     OUSTER_API_FUNCTION void set_fused_cloud(FusedCloud* cloud);
+    /// Header-only batching: keep the state machine and the per-column / per-packet headers but
+    /// skip the pixel decode (no GPU work; pixel fields are left untouched).
+    OUSTER_API_FUNCTION void set_headers_only(bool on);
     /// Kernel launches issued by this batcher.
     OUSTER_API_FUNCTION size_t gpu_launches() const;
 
@@ -258,6 +261,7 @@ class OUSTER_API_CLASS FrameBatcher {
     struct Staging;
     std::unique_ptr<Staging> stg_;
     FusedCloud* fused_{nullptr};
+    bool headers_only_{false};
     size_t launches_{0};
 
     bool batch_impl(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f);

@@ -77,6 +77,10 @@ class OUSTER_API_CLASS PacketFormat {
     OUSTER_API_FUNCTION int block_parsable() const;
     OUSTER_API_FUNCTION const FieldDecodeInfo& field_decode_info(const std::string& f) const;
     OUSTER_API_FUNCTION bool has_field(const std::string& f) const;
+    /// Decode infos of the per-column headers, relative to the column start (parsing.cpp:499-538).
+    OUSTER_API_FUNCTION const FieldDecodeInfo& col_timestamp_info() const;
+    OUSTER_API_FUNCTION const FieldDecodeInfo& col_measurement_id_info() const;
+    OUSTER_API_FUNCTION const FieldDecodeInfo& col_status_info() const;
 
     /// Decode one column of one field (host; throws "Dest type too small for specified field").
     template <typename T>

@@ -201,6 +201,28 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
                            const int32_t* pixel_shift_by_row /* nullable, h, host */, size_t n_shifts,
                            ob_stream* s);
 
+/* Uniformly strided batch of COMPLETE, in-order frames (identity column map): frame f of every
+ * array lives `*_frame_stride` BYTES after frame f-1.  Same products as ob_decode_frames with O(1)
+ * host work per call -- the form a packet ring / frame pool uses. */
+typedef struct ob_decode_batch {
+    uint32_t n_frames;
+    const uint8_t* packets; /* frame f, slot k at packets + f*packets_frame_stride + k*packet_stride */
+    size_t n_slots, packet_stride, packets_frame_stride;
+    void* fields[OB_MAX_FIELDS];
+    size_t field_frame_stride[OB_MAX_FIELDS];
+    uint64_t* timestamp;
+    uint16_t* measurement_id;
+    uint32_t* status;
+    size_t timestamp_frame_stride, measurement_id_frame_stride, status_frame_stride;
+    void* xyz[OB_MAX_RETURNS];
+    size_t xyz_frame_stride;
+    uint32_t* range_destaggered[OB_MAX_RETURNS];
+    size_t rd_frame_stride;
+} ob_decode_batch;
+
+ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* batch, const ob_lut* lut,
+                              const int32_t* pixel_shift_by_row, size_t n_shifts, ob_stream* s);
+
 #ifdef __cplusplus
 }
 #endif

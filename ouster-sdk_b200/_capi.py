@@ -51,6 +51,17 @@ class DecodeIO(C.Structure):
                 ("xyz", vp * OB_MAX_RETURNS), ("range_destaggered", vp * OB_MAX_RETURNS)]
 
 
+class DecodeBatch(C.Structure):
+    _fields_ = [("n_frames", u32), ("packets", vp), ("n_slots", sz), ("packet_stride", sz),
+                ("packets_frame_stride", sz),
+                ("fields", vp * OB_MAX_FIELDS), ("field_frame_stride", sz * OB_MAX_FIELDS),
+                ("timestamp", vp), ("measurement_id", vp), ("status", vp),
+                ("timestamp_frame_stride", sz), ("measurement_id_frame_stride", sz),
+                ("status_frame_stride", sz),
+                ("xyz", vp * OB_MAX_RETURNS), ("xyz_frame_stride", sz),
+                ("range_destaggered", vp * OB_MAX_RETURNS), ("rd_frame_stride", sz)]
+
+
 def _sig(name, restype, *argtypes):
     f = getattr(lib, name)
     f.restype = restype
@@ -85,6 +96,7 @@ if hasattr(lib, "ob_decoder_create"):
          C.POINTER(vp))
     _sig("ob_decoder_destroy", i32, vp)
     _sig("ob_decode_frames", i32, vp, C.POINTER(DecodeIO), sz, vp, vp, sz, vp)
+    _sig("ob_decode_batch_run", i32, vp, C.POINTER(DecodeBatch), vp, vp, sz, vp)
 
 
 class OusterB200Error(RuntimeError):

@@ -372,6 +372,68 @@ class Decoder:
         check(lib.ob_decode_frames(self._h, ios, len(frames), lut._h if lut is not None else None,
                                    sh.ctypes.data if sh is not None else None, nsh, st.h))
 
+    @classmethod
+    def from_sensor(cls, info, frame, device=0):
+        """Decoder for the fields `frame` (host LidarFrame) shares with the sensor's PacketFormat."""
+        L = info.layout
+        layout = {k: getattr(L, k) for k in ("packet_header_size", "col_header_size", "channel_data_size",
+                                             "col_size", "packet_size", "columns_per_packet",
+                                             "pixels_per_column", "columns_per_frame")}
+        for k in ("col_timestamp", "col_measurement_id", "col_status"):
+            d = getattr(L, k)
+            layout[k] = (d.offset, d.mask, d.shift)
+        fields = []
+        have = set(frame.fields)
+        for name, tag, off, mask, shift, nel, vm in info.fields():
+            if name not in have:
+                continue
+            a = frame.field(name)
+            es = a.dtype.itemsize * (a.shape[2] if a.ndim == 3 else 1)
+            fields.append({"name": name, "offset": off, "mask": mask, "shift": shift, "elem_size": es,
+                           "range_return": {"RANGE": 0, "RANGE2": 1}.get(name, -1),
+                           "zero_pattern": 0x7e00 if name == "RGB" else 0})
+        return cls(layout, fields, device)
+
+    def decode_batch(self, n_frames, packets, n_slots, packet_stride, packets_frame_stride, fields,
+                     lut=None, pixel_shift_by_row=None, xyz=None, range_destaggered=None,
+                     timestamp=None, measurement_id=None, status=None, stream=None):
+        """Uniformly strided batch of complete frames (ob_decode_batch_run).  `fields` maps a field
+        name to an array/tensor shaped [n_frames, H, W(, k)]; xyz / range_destaggered are lists (one
+        entry per return) of [n_frames, H*W, 3] / [n_frames, H, W] arrays."""
+        from ._capi import DecodeBatch
+        st = _stream(stream, self.device)
+        b = DecodeBatch()
+        b.n_frames = n_frames
+        b.packets, b.n_slots = _ptr(packets), n_slots
+        b.packet_stride, b.packets_frame_stride = packet_stride, packets_frame_stride
+        n_px = self.h_px * self.w_px
+        for k, f in enumerate(self.fields):
+            a = fields.get(f["name"])
+            if a is not None:
+                b.fields[k] = _ptr(a)
+                b.field_frame_stride[k] = n_px * f["elem_size"]
+        if timestamp is not None:
+            b.timestamp, b.timestamp_frame_stride = _ptr(timestamp), self.w_px * 8
+        if measurement_id is not None:
+            b.measurement_id, b.measurement_id_frame_stride = _ptr(measurement_id), self.w_px * 2
+        if status is not None:
+            b.status, b.status_frame_stride = _ptr(status), self.w_px * 4
+        esz = 8 if (lut is not None and lut.dtype == np.float64) else 4
+        for r, a in enumerate(xyz or []):
+            if a is not None:
+                b.xyz[r] = _ptr(a)
+        b.xyz_frame_stride = n_px * 3 * esz
+        for r, a in enumerate(range_destaggered or []):
+            if a is not None:
+                b.range_destaggered[r] = _ptr(a)
+        b.rd_frame_stride = n_px * 4
+        sh, nsh = None, 0
+        if pixel_shift_by_row is not None:
+            sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
+            nsh = sh.size
+        check(lib.ob_decode_batch_run(self._h, C.byref(b), lut._h if lut is not None else None,
+                                      sh.ctypes.data if sh is not None else None, nsh, st.h))
+
     def __del__(self):
         if getattr(self, "_h", None) and lib is not None:
             try:

@@ -201,4 +201,114 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
     return OB_OK;
 }
 
+ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, const ob_lut* lut,
+                              const int32_t* shifts, size_t n_shifts, ob_stream* s) {
+    if (!dec || !b || !s) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (b->n_frames == 0) return OB_OK;
+    const DecodeLayout& L = dec->L;
+    const int device = stream_device(s);
+    if (device != dec->device) return fail(OB_INVALID_ARGUMENT, "decoder and stream are on different devices");
+    ob_status rs = require_device(device);
+    if (rs != OB_OK) return rs;
+    if (!b->packets || b->n_slots == 0) return fail(OB_INVALID_ARGUMENT, "null packet buffer");
+    if (b->packet_stride < L.packet_size)
+        return fail(OB_INVALID_ARGUMENT, "packet_stride smaller than the lidar packet size");
+    const void *ldir = nullptr, *loff = nullptr;
+    int ldtype = OB_F32;
+    if (lut) {
+        size_t lh, lw;
+        int ldev;
+        lut_view(lut, &ldir, &loff, &ldtype, &lh, &lw, &ldev);
+        if (lh != L.H || lw != L.W) return fail(OB_INVALID_ARGUMENT, "unexpected image dimensions");
+        if (ldev != device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
+    }
+    std::vector<uint16_t> sh;
+    if (shifts) {
+        if (n_shifts != L.H) return fail(OB_INVALID_ARGUMENT, "image height does not match shifts size");
+        if (L.H > static_cast<uint32_t>(kMaxRows))
+            return fail(OB_INVALID_ARGUMENT, "fused destagger supports at most 512 rows");
+        reduce_shifts(shifts, L.H, L.W, 0, sh);
+    }
+    const size_t F = b->n_frames;
+    const size_t esz = ldtype == OB_F64 ? 8 : 4;
+    const size_t n_px = static_cast<size_t>(L.H) * L.W;
+    cudaStream_t st = stream_handle(s);
+    Staging stg(st);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    auto span = [&](size_t stride, size_t last) { return (F - 1) * stride + last; };
+    bool vec_ok = !lut || (al16(ldir) && al16(loff));
+
+    const void* dpk = nullptr;
+    cudaError_t e = stg.in(b->packets,
+                           span(b->packets_frame_stride, (b->n_slots - 1) * b->packet_stride + L.packet_size),
+                           &dpk);
+    if (e != cudaSuccess) return fail_cuda(e, "stage packets");
+    void* dfields[OB_MAX_FIELDS] = {};
+    for (uint32_t k = 0; k < L.n_fields; ++k) {
+        if (!b->fields[k]) continue;
+        e = stg.out(b->fields[k], span(b->field_frame_stride[k], n_px * L.fields[k].elem_size), &dfields[k]);
+        if (e != cudaSuccess) return fail_cuda(e, "stage field output");
+    }
+    void *dts = nullptr, *dmid = nullptr, *dstat = nullptr;
+    if (b->timestamp) e = stg.out(b->timestamp, span(b->timestamp_frame_stride, L.W * 8ull), &dts);
+    if (e == cudaSuccess && b->measurement_id)
+        e = stg.out(b->measurement_id, span(b->measurement_id_frame_stride, L.W * 2ull), &dmid);
+    if (e == cudaSuccess && b->status) e = stg.out(b->status, span(b->status_frame_stride, L.W * 4ull), &dstat);
+    if (e != cudaSuccess) return fail_cuda(e, "stage headers");
+    void* dxyz[OB_MAX_RETURNS] = {};
+    void* drd[OB_MAX_RETURNS] = {};
+    for (int r = 0; r < OB_MAX_RETURNS; ++r) {
+        if (b->xyz[r]) {
+            if (!lut) return fail(OB_INVALID_ARGUMENT, "xyz output requested without a lut");
+            e = stg.out(b->xyz[r], span(b->xyz_frame_stride, n_px * 3 * esz), &dxyz[r]);
+            if (e != cudaSuccess) return fail_cuda(e, "stage xyz");
+            if (!al16(dxyz[r]) || b->xyz_frame_stride % 16) vec_ok = false;
+        }
+        if (b->range_destaggered[r]) {
+            if (!shifts) return fail(OB_INVALID_ARGUMENT, "image height does not match shifts size");
+            e = stg.out(b->range_destaggered[r], span(b->rd_frame_stride, n_px * 4), &drd[r]);
+            if (e != cudaSuccess) return fail_cuda(e, "stage range_destaggered");
+        }
+    }
+    std::vector<DecodeFrame> hf(F);
+    const bool bulk_ok = al16(dpk) && b->packet_stride % 16 == 0 && L.packet_size % 16 == 0 &&
+                         b->packets_frame_stride % 16 == 0;
+    for (size_t f = 0; f < F; ++f) {
+        DecodeFrame& d = hf[f];
+        std::memset(&d, 0, sizeof(d));
+        d.packets = static_cast<const uint8_t*>(dpk) + f * b->packets_frame_stride;
+        d.packet_stride = b->packet_stride;
+        d.n_slots = static_cast<uint32_t>(b->n_slots);
+        d.flags = 1u | (bulk_ok ? 2u : 0u);
+        for (uint32_t k = 0; k < L.n_fields; ++k)
+            if (dfields[k]) d.fields[k] = static_cast<uint8_t*>(dfields[k]) + f * b->field_frame_stride[k];
+        if (dts) d.timestamp = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(dts) + f * b->timestamp_frame_stride);
+        if (dmid) d.measurement_id = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(dmid) + f * b->measurement_id_frame_stride);
+        if (dstat) d.status = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(dstat) + f * b->status_frame_stride);
+        for (int r = 0; r < OB_MAX_RETURNS; ++r) {
+            if (dxyz[r]) d.xyz[r] = static_cast<uint8_t*>(dxyz[r]) + f * b->xyz_frame_stride;
+            if (drd[r]) d.rd[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(drd[r]) + f * b->rd_frame_stride);
+        }
+    }
+    void* fdev = nullptr;
+    e = stg.scratch(F * sizeof(DecodeFrame), &fdev);
+    if (e != cudaSuccess) return fail_cuda(e, "frame table alloc");
+    e = cudaMemcpyAsync(fdev, hf.data(), F * sizeof(DecodeFrame), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
+    DecodeLaunch a;
+    a.layout_host = &L;
+    a.frames_dev = static_cast<const DecodeFrame*>(fdev);
+    a.n_frames = static_cast<uint32_t>(F);
+    a.lut_dir = ldir;
+    a.lut_off = loff;
+    a.lut_dtype = ldtype;
+    a.shift_host = shifts ? sh.data() : nullptr;
+    a.vec_ok = vec_ok;
+    e = launch_decode(a, device, st);
+    if (e != cudaSuccess) return fail_cuda(e, "decode launch");
+    e = stg.flush();
+    if (e != cudaSuccess) return fail_cuda(e, "decode D2H");
+    return OB_OK;
+}
+
 }  // extern "C"

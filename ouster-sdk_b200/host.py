@@ -1,0 +1,348 @@
+"""Python mirror of the reference's LidarScan / ScanBatcher / PacketFormat objects over the host
+C ABI (include/ouster_b200_host.h).  Names follow python/src/ouster/sdk/core/__init__.py:140-142
+(LidarFrame/LidarScan, FrameBatcher/ScanBatcher)."""
+import ctypes as C
+
+import numpy as np
+
+from ._capi import FieldDesc, PacketLayout, check, lib
+
+vp, sz, i32, u32, u64, i64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64, C.c_int64
+PP = C.POINTER
+
+
+def _sig(name, restype, *argtypes):
+    f = getattr(lib, name)
+    f.restype, f.argtypes = restype, list(argtypes)
+
+
+_sig("obh_sensor_create", i32, C.c_char_p, i32, u32, u32, u32, vp, u32, u64, C.c_char_p, u32, u32, PP(vp))
+_sig("obh_sensor_set_intrinsics", i32, vp, vp, sz, vp, sz, vp, vp, vp)
+_sig("obh_sensor_set_custom_fields", i32, vp, sz, PP(C.c_char_p), vp, vp, vp, vp, sz)
+_sig("obh_sensor_layout", i32, vp, PP(PacketLayout))
+_sig("obh_sensor_n_fields", sz, vp)
+_sig("obh_sensor_field", i32, vp, sz, C.c_char_p, sz, PP(C.c_int32), PP(u64), PP(u64), PP(C.c_int32),
+     PP(C.c_int32), PP(u64))
+_sig("obh_sensor_block_parsable", i32, vp)
+_sig("obh_sensor_frame_id_difference", i32, vp, u32, u32)
+_sig("obh_sensor_packet_frame_id", u32, vp, vp)
+_sig("obh_sensor_packet_init_id", u32, vp, vp)
+_sig("obh_sensor_packet_prod_sn", u64, vp, vp)
+_sig("obh_sensor_calculate_crc", u64, vp, vp, sz)
+_sig("obh_sensor_destroy", i32, vp)
+_sig("obh_frame_create", i32, vp, PP(vp))
+_sig("obh_frame_add_field", i32, vp, C.c_char_p, C.c_int32, sz)
+_sig("obh_frame_n_fields", sz, vp)
+_sig("obh_frame_field_at", i32, vp, sz, C.c_char_p, sz, PP(C.c_int32), PP(sz), PP(vp))
+_sig("obh_frame_field", i32, vp, C.c_char_p, PP(C.c_int32), PP(sz), PP(vp))
+_sig("obh_frame_headers", i32, vp, PP(vp), PP(vp), PP(vp), PP(vp), PP(vp), PP(sz), PP(sz), PP(sz))
+_sig("obh_frame_get_frame_id", i64, vp)
+_sig("obh_frame_set_frame_id", None, vp, i64)
+_sig("obh_frame_get_status", u64, vp, PP(C.c_uint8), PP(C.c_uint8))
+_sig("obh_frame_set_status", None, vp, u64, C.c_uint8, C.c_uint8)
+_sig("obh_frame_destroy", i32, vp)
+_sig("obh_frame_to_packets", i32, vp, vp, u32, u64, vp, vp, PP(sz))
+_sig("obh_batcher_create", i32, vp, PP(vp))
+_sig("obh_batcher_batch", i32, vp, vp, sz, u64, vp, PP(i32))
+_sig("obh_batcher_flush", i32, vp, vp)
+_sig("obh_batcher_batch_burst", i32, vp, vp, sz, sz, sz, vp, vp, PP(sz), PP(i32))
+_sig("obh_batcher_reset", i32, vp)
+_sig("obh_batcher_batched_packets", sz, vp)
+_sig("obh_batcher_dropped_packets", sz, vp)
+_sig("obh_batcher_gpu_launches", sz, vp)
+_sig("obh_batcher_set_max_cache_size", i32, vp, sz)
+_sig("obh_batcher_set_fused", i32, vp, vp, vp, sz)
+_sig("obh_batcher_set_headers_only", i32, vp, i32)
+_sig("obh_batcher_fused_outputs", i32, vp, i32, PP(vp), PP(sz), PP(vp))
+_sig("obh_batcher_destroy", i32, vp)
+
+# ChanFieldType tags (chanfield.h:111-128)
+TAG_NP = {1: np.uint8, 2: np.uint16, 3: np.uint32, 4: np.uint64, 5: np.int8, 6: np.int16,
+          7: np.int32, 8: np.int64, 9: np.float32, 10: np.float64, 12: np.uint16}
+NP_TAG = {np.dtype(np.uint8): 1, np.dtype(np.uint16): 2, np.dtype(np.uint32): 3,
+          np.dtype(np.uint64): 4, np.dtype(np.int8): 5, np.dtype(np.int16): 6,
+          np.dtype(np.int32): 7, np.dtype(np.int64): 8, np.dtype(np.float32): 9,
+          np.dtype(np.float64): 10}
+
+
+def _as_array(ptr, dtype, shape):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if n == 0:
+        return np.empty(shape, dtype)
+    raw = np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr))
+    return raw.view(dtype).reshape(shape)
+
+
+class SensorInfo:
+    """SensorInfo + PacketFormat of one sensor stream."""
+
+    def __init__(self, profile, h, w, columns_per_packet=16, header_type="STANDARD",
+                 pixel_shift_by_row=None, init_id=0, sn=0, fw_rev="UNKNOWN", column_window=None):
+        cw = column_window or (0, w - 1)
+        sh = None
+        if pixel_shift_by_row is not None:
+            sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
+            if sh.size != h:
+                raise ValueError("pixel_shift_by_row must have one entry per row")
+        hd = vp()
+        check(lib.obh_sensor_create(profile.encode(), int(header_type == "FUSA"), h, w,
+                                    columns_per_packet, sh.ctypes.data if sh is not None else None,
+                                    init_id, sn, fw_rev.encode(), cw[0], cw[1], C.byref(hd)))
+        self._h = hd
+        self.profile, self.h, self.w, self.columns_per_packet = profile, h, w, columns_per_packet
+        self.pixel_shift_by_row = sh if sh is not None else np.zeros(h, np.int32)
+        self.init_id, self.sn = init_id, sn
+
+    @classmethod
+    def from_meta(cls, meta, fw_rev="UNKNOWN"):
+        """From a tests/golden/*.json fixture dict."""
+        s = cls(meta["profile"], meta["h"], meta["w"], meta["columns_per_packet"], meta["header_type"],
+                meta["pixel_shift_by_row"], meta["init_id"], meta["prod_sn"], fw_rev,
+                tuple(meta["column_window"]))
+        s.set_intrinsics(meta["beam_azimuth_angles"], meta["beam_altitude_angles"],
+                         meta["beam_to_lidar_transform"], meta["lidar_to_sensor_transform"])
+        return s
+
+    def set_intrinsics(self, az, alt, beam_to_lidar, lidar_to_sensor, sensor_to_body=None):
+        az = np.ascontiguousarray(az, np.float64)
+        alt = np.ascontiguousarray(alt, np.float64)
+        b2l = np.ascontiguousarray(beam_to_lidar, np.float64).reshape(16)
+        l2s = np.ascontiguousarray(lidar_to_sensor, np.float64).reshape(16)
+        s2b = None if sensor_to_body is None else np.ascontiguousarray(sensor_to_body, np.float64).reshape(16)
+        check(lib.obh_sensor_set_intrinsics(self._h, az.ctypes.data, az.size, alt.ctypes.data, alt.size,
+                                            b2l.ctypes.data, l2s.ctypes.data,
+                                            s2b.ctypes.data if s2b is not None else None))
+        self.beam_azimuth_angles, self.beam_altitude_angles = az, alt
+        self.beam_to_lidar_transform, self.lidar_to_sensor_transform = b2l.reshape(4, 4), l2s.reshape(4, 4)
+        self.sensor_to_body = None if s2b is None else s2b.reshape(4, 4)
+
+    def set_custom_fields(self, fields, channel_data_size):
+        """fields: list of (name, ty_tag, offset, mask, shift) -- add_custom_profile analogue."""
+        n = len(fields)
+        names = (C.c_char_p * n)(*[f[0].encode() for f in fields])
+        tags = np.array([f[1] for f in fields], np.int32)
+        offs = np.array([f[2] for f in fields], np.uint64)
+        masks = np.array([f[3] for f in fields], np.uint64)
+        shifts = np.array([f[4] for f in fields], np.int32)
+        check(lib.obh_sensor_set_custom_fields(self._h, n, names, tags.ctypes.data, offs.ctypes.data,
+                                               masks.ctypes.data, shifts.ctypes.data, channel_data_size))
+
+    @property
+    def layout(self):
+        L = PacketLayout()
+        check(lib.obh_sensor_layout(self._h, C.byref(L)))
+        return L
+
+    @property
+    def lidar_packet_size(self):
+        return self.layout.packet_size
+
+    def fields(self):
+        """[(name, ty_tag, offset, mask, shift, num_elements, value_mask)] in PacketFormat order."""
+        out = []
+        for i in range(lib.obh_sensor_n_fields(self._h)):
+            name = C.create_string_buffer(32)
+            tag, sh, nel = C.c_int32(), C.c_int32(), C.c_int32()
+            off, mask, vm = u64(), u64(), u64()
+            check(lib.obh_sensor_field(self._h, i, name, 32, C.byref(tag), C.byref(off), C.byref(mask),
+                                       C.byref(sh), C.byref(nel), C.byref(vm)))
+            out.append((name.value.decode(), tag.value, off.value, mask.value, sh.value, nel.value, vm.value))
+        return out
+
+    def block_parsable(self):
+        return lib.obh_sensor_block_parsable(self._h)
+
+    def frame_id_difference(self, cur, other):
+        return lib.obh_sensor_frame_id_difference(self._h, cur, other)
+
+    def _pad(self, buf):
+        b = np.frombuffer(bytes(buf), np.uint8) if not isinstance(buf, np.ndarray) else buf
+        return np.concatenate([b, np.zeros(8, np.uint8)])
+
+    def frame_id(self, packet):
+        p = self._pad(packet)
+        return lib.obh_sensor_packet_frame_id(self._h, p.ctypes.data)
+
+    def packet_init_id(self, packet):
+        p = self._pad(packet)
+        return lib.obh_sensor_packet_init_id(self._h, p.ctypes.data)
+
+    def packet_prod_sn(self, packet):
+        p = self._pad(packet)
+        return lib.obh_sensor_packet_prod_sn(self._h, p.ctypes.data)
+
+    def calculate_crc(self, packet):
+        p = np.ascontiguousarray(packet)
+        return lib.obh_sensor_calculate_crc(self._h, p.ctypes.data, p.size)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            try:
+                lib.obh_sensor_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class LidarFrame:
+    """LidarFrame / LidarScan: named row-major fields + per-column / per-packet headers (host)."""
+
+    def __init__(self, info):
+        hd = vp()
+        check(lib.obh_frame_create(info._h, C.byref(hd)))
+        self._h, self.info = hd, info
+        ts, mid, st, pts, af = vp(), vp(), vp(), vp(), vp()
+        w, h, npk = sz(), sz(), sz()
+        check(lib.obh_frame_headers(hd, C.byref(ts), C.byref(mid), C.byref(st), C.byref(pts), C.byref(af),
+                                    C.byref(w), C.byref(h), C.byref(npk)))
+        self.w, self.h, self.n_packets = w.value, h.value, npk.value
+        self.timestamp = _as_array(ts.value, np.uint64, (self.w,))
+        self.measurement_id = _as_array(mid.value, np.uint16, (self.w,))
+        self.status = _as_array(st.value, np.uint32, (self.w,))
+        self.packet_timestamp = _as_array(pts.value, np.uint64, (self.n_packets,))
+        self.alert_flags = _as_array(af.value, np.uint8, (self.n_packets,))
+
+    def add_field(self, name, dtype, extra_dim=1):
+        check(lib.obh_frame_add_field(self._h, name.encode(), NP_TAG[np.dtype(dtype)], extra_dim))
+
+    @property
+    def fields(self):
+        out = []
+        for i in range(lib.obh_frame_n_fields(self._h)):
+            name = C.create_string_buffer(32)
+            check(lib.obh_frame_field_at(self._h, i, name, 32, None, None, None))
+            out.append(name.value.decode())
+        return out
+
+    def has_field(self, name):
+        return name in self.fields
+
+    def field(self, name):
+        tag, eb, data = C.c_int32(), sz(), vp()
+        check(lib.obh_frame_field(self._h, name.encode(), C.byref(tag), C.byref(eb), C.byref(data)))
+        dt = np.dtype(TAG_NP[tag.value])
+        k = eb.value // dt.itemsize
+        shape = (self.h, self.w) if k == 1 else (self.h, self.w, k)
+        return _as_array(data.value, dt, shape)
+
+    @property
+    def frame_id(self):
+        return lib.obh_frame_get_frame_id(self._h)
+
+    @frame_id.setter
+    def frame_id(self, v):
+        lib.obh_frame_set_frame_id(self._h, v)
+
+    @property
+    def frame_status(self):
+        return lib.obh_frame_get_status(self._h, None, None)
+
+    def status_tuple(self):
+        a, b = C.c_uint8(), C.c_uint8()
+        s = lib.obh_frame_get_status(self._h, C.byref(a), C.byref(b))
+        return s, a.value, b.value
+
+    def set_status(self, frame_status, shutdown_countdown=0, shot_limiting_countdown=0):
+        lib.obh_frame_set_status(self._h, frame_status, shutdown_countdown, shot_limiting_countdown)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            try:
+                lib.obh_frame_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def frame_to_packets(frame, info, init_id=0, prod_sn=0):
+    """impl::frame_to_packets -> (packets uint8 [n, size], host_ts uint64 [n])."""
+    psz = info.lidar_packet_size
+    out = np.zeros((frame.n_packets, psz), np.uint8)
+    ts = np.zeros(frame.n_packets, np.uint64)
+    n = sz()
+    check(lib.obh_frame_to_packets(frame._h, info._h, init_id, prod_sn, out.ctypes.data, ts.ctypes.data,
+                                   C.byref(n)))
+    return out[:n.value].copy(), ts[:n.value].copy()
+
+
+class FrameBatcher:
+    """FrameBatcher / ScanBatcher: host state machine + one fused GPU decode per frame."""
+
+    def __init__(self, info):
+        hd = vp()
+        check(lib.obh_batcher_create(info._h, C.byref(hd)))
+        self._h, self.info = hd, info
+        self._lut = None
+
+    def batch(self, packet, host_timestamp, frame):
+        b = packet if isinstance(packet, np.ndarray) else np.frombuffer(bytes(packet), np.uint8)
+        done = i32(0)
+        check(lib.obh_batcher_batch(self._h, b.ctypes.data, b.size, int(host_timestamp), frame._h,
+                                    C.byref(done)))
+        return bool(done.value)
+
+    __call__ = batch
+
+    def batch_burst(self, packets, host_timestamps, frame):
+        """Feed a [n, packet_size] uint8 burst; returns (packets consumed, frame complete)."""
+        ts = np.ascontiguousarray(host_timestamps, np.uint64)
+        n, stride = packets.shape[0], packets.strides[0]
+        used, done = sz(0), i32(0)
+        check(lib.obh_batcher_batch_burst(self._h, packets.ctypes.data, n, stride, packets.shape[1],
+                                          ts.ctypes.data, frame._h, C.byref(used), C.byref(done)))
+        return used.value, bool(done.value)
+
+    def flush(self, frame):
+        check(lib.obh_batcher_flush(self._h, frame._h))
+
+    def reset(self):
+        check(lib.obh_batcher_reset(self._h))
+
+    @property
+    def batched_packets(self):
+        return lib.obh_batcher_batched_packets(self._h)
+
+    @property
+    def dropped_packets(self):
+        return lib.obh_batcher_dropped_packets(self._h)
+
+    @property
+    def gpu_launches(self):
+        return lib.obh_batcher_gpu_launches(self._h)
+
+    def set_max_cache_size(self, n):
+        check(lib.obh_batcher_set_max_cache_size(self._h, n))
+
+    def set_headers_only(self, on=True):
+        check(lib.obh_batcher_set_headers_only(self._h, int(on)))
+
+    def set_fused_cloud(self, lut, pixel_shift_by_row=None):
+        self._lut = lut
+        sh, n = None, 0
+        if pixel_shift_by_row is not None:
+            sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
+            n = sh.size
+        check(lib.obh_batcher_set_fused(self._h, lut._h if lut is not None else None,
+                                        sh.ctypes.data if sh is not None else None, n))
+
+    def fused_outputs(self, ret):
+        xyz, nb, rd = vp(), sz(), vp()
+        check(lib.obh_batcher_fused_outputs(self._h, ret, C.byref(xyz), C.byref(nb), C.byref(rd)))
+        dt = self._lut.dtype
+        n = nb.value // dt.itemsize
+        pts = _as_array(xyz.value, dt, (n // 3, 3)) if n else None
+        h, w = self.info.h, self.info.w
+        rdd = _as_array(rd.value, np.uint32, (h, w)) if rd.value else None
+        return pts, rdd
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            try:
+                lib.obh_batcher_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+
+LidarScan = LidarFrame
+ScanBatcher = FrameBatcher

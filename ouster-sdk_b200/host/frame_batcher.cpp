@@ -1,0 +1,465 @@
+// frame_batcher.cpp -- FrameBatcher (ScanBatcher): the reference's per-packet state machine on the
+// host (ouster_core/src/lidar_frame.cpp:1248-1267, 1530-1576, 1698-1959) with the per-pixel work
+// deferred to one fused GPU launch per frame (ob_decode_frames).
+//
+// Host side, per packet (cheap: 16 column headers): frame-id ordering / cache / init-id handling,
+// per-packet and per-column headers written straight into the LidarFrame, and a column map
+// col_src[w] that records, with the same sequencing as parse_by_block / parse_by_col /
+// zero_fields, which packet column (or "zero") is the last operation applied to every frame
+// column.  The packet bytes are appended to a pinned staging buffer.
+// Device side, when the frame is finalized: decode of every field of every pixel + zero fill
+// (+ optional destagger and XYZ), reading the staged packets once.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "ouster/core/b200_runtime.h"
+#include "ouster/core/lidar_frame.h"
+
+namespace ouster {
+namespace sdk {
+namespace core {
+
+struct FrameBatcher::Staging {
+    uint8_t* pinned{nullptr};
+    size_t capacity{0};  // packets
+    size_t stride{0};    // bytes per slot (multiple of 16)
+    size_t n_slots{0};
+    std::vector<int32_t> col_src;
+    ob_decoder* dec{nullptr};
+    std::string signature;
+    std::vector<std::string> field_names;
+    std::vector<size_t> field_bytes;
+    int device{0};
+
+    bool pinned_is_cuda{false};
+
+    ~Staging() {
+        release();
+        if (dec) ob_decoder_destroy(dec);
+    }
+    void release() {
+        if (!pinned) return;
+        if (pinned_is_cuda) ob_host_free(pinned);
+        else std::free(pinned);
+        pinned = nullptr;
+    }
+    void reserve(size_t packets) {
+        if (packets <= capacity) return;
+        size_t cap = std::max<size_t>(packets, capacity ? capacity * 2 : 16);
+        void* p = nullptr;
+        // pinned memory when a device exists; plain memory keeps the header-only mode usable
+        // on machines without one (decode itself still fails loudly there)
+        const bool cuda = ob_device_count() > 0;
+        if (cuda) b200::check(ob_host_alloc(cap * stride, &p));
+        else p = std::malloc(cap * stride);
+        if (!p) throw std::runtime_error("out of memory staging lidar packets");
+        if (pinned) std::memcpy(p, pinned, n_slots * stride);
+        release();
+        pinned = static_cast<uint8_t*>(p);
+        pinned_is_cuda = cuda;
+        capacity = cap;
+    }
+};
+
+FrameBatcher::FrameBatcher(const std::shared_ptr<SensorInfo>& info)
+    : pf(get_format(*info)), last_init_id_(info->init_id), sensor_info_(info) {
+    if (info->format.columns_per_packet == 0)
+        throw std::invalid_argument("unexpected columns_per_packet: 0");
+    if (info->format.pixels_per_column == 0)
+        throw std::invalid_argument("unexpected pixels_per_column: 0");
+    expected_lidar_packets_ = static_cast<size_t>(info->format.lidar_packets_per_frame());
+    stg_ = std::make_unique<Staging>();
+    stg_->stride = (pf.lidar_packet_size + 15) & ~static_cast<size_t>(15);
+    stg_->col_src.assign(info->format.columns_per_frame, -1);
+    stg_->device = b200::device();
+}
+
+FrameBatcher::FrameBatcher(const SensorInfo& info) : FrameBatcher(std::make_shared<SensorInfo>(info)) {}
+
+FrameBatcher::~FrameBatcher() = default;
+
+size_t FrameBatcher::batched_packets() const { return batched_lidar_packets_; }
+size_t FrameBatcher::dropped_packets() const { return dropped_packets_; }
+size_t FrameBatcher::gpu_launches() const { return launches_; }
+void FrameBatcher::set_fused_cloud(FusedCloud* cloud) { fused_ = cloud; }
+
+void FrameBatcher::set_max_cache_size(size_t n) {
+    if (n == 0) throw std::invalid_argument("max_cache_size must be > 0");
+    max_cache_size_ = n;
+}
+size_t FrameBatcher::get_max_cache_size() const { return max_cache_size_; }
+
+void FrameBatcher::reset() {
+    reset_frame_ = true;
+    finished_frame_id_ = -1;
+    next_valid_m_id_ = 0;
+    batched_lidar_packets_ = 0;
+    cache_.clear();
+    stg_->n_slots = 0;
+    std::fill(stg_->col_src.begin(), stg_->col_src.end(), -1);
+}
+
+void FrameBatcher::cache_packet(const uint8_t* buf, size_t size, uint64_t host_ts) {
+    CachedPacket c;
+    c.buf.assign(buf, buf + size);
+    c.buf.resize(size + 8, 0);  // header getters read 8 bytes
+    c.host_timestamp = host_ts;
+    c.seq = cache_seq_++;
+    cache_.push_back(std::move(c));
+}
+
+// the packet a frame-id ordered priority queue would pop: the oldest frame id, FIFO among equals
+size_t FrameBatcher::cache_top() const {
+    size_t best = 0;
+    for (size_t i = 1; i < cache_.size(); ++i) {
+        const int d = pf.frame_id_difference(pf.frame_id(cache_[best].buf.data()),
+                                             pf.frame_id(cache_[i].buf.data()));
+        if (d < 0 || (d == 0 && cache_[i].seq < cache_[best].seq)) best = i;
+    }
+    return best;
+}
+
+void FrameBatcher::start_frame(int64_t f_id, const uint8_t* packet_buf, LidarFrame& f) {
+    finished_frame_id_ = -1;
+    next_valid_m_id_ = 0;
+    batched_lidar_packets_ = 0;
+    f.frame_id = f_id;
+    f.timestamp().setZero();
+    f.measurement_id().setZero();
+    f.status().setZero();
+    f.packet_timestamp().setZero();
+    const uint8_t thermal = static_cast<uint8_t>(pf.thermal_shutdown(packet_buf));
+    const uint8_t shot = static_cast<uint8_t>(pf.shot_limiting(packet_buf));
+    f.frame_status = static_cast<uint64_t>(thermal & 0x0f) | (static_cast<uint64_t>(shot & 0x0f) << 4);
+    f.shutdown_countdown = static_cast<uint8_t>(pf.countdown_thermal_shutdown(packet_buf));
+    f.shot_limiting_countdown = static_cast<uint8_t>(pf.countdown_shot_limiting(packet_buf));
+    f.sensor_info = sensor_info_;
+    stg_->n_slots = 0;
+    std::fill(stg_->col_src.begin(), stg_->col_src.end(), -1);
+}
+
+void FrameBatcher::batch_lidar_packet(const uint8_t* packet_buf, uint64_t host_ts, LidarFrame& f) {
+    const int cpp = pf.columns_per_packet;
+    const uint16_t first_m_id = pf.col_measurement_id(pf.nth_col(0, packet_buf));
+    const uint16_t packet_id = static_cast<uint16_t>(first_m_id / cpp);
+    if (packet_id < f.packet_timestamp().rows()) {
+        f.packet_timestamp()[packet_id] = host_ts;
+        f.alert_flags()[packet_id] = pf.alert_flags(packet_buf);
+    }
+
+    // stage the wire bytes
+    Staging& s = *stg_;
+    s.reserve(s.n_slots + 1);
+    const size_t slot = s.n_slots++;
+    std::memcpy(s.pinned + slot * s.stride, packet_buf, pf.lidar_packet_size);
+    const int32_t src0 = static_cast<int32_t>(slot) * cpp;
+
+    // block path preconditions (lidar_frame.cpp:1542-1567)
+    int block = pf.block_parsable();
+    for (int icol = 0; icol < cpp && block; icol++) {
+        const uint8_t* col = pf.nth_col(icol, packet_buf);
+        if (!(pf.col_status(col) & 0x01) || pf.col_measurement_id(col) >= f.w) block = 0;
+    }
+    for (int icol = 0; icol < cpp && block; icol += block) {
+        if (static_cast<size_t>(pf.col_measurement_id(pf.nth_col(icol, packet_buf))) + block > f.w)
+            block = 0;
+    }
+
+    auto timestamp = f.timestamp();
+    auto measurement_id = f.measurement_id();
+    auto status = f.status();
+    auto zero_gap = [&](size_t from, size_t to) {  // zero_fields + zero_header_cols
+        for (size_t j = from; j < to; ++j) {
+            s.col_src[j] = -1;
+            timestamp[j] = 0;
+            measurement_id[j] = 0;
+            status[j] = 0;
+        }
+    };
+
+    if (block != 0) {  // parse_by_block, lidar_frame.cpp:1492-1528
+        if (first_m_id >= next_valid_m_id_) {
+            zero_gap(next_valid_m_id_, first_m_id);
+            next_valid_m_id_ = static_cast<uint16_t>(first_m_id + cpp);
+        }
+        for (int icol = 0; icol < cpp; icol++) {
+            const uint8_t* col = pf.nth_col(icol, packet_buf);
+            const uint16_t m_id = pf.col_measurement_id(col);
+            measurement_id[m_id] = m_id;
+            timestamp[m_id] = pf.col_timestamp(col);
+            status[m_id] = pf.col_status(col);
+        }
+        // block_field places a group at the measurement id of its first column (parsing.cpp:647-653)
+        for (int icol = 0; icol < cpp; icol += block) {
+            const uint16_t m0 = pf.col_measurement_id(pf.nth_col(icol, packet_buf));
+            for (int x = 0; x < block; ++x) s.col_src[m0 + x] = src0 + icol + x;
+        }
+    } else {  // parse_by_col, lidar_frame.cpp:1422-1466
+        for (int icol = 0; icol < cpp; icol++) {
+            const uint8_t* col = pf.nth_col(icol, packet_buf);
+            const uint16_t m_id = pf.col_measurement_id(col);
+            const uint32_t st = pf.col_status(col);
+            if (m_id >= f.w) continue;
+            if (!(st & 0x01)) continue;
+            if (m_id >= next_valid_m_id_) {
+                zero_gap(next_valid_m_id_, m_id);
+                next_valid_m_id_ = static_cast<uint16_t>(m_id + 1);
+            }
+            timestamp[m_id] = pf.col_timestamp(col);
+            measurement_id[m_id] = m_id;
+            status[m_id] = st;
+            s.col_src[m_id] = src0 + icol;
+        }
+    }
+    batched_lidar_packets_++;
+}
+
+bool FrameBatcher::check_frame_complete(const LidarFrame& f) const {
+    return pf.udp_profile_lidar == UDPProfileLidar::OFF ||
+           (batched_lidar_packets_ >= expected_lidar_packets_ &&
+            f.packet_timestamp().count() == expected_lidar_packets_);
+}
+
+void FrameBatcher::finalize_frame(LidarFrame& f) {
+    // tail zero fill (lidar_frame.cpp:1906-1908), then the GPU pass materialises the pixel fields
+    for (size_t j = next_valid_m_id_; j < f.w; ++j) stg_->col_src[j] = -1;
+    decode_staged(f);
+
+    if (f.sensor_info && f.sensor_info->init_id == last_init_id_ && f.frame_id <= last_frame_id_ &&
+        pf.header_type == HeaderType::FUSA)
+        throw std::runtime_error("32-bit frame id did not increase since the last frame");
+
+    finished_frame_id_ = f.frame_id;
+    last_frame_id_ = f.frame_id;
+    batched_lidar_packets_ = 0;
+}
+
+void FrameBatcher::flush(LidarFrame& f) { decode_staged(f); }
+
+void FrameBatcher::set_headers_only(bool on) { headers_only_ = on; }
+
+void FrameBatcher::decode_staged(LidarFrame& f) {
+    Staging& s = *stg_;
+    if (headers_only_) return;
+    // (re)build the device decode table for the fields this frame shares with the profile
+    // (foreach_channel_field: profile order, only fields the frame has; impl/lidar_frame_impl.h:367-375)
+    std::string sig;
+    std::vector<std::string> names;
+    std::vector<ob_field_desc> descs;
+    for (auto it = pf.begin(); it != pf.end(); ++it) {
+        const std::string& name = it->first;
+        if (!f.has_field(name) || name == ChanField::RAW_HEADERS) continue;
+        const Field& fld = f.field(name);
+        const FieldDecodeInfo& info = pf.field_decode_info(name);
+        size_t elem = fld.element_size();
+        if (fld.shape().size() > 2)
+            for (size_t d = 2; d < fld.shape().size(); ++d) elem *= fld.shape()[d];
+        if (elem < field_type_size(info.ty_tag) * static_cast<size_t>(info.num_elements))
+            throw std::invalid_argument("Dest type too small for specified field");
+        if (fld.shape().size() < 2 || fld.shape()[0] != f.h || fld.shape()[1] != f.w) continue;
+        ob_field_desc d{};
+        d.offset = static_cast<uint32_t>(info.offset);
+        d.elem_size = static_cast<uint32_t>(elem);
+        d.mask = info.mask;
+        d.shift = info.shift;
+        d.range_return = name == ChanField::RANGE ? 0 : (name == ChanField::RANGE2 ? 1 : -1);
+        if (d.range_return >= 0 && elem != 4) d.range_return = -1;
+        d.zero_pattern = fld.tag() == ChanFieldType::FLOAT16 ? 0x7e00u : 0u;
+        descs.push_back(d);
+        names.push_back(name);
+        sig += name + ":" + std::to_string(elem) + ":" + std::to_string(info.offset) + ":" +
+               std::to_string(info.mask) + ":" + std::to_string(info.shift) + ";";
+    }
+    if (descs.size() > OB_MAX_FIELDS) throw std::invalid_argument("too many fields to decode");
+    if (!s.dec || sig != s.signature) {
+        if (s.dec) ob_decoder_destroy(s.dec);
+        s.dec = nullptr;
+        ob_packet_layout L{};
+        L.packet_header_size = static_cast<uint32_t>(pf.packet_header_size);
+        L.col_header_size = static_cast<uint32_t>(pf.col_header_size);
+        L.channel_data_size = static_cast<uint32_t>(pf.channel_data_size);
+        L.col_size = static_cast<uint32_t>(pf.col_size);
+        L.packet_size = static_cast<uint32_t>(pf.lidar_packet_size);
+        L.columns_per_packet = static_cast<uint32_t>(pf.columns_per_packet);
+        L.pixels_per_column = static_cast<uint32_t>(pf.pixels_per_column);
+        L.columns_per_frame = static_cast<uint32_t>(f.w);
+        // column headers are written on the host; the device copies are not requested here
+        auto conv = [](const FieldDecodeInfo& fi) {
+            ob_field_desc d{};
+            d.offset = static_cast<uint32_t>(fi.offset);
+            d.elem_size = 8;
+            d.mask = fi.mask;
+            d.shift = fi.shift;
+            d.range_return = -1;
+            return d;
+        };
+        L.col_timestamp = conv(pf.col_timestamp_info());
+        L.col_measurement_id = conv(pf.col_measurement_id_info());
+        L.col_status = conv(pf.col_status_info());
+        b200::check(ob_decoder_create(&L, descs.data(), descs.size(), s.device, &s.dec));
+        s.signature = sig;
+    }
+
+    ob_decode_io io{};
+    io.packets = s.pinned;
+    io.n_slots = s.n_slots;
+    io.packet_stride = s.stride;
+    bool identity = s.n_slots * static_cast<size_t>(pf.columns_per_packet) >= f.w;
+    for (size_t j = 0; j < f.w && identity; ++j) identity = s.col_src[j] == static_cast<int32_t>(j);
+    io.col_src = identity ? nullptr : s.col_src.data();
+    for (size_t i = 0; i < names.size(); ++i) io.fields[i] = f.field(names[i]).get();
+
+    const ob_lut* lut = nullptr;
+    const int32_t* shifts = nullptr;
+    size_t n_shifts = 0;
+    if (fused_ && fused_->lut) {
+        lut = fused_->lut.get();
+        const size_t n = f.h * f.w;
+        int n_ret = 0;
+        for (const auto& d : descs) n_ret = std::max(n_ret, d.range_return + 1);
+        for (int r = 0; r < n_ret; ++r) {
+            if (fused_->lut_is_f64) {
+                fused_->xyz_f64[r].resize(n * 3);
+                io.xyz[r] = fused_->xyz_f64[r].data();
+            } else {
+                fused_->xyz_f32[r].resize(n * 3);
+                io.xyz[r] = fused_->xyz_f32[r].data();
+            }
+            if (!fused_->pixel_shift_by_row.empty()) {
+                fused_->range_destaggered[r].resize(n);
+                io.range_destaggered[r] = fused_->range_destaggered[r].data();
+            }
+        }
+        if (!fused_->pixel_shift_by_row.empty()) {
+            shifts = fused_->pixel_shift_by_row.data();
+            n_shifts = fused_->pixel_shift_by_row.size();
+        }
+    }
+    if (names.empty() && !lut) return;
+    ob_stream* st = b200::thread_stream();
+    b200::check(ob_decode_frames(s.dec, &io, 1, lut, shifts, n_shifts, st));
+    b200::check(ob_stream_sync(st));
+    launches_++;
+}
+
+bool FrameBatcher::batch_with_caching(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f) {
+    cache_packet(buf, size, host_ts);
+    while (!cache_.empty()) {
+        const size_t top = cache_top();
+        const uint8_t* pbuf = cache_[top].buf.data();
+        const int64_t f_id = pf.frame_id(pbuf);
+
+        if (finished_frame_id_ >= 0 &&
+            pf.frame_id_difference(static_cast<uint32_t>(finished_frame_id_), static_cast<uint32_t>(f_id)) <= 0) {
+            dropped_packets_++;  // belongs to a frame that was already released
+            cache_.erase(cache_.begin() + static_cast<std::ptrdiff_t>(top));
+            continue;
+        }
+        if (f.frame_id == -1 || finished_frame_id_ >= 0) start_frame(f_id, pbuf, f);
+
+        const int diff = pf.frame_id_difference(static_cast<uint32_t>(f.frame_id), static_cast<uint32_t>(f_id));
+        if (diff < 0) {
+            dropped_packets_++;
+            cache_.erase(cache_.begin() + static_cast<std::ptrdiff_t>(top));
+        } else if (diff > 0) {
+            if (cache_.size() >= max_cache_size_) {  // give up waiting for the current frame
+                finalize_frame(f);
+                return true;
+            }
+            return false;
+        } else {
+            batch_lidar_packet(pbuf, cache_[top].host_timestamp, f);
+            cache_.erase(cache_.begin() + static_cast<std::ptrdiff_t>(top));
+            if (check_frame_complete(f)) {
+                finalize_frame(f);
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+bool FrameBatcher::handle_init_id_change(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f) {
+    last_init_id_ = pf.init_id(buf);
+    if (f.frame_id == -1 || finished_frame_id_ >= 0) {  // no frame in flight: just start over
+        reset();
+        reset_frame_ = false;
+        start_frame(pf.frame_id(buf), buf, f);
+        batch_lidar_packet(buf, host_ts, f);
+        if (check_frame_complete(f)) {
+            finalize_frame(f);
+            return true;
+        }
+        return false;
+    }
+    finalize_frame(f);  // release what we have, keep this packet for the next frame
+    reset();
+    cache_packet(buf, size, host_ts);
+    return true;
+}
+
+bool FrameBatcher::batch_impl(const uint8_t* buf_in, size_t size, uint64_t host_ts, LidarFrame& f) {
+    if (reset_frame_) {
+        f.frame_id = -1;
+        reset_frame_ = false;
+    }
+    if (f.w != sensor_info_->format.columns_per_frame || f.h != sensor_info_->format.pixels_per_column)
+        throw std::invalid_argument("unexpected frame dimensions");
+    if (f.packet_timestamp().rows() != f.w / static_cast<size_t>(pf.columns_per_packet))
+        throw std::invalid_argument("unexpected frame columns_per_packet: " +
+                                    std::to_string(pf.columns_per_packet));
+    if (size < pf.lidar_packet_size) throw std::invalid_argument("lidar packet buffer too small");
+
+    // every header getter reads 8 bytes that lie inside the packet (packet header >= 32 bytes or,
+    // for LEGACY, column header 16 bytes; the LEGACY status window ends with its column)
+    const uint8_t* buf = buf_in;
+
+    if (pf.udp_profile_lidar != UDPProfileLidar::LEGACY && pf.init_id(buf) != last_init_id_)
+        return handle_init_id_change(buf, pf.lidar_packet_size, host_ts, f);
+
+    const int64_t f_id = pf.frame_id(buf);
+    if (cache_.empty()) {
+        if (finished_frame_id_ >= 0 &&
+            pf.frame_id_difference(static_cast<uint32_t>(finished_frame_id_), static_cast<uint32_t>(f_id)) <= 0) {
+            dropped_packets_++;
+            return false;
+        }
+        if (f.frame_id == -1 || finished_frame_id_ >= 0) {
+            start_frame(f_id, buf, f);
+            batch_lidar_packet(buf, host_ts, f);
+            if (check_frame_complete(f)) {
+                finalize_frame(f);
+                return true;
+            }
+            return false;
+        }
+    }
+    if (f.frame_id == f_id && finished_frame_id_ < 0) {
+        batch_lidar_packet(buf, host_ts, f);
+        if (check_frame_complete(f)) {
+            finalize_frame(f);
+            return true;
+        }
+        return false;
+    }
+    return batch_with_caching(buf, pf.lidar_packet_size, host_ts, f);
+}
+
+bool FrameBatcher::batch(const uint8_t* buf, size_t size, uint64_t host_timestamp, LidarFrame& f) {
+    return batch_impl(buf, size, host_timestamp, f);
+}
+
+bool FrameBatcher::batch(const Packet& packet, LidarFrame& f) {
+    if (packet.type() == PacketType::Imu || packet.type() == PacketType::Zone)
+        return false;  // IMU / zone-monitor packets are outside the accelerated path
+    return batch_impl(packet.buf.data(), packet.buf.size(), packet.host_timestamp, f);
+}
+
+bool FrameBatcher::operator()(const Packet& packet, LidarFrame& f) { return batch(packet, f); }
+
+}  // namespace core
+}  // namespace sdk
+}  // namespace ouster

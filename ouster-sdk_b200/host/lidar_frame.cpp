@@ -1,0 +1,254 @@
+// lidar_frame.cpp -- Field / LidarFrame host containers and the default field sets
+// (host mirror of ouster_core/src/lidar_frame.cpp:73-446, 1038-1117 and field.cpp:247-275).
+#include <algorithm>
+#include <stdexcept>
+
+#include "ouster/core/lidar_frame.h"
+
+namespace ouster {
+namespace sdk {
+namespace core {
+
+// ---- Field ----
+Field::Field(ChanFieldType tag, const std::vector<size_t>& shape) : tag_(tag), shape_(shape) {
+    size_t n = field_type_size(tag);
+    for (size_t d : shape) n *= d;
+    buf_.assign(n, 0);
+}
+
+void Field::set_zero() { std::fill(buf_.begin(), buf_.end(), 0); }
+
+// ---- default field sets ----
+namespace {
+using T = ChanFieldType;
+struct Slot {
+    const char* name;
+    T type;
+};
+struct SlotSet {
+    UDPProfileLidar profile;
+    std::vector<Slot> slots;
+};
+const std::vector<SlotSet>& slot_sets() {
+    using P = UDPProfileLidar;
+    namespace F = ChanField;
+    static const std::vector<SlotSet> sets = {
+        {P::LEGACY,
+         {{F::RANGE, T::UINT32}, {F::SIGNAL, T::UINT16}, {F::NEAR_IR, T::UINT16},
+          {F::REFLECTIVITY, T::UINT8}, {F::FLAGS, T::UINT8}}},
+        {P::RNG19_RFL8_SIG16_NIR16_DUAL,
+         {{F::RANGE, T::UINT32}, {F::RANGE2, T::UINT32}, {F::SIGNAL, T::UINT16},
+          {F::SIGNAL2, T::UINT16}, {F::REFLECTIVITY, T::UINT8}, {F::REFLECTIVITY2, T::UINT8},
+          {F::FLAGS, T::UINT8}, {F::FLAGS2, T::UINT8}, {F::NEAR_IR, T::UINT16}, {F::WINDOW, T::UINT8}}},
+        {P::RNG19_RFL8_SIG16_NIR16,
+         {{F::RANGE, T::UINT32}, {F::SIGNAL, T::UINT16}, {F::REFLECTIVITY, T::UINT8},
+          {F::FLAGS, T::UINT8}, {F::NEAR_IR, T::UINT16}, {F::WINDOW, T::UINT8}}},
+        {P::RNG15_RFL8_NIR8,
+         {{F::RANGE, T::UINT32}, {F::REFLECTIVITY, T::UINT8}, {F::NEAR_IR, T::UINT16}, {F::FLAGS, T::UINT8}}},
+        {P::RNG15_RFL8_WIN8,
+         {{F::RANGE, T::UINT32}, {F::REFLECTIVITY, T::UINT8}, {F::WINDOW, T::UINT8}, {F::FLAGS, T::UINT8}}},
+        {P::FIVE_WORD_PIXEL,
+         {{F::RAW32_WORD1, T::UINT32}, {F::RAW32_WORD2, T::UINT32}, {F::RAW32_WORD3, T::UINT32},
+          {F::RAW32_WORD4, T::UINT32}, {F::RAW32_WORD5, T::UINT32}}},
+        {P::FUSA_RNG15_RFL8_NIR8_DUAL,
+         {{F::RANGE, T::UINT32}, {F::REFLECTIVITY, T::UINT8}, {F::NEAR_IR, T::UINT16},
+          {F::RANGE2, T::UINT32}, {F::REFLECTIVITY2, T::UINT8}, {F::FLAGS, T::UINT8},
+          {F::FLAGS2, T::UINT8}, {F::WINDOW, T::UINT8}}},
+        {P::RNG15_RFL8_NIR8_DUAL,
+         {{F::RANGE, T::UINT32}, {F::REFLECTIVITY, T::UINT8}, {F::NEAR_IR, T::UINT16},
+          {F::RANGE2, T::UINT32}, {F::REFLECTIVITY2, T::UINT8}, {F::FLAGS, T::UINT8},
+          {F::FLAGS2, T::UINT8}, {F::WINDOW, T::UINT8}}},
+        {P::OFF, {}},
+        {P::RNG15_RFL8_NIR8_ZONE16,
+         {{F::RANGE, T::UINT32}, {F::REFLECTIVITY, T::UINT8}, {F::NEAR_IR, T::UINT16},
+          {F::FLAGS, T::UINT8}, {F::ZONE_MASK, T::UINT16}, {F::WINDOW, T::UINT8}}},
+        {P::RNG19_RFL8_SIG16_NIR16_ZONE16,
+         {{F::RANGE, T::UINT32}, {F::SIGNAL, T::UINT16}, {F::REFLECTIVITY, T::UINT8},
+          {F::FLAGS, T::UINT8}, {F::NEAR_IR, T::UINT16}, {F::ZONE_MASK, T::UINT16}, {F::WINDOW, T::UINT8}}},
+        {P::RNG19_RFL8_SIG16_ZONE16_DUAL,
+         {{F::RANGE, T::UINT32}, {F::RANGE2, T::UINT32}, {F::SIGNAL, T::UINT16},
+          {F::SIGNAL2, T::UINT16}, {F::REFLECTIVITY, T::UINT8}, {F::REFLECTIVITY2, T::UINT8},
+          {F::FLAGS, T::UINT8}, {F::FLAGS2, T::UINT8}, {F::ZONE_MASK, T::UINT16}, {F::WINDOW, T::UINT8}}},
+        {P::RNG19_RFL8_SIG16_NIR16_RGB16,
+         {{F::RANGE, T::UINT32}, {F::SIGNAL, T::UINT16}, {F::REFLECTIVITY, T::UINT8},
+          {F::NEAR_IR, T::UINT16}, {F::RGB, T::FLOAT16}, {F::FLAGS, T::UINT8}}},
+        {P::RNG19_RFL8_SIG16_NIR16_RGB16_DUAL,
+         {{F::RANGE, T::UINT32}, {F::RANGE2, T::UINT32}, {F::SIGNAL, T::UINT16},
+          {F::SIGNAL2, T::UINT16}, {F::REFLECTIVITY, T::UINT8}, {F::REFLECTIVITY2, T::UINT8},
+          {F::NEAR_IR, T::UINT16}, {F::RGB, T::FLOAT16}, {F::FLAGS, T::UINT8}, {F::FLAGS2, T::UINT8}}},
+    };
+    return sets;
+}
+}  // namespace
+
+LidarFrameFieldTypes get_field_types(UDPProfileLidar profile) {
+    for (const auto& s : slot_sets()) {
+        if (s.profile != profile) continue;
+        LidarFrameFieldTypes out;
+        for (const auto& sl : s.slots) {
+            FieldType ft(sl.name, sl.type, {}, FieldClass::PIXEL_FIELD);
+            if (ft.name == ChanField::RGB) ft.extra_dims.push_back(3);  // H x W x 3
+            out.push_back(ft);
+        }
+        return out;
+    }
+    throw std::invalid_argument("Unknown lidar udp profile");
+}
+
+LidarFrameFieldTypes get_field_types(const DataFormat& format, const Version& fw) {
+    LidarFrameFieldTypes out = get_field_types(format.udp_profile_lidar);
+    const bool zone = format.udp_profile_lidar == UDPProfileLidar::RNG19_RFL8_SIG16_NIR16_ZONE16 ||
+                      format.udp_profile_lidar == UDPProfileLidar::RNG15_RFL8_NIR8_ZONE16;
+    // WINDOW only exists from firmware 3.2.0 (3.2.1 for the zone profiles)
+    if (fw < Version{3, 2, 0} || (zone && fw < Version{3, 2, 1})) {
+        auto it = std::find_if(out.begin(), out.end(),
+                               [](const FieldType& f) { return f.name == ChanField::WINDOW; });
+        if (it != out.end()) out.erase(it);
+    }
+    return out;
+}
+
+LidarFrameFieldTypes get_field_types(const SensorInfo& info) {
+    return get_field_types(info.format, info.get_version());
+}
+
+// ---- LidarFrame ----
+LidarFrame::LidarFrame() = default;
+
+void LidarFrame::init_headers(size_t columns_per_packet) {
+    timestamp_.assign(w, 0);
+    measurement_id_.assign(w, 0);
+    status_.assign(w, 0);
+    const size_t np = columns_per_packet ? w / columns_per_packet : 0;
+    packet_timestamp_.assign(np, 0);
+    alert_flags_.assign(np, 0);
+}
+
+LidarFrame::LidarFrame(size_t h_, size_t w_, const LidarFrameFieldTypes& field_types,
+                       size_t columns_per_packet)
+    : w(w_), h(h_) {
+    init_headers(columns_per_packet);
+    for (const auto& ft : field_types) add_field(ft);
+}
+
+LidarFrame::LidarFrame(size_t h_, size_t w_, UDPProfileLidar profile, size_t columns_per_packet)
+    : LidarFrame(h_, w_, get_field_types(profile), columns_per_packet) {}
+
+LidarFrame::LidarFrame(std::shared_ptr<SensorInfo> info, const std::vector<FieldType>& field_types)
+    : LidarFrame(info->format.pixels_per_column, info->format.columns_per_frame, field_types,
+                 info->format.columns_per_packet) {
+    sensor_info = std::move(info);
+}
+
+LidarFrame::LidarFrame(std::shared_ptr<SensorInfo> info)
+    : LidarFrame(info, get_field_types(*info)) {}
+
+LidarFrame::LidarFrame(const SensorInfo& info) : LidarFrame(std::make_shared<SensorInfo>(info)) {}
+
+ThermalShutdownStatus LidarFrame::thermal_shutdown() const {
+    return static_cast<ThermalShutdownStatus>(frame_status & 0x0f);
+}
+ShotLimitingStatus LidarFrame::shot_limiting() const {
+    return static_cast<ShotLimitingStatus>((frame_status & 0xf0) >> 4);
+}
+
+bool LidarFrame::has_field(const std::string& name) const { return fields_.count(name) != 0; }
+
+Field& LidarFrame::field(const std::string& name) {
+    auto it = fields_.find(name);
+    if (it == fields_.end()) throw std::invalid_argument("Invalid field for LidarFrame");
+    return it->second;
+}
+const Field& LidarFrame::field(const std::string& name) const {
+    auto it = fields_.find(name);
+    if (it == fields_.end()) throw std::invalid_argument("Invalid field for LidarFrame");
+    return it->second;
+}
+
+Field& LidarFrame::checked(const std::string& name, ChanFieldType tag) {
+    Field& f = field(name);
+    if (f.tag() != tag)
+        throw std::invalid_argument("Accessed field at wrong type. Field is " + to_string(f.tag()) +
+                                    " but was accessed as " + to_string(tag));
+    return f;
+}
+
+Field& LidarFrame::add_field(const std::string& name, ChanFieldType type,
+                             const std::vector<size_t>& extra_dims, FieldClass field_class) {
+    if (has_field(name)) throw std::invalid_argument("Duplicated field '" + name + "'");
+    std::vector<size_t> shape;
+    switch (field_class) {
+        case FieldClass::PIXEL_FIELD: shape = {h, w}; break;
+        case FieldClass::COLUMN_FIELD: shape = {w}; break;
+        case FieldClass::PACKET_FIELD: shape = {packet_timestamp_.size()}; break;
+        default: break;
+    }
+    shape.insert(shape.end(), extra_dims.begin(), extra_dims.end());
+    field_class_[name] = field_class;
+    return fields_.emplace(name, Field(type, shape)).first->second;
+}
+
+Field& LidarFrame::add_field(const FieldType& t) {
+    return add_field(t.name, t.element_type, t.extra_dims, t.field_class);
+}
+
+Field LidarFrame::del_field(const std::string& name) {
+    auto it = fields_.find(name);
+    if (it == fields_.end())
+        throw std::invalid_argument("Attempted deleting non existing field '" + name + "'");
+    Field out = std::move(it->second);
+    fields_.erase(it);
+    field_class_.erase(name);
+    return out;
+}
+
+ChanFieldType LidarFrame::field_type(const std::string& name) const {
+    return has_field(name) ? fields_.at(name).tag() : ChanFieldType::VOID;
+}
+
+LidarFrameFieldTypes LidarFrame::field_types() const {
+    LidarFrameFieldTypes out;
+    for (const auto& kv : fields_) {
+        const auto& shp = kv.second.shape();
+        const FieldClass fc = field_class_.count(kv.first) ? field_class_.at(kv.first) : FieldClass::PIXEL_FIELD;
+        const size_t base = fc == FieldClass::PIXEL_FIELD ? 2 : (fc == FieldClass::FRAME_FIELD ? 0 : 1);
+        std::vector<size_t> extra(shp.begin() + std::min(base, shp.size()), shp.end());
+        out.emplace_back(kv.first, kv.second.tag(), extra, fc);
+    }
+    return out;
+}
+
+bool LidarFrame::complete(ColumnWindow window) const {
+    const size_t a = window.first, b = window.second;
+    auto valid = [&](size_t i) { return (status_[i] & 0x01) != 0; };
+    if (a <= b) {
+        for (size_t i = a; i <= b && i < w; ++i)
+            if (!valid(i)) return false;
+        return true;
+    }
+    for (size_t i = 0; i <= b && i < w; ++i)
+        if (!valid(i)) return false;
+    for (size_t i = a; i < w; ++i)
+        if (!valid(i)) return false;
+    return true;
+}
+
+bool LidarFrame::complete() const {
+    if (sensor_info) return complete(sensor_info->format.column_window);
+    return complete({0, static_cast<uint16_t>(w - 1)});
+}
+
+bool LidarFrame::equals(const LidarFrame& o) const {
+    return w == o.w && h == o.h && frame_id == o.frame_id && frame_status == o.frame_status &&
+           shutdown_countdown == o.shutdown_countdown &&
+           shot_limiting_countdown == o.shot_limiting_countdown && fields_ == o.fields_ &&
+           timestamp_ == o.timestamp_ && measurement_id_ == o.measurement_id_ &&
+           status_ == o.status_ && packet_timestamp_ == o.packet_timestamp_ &&
+           alert_flags_ == o.alert_flags_;
+}
+
+bool operator==(const LidarFrame& a, const LidarFrame& b) { return a.equals(b); }
+
+}  // namespace core
+}  // namespace sdk
+}  // namespace ouster

@@ -298,6 +298,10 @@ const uint8_t* PacketFormat::nth_px(size_t px, const uint8_t* col_buf) const {
     return col_buf + col_header_size + px * channel_data_size;
 }
 
+const FieldDecodeInfo& PacketFormat::col_timestamp_info() const { return impl_->col_timestamp; }
+const FieldDecodeInfo& PacketFormat::col_measurement_id_info() const { return impl_->col_measurement_id; }
+const FieldDecodeInfo& PacketFormat::col_status_info() const { return impl_->col_status; }
+
 // ---- channel fields ----
 bool PacketFormat::has_field(const std::string& f) const { return impl_->fields.count(f) != 0; }
 const FieldDecodeInfo& PacketFormat::field_decode_info(const std::string& f) const {

@@ -1,0 +1,144 @@
+// dropin_example.cpp -- compiles against the replacement headers exactly like code written for
+// ouster_core (cf. examples/representations_example.cpp:38-54, 85-131 of the reference):
+//   XYZLut lut(info); auto cloud = lut(scan); destagger<double>(info, x_image) ...
+// and exercises ScanBatcher / LidarScan (deprecated spellings) end to end on the GPU.
+// Prints "DROPIN OK" when every check passes.  Built and run by tests/test_gpu_cpp_dropin.py.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ouster/core/lidar_scan.h"  // deprecated forwarding header
+#include "ouster/core/xyzlut.h"
+
+using namespace ouster::sdk::core;
+
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            std::exit(1);                                                  \
+        }                                                                  \
+    } while (0)
+
+template <typename Ex, typename F>
+static void expect_throw(F&& fn, const std::string& text) {
+    try {
+        fn();
+    } catch (const Ex& e) {
+        if (std::string(e.what()).find(text) == std::string::npos) {
+            std::fprintf(stderr, "wrong message: '%s' (wanted '%s')\n", e.what(), text.c_str());
+            std::exit(1);
+        }
+        return;
+    }
+    std::fprintf(stderr, "expected exception '%s'\n", text.c_str());
+    std::exit(1);
+}
+
+int main() {
+    // ---- config 1 plumbing: OS1-64 1024x64 default sensor (SensorInfo::from_default) ----
+    auto info = SensorInfo::from_default(LidarMode{1024, 10});
+    info->format.udp_profile_lidar = UDPProfileLidar::RNG19_RFL8_SIG16_NIR16;
+    info->fw_rev = "v3.2.1";
+    const size_t h = info->format.pixels_per_column, w = info->format.columns_per_frame;
+    CHECK(h == 64 && w == 1024);
+
+    LidarScan scan(info);  // deprecated alias of LidarFrame
+    CHECK(scan.has_field(ChanField::RANGE) && scan.has_field(ChanField::WINDOW));
+    std::mt19937 gen(42);
+    auto range = scan.field<uint32_t>(ChanField::RANGE);
+    for (size_t i = 0; i < range.size(); ++i) range(i) = (gen() & 1) ? 0u : 1u + gen() % 10000u;
+    auto refl = scan.field<uint8_t>(ChanField::REFLECTIVITY);
+    for (size_t i = 0; i < refl.size(); ++i) refl(i) = static_cast<uint8_t>(gen());
+    for (size_t c = 0; c < w; ++c) {
+        scan.status()[c] = 1;
+        scan.measurement_id()[c] = static_cast<uint16_t>(c);
+        scan.timestamp()[c] = 1000 + c;
+    }
+    for (size_t p = 0; p < w / 16; ++p) scan.packet_timestamp()[p] = 10 + p;
+    scan.frame_id = 700;
+
+    // ---- XYZLut + cartesian ----
+    XYZLut lut(*info);                 // double, built on the GPU from the beam intrinsics
+    XYZLutT<float> lutf(lut);          // converting constructor
+    CHECK(lut.direction.rows() == h * w && lut.h == h && lut.w == w);
+    PointCloudXYZd cloud = lut(scan);
+    PointCloudXYZf cloudf = lutf(scan);
+    PointCloudXYZd cloud2 = cartesian(scan, lut);  // deprecated free function
+    CHECK(cloud == cloud2);
+    for (size_t i = 0; i < h * w; ++i) {
+        const uint32_t r = range(i);
+        for (int k = 0; k < 3; ++k) {
+            const double want = r == 0 ? 0.0 : r * lut.direction(i, k) + lut.offset(i, k);
+            CHECK(cloud(i, k) == want);  // same two roundings as the reference loop
+            const float wantf = r == 0 ? 0.0f : r * lutf.direction(i, k) + lutf.offset(i, k);
+            CHECK(cloudf(i, k) == wantf);
+        }
+    }
+    // doc formula spot check of the LUT (python/src/ouster/sdk/examples/reference.py:18-76)
+    {
+        const size_t u = 5, v = 100, i = u * w + v;
+        const double n = info->beam_to_lidar_transform(0, 3);
+        const double te = 2.0 * M_PI * (1.0 - double(v) / w);
+        const double ta = -2.0 * M_PI * info->beam_azimuth_angles[u] / 360.0;
+        const double phi = 2.0 * M_PI * info->beam_altitude_angles[u] / 360.0;
+        const double r = 5000;
+        const double x = (r - n) * std::cos(te + ta) * std::cos(phi) + n * std::cos(te);
+        const double z = (r - n) * std::sin(phi);
+        const double gx = r * lut.direction(i, 0) + lut.offset(i, 0);
+        const double gz = r * lut.direction(i, 2) + lut.offset(i, 2);
+        CHECK(std::fabs(gx - (-x) * 0.001) < 1e-9);  // lidar_to_sensor = diag(-1,-1,1), tz = 36.18
+        CHECK(std::fabs(gz - (z + 36.18) * 0.001) < 1e-9);
+    }
+
+    // ---- destagger / stagger ----
+    img_t<uint32_t> destag = destagger<uint32_t>(*info, range);
+    for (size_t u = 0; u < h; ++u) {
+        const int s = info->format.pixel_shift_by_row[u];
+        for (size_t j = 0; j < w; ++j) CHECK(destag(u, (j + s) % w) == range(u, j));
+    }
+    img_t<uint32_t> back = stagger<uint32_t>(*info, destag);
+    for (size_t i = 0; i < h * w; ++i) CHECK(back(i) == range(i));
+    expect_throw<std::invalid_argument>(
+        [&] { destagger<uint32_t>(ArrayRef<const uint32_t>(range), std::vector<int>(h - 1, 0)); },
+        "image height does not match shifts size");
+    expect_throw<std::invalid_argument>(
+        [&] {
+            img_t<uint32_t> small(h, w / 2);
+            destagger<uint32_t>(*info, small);
+        },
+        "Image resolution must match SensorInfo.");
+    expect_throw<std::invalid_argument>(
+        [&] {
+            img_t<uint32_t> small(h, w / 2);
+            cartesian(ArrayRef<const uint32_t>(small), lut);
+        },
+        "unexpected image dimensions");
+
+    // ---- frame_to_packets -> ScanBatcher -> LidarScan round trip ----
+    PacketFormat pf(*info);
+    std::vector<Packet> packets = impl::frame_to_packets(scan, pf, 0, 0);
+    CHECK(packets.size() == w / 16);
+    LidarScan out(info);
+    ScanBatcher batcher(*info);  // deprecated alias of FrameBatcher
+    for (size_t i = 0; i < packets.size(); ++i) {
+        const bool done = batcher(packets[i], out);
+        CHECK(done == (i + 1 == packets.size()));
+    }
+    CHECK(out.frame_id == 700);
+    for (const auto& name : {ChanField::RANGE, ChanField::REFLECTIVITY}) CHECK(out.field(name) == scan.field(name));
+    for (size_t c = 0; c < w; ++c) CHECK(out.timestamp()[c] == 1000 + c && out.status()[c] == 1);
+    expect_throw<std::invalid_argument>(
+        [&] {
+            LidarScan wrong(32, 512, UDPProfileLidar::RNG19_RFL8_SIG16_NIR16, 16);
+            batcher.batch(packets[0], wrong);
+        },
+        "unexpected frame dimensions");
+
+    std::printf("DROPIN OK launches=%zu\n", batcher.gpu_launches());
+    return 0;
+}

@@ -165,6 +165,11 @@ def main():
         json.dump(meta, open(os.path.join(OUT, name + ".json"), "w"), indent=1)
         print(name, arr.shape, meta["profile"])
 
+    # packets carrying a sensor-computed CRC64 (fw 3.2): pins crc64 (parsing.cpp:1183-1234)
+    crc_pk = read_pcap_udp(os.path.join(PCAPS, "crc_test.pcap"))[:4]
+    np.savez_compressed(os.path.join(OUT, "crc_test.npz"),
+                        packets=np.frombuffer(b"".join(crc_pk), np.uint8).reshape(4, -1))
+
     # ---- outputs of the reference's own python restatements ----
     ref = import_reference_py()
     rng = np.random.default_rng(1234)
@@ -198,5 +203,44 @@ def main():
     print("reference.py vectors written")
 
 
+def extract_profile_tables():
+    """Parse the profile tables out of the reference SOURCE TEXT (ouster_core/src/parsing.cpp:170-356)
+    into tests/golden/profile_tables.json: {profile: {chan_data_size, fields: {name: [bit, bits,
+    upshift, num_elements]}}}.  Pins the oracle's and the product's transcriptions of every profile,
+    including those without a pcap fixture."""
+    import re
+    src = open(os.path.join(REF, "ouster_core", "src", "parsing.cpp")).read()
+    tables = {}
+    for m in re.finditer(r"static const Table<std::string, FieldDecodeInfo, \d+> (\w+)\{\{(.*?)\}\};", src, re.S):
+        name, body = m.group(1), m.group(2)
+        fields = {}
+        for fm in re.finditer(r"\{ChanField::(\w+),\s*field_info\(([^)]*)\)\}", body):
+            args = [a.strip() for a in fm.group(2).split(",")]
+            vals = [int(eval(re.sub(r"size_t\{(\d+)\}", r"\1", a))) for a in args]
+            bit, bits = vals[0], vals[1]
+            up = vals[2] if len(vals) > 2 else 0
+            nel = vals[4] if len(vals) > 4 else 1
+            fields[fm.group(1)] = [bit, bits, up, nel]
+        tables[name] = fields
+    out = {}
+    for m in re.finditer(r"\{UDPProfileLidar::(\w+),\s*\{(\w+)\.data\(\), \w+\.size\(\), (\d+)\}\}", src):
+        prof, tab, cds = m.group(1), m.group(2), int(m.group(3))
+        out[prof] = {"chan_data_size": cds, "fields": tables.get(tab, {})}
+    assert len(out) == 14, sorted(out)
+    json.dump(out, open(os.path.join(OUT, "profile_tables.json"), "w"), indent=1, sort_keys=True)
+    # default LidarFrame field slots (ouster_core/src/lidar_frame.cpp:73-226)
+    src2 = open(os.path.join(REF, "ouster_core", "src", "lidar_frame.cpp")).read()
+    slots = {}
+    for m in re.finditer(r"static const Table<std::string, ChanFieldType, \d+> (\w+)\{\s*\{(.*?)\}\};", src2, re.S):
+        slots[m.group(1)] = re.findall(r"\{ChanField::(\w+),\s*ChanFieldType::(\w+)\}", m.group(2))
+    dflt = {}
+    for m in re.finditer(r"\{UDPProfileLidar::(\w+),\s*\{(\w+)\.data\(\), \w+\.size\(\)\}\}", src2):
+        dflt[m.group(1)] = slots.get(m.group(2), [])
+    assert len(dflt) == 14, sorted(dflt)
+    json.dump(dflt, open(os.path.join(OUT, "default_field_slots.json"), "w"), indent=1, sort_keys=True)
+    print("profile tables:", len(out), "default slots:", len(dflt))
+
+
 if __name__ == "__main__":
     main()
+    extract_profile_tables()
