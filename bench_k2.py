@@ -84,10 +84,7 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
     rs = np.random.default_rng(43)
     d = (rs.random((H * W, 3)) + 0.5).astype(np.float32)
     o = (rs.random((H * W, 3)) * 0.01).astype(np.float32)
-    t_dir, t_off = torch.from_numpy(d).to(dev), torch.from_numpy(o).to(dev)
-    if dist is not None:
-        dist.broadcast(t_dir, 0)
-        dist.broadcast(t_off, 0)
+    t_dir, t_off = ob.sharding.broadcast_lut(d, o, dist, src=0, device=dev)
     lut = ob.XYZLutT.from_arrays(t_dir, t_off, H, W, device=local_rank)
     dec = ob.Decoder.from_sensor(si, src_frames[0], device=local_rank)
     tdt = {1: torch.uint8, 2: torch.int16, 4: torch.int32}

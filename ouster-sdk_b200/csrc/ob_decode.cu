@@ -43,6 +43,13 @@ struct DecodeParams {
     uint32_t n_returns;         // returns with a range field tagged
     uint32_t vec_ok;            // XYZ rows are 16-byte aligned (W % 4 == 0, aligned pointers)
     uint32_t has_shift;
+    struct Plan {        // per-field extraction plan, precomputed on the host (see make_plan)
+        uint32_t wa;     // aligned 32-bit word (from the pixel start) holding the field's LSB
+        uint32_t ma, mb; // masks of that word and the next one
+        uint32_t rs;     // funnel right shift (0..31) that brings the field's LSB to bit 0
+        int32_t d;       // post shift: >= 0 left, < 0 right (upshift / partial down-shift)
+        uint32_t fast;   // 1: 32-bit plan valid (value fits 32 bits, layout word aligned)
+    } plan[OB_MAX_FIELDS];
     unsigned short shift[kMaxRows];
 };
 
@@ -287,47 +294,71 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
             }
         }
 
-        // ---- phase A: decode every pixel once, all fields; lane = frame column ----
-        const unsigned col_groups = (tc + 31) / 32;  // 32-column lane groups per row
-        for (unsigned item = warp; item < L.H * col_groups; item += nwarps) {
-            const unsigned row = item / col_groups;
-            const unsigned t = (item - row * col_groups) * 32 + lane;
-            if (t >= tc) continue;
-            const int src = c.col_src[t];
-            const unsigned g = t / L.cpp;
-            const uint8_t* px = st + static_cast<size_t>(g) * p.pkt_stride_s + L.packet_header_size +
-                                static_cast<size_t>(t - g * L.cpp) * L.col_size + L.col_header_size +
-                                static_cast<size_t>(row) * L.channel_data_size;
-            uint32_t w[8];
-            if (p.n_words && src >= 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    w[i] = (static_cast<uint32_t>(i) < p.n_words) ? lds_u32_any(px + 4 * i, aligned) : 0u;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = 0u;
-            }
-            const size_t pix = static_cast<size_t>(row) * L.W + j0 + t;
-            int dcol = static_cast<int>(j0 + t);
-            if (p.has_shift) {
-                dcol += p.shift[row];
-                dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
-            }
-            const size_t dpix = static_cast<size_t>(row) * L.W + dcol;
+        // ---- phase A: decode; lane = frame column, warp = row (strided), fields outermost ----
+        // Per-lane constants are computed once per tile; every field then runs a tight row loop:
+        // 1-2 LDS + mask/funnel-shift + one coalesced store per pixel (no 64-bit math, no divides).
+        for (unsigned cg = 0; cg * 32 < tc; ++cg) {
+            const unsigned t = cg * 32 + lane;
+            const bool lane_on = t < tc;
+            const unsigned tt = lane_on ? t : 0;
+            const int src = lane_on ? c.col_src[tt] : -1;
+            const unsigned g = tt / L.cpp;
+            const uint8_t* px0 = st + static_cast<size_t>(g) * p.pkt_stride_s + L.packet_header_size +
+                                 static_cast<size_t>(tt - g * L.cpp) * L.col_size + L.col_header_size;
+            const unsigned cds = L.channel_data_size;
+            const size_t pix0 = static_cast<size_t>(j0) + tt;
             for (unsigned fi = 0; fi < L.n_fields; ++fi) {
                 const DecodeField& fd = L.fields[fi];
-                void* out = fr.fields[fi];
-                if (out == nullptr && fd.range_return < 0) continue;
-                uint64_t v;
-                if (src < 0) v = zero_value(fd);
-                else if (p.n_words) v = extract_regs(w, fd);
-                else v = extract_smem(px, fd, aligned);
-                if (out != nullptr) store_elem(out, pix, fd.elem_size, v);
-                if (fd.range_return >= 0) {
-                    const uint32_t rv = static_cast<uint32_t>(v);
-                    const int r = fd.range_return;
-                    rtile[(static_cast<size_t>(r) * L.H + row) * p.TC + t] = rv;
-                    if (fr.rd[r] != nullptr) fr.rd[r][dpix] = rv;
+                uint8_t* out = static_cast<uint8_t*>(fr.fields[fi]);
+                const int rr = fd.range_return;
+                if (out == nullptr && rr < 0) continue;
+                const DecodeParams::Plan pl = p.plan[fi];
+                const uint32_t es = fd.elem_size;
+                uint32_t* rt = rr >= 0 ? rtile + static_cast<size_t>(rr) * L.H * p.TC + tt : nullptr;
+                uint32_t* rdp = rr >= 0 ? fr.rd[rr] : nullptr;
+                if (pl.fast && es <= 4) {
+                    const uint32_t zv = (fd.zero_pattern & 0xffffu) | ((fd.zero_pattern & 0xffffu) << 16);
+                    const bool need_b = pl.mb != 0;
+#pragma unroll 4
+                    for (unsigned row = warp; row < L.H; row += nwarps) {
+                        const uint32_t* w = reinterpret_cast<const uint32_t*>(px0 + row * cds) + pl.wa;
+                        uint32_t a = w[0] & pl.ma;
+                        uint32_t b = need_b ? (w[1] & pl.mb) : 0u;
+                        uint32_t v = __funnelshift_r(a, b, pl.rs);
+                        v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
+                        if (src < 0) v = zv;
+                        if (!lane_on) continue;
+                        const size_t pix = static_cast<size_t>(row) * L.W + pix0;
+                        if (out != nullptr) {
+                            if (es == 4) reinterpret_cast<uint32_t*>(out)[pix] = v;
+                            else if (es == 2) reinterpret_cast<uint16_t*>(out)[pix] = static_cast<uint16_t>(v);
+                            else out[pix] = static_cast<uint8_t>(v);
+                        }
+                        if (rr >= 0) {
+                            rt[static_cast<size_t>(row) * p.TC] = v;
+                            if (rdp != nullptr) {
+                                int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
+                                dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
+                                rdp[static_cast<size_t>(row) * L.W + dcol] = v;
+                            }
+                        }
+                    }
+                } else {  // wide or unaligned fields: generic 64-bit extraction
+                    for (unsigned row = warp; row < L.H; row += nwarps) {
+                        if (!lane_on) continue;
+                        const uint8_t* px = px0 + row * cds;
+                        const uint64_t v = src < 0 ? zero_value(fd) : extract_smem(px, fd, aligned);
+                        const size_t pix = static_cast<size_t>(row) * L.W + pix0;
+                        if (out != nullptr) store_elem(out, pix, es, v);
+                        if (rr >= 0) {
+                            rt[static_cast<size_t>(row) * p.TC] = static_cast<uint32_t>(v);
+                            if (rdp != nullptr) {
+                                int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
+                                dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
+                                rdp[static_cast<size_t>(row) * L.W + dcol] = static_cast<uint32_t>(v);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -336,7 +367,7 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         // refill this stage as early as possible
         if (tid == 0 && (k + S) < n_my) issue(k + S);
 
-        // ---- phase B: XYZ from the range tile ----
+        // ---- phase B: XYZ from the range tile; lane = 16-byte chunk of a row segment ----
         if (p.lut_dir != nullptr) {
             const T* dir = static_cast<const T*>(p.lut_dir);
             const T* offs = static_cast<const T*>(p.lut_off);
@@ -344,25 +375,44 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
             if (p.vec_ok && (tc % 4u) == 0) {
                 using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
                 const unsigned nvr = 3u * tc / VN;  // chunks per row segment
-                for (unsigned idx = tid; idx < L.H * nvr; idx += nthreads) {
-                    const unsigned row = idx / nvr, q = idx - row * nvr;
+                // (row, q) advance without divisions: idx = tid + i * nthreads
+                unsigned row = static_cast<unsigned>(tid) / nvr, q = static_cast<unsigned>(tid) - row * nvr;
+                const unsigned drow = static_cast<unsigned>(nthreads) / nvr;
+                const unsigned dq = static_cast<unsigned>(nthreads) - drow * nvr;
+                T* xo0 = static_cast<T*>(fr.xyz[0]);
+                T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
+#pragma unroll 2
+                for (; row < L.H; row += drow) {
                     const size_t ebase = (static_cast<size_t>(row) * L.W + j0) * 3 + static_cast<size_t>(q) * VN;
                     const V dv = *reinterpret_cast<const V*>(dir + ebase);
                     const V ov = *reinterpret_cast<const V*>(offs + ebase);
                     const T* de = reinterpret_cast<const T*>(&dv);
                     const T* oe = reinterpret_cast<const T*>(&ov);
-                    for (unsigned r = 0; r < n_ret; ++r) {
-                        T* xo = static_cast<T*>(fr.xyz[r]);
-                        if (xo == nullptr) continue;
-                        const uint32_t* rrow = rtile + (static_cast<size_t>(r) * L.H + row) * p.TC;
+                    const unsigned e0 = q * VN;
+                    const unsigned p0 = e0 / 3u;              // first pixel touched by this chunk
+                    const unsigned k0 = e0 - 3u * p0;         // component of element 0 inside pixel p0
+                    const uint32_t* rrow0 = rtile + static_cast<size_t>(row) * p.TC + p0;
+                    if (xo0 != nullptr) {
+                        const uint32_t ra = rrow0[0], rb = rrow0[(p0 + 1 < tc) ? 1 : 0];
                         V outv;
-                        T* oe2 = reinterpret_cast<T*>(&outv);
+                        T* o2 = reinterpret_cast<T*>(&outv);
 #pragma unroll
-                        for (int e = 0; e < VN; ++e) {
-                            const unsigned el = q * VN + e;
-                            oe2[e] = project1(rrow[el / 3u], de[e], oe[e]);
-                        }
-                        *reinterpret_cast<V*>(xo + ebase) = outv;
+                        for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
+                        *reinterpret_cast<V*>(xo0 + ebase) = outv;
+                    }
+                    if (xo1 != nullptr) {
+                        const uint32_t* rrow1 = rrow0 + static_cast<size_t>(L.H) * p.TC;
+                        const uint32_t ra = rrow1[0], rb = rrow1[(p0 + 1 < tc) ? 1 : 0];
+                        V outv;
+                        T* o2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
+                        *reinterpret_cast<V*>(xo1 + ebase) = outv;
+                    }
+                    q += dq;
+                    if (q >= nvr) {
+                        q -= nvr;
+                        row += 1;
                     }
                 }
             } else {
@@ -415,6 +465,32 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
     }
     const uint32_t need_words = (max_end + 3) / 4;
     p.n_words = (word_aligned && need_words <= 8) ? need_words : 0;
+    // per-field 32-bit extraction plans: core = ((window & mask) >> tz), value = core << (tz - shift)
+    for (uint32_t i = 0; i < OB_MAX_FIELDS; ++i) {
+        DecodeParams::Plan pl{};
+        if (i < L.n_fields && word_aligned) {
+            const DecodeField& f = L.fields[i];
+            const uint64_t mask = f.mask;
+            if (mask == 0) {
+                pl.fast = 1;  // always zero
+            } else {
+                const int tz = __builtin_ctzll(mask);
+                const uint64_t core = mask >> tz;
+                if (core <= 0xffffffffull) {
+                    const uint32_t a = (f.offset & 3u) * 8u + static_cast<uint32_t>(tz);  // bit index from word f.offset/4
+                    pl.wa = (f.offset >> 2) + a / 32u;
+                    pl.rs = a % 32u;
+                    const unsigned __int128 m96 = static_cast<unsigned __int128>(core) << pl.rs;
+                    pl.ma = static_cast<uint32_t>(m96 & 0xffffffffu);
+                    pl.mb = static_cast<uint32_t>((m96 >> 32) & 0xffffffffu);
+                    const int d = tz - f.shift;
+                    pl.d = d > 31 ? 32 : (d < -31 ? -32 : d);
+                    pl.fast = (d > 31 || d < -31) ? 0 : 1;
+                }
+            }
+        }
+        p.plan[i] = pl;
+    }
     p.vec_ok = (L.W % 4 == 0) ? 1 : 0;  // caller (ob_decode_frames) also checks pointer alignment
     p.has_shift = a.shift_host != nullptr ? 1 : 0;
     for (int i = 0; i < kMaxRows; ++i)
