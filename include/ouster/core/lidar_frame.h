@@ -52,6 +52,32 @@ struct OUSTER_API_CLASS FieldType {
 };
 using LidarFrameFieldTypes = std::vector<FieldType>;
 
+/// Zero-initialised host byte buffer.  When a CUDA device is present the bytes come from a
+/// process-wide pool of page-locked blocks so that H2D/D2H of fields run at full PCIe rate;
+/// without a device it is plain calloc memory (the reference uses calloc, field.cpp:252-254).
+class OUSTER_API_CLASS HostBuffer {
+   public:
+    HostBuffer() = default;
+    OUSTER_API_FUNCTION explicit HostBuffer(size_t bytes);
+    OUSTER_API_FUNCTION HostBuffer(const HostBuffer& o);
+    OUSTER_API_FUNCTION HostBuffer(HostBuffer&& o) noexcept;
+    OUSTER_API_FUNCTION HostBuffer& operator=(const HostBuffer& o);
+    OUSTER_API_FUNCTION HostBuffer& operator=(HostBuffer&& o) noexcept;
+    OUSTER_API_FUNCTION ~HostBuffer();
+    uint8_t* data() { return p_; }
+    const uint8_t* data() const { return p_; }
+    size_t size() const { return n_; }
+    OUSTER_API_FUNCTION void resize(size_t bytes);  ///< contents are zeroed
+    OUSTER_API_FUNCTION bool operator==(const HostBuffer& o) const;
+
+   private:
+    void release();
+    uint8_t* p_{nullptr};
+    size_t n_{0};
+    size_t cap_{0};
+    bool pinned_{false};
+};
+
 /// Typed dense buffer (field.h:828+).  Zero-initialised like the reference's calloc (field.cpp:254).
 class OUSTER_API_CLASS Field {
    public:
@@ -75,7 +101,7 @@ class OUSTER_API_CLASS Field {
    private:
     ChanFieldType tag_{ChanFieldType::VOID};
     std::vector<size_t> shape_;
-    std::vector<uint8_t> buf_;
+    HostBuffer buf_;
 };
 
 /// 1-D header view with Eigen-like element access.
@@ -197,9 +223,11 @@ struct OUSTER_API_CLASS FusedCloud {
     std::shared_ptr<ob_lut> lut;           ///< float or double device LUT (see XYZLutT::device_lut())
     bool lut_is_f64{false};
     std::vector<int> pixel_shift_by_row;   ///< empty: no destaggered range
-    std::vector<float> xyz_f32[2];         ///< (h*w) x 3 per return, staggered order
-    std::vector<double> xyz_f64[2];
-    std::vector<uint32_t> range_destaggered[2];
+    HostBuffer xyz[2];                     ///< (h*w) x 3 of float|double per return, staggered order
+    HostBuffer range_destaggered[2];       ///< h x w uint32 per return
+    const float* xyz_f32(int r) const { return reinterpret_cast<const float*>(xyz[r].data()); }
+    const double* xyz_f64(int r) const { return reinterpret_cast<const double*>(xyz[r].data()); }
+    const uint32_t* rd(int r) const { return reinterpret_cast<const uint32_t*>(range_destaggered[r].data()); }
 };
 
 class OUSTER_API_CLASS FrameBatcher {

@@ -47,7 +47,8 @@ static Tunables& tunables_mut(int device) {
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
         t.decode_stages = std::max(1, env_int("OB_DECODE_STAGES", 1));
         t.decode_threads = std::min(1024, std::max(64, env_int("OB_DECODE_THREADS", 512)));
-        t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 2));
+        t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
+        t.decode_tile_packets = std::max(1, env_int("OB_DECODE_TILE_PACKETS", 2));
         t.force_fallback = env_int("OB_FORCE_FALLBACK", 0);
         int sm = 148;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
@@ -77,6 +78,7 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "decode_stages") t.decode_stages = std::max(1, value);
     else if (n == "decode_threads") t.decode_threads = std::min(1024, std::max(64, value / 32 * 32));
     else if (n == "decode_ctas_per_sm") t.decode_ctas_per_sm = std::max(1, value);
+    else if (n == "decode_tile_packets") t.decode_tile_packets = std::max(1, value);
     else if (n == "force_fallback") t.force_fallback = value;
     else return false;
     return true;

@@ -43,6 +43,9 @@ struct DecodeParams {
     uint32_t n_returns;         // returns with a range field tagged
     uint32_t vec_ok;            // XYZ rows are 16-byte aligned (W % 4 == 0, aligned pointers)
     uint32_t has_shift;
+    int32_t cpp_shift;          // log2(columns_per_packet) or -1
+    uint32_t range_field[OB_MAX_RETURNS];  // index of the range field of each return
+    uint32_t plan_ranges_fast;  // the range fields have 32-bit plans
     struct Plan {        // per-field extraction plan, precomputed on the host (see make_plan)
         uint32_t wa;     // aligned 32-bit word (from the pixel start) holding the field's LSB
         uint32_t ma, mb; // masks of that word and the next one
@@ -54,7 +57,9 @@ struct DecodeParams {
 };
 
 struct TileCtl {  // per-stage bookkeeping written by the producer thread
+    int regular;                // 1: identity map, whole packets present (tables below unused)
     int col_src[kMaxTileCols];  // source packet column (slot*cpp + c) or -1
+    int col_off[kMaxTileCols];  // byte offset of the column's pixel 0 inside the stage, or -1
     unsigned char group_fast[kMaxTileCols];
 };
 
@@ -139,6 +144,66 @@ __device__ __forceinline__ double project1(uint32_t r, double d, double o) {
     return r == 0 ? 0.0 : __dadd_rn(__dmul_rn(static_cast<double>(r), d), o);
 }
 
+// Row loop of phase A for one field, specialised on the destination element size, on whether the
+// field straddles two aligned words, on whether it is a range image (destaggered copy) and on
+// whether the plain (staggered) image is requested.  ~12 instructions per pixel.
+template <int ES, bool NEED_B, bool RR, bool HAS_OUT>
+__device__ __forceinline__ void decode_rows(const uint8_t* px0, unsigned cds, const DecodeParams::Plan& pl,
+                                            bool col_valid, uint32_t zv, bool lane_on, uint8_t* out,
+                                            size_t pix0, unsigned W, unsigned H, int warp, int nwarps,
+                                            uint32_t* rdp, const DecodeParams& p) {
+    const uint32_t lsh = pl.d > 0 ? static_cast<uint32_t>(pl.d) : 0u;
+    const uint32_t rsh = pl.d < 0 ? static_cast<uint32_t>(-pl.d) : 0u;
+#pragma unroll 4
+    for (unsigned row = warp; row < H; row += nwarps) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(px0 + row * cds) + pl.wa;
+        const uint32_t a = w[0] & pl.ma;
+        uint32_t v;
+        if (NEED_B) v = __funnelshift_r(a, w[1] & pl.mb, pl.rs);
+        else v = a >> pl.rs;
+        v = (v << lsh) >> rsh;
+        v = col_valid ? v : zv;
+        if (!lane_on) continue;
+        const size_t pix = static_cast<size_t>(row) * W + pix0;
+        if (HAS_OUT) {
+            if (ES == 4) reinterpret_cast<uint32_t*>(out)[pix] = v;
+            else if (ES == 2) reinterpret_cast<uint16_t*>(out)[pix] = static_cast<uint16_t>(v);
+            else out[pix] = static_cast<uint8_t>(v);
+        }
+        if (RR) {
+            int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
+            dcol = dcol >= static_cast<int>(W) ? dcol - static_cast<int>(W) : dcol;
+            rdp[static_cast<size_t>(row) * W + dcol] = v;
+        }
+    }
+}
+
+template <int ES, bool NEED_B>
+__device__ __forceinline__ void decode_rows_dispatch(bool has_out, bool has_rd, const uint8_t* px0,
+                                                     unsigned cds, const DecodeParams::Plan& pl,
+                                                     bool col_valid, uint32_t zv, bool lane_on,
+                                                     uint8_t* out, size_t pix0, unsigned W, unsigned H,
+                                                     int warp, int nwarps, uint32_t* rdp,
+                                                     const DecodeParams& p) {
+    if (has_out && has_rd)
+        decode_rows<ES, NEED_B, true, true>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+    else if (has_out)
+        decode_rows<ES, NEED_B, false, true>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+    else if (has_rd)
+        decode_rows<ES, NEED_B, true, false>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+}
+
+// range of pixel (row, column offset `co`) straight from the staged packet bytes
+__device__ __forceinline__ uint32_t range_from_stage(const uint8_t* st, int co, unsigned row, unsigned cds,
+                                                     const DecodeParams::Plan& pl) {
+    if (co < 0) return 0u;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(st + co + row * cds) + pl.wa;
+    const uint32_t a = w[0] & pl.ma;
+    const uint32_t b = pl.mb ? (w[1] & pl.mb) : 0u;
+    uint32_t v = __funnelshift_r(a, b, pl.rs);
+    return pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -148,13 +213,11 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
     const int S = p.stages;
 
     // ---- shared memory carve-up ----
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                       // kMaxStages
-    TileCtl* ctl = reinterpret_cast<TileCtl*>(smem + 64);                      // S entries
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // kMaxStages
+    TileCtl* ctl = reinterpret_cast<TileCtl*>(smem + 64);  // kMaxStages entries
     size_t off = 64 + static_cast<size_t>(kMaxStages) * sizeof(TileCtl);
     off = (off + 127) & ~static_cast<size_t>(127);
     uint8_t* stage0 = smem + off;
-    uint32_t* rtile = reinterpret_cast<uint32_t*>(stage0 + static_cast<size_t>(S) * p.stage_bytes);
-    // rtile[r][row][TC]
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -174,6 +237,12 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         j0 = (t - f * p.tiles_per_frame) * p.TC;
         tc = min(p.TC, L.W - j0);
     };
+    // byte offset (inside a stage) of pixel 0 of tile column t
+    auto col_offset = [&](unsigned t) -> int {
+        const unsigned g = p.cpp_shift >= 0 ? (t >> p.cpp_shift) : (t / L.cpp);
+        return static_cast<int>(g * p.pkt_stride_s + L.packet_header_size + (t - g * L.cpp) * L.col_size +
+                                L.col_header_size);
+    };
 
     auto issue = [&](unsigned k) {  // producer: thread 0
         unsigned f, j0, tc;
@@ -184,9 +253,20 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
         const bool identity = (fr.flags & 1u) != 0;
         const bool bulk_ok = (fr.flags & 2u) != 0;
-        uint32_t tx = 0;
         const unsigned n_groups = (tc + L.cpp - 1) / L.cpp;
-        // pass 1: classify
+        // regular tile: identity map, whole packets present -> no per-column bookkeeping
+        if (identity && bulk_ok && (tc % L.cpp) == 0 && (j0 + tc) / L.cpp <= fr.n_slots) {
+            c.regular = 1;
+            mbar_expect_tx(&full[s], n_groups * L.packet_size);
+            const unsigned slot0 = j0 / L.cpp;
+            for (unsigned g = 0; g < n_groups; ++g)
+                bulk_g2s_hint(st + static_cast<size_t>(g) * p.pkt_stride_s,
+                              fr.packets + static_cast<size_t>(slot0 + g) * fr.packet_stride,
+                              L.packet_size, &full[s], pol_stream);
+            return;
+        }
+        c.regular = 0;
+        uint32_t tx = 0;
         for (unsigned g = 0; g < n_groups; ++g) {
             const unsigned jg = j0 + g * L.cpp;
             const unsigned ncol = min(L.cpp, L.W - jg);
@@ -201,6 +281,7 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
                     src = fr.col_src[jg + i];
                 }
                 c.col_src[g * L.cpp + i] = src;
+                c.col_off[g * L.cpp + i] = src < 0 ? -1 : col_offset(g * L.cpp + i);
                 if (src < 0) {
                     fast = false;
                 } else {
@@ -226,10 +307,10 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         const unsigned pre = min(n_my, static_cast<unsigned>(S));
         for (unsigned k = 0; k < pre; ++k) issue(k);
     }
-    __syncthreads();
 
     const bool aligned = p.word_aligned != 0;
     const unsigned n_ret = p.n_returns;
+    const unsigned cds = L.channel_data_size;
 
     for (unsigned k = 0; k < n_my; ++k) {
         const int s = k % S;
@@ -240,9 +321,10 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
 
         mbar_wait(&full[s], (k / S) & 1);
+        const bool regular = c.regular != 0;
 
         // ---- irregular groups: gather the columns with ordinary loads ----
-        {
+        if (!regular) {
             const unsigned n_groups = (tc + L.cpp - 1) / L.cpp;
             bool any_slow = false;
             for (unsigned g = 0; g < n_groups; ++g) any_slow |= (c.group_fast[g] == 0);
@@ -257,15 +339,13 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
                                           L.packet_header_size + static_cast<size_t>(ci) * L.col_size;
                     uint8_t* dst = st + static_cast<size_t>(g) * p.pkt_stride_s + L.packet_header_size +
                                    static_cast<size_t>(t - g * L.cpp) * L.col_size;
-                    // copy the column plus the 8 bytes a trailing field read may touch,
-                    // clamped to the end of the source packet
+                    // the column plus the 8 bytes a trailing field read may touch (clamped to the packet)
                     const size_t col_end = L.packet_header_size + static_cast<size_t>(ci + 1) * L.col_size;
                     const size_t extra = min(static_cast<size_t>(8), L.packet_size - col_end);
                     const unsigned nbytes = L.col_size + static_cast<unsigned>(extra);
                     if (aligned && ((reinterpret_cast<uintptr_t>(gsrc) & 3u) == 0)) {
                         for (unsigned b = lane * 4; b + 4 <= nbytes; b += 128)
-                            *reinterpret_cast<uint32_t*>(dst + b) =
-                                *reinterpret_cast<const uint32_t*>(gsrc + b);
+                            *reinterpret_cast<uint32_t*>(dst + b) = *reinterpret_cast<const uint32_t*>(gsrc + b);
                         for (unsigned b = (nbytes & ~3u) + lane; b < nbytes; b += 32) dst[b] = gsrc[b];
                     } else {
                         for (unsigned b = lane; b < nbytes; b += 32) dst[b] = gsrc[b];
@@ -278,12 +358,10 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         // ---- column headers (timestamp / measurement_id / status) ----
         if (fr.timestamp != nullptr || fr.measurement_id != nullptr || fr.status != nullptr) {
             for (unsigned t = tid; t < tc; t += nthreads) {
-                const int src = c.col_src[t];
+                const int co = regular ? col_offset(t) : c.col_off[t];
                 uint64_t ts = 0, mid = 0, stt = 0;
-                if (src >= 0) {
-                    const unsigned g = t / L.cpp;
-                    const uint8_t* colp = st + static_cast<size_t>(g) * p.pkt_stride_s +
-                                          L.packet_header_size + static_cast<size_t>(t - g * L.cpp) * L.col_size;
+                if (co >= 0) {
+                    const uint8_t* colp = st + co - L.col_header_size;
                     ts = extract_smem(colp, L.ts, aligned);
                     mid = extract_smem(colp, L.mid, aligned);
                     stt = extract_smem(colp, L.status, aligned);
@@ -295,92 +373,66 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         }
 
         // ---- phase A: decode; lane = frame column, warp = row (strided), fields outermost ----
-        // Per-lane constants are computed once per tile; every field then runs a tight row loop:
-        // 1-2 LDS + mask/funnel-shift + one coalesced store per pixel (no 64-bit math, no divides).
         for (unsigned cg = 0; cg * 32 < tc; ++cg) {
             const unsigned t = cg * 32 + lane;
             const bool lane_on = t < tc;
             const unsigned tt = lane_on ? t : 0;
-            const int src = lane_on ? c.col_src[tt] : -1;
-            const unsigned g = tt / L.cpp;
-            const uint8_t* px0 = st + static_cast<size_t>(g) * p.pkt_stride_s + L.packet_header_size +
-                                 static_cast<size_t>(tt - g * L.cpp) * L.col_size + L.col_header_size;
-            const unsigned cds = L.channel_data_size;
+            const int co = regular ? col_offset(tt) : c.col_off[tt];
+            const bool col_valid = co >= 0;
+            const uint8_t* px0 = st + (col_valid ? co : col_offset(tt));
             const size_t pix0 = static_cast<size_t>(j0) + tt;
             for (unsigned fi = 0; fi < L.n_fields; ++fi) {
                 const DecodeField& fd = L.fields[fi];
                 uint8_t* out = static_cast<uint8_t*>(fr.fields[fi]);
                 const int rr = fd.range_return;
-                if (out == nullptr && rr < 0) continue;
-                const DecodeParams::Plan pl = p.plan[fi];
-                const uint32_t es = fd.elem_size;
-                uint32_t* rt = rr >= 0 ? rtile + static_cast<size_t>(rr) * L.H * p.TC + tt : nullptr;
                 uint32_t* rdp = rr >= 0 ? fr.rd[rr] : nullptr;
+                if (out == nullptr && rdp == nullptr) continue;
+                const DecodeParams::Plan& pl = p.plan[fi];
+                const uint32_t es = fd.elem_size;
                 if (pl.fast && es <= 4) {
                     const uint32_t zv = (fd.zero_pattern & 0xffffu) | ((fd.zero_pattern & 0xffffu) << 16);
-                    const bool need_b = pl.mb != 0;
-#pragma unroll 4
-                    for (unsigned row = warp; row < L.H; row += nwarps) {
-                        const uint32_t* w = reinterpret_cast<const uint32_t*>(px0 + row * cds) + pl.wa;
-                        uint32_t a = w[0] & pl.ma;
-                        uint32_t b = need_b ? (w[1] & pl.mb) : 0u;
-                        uint32_t v = __funnelshift_r(a, b, pl.rs);
-                        v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
-                        if (src < 0) v = zv;
-                        if (!lane_on) continue;
-                        const size_t pix = static_cast<size_t>(row) * L.W + pix0;
-                        if (out != nullptr) {
-                            if (es == 4) reinterpret_cast<uint32_t*>(out)[pix] = v;
-                            else if (es == 2) reinterpret_cast<uint16_t*>(out)[pix] = static_cast<uint16_t>(v);
-                            else out[pix] = static_cast<uint8_t>(v);
-                        }
-                        if (rr >= 0) {
-                            rt[static_cast<size_t>(row) * p.TC] = v;
-                            if (rdp != nullptr) {
-                                int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
-                                dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
-                                rdp[static_cast<size_t>(row) * L.W + dcol] = v;
-                            }
-                        }
+                    const bool ho = out != nullptr, hr = rdp != nullptr;
+                    if (pl.mb != 0) {
+                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                    } else {
+                        if (es == 4) decode_rows_dispatch<4, false>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, false>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                        else decode_rows_dispatch<1, false>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
                     }
                 } else {  // wide or unaligned fields: generic 64-bit extraction
                     for (unsigned row = warp; row < L.H; row += nwarps) {
                         if (!lane_on) continue;
                         const uint8_t* px = px0 + row * cds;
-                        const uint64_t v = src < 0 ? zero_value(fd) : extract_smem(px, fd, aligned);
+                        const uint64_t v = !col_valid ? zero_value(fd) : extract_smem(px, fd, aligned);
                         const size_t pix = static_cast<size_t>(row) * L.W + pix0;
                         if (out != nullptr) store_elem(out, pix, es, v);
-                        if (rr >= 0) {
-                            rt[static_cast<size_t>(row) * p.TC] = static_cast<uint32_t>(v);
-                            if (rdp != nullptr) {
-                                int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
-                                dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
-                                rdp[static_cast<size_t>(row) * L.W + dcol] = static_cast<uint32_t>(v);
-                            }
+                        if (rdp != nullptr) {
+                            int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
+                            dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
+                            rdp[static_cast<size_t>(row) * L.W + dcol] = static_cast<uint32_t>(v);
                         }
                     }
                 }
             }
         }
-        __syncthreads();  // rtile complete; packet stage no longer read
 
-        // refill this stage as early as possible
-        if (tid == 0 && (k + S) < n_my) issue(k + S);
-
-        // ---- phase B: XYZ from the range tile; lane = 16-byte chunk of a row segment ----
-        if (p.lut_dir != nullptr) {
+        // ---- phase B: XYZ; lane = 16-byte chunk of a row segment, ranges re-read from the stage ----
+        if (p.lut_dir != nullptr && n_ret > 0) {
             const T* dir = static_cast<const T*>(p.lut_dir);
             const T* offs = static_cast<const T*>(p.lut_off);
             constexpr int VN = 16 / sizeof(T);  // scalars per 16-byte chunk
-            if (p.vec_ok && (tc % 4u) == 0) {
+            const DecodeParams::Plan& pl0 = p.plan[p.range_field[0]];
+            const DecodeParams::Plan& pl1 = p.plan[p.range_field[n_ret > 1 ? 1 : 0]];
+            T* xo0 = static_cast<T*>(fr.xyz[0]);
+            T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
+            if (p.vec_ok && (tc % 4u) == 0 && p.plan_ranges_fast) {
                 using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
                 const unsigned nvr = 3u * tc / VN;  // chunks per row segment
-                // (row, q) advance without divisions: idx = tid + i * nthreads
                 unsigned row = static_cast<unsigned>(tid) / nvr, q = static_cast<unsigned>(tid) - row * nvr;
                 const unsigned drow = static_cast<unsigned>(nthreads) / nvr;
                 const unsigned dq = static_cast<unsigned>(nthreads) - drow * nvr;
-                T* xo0 = static_cast<T*>(fr.xyz[0]);
-                T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
 #pragma unroll 2
                 for (; row < L.H; row += drow) {
                     const size_t ebase = (static_cast<size_t>(row) * L.W + j0) * 3 + static_cast<size_t>(q) * VN;
@@ -389,11 +441,14 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
                     const T* de = reinterpret_cast<const T*>(&dv);
                     const T* oe = reinterpret_cast<const T*>(&ov);
                     const unsigned e0 = q * VN;
-                    const unsigned p0 = e0 / 3u;              // first pixel touched by this chunk
-                    const unsigned k0 = e0 - 3u * p0;         // component of element 0 inside pixel p0
-                    const uint32_t* rrow0 = rtile + static_cast<size_t>(row) * p.TC + p0;
+                    const unsigned p0 = e0 / 3u;       // first pixel touched by this chunk
+                    const unsigned k0 = e0 - 3u * p0;  // component of element 0 inside pixel p0
+                    const unsigned p1 = (p0 + 1 < tc) ? p0 + 1 : p0;
+                    const int co0 = regular ? col_offset(p0) : c.col_off[p0];
+                    const int co1 = regular ? col_offset(p1) : c.col_off[p1];
                     if (xo0 != nullptr) {
-                        const uint32_t ra = rrow0[0], rb = rrow0[(p0 + 1 < tc) ? 1 : 0];
+                        const uint32_t ra = range_from_stage(st, co0, row, cds, pl0);
+                        const uint32_t rb = range_from_stage(st, co1, row, cds, pl0);
                         V outv;
                         T* o2 = reinterpret_cast<T*>(&outv);
 #pragma unroll
@@ -401,8 +456,8 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
                         *reinterpret_cast<V*>(xo0 + ebase) = outv;
                     }
                     if (xo1 != nullptr) {
-                        const uint32_t* rrow1 = rrow0 + static_cast<size_t>(L.H) * p.TC;
-                        const uint32_t ra = rrow1[0], rb = rrow1[(p0 + 1 < tc) ? 1 : 0];
+                        const uint32_t ra = range_from_stage(st, co0, row, cds, pl1);
+                        const uint32_t rb = range_from_stage(st, co1, row, cds, pl1);
                         V outv;
                         T* o2 = reinterpret_cast<T*>(&outv);
 #pragma unroll
@@ -418,11 +473,14 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
             } else {
                 for (unsigned idx = tid; idx < L.H * tc; idx += nthreads) {
                     const unsigned row = idx / tc, t = idx - row * tc;
+                    const int co = regular ? col_offset(t) : c.col_off[t];
                     const size_t ebase = (static_cast<size_t>(row) * L.W + j0 + t) * 3;
                     for (unsigned r = 0; r < n_ret; ++r) {
                         T* xo = static_cast<T*>(fr.xyz[r]);
                         if (xo == nullptr) continue;
-                        const uint32_t rv = rtile[(static_cast<size_t>(r) * L.H + row) * p.TC + t];
+                        const DecodeField& fd = L.fields[p.range_field[r]];
+                        const uint32_t rv = co < 0 ? 0u
+                                                   : static_cast<uint32_t>(extract_smem(st + co + row * cds, fd, aligned));
 #pragma unroll
                         for (int cidx = 0; cidx < 3; ++cidx)
                             xo[ebase + cidx] = project1(rv, dir[ebase + cidx], offs[ebase + cidx]);
@@ -430,7 +488,8 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
                 }
             }
         }
-        __syncthreads();  // rtile free for the next tile
+        __syncthreads();  // every warp is done with this stage
+        if (tid == 0 && (k + S) < n_my) issue(k + S);
     }
 }
 
@@ -445,7 +504,7 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
     p.lut_dir = a.lut_dir;
     p.lut_off = a.lut_off;
     p.n_frames = a.n_frames;
-    p.P = std::max<uint32_t>(1, 32 / L.cpp);
+    p.P = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(std::max(tn.decode_tile_packets, 1)), 64 / L.cpp));
     p.TC = p.P * L.cpp;
     p.tiles_per_frame = (L.W + p.TC - 1) / p.TC;
     p.n_tiles = p.tiles_per_frame * a.n_frames;
@@ -491,6 +550,18 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
         }
         p.plan[i] = pl;
     }
+    p.cpp_shift = -1;
+    for (int b = 0; b < 8; ++b)
+        if ((1u << b) == L.cpp) p.cpp_shift = b;
+    p.range_field[0] = p.range_field[1] = 0;
+    p.plan_ranges_fast = 1;
+    for (uint32_t i = 0; i < L.n_fields; ++i) {
+        const int r = L.fields[i].range_return;
+        if (r >= 0 && r < OB_MAX_RETURNS) {
+            p.range_field[r] = i;
+            if (!p.plan[i].fast) p.plan_ranges_fast = 0;
+        }
+    }
     p.vec_ok = (L.W % 4 == 0) ? 1 : 0;  // caller (ob_decode_frames) also checks pointer alignment
     p.has_shift = a.shift_host != nullptr ? 1 : 0;
     for (int i = 0; i < kMaxRows; ++i)
@@ -498,7 +569,7 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
     if (a.shift_host != nullptr && L.H > static_cast<uint32_t>(kMaxRows)) return cudaErrorInvalidValue;
     if (!a.vec_ok) p.vec_ok = 0;
 
-    const size_t rtile_bytes = static_cast<size_t>(std::max<uint32_t>(p.n_returns, 1)) * L.H * p.TC * 4;
+    const size_t rtile_bytes = 0;  // ranges are re-read from the staged packets in phase B
     size_t ctl_off = 64 + static_cast<size_t>(kMaxStages) * sizeof(TileCtl);
     ctl_off = (ctl_off + 127) & ~static_cast<size_t>(127);
     size_t smem = ctl_off + static_cast<size_t>(p.stages) * p.stage_bytes + rtile_bytes;

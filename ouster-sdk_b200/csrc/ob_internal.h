@@ -20,6 +20,7 @@ struct Tunables {
     int decode_stages;
     int decode_threads;
     int decode_ctas_per_sm;
+    int decode_tile_packets;  // packets (groups of columns_per_packet columns) per tile
     int force_fallback;    // 1: use the generic (non-TMA) kernels
     int sm_count;
 };

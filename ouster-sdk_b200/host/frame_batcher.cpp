@@ -321,16 +321,12 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
         int n_ret = 0;
         for (const auto& d : descs) n_ret = std::max(n_ret, d.range_return + 1);
         for (int r = 0; r < n_ret; ++r) {
-            if (fused_->lut_is_f64) {
-                fused_->xyz_f64[r].resize(n * 3);
-                io.xyz[r] = fused_->xyz_f64[r].data();
-            } else {
-                fused_->xyz_f32[r].resize(n * 3);
-                io.xyz[r] = fused_->xyz_f32[r].data();
-            }
+            const size_t xb = n * 3 * (fused_->lut_is_f64 ? 8 : 4);
+            if (fused_->xyz[r].size() != xb) fused_->xyz[r].resize(xb);
+            io.xyz[r] = fused_->xyz[r].data();
             if (!fused_->pixel_shift_by_row.empty()) {
-                fused_->range_destaggered[r].resize(n);
-                io.range_destaggered[r] = fused_->range_destaggered[r].data();
+                if (fused_->range_destaggered[r].size() != n * 4) fused_->range_destaggered[r].resize(n * 4);
+                io.range_destaggered[r] = reinterpret_cast<uint32_t*>(fused_->range_destaggered[r].data());
             }
         }
         if (!fused_->pixel_shift_by_row.empty()) {

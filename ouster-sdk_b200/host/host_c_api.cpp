@@ -356,14 +356,12 @@ ob_status obh_batcher_fused_outputs(obh_batcher* b, int ret, void** xyz, size_t*
                                     uint32_t** rd) {
     return guard([&] {
         if (!b || ret < 0 || ret >= 2) throw std::invalid_argument("bad return index");
-        if (b->fused.lut_is_f64) {
-            if (xyz) *xyz = b->fused.xyz_f64[ret].data();
-            if (xyz_bytes) *xyz_bytes = b->fused.xyz_f64[ret].size() * 8;
-        } else {
-            if (xyz) *xyz = b->fused.xyz_f32[ret].data();
-            if (xyz_bytes) *xyz_bytes = b->fused.xyz_f32[ret].size() * 4;
-        }
-        if (rd) *rd = b->fused.range_destaggered[ret].empty() ? nullptr : b->fused.range_destaggered[ret].data();
+        if (xyz) *xyz = b->fused.xyz[ret].data();
+        if (xyz_bytes) *xyz_bytes = b->fused.xyz[ret].size();
+        if (rd)
+            *rd = b->fused.range_destaggered[ret].size()
+                      ? reinterpret_cast<uint32_t*>(b->fused.range_destaggered[ret].data())
+                      : nullptr;
     });
 }
 

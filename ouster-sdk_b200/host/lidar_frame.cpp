@@ -1,22 +1,127 @@
 // lidar_frame.cpp -- Field / LidarFrame host containers and the default field sets
 // (host mirror of ouster_core/src/lidar_frame.cpp:73-446, 1038-1117 and field.cpp:247-275).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
 #include <stdexcept>
 
 #include "ouster/core/lidar_frame.h"
+#include "ouster_b200.h"
 
 namespace ouster {
 namespace sdk {
 namespace core {
 
+// ---- HostBuffer: pooled page-locked blocks ----
+namespace {
+struct PinnedPool {
+    std::mutex mx;
+    std::multimap<size_t, void*> free_blocks;  // capacity -> block
+    bool use_cuda = ob_device_count() > 0;
+    static size_t round_up(size_t n) { return (n + 65535) & ~static_cast<size_t>(65535); }
+    void* acquire(size_t bytes, size_t* cap, bool* pinned) {
+        const size_t want = round_up(std::max<size_t>(bytes, 1));
+        if (use_cuda) {
+            {
+                std::lock_guard<std::mutex> lk(mx);
+                auto it = free_blocks.lower_bound(want);
+                if (it != free_blocks.end() && it->first <= want * 2) {
+                    void* p = it->second;
+                    *cap = it->first;
+                    free_blocks.erase(it);
+                    *pinned = true;
+                    return p;
+                }
+            }
+            void* p = nullptr;
+            if (ob_host_alloc(want, &p) == OB_OK && p) {
+                *cap = want;
+                *pinned = true;
+                return p;
+            }
+        }
+        void* p = std::malloc(want);
+        if (!p) throw std::bad_alloc();
+        *cap = want;
+        *pinned = false;
+        return p;
+    }
+    void give_back(void* p, size_t cap, bool pinned) {
+        if (!p) return;
+        if (!pinned) {
+            std::free(p);
+            return;
+        }
+        std::lock_guard<std::mutex> lk(mx);
+        free_blocks.emplace(cap, p);  // kept for reuse for the life of the process
+    }
+};
+PinnedPool& pool() {
+    static PinnedPool* p = new PinnedPool();  // intentionally leaked: outlives static destructors
+    return *p;
+}
+}  // namespace
+
+HostBuffer::HostBuffer(size_t bytes) { resize(bytes); }
+HostBuffer::HostBuffer(const HostBuffer& o) {
+    resize(o.n_);
+    if (o.n_) std::memcpy(p_, o.p_, o.n_);
+}
+HostBuffer::HostBuffer(HostBuffer&& o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_), pinned_(o.pinned_) {
+    o.p_ = nullptr;
+    o.n_ = o.cap_ = 0;
+}
+HostBuffer& HostBuffer::operator=(const HostBuffer& o) {
+    if (this != &o) {
+        resize(o.n_);
+        if (o.n_) std::memcpy(p_, o.p_, o.n_);
+    }
+    return *this;
+}
+HostBuffer& HostBuffer::operator=(HostBuffer&& o) noexcept {
+    if (this != &o) {
+        release();
+        p_ = o.p_;
+        n_ = o.n_;
+        cap_ = o.cap_;
+        pinned_ = o.pinned_;
+        o.p_ = nullptr;
+        o.n_ = o.cap_ = 0;
+    }
+    return *this;
+}
+HostBuffer::~HostBuffer() { release(); }
+void HostBuffer::release() {
+    pool().give_back(p_, cap_, pinned_);
+    p_ = nullptr;
+    n_ = cap_ = 0;
+}
+void HostBuffer::resize(size_t bytes) {
+    if (bytes > cap_ || p_ == nullptr) {
+        release();
+        if (bytes == 0) return;
+        p_ = static_cast<uint8_t*>(pool().acquire(bytes, &cap_, &pinned_));
+    }
+    n_ = bytes;
+    if (n_) std::memset(p_, 0, n_);
+}
+bool HostBuffer::operator==(const HostBuffer& o) const {
+    return n_ == o.n_ && (n_ == 0 || std::memcmp(p_, o.p_, n_) == 0);
+}
+
 // ---- Field ----
 Field::Field(ChanFieldType tag, const std::vector<size_t>& shape) : tag_(tag), shape_(shape) {
     size_t n = field_type_size(tag);
     for (size_t d : shape) n *= d;
-    buf_.assign(n, 0);
+    buf_.resize(n);
 }
 
-void Field::set_zero() { std::fill(buf_.begin(), buf_.end(), 0); }
+void Field::set_zero() {
+    if (buf_.size()) std::memset(buf_.data(), 0, buf_.size());
+}
 
 // ---- default field sets ----
 namespace {

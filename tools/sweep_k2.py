@@ -26,11 +26,11 @@ def step():
     dec.decode_batch(F, t_pk, n_slots, psz, n_slots * psz, fields, lut=lut, pixel_shift_by_row=k2.SHIFTS,
                      xyz=xyz, range_destaggered=rd, stream=st)
 rows = []
-for stg, th, cta in itertools.product([1, 2, 3], [256, 384, 512, 768, 1024], [1, 2, 3]):
-    smem = 2048 + stg * 66176 + 32768
+for tp, stg, th, cta in itertools.product([1, 2], [1, 2, 3], [256, 384, 512, 768, 1024], [1, 2, 3, 4, 5, 6]):
+    smem = 5120 + stg * 33152 * tp
     if smem * cta > 227 * 1024 or th * cta > 2048:
         continue
-    for k, v in (("decode_stages", stg), ("decode_threads", th), ("decode_ctas_per_sm", cta)):
+    for k, v in (("decode_tile_packets", tp), ("decode_stages", stg), ("decode_threads", th), ("decode_ctas_per_sm", cta)):
         ob.set_tunable(k, v)
     try:
         for _ in range(2):
@@ -48,7 +48,7 @@ for stg, th, cta in itertools.product([1, 2, 3], [256, 384, 512, 768, 1024], [1,
         print("fail", stg, th, cta, ex)
         continue
     gbps = k2.K2_BYTES_PER_FRAME_F32 * F / (ms * 1e-3) / 1e9
-    rows.append({"stages": stg, "threads": th, "ctas": cta, "ms": ms, "gbps": gbps, "frac": gbps / peak})
+    rows.append({"tile_packets": tp, "stages": stg, "threads": th, "ctas": cta, "ms": ms, "gbps": gbps, "frac": gbps / peak})
 rows.sort(key=lambda r: -r["gbps"])
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/sweep_k2.json", "w"), indent=0)
