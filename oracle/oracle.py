@@ -208,8 +208,11 @@ class Frame:
             lib().orc_frame_add_field(self.p, name.encode(), ty)
 
     def __del__(self):
-        if getattr(self, "p", None):
-            lib().orc_frame_destroy(self.p)
+        if getattr(self, "p", None) and _lib is not None:
+            try:
+                _lib.orc_frame_destroy(self.p)
+            except Exception:
+                pass
             self.p = None
 
     @property
@@ -286,8 +289,11 @@ class Batcher:
             raise ValueError("unexpected columns_per_packet/pixels_per_column: 0")
 
     def __del__(self):
-        if getattr(self, "p", None):
-            lib().orc_batcher_destroy(self.p)
+        if getattr(self, "p", None) and _lib is not None:
+            try:
+                _lib.orc_batcher_destroy(self.p)
+            except Exception:
+                pass
             self.p = None
 
     def batch(self, buf, host_timestamp, frame):

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Small end-to-end invocations of every kernel, checked against the oracle; meant to run under
+    compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_cases.py
+(kept tiny: the sanitizer slows kernels down by orders of magnitude)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as graft
+from oracle import oracle as orc
+from tests.helpers import (col_map_from_packets, decoder_desc_from_oracle, oracle_pf, random_frame,
+                           random_lut, random_range)
+
+ob = graft.load_package()
+st = ob.Stream(0)
+h, w = 16, 256
+for dtype in (np.float32, np.float64):
+    for R in (1, 2):
+        for aligned in (True, False):
+            rs = np.random.default_rng(3)
+            rng = np.stack([np.stack([random_range(h, w, 10 * f + r) for r in range(R)]) for f in range(2)])
+            d, o = random_lut(h * w, 1, dtype)
+            sh = rs.integers(-20, 21, h).astype(np.int32)
+            if aligned:
+                sh = sh // 4 * 4
+            lut = ob.XYZLutT.from_arrays(d, o, h, w)
+            xyz = np.zeros((2, R, h * w, 3), dtype)
+            rd = np.zeros((2, R, h, w), np.uint32)
+            xd = np.zeros((2, R, h, w, 3), dtype)
+            ob.scan_to_cloud(lut, sh, rng, xyz=xyz, range_destaggered=rd, xyz_destaggered=xd, stream=st)
+            st.sync()
+            for f in range(2):
+                for r in range(R):
+                    want = orc.cartesian(rng[f, r], d, o)
+                    assert np.array_equal(xyz[f, r], want)
+                    assert np.array_equal(rd[f, r], orc.destagger(rng[f, r], sh))
+                    assert np.array_equal(xd[f, r], orc.destagger(want.reshape(h, w, 3), sh))
+print("K1 ok")
+img = np.random.default_rng(1).integers(0, 255, (h, w), dtype=np.uint8)
+sh = np.arange(h, dtype=np.int32) - 5
+assert np.array_equal(ob.destagger(img, sh), orc.destagger(img, sh))
+img64 = np.random.default_rng(1).random((9, 35))
+assert np.array_equal(ob.destagger(img64, np.arange(9, dtype=np.int32)), orc.destagger(img64, np.arange(9)))
+print("destagger ok")
+ident = np.eye(4)
+l = ob.XYZLutT.from_intrinsics(64, 8, 0.001, ident, ident, np.linspace(-3, 3, 8), np.linspace(-10, 10, 8))
+assert np.all(np.isfinite(l.direction))
+print("lut ok")
+for profile, hh, ww in (("RNG19_RFL8_SIG16_NIR16_DUAL", 16, 128), ("LEGACY", 16, 64), ("RNG19_RFL8_SIG16_NIR16_RGB16", 8, 64)):
+    pf = oracle_pf(profile, hh, ww)
+    src = random_frame(pf, seed=4)
+    pk, ts = orc.frame_to_packets(src, pf)
+    layout, fields = decoder_desc_from_oracle(pf, src)
+    dec = ob.Decoder(layout, fields)
+    d, o = random_lut(hh * ww, 2)
+    lut = ob.XYZLutT.from_arrays(d, o, hh, ww)
+    shifts = (np.arange(hh, dtype=np.int32) * 3) % 17
+    for cmap in (None, "faulty"):
+        pkk = pk.copy()
+        col_src = None
+        ref = src
+        if cmap:
+            pkk = np.delete(pkk, 1, axis=0)
+            col_src = col_map_from_packets(pf, pkk)
+            ref = orc.Frame(pf, with_window=True)
+            b = orc.Batcher(pf)
+            for p in pkk:
+                b.batch(p, 5, ref)
+            b.batch(orc.frame_to_packets(random_frame(pf, 9, frame_id=701), pf)[0][0], 5, ref)  # finalize
+        outs = {f["name"]: np.zeros(ref.field(f["name"]).shape, ref.field(f["name"]).dtype) for f in fields}
+        io = {"packets": np.ascontiguousarray(pkk), "n_slots": len(pkk), "packet_stride": pkk.shape[1],
+              "col_src": col_src, "fields": outs, "timestamp": np.zeros(ww, np.uint64)}
+        has_r = ref.has_field("RANGE")
+        if has_r:
+            io["xyz"] = [np.zeros((hh * ww, 3), np.float32)]
+            io["range_destaggered"] = [np.zeros((hh, ww), np.uint32)]
+        dec.decode([io], lut=lut if has_r else None, pixel_shift_by_row=shifts if has_r else None, stream=st)
+        st.sync()
+        for n, a in outs.items():
+            assert np.array_equal(a, ref.field(n)), (profile, cmap, n)
+        if has_r:
+            assert np.array_equal(io["xyz"][0], orc.cartesian(ref.field("RANGE"), d, o))
+            assert np.array_equal(io["range_destaggered"][0], orc.destagger(ref.field("RANGE"), shifts))
+print("K2 ok")
+print("SANITIZE CASES OK")
