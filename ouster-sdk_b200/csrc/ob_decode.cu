@@ -154,27 +154,37 @@ __device__ __forceinline__ void decode_rows(const uint8_t* px0, unsigned cds, co
                                             uint32_t* rdp, const DecodeParams& p) {
     const uint32_t lsh = pl.d > 0 ? static_cast<uint32_t>(pl.d) : 0u;
     const uint32_t rsh = pl.d < 0 ? static_cast<uint32_t>(-pl.d) : 0u;
+    // all addresses advance by loop-invariant strides
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(px0 + static_cast<size_t>(warp) * cds) + pl.wa;
+    const unsigned wstep = static_cast<unsigned>(nwarps) * cds / 4u;
+    uint8_t* o = HAS_OUT ? out + (static_cast<size_t>(warp) * W + pix0) * ES : nullptr;
+    const size_t ostep = static_cast<size_t>(nwarps) * W * ES;
+    uint32_t* rrow = RR ? rdp + static_cast<size_t>(warp) * W : nullptr;
+    const size_t rstep = static_cast<size_t>(nwarps) * W;
+    const int col = static_cast<int>(pix0), Wi = static_cast<int>(W);
 #pragma unroll 4
     for (unsigned row = warp; row < H; row += nwarps) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(px0 + row * cds) + pl.wa;
         const uint32_t a = w[0] & pl.ma;
         uint32_t v;
         if (NEED_B) v = __funnelshift_r(a, w[1] & pl.mb, pl.rs);
         else v = a >> pl.rs;
         v = (v << lsh) >> rsh;
         v = col_valid ? v : zv;
-        if (!lane_on) continue;
-        const size_t pix = static_cast<size_t>(row) * W + pix0;
-        if (HAS_OUT) {
-            if (ES == 4) reinterpret_cast<uint32_t*>(out)[pix] = v;
-            else if (ES == 2) reinterpret_cast<uint16_t*>(out)[pix] = static_cast<uint16_t>(v);
-            else out[pix] = static_cast<uint8_t>(v);
+        if (lane_on) {
+            if (HAS_OUT) {
+                if (ES == 4) *reinterpret_cast<uint32_t*>(o) = v;
+                else if (ES == 2) *reinterpret_cast<uint16_t*>(o) = static_cast<uint16_t>(v);
+                else *o = static_cast<uint8_t>(v);
+            }
+            if (RR) {
+                int dcol = col + (p.has_shift ? p.shift[row] : 0);
+                dcol = dcol >= Wi ? dcol - Wi : dcol;
+                rrow[dcol] = v;
+            }
         }
-        if (RR) {
-            int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
-            dcol = dcol >= static_cast<int>(W) ? dcol - static_cast<int>(W) : dcol;
-            rdp[static_cast<size_t>(row) * W + dcol] = v;
-        }
+        w += wstep;
+        if (HAS_OUT) o += ostep;
+        if (RR) rrow += rstep;
     }
 }
 
@@ -429,45 +439,57 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
             T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
             if (p.vec_ok && (tc % 4u) == 0 && p.plan_ranges_fast) {
                 using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-                const unsigned nvr = 3u * tc / VN;  // chunks per row segment
-                unsigned row = static_cast<unsigned>(tid) / nvr, q = static_cast<unsigned>(tid) - row * nvr;
-                const unsigned drow = static_cast<unsigned>(nthreads) / nvr;
-                const unsigned dq = static_cast<unsigned>(nthreads) - drow * nvr;
-#pragma unroll 2
-                for (; row < L.H; row += drow) {
-                    const size_t ebase = (static_cast<size_t>(row) * L.W + j0) * 3 + static_cast<size_t>(q) * VN;
-                    const V dv = *reinterpret_cast<const V*>(dir + ebase);
-                    const V ov = *reinterpret_cast<const V*>(offs + ebase);
-                    const T* de = reinterpret_cast<const T*>(&dv);
-                    const T* oe = reinterpret_cast<const T*>(&ov);
+                const unsigned nvr = 3u * tc / VN;  // 16-byte chunks per row segment
+                // every thread owns one chunk position q of the row segment and walks down the rows:
+                // pixel indices, column offsets and masks are loop invariants
+                const unsigned rows_per_pass = static_cast<unsigned>(nthreads) / nvr;
+                if (rows_per_pass > 0 && static_cast<unsigned>(tid) < rows_per_pass * nvr) {
+                    const unsigned row0 = static_cast<unsigned>(tid) / nvr;
+                    const unsigned q = static_cast<unsigned>(tid) - row0 * nvr;
                     const unsigned e0 = q * VN;
                     const unsigned p0 = e0 / 3u;       // first pixel touched by this chunk
                     const unsigned k0 = e0 - 3u * p0;  // component of element 0 inside pixel p0
                     const unsigned p1 = (p0 + 1 < tc) ? p0 + 1 : p0;
                     const int co0 = regular ? col_offset(p0) : c.col_off[p0];
                     const int co1 = regular ? col_offset(p1) : c.col_off[p1];
-                    if (xo0 != nullptr) {
-                        const uint32_t ra = range_from_stage(st, co0, row, cds, pl0);
-                        const uint32_t rb = range_from_stage(st, co1, row, cds, pl0);
-                        V outv;
-                        T* o2 = reinterpret_cast<T*>(&outv);
+                    const bool v0 = co0 >= 0, v1 = co1 >= 0;
+                    const uint32_t* wa0 = reinterpret_cast<const uint32_t*>(st + (v0 ? co0 : 0) + static_cast<size_t>(row0) * cds);
+                    const uint32_t* wb0 = reinterpret_cast<const uint32_t*>(st + (v1 ? co1 : 0) + static_cast<size_t>(row0) * cds);
+                    const unsigned wstep = rows_per_pass * cds / 4u;
+                    size_t ebase = (static_cast<size_t>(row0) * L.W + j0) * 3 + static_cast<size_t>(q) * VN;
+                    const size_t estep = static_cast<size_t>(rows_per_pass) * L.W * 3;
+                    auto rng = [](const uint32_t* w, const DecodeParams::Plan& pl, bool valid) -> uint32_t {
+                        const uint32_t a = w[pl.wa] & pl.ma;
+                        const uint32_t b = pl.mb ? (w[pl.wa + 1] & pl.mb) : 0u;
+                        uint32_t v = __funnelshift_r(a, b, pl.rs);
+                        v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
+                        return valid ? v : 0u;
+                    };
+#pragma unroll 2
+                    for (unsigned row = row0; row < L.H; row += rows_per_pass) {
+                        const V dv = *reinterpret_cast<const V*>(dir + ebase);
+                        const V ov = *reinterpret_cast<const V*>(offs + ebase);
+                        const T* de = reinterpret_cast<const T*>(&dv);
+                        const T* oe = reinterpret_cast<const T*>(&ov);
+                        if (xo0 != nullptr) {
+                            const uint32_t ra = rng(wa0, pl0, v0), rb = rng(wb0, pl0, v1);
+                            V outv;
+                            T* o2 = reinterpret_cast<T*>(&outv);
 #pragma unroll
-                        for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
-                        *reinterpret_cast<V*>(xo0 + ebase) = outv;
-                    }
-                    if (xo1 != nullptr) {
-                        const uint32_t ra = range_from_stage(st, co0, row, cds, pl1);
-                        const uint32_t rb = range_from_stage(st, co1, row, cds, pl1);
-                        V outv;
-                        T* o2 = reinterpret_cast<T*>(&outv);
+                            for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
+                            *reinterpret_cast<V*>(xo0 + ebase) = outv;
+                        }
+                        if (xo1 != nullptr) {
+                            const uint32_t ra = rng(wa0, pl1, v0), rb = rng(wb0, pl1, v1);
+                            V outv;
+                            T* o2 = reinterpret_cast<T*>(&outv);
 #pragma unroll
-                        for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
-                        *reinterpret_cast<V*>(xo1 + ebase) = outv;
-                    }
-                    q += dq;
-                    if (q >= nvr) {
-                        q -= nvr;
-                        row += 1;
+                            for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
+                            *reinterpret_cast<V*>(xo1 + ebase) = outv;
+                        }
+                        wa0 += wstep;
+                        wb0 += wstep;
+                        ebase += estep;
                     }
                 }
             } else {
