@@ -194,6 +194,8 @@ typedef struct ob_decode_io {
     uint32_t* status;         /* w */
     void* xyz[OB_MAX_RETURNS];
     uint32_t* range_destaggered[OB_MAX_RETURNS];
+    const ob_lut* lut; /* optional per-frame LUT (frames of different sensors in one launch); must
+                          have the dtype of the call-level lut, which it overrides for this frame */
 } ob_decode_io;
 
 ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, size_t n_frames,
@@ -218,6 +220,8 @@ typedef struct ob_decode_batch {
     size_t xyz_frame_stride;
     uint32_t* range_destaggered[OB_MAX_RETURNS];
     size_t rd_frame_stride;
+    const ob_lut* const* frame_luts; /* optional: n_frames LUT handles, one per frame (independent
+                                        sensor streams batched into one launch); NULL = call-level lut */
 } ob_decode_batch;
 
 ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* batch, const ob_lut* lut,

@@ -59,7 +59,8 @@ class DecodeBatch(C.Structure):
                 ("timestamp_frame_stride", sz), ("measurement_id_frame_stride", sz),
                 ("status_frame_stride", sz),
                 ("xyz", vp * OB_MAX_RETURNS), ("xyz_frame_stride", sz),
-                ("range_destaggered", vp * OB_MAX_RETURNS), ("rd_frame_stride", sz)]
+                ("range_destaggered", vp * OB_MAX_RETURNS), ("rd_frame_stride", sz),
+                ("frame_luts", C.POINTER(vp))]
 
 
 def _sig(name, restype, *argtypes):

@@ -365,6 +365,8 @@ class Decoder:
             for r, a in enumerate(fr.get("range_destaggered", []) or []):
                 if a is not None:
                     io.range_destaggered[r] = _ptr(a)
+            if fr.get("lut") is not None:
+                io.lut = fr["lut"]._h
         sh, nsh = None, 0
         if pixel_shift_by_row is not None:
             sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
@@ -396,7 +398,7 @@ class Decoder:
 
     def decode_batch(self, n_frames, packets, n_slots, packet_stride, packets_frame_stride, fields,
                      lut=None, pixel_shift_by_row=None, xyz=None, range_destaggered=None,
-                     timestamp=None, measurement_id=None, status=None, stream=None):
+                     timestamp=None, measurement_id=None, status=None, stream=None, frame_luts=None):
         """Uniformly strided batch of complete frames (ob_decode_batch_run).  `fields` maps a field
         name to an array/tensor shaped [n_frames, H, W(, k)]; xyz / range_destaggered are lists (one
         entry per return) of [n_frames, H*W, 3] / [n_frames, H, W] arrays."""
@@ -418,7 +420,11 @@ class Decoder:
             b.measurement_id, b.measurement_id_frame_stride = _ptr(measurement_id), self.w_px * 2
         if status is not None:
             b.status, b.status_frame_stride = _ptr(status), self.w_px * 4
-        esz = 8 if (lut is not None and lut.dtype == np.float64) else 4
+        any_lut = lut if lut is not None else (frame_luts[0] if frame_luts else None)
+        esz = 8 if (any_lut is not None and any_lut.dtype == np.float64) else 4
+        if frame_luts:
+            arr = (C.c_void_p * n_frames)(*[l._h.value for l in frame_luts])
+            b.frame_luts = C.cast(arr, C.POINTER(C.c_void_p))
         for r, a in enumerate(xyz or []):
             if a is not None:
                 b.xyz[r] = _ptr(a)

@@ -109,7 +109,6 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
             return fail(OB_INVALID_ARGUMENT, "fused destagger supports at most 512 rows");
         reduce_shifts(shifts, L.H, L.W, 0, sh);
     }
-    const size_t esz = ldtype == OB_F64 ? 8 : 4;
     const size_t n_px = static_cast<size_t>(L.H) * L.W;
     cudaStream_t st = stream_handle(s);
     Staging stg(st);
@@ -164,10 +163,23 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
             if (e != cudaSuccess) return fail_cuda(e, "stage status");
             f.status = static_cast<uint32_t*>(o);
         }
+        if (io.lut) {
+            const void *fd = nullptr, *fo = nullptr;
+            int fdt, fdev;
+            size_t fh, fw;
+            lut_view(io.lut, &fd, &fo, &fdt, &fh, &fw, &fdev);
+            if (fh != L.H || fw != L.W) return fail(OB_INVALID_ARGUMENT, "unexpected image dimensions");
+            if (fdev != device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
+            if (lut && fdt != ldtype) return fail(OB_INVALID_ARGUMENT, "per-frame lut dtype differs from the call-level lut");
+            if (!lut) ldtype = fdt;
+            f.lut_dir = fd;
+            f.lut_off = fo;
+            if (!al16(fd) || !al16(fo)) vec_ok = false;
+        }
         for (int r = 0; r < OB_MAX_RETURNS; ++r) {
             if (io.xyz[r]) {
-                if (!lut) return fail(OB_INVALID_ARGUMENT, "xyz output requested without a lut");
-                e = stg.out(io.xyz[r], n_px * 3 * esz, &o);
+                if (!lut && !io.lut) return fail(OB_INVALID_ARGUMENT, "xyz output requested without a lut");
+                e = stg.out(io.xyz[r], n_px * 3 * (ldtype == OB_F64 ? 8 : 4), &o);
                 if (e != cudaSuccess) return fail_cuda(e, "stage xyz");
                 f.xyz[r] = o;
                 if (!al16(o)) vec_ok = false;
@@ -230,7 +242,6 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
         reduce_shifts(shifts, L.H, L.W, 0, sh);
     }
     const size_t F = b->n_frames;
-    const size_t esz = ldtype == OB_F64 ? 8 : 4;
     const size_t n_px = static_cast<size_t>(L.H) * L.W;
     cudaStream_t st = stream_handle(s);
     Staging stg(st);
@@ -255,12 +266,30 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
         e = stg.out(b->measurement_id, span(b->measurement_id_frame_stride, L.W * 2ull), &dmid);
     if (e == cudaSuccess && b->status) e = stg.out(b->status, span(b->status_frame_stride, L.W * 4ull), &dstat);
     if (e != cudaSuccess) return fail_cuda(e, "stage headers");
+    std::vector<const void*> fl_dir, fl_off;
+    if (b->frame_luts) {
+        fl_dir.resize(F);
+        fl_off.resize(F);
+        for (size_t f = 0; f < F; ++f) {
+            if (!b->frame_luts[f]) return fail(OB_INVALID_ARGUMENT, "null per-frame lut");
+            int fdt, fdev;
+            size_t fh, fw;
+            lut_view(b->frame_luts[f], &fl_dir[f], &fl_off[f], &fdt, &fh, &fw, &fdev);
+            if (fh != L.H || fw != L.W) return fail(OB_INVALID_ARGUMENT, "unexpected image dimensions");
+            if (fdev != device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
+            if ((lut || f > 0) && fdt != ldtype)
+                return fail(OB_INVALID_ARGUMENT, "per-frame lut dtype differs");
+            ldtype = fdt;
+            if (!al16(fl_dir[f]) || !al16(fl_off[f])) vec_ok = false;
+        }
+    }
+    const size_t esz2 = ldtype == OB_F64 ? 8 : 4;
     void* dxyz[OB_MAX_RETURNS] = {};
     void* drd[OB_MAX_RETURNS] = {};
     for (int r = 0; r < OB_MAX_RETURNS; ++r) {
         if (b->xyz[r]) {
-            if (!lut) return fail(OB_INVALID_ARGUMENT, "xyz output requested without a lut");
-            e = stg.out(b->xyz[r], span(b->xyz_frame_stride, n_px * 3 * esz), &dxyz[r]);
+            if (!lut && !b->frame_luts) return fail(OB_INVALID_ARGUMENT, "xyz output requested without a lut");
+            e = stg.out(b->xyz[r], span(b->xyz_frame_stride, n_px * 3 * esz2), &dxyz[r]);
             if (e != cudaSuccess) return fail_cuda(e, "stage xyz");
             if (!al16(dxyz[r]) || b->xyz_frame_stride % 16) vec_ok = false;
         }
@@ -285,6 +314,10 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
         if (dts) d.timestamp = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(dts) + f * b->timestamp_frame_stride);
         if (dmid) d.measurement_id = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(dmid) + f * b->measurement_id_frame_stride);
         if (dstat) d.status = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(dstat) + f * b->status_frame_stride);
+        if (!fl_dir.empty()) {
+            d.lut_dir = fl_dir[f];
+            d.lut_off = fl_off[f];
+        }
         for (int r = 0; r < OB_MAX_RETURNS; ++r) {
             if (dxyz[r]) d.xyz[r] = static_cast<uint8_t*>(dxyz[r]) + f * b->xyz_frame_stride;
             if (drd[r]) d.rd[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(drd[r]) + f * b->rd_frame_stride);

@@ -429,9 +429,11 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
         }
 
         // ---- phase B: XYZ; lane = 16-byte chunk of a row segment, ranges re-read from the stage ----
-        if (p.lut_dir != nullptr && n_ret > 0) {
-            const T* dir = static_cast<const T*>(p.lut_dir);
-            const T* offs = static_cast<const T*>(p.lut_off);
+        const void* lut_dir_f = fr.lut_dir != nullptr ? fr.lut_dir : p.lut_dir;
+        const void* lut_off_f = fr.lut_dir != nullptr ? fr.lut_off : p.lut_off;
+        if (lut_dir_f != nullptr && n_ret > 0) {
+            const T* dir = static_cast<const T*>(lut_dir_f);
+            const T* offs = static_cast<const T*>(lut_off_f);
             constexpr int VN = 16 / sizeof(T);  // scalars per 16-byte chunk
             const DecodeParams::Plan& pl0 = p.plan[p.range_field[0]];
             const DecodeParams::Plan& pl1 = p.plan[p.range_field[n_ret > 1 ? 1 : 0]];

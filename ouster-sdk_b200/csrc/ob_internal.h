@@ -86,6 +86,8 @@ struct DecodeFrame {  // one per frame of a batched launch, lives in device memo
     uint32_t* status;
     void* xyz[OB_MAX_RETURNS];
     uint32_t* rd[OB_MAX_RETURNS];
+    const void* lut_dir;  // per-frame LUT (independent sensor streams in one launch); null: launch-level
+    const void* lut_off;
 };
 
 struct DecodeLaunch {

@@ -205,3 +205,34 @@ def test_custom_profile_widening_decode(ob):
                     ("REFLECTIVITY", orc.UINT8, 1, 0xff00, 8), ("NEAR_IR", orc.UINT16, 2, 0xff00, 4)], 4)
     io = gpu_decode(ob, alt, ref, packets, col_map_from_packets(alt, packets))
     check_frame(io, ref)
+
+
+def test_multi_stream_batch_with_per_frame_luts(ob):
+    """Frames of different sensors (own LUT each) decoded by ONE launch (BASELINE configs[3])."""
+    torch = pytest.importorskip("torch")
+    pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", 32, 512)
+    h, w, F = 32, 512, 4
+    srcs = [random_frame(pf, seed=200 + i, frame_id=700 + i) for i in range(F)]
+    pk = np.stack([orc.frame_to_packets(s, pf)[0] for s in srcs])
+    layout, fields = decoder_desc_from_oracle(pf, srcs[0])
+    dec = ob.Decoder(layout, fields)
+    luts_host = [random_lut(h * w, 30 + i) for i in range(F)]
+    luts = [ob.XYZLutT.from_arrays(d, o, h, w) for d, o in luts_host]
+    shifts = np.arange(h, dtype=np.int32) % 7
+    t_pk = torch.from_numpy(pk).cuda()
+    tdt = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
+    outs = {f["name"]: torch.empty((F, h, w), dtype=tdt[f["elem_size"]], device="cuda") for f in fields}
+    xyz = [torch.empty((F, h * w, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
+    rd = [torch.empty((F, h, w), dtype=torch.int32, device="cuda") for _ in range(2)]
+    st = ob.Stream(0, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    dec.decode_batch(F, t_pk, pk.shape[1], pk.shape[2], pk.shape[1] * pk.shape[2], outs, lut=None,
+                     pixel_shift_by_row=shifts, xyz=xyz, range_destaggered=rd, stream=st, frame_luts=luts)
+    torch.cuda.synchronize()
+    for i in range(F):
+        d, o = luts_host[i]
+        for f in fields:
+            got = outs[f["name"]][i].cpu().numpy().view(srcs[i].field(f["name"]).dtype)
+            assert np.array_equal(got, srcs[i].field(f["name"]))
+        for r, nm in enumerate(["RANGE", "RANGE2"]):
+            assert np.array_equal(xyz[r][i].cpu().numpy(), orc.cartesian(srcs[i].field(nm), d, o)), (i, nm)
+            assert np.array_equal(rd[r][i].cpu().numpy().view(np.uint32), orc.destagger(srcs[i].field(nm), shifts))
