@@ -191,6 +191,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not os.environ.get("OB_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     if args.workload == "k2":

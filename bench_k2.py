@@ -165,6 +165,7 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
         parity = ok
 
     # ---- e2e: host packets -> product FrameBatcher -> host LidarFrame + fused cloud ----
+    ob.set_device(local_rank)
     batcher = ob.FrameBatcher(si)
     batcher.set_fused_cloud(lut, SHIFTS)
     frame = ob.LidarFrame(si)

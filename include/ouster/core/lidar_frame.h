@@ -109,6 +109,9 @@ template <typename T>
 class HeaderRef {
    public:
     HeaderRef(T* d, size_t n) : d_(d), n_(n) {}
+    /// view-of-mutable converts to view-of-const
+    template <typename U, typename = typename std::enable_if<std::is_same<const U, T>::value>::type>
+    HeaderRef(const HeaderRef<U>& o) : d_(o.data()), n_(o.size()) {}
     T* data() const { return d_; }
     size_t rows() const { return n_; }
     size_t size() const { return n_; }
@@ -214,6 +217,17 @@ inline bool operator!=(const LidarFrame& a, const LidarFrame& b) { return !(a ==
 OUSTER_API_FUNCTION LidarFrameFieldTypes get_field_types(UDPProfileLidar profile);
 OUSTER_API_FUNCTION LidarFrameFieldTypes get_field_types(const DataFormat& format, const Version& fw);
 OUSTER_API_FUNCTION LidarFrameFieldTypes get_field_types(const SensorInfo& info);
+
+/// Field-level destagger (field.h:920, src/field.cpp:329-337): dispatches on the element type;
+/// 2-D integer/float fields only -- other types yield a zero-filled field, as in the reference
+/// (impl/lidar_frame_impl.h:143-161).  Throws like destagger_into<T>.
+OUSTER_API_FUNCTION Field destagger(const SensorInfo& info, const Field& field, bool inverse = false);
+
+/// Timestamp of the staggered column a destaggered pixel came from (lidar_frame.h:955,
+/// src/lidar_frame.cpp:893-905).  Throws std::invalid_argument("row or column is out of range").
+OUSTER_API_FUNCTION uint64_t column_timestamp_at_destaggered_pixel(
+    size_t row, size_t col, const std::vector<int>& pixel_shift_by_row,
+    const HeaderRef<const uint64_t>& column_timestamps);
 
 /// Optional fused products of FrameBatcher's GPU pass (an extension over the reference API):
 /// when attached, the same launch that decodes the frame also writes the XYZ of every return

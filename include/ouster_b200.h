@@ -49,6 +49,9 @@ typedef struct ob_decoder ob_decoder; /* device-resident PacketFormat decode tab
 
 /* ---- library ---- */
 int ob_abi_version(void);
+/* sizeof() of a public struct by name ("ob_cloud_io", "ob_field_desc", "ob_packet_layout",
+ * "ob_decode_io", "ob_decode_batch"); 0 for unknown names.  Lets FFI bindings verify their layout. */
+size_t ob_abi_sizeof(const char* struct_name);
 const char* ob_last_error(void);
 /* number of visible CUDA devices (0 without a driver/GPU); never fails */
 int ob_device_count(void);

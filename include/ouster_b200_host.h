@@ -18,6 +18,11 @@ typedef struct obh_sensor obh_sensor;   /* SensorInfo + its PacketFormat */
 typedef struct obh_frame obh_frame;     /* LidarFrame (LidarScan) */
 typedef struct obh_batcher obh_batcher; /* FrameBatcher (ScanBatcher) */
 
+/* CUDA device used by the calling thread's host-mirror objects (FrameBatcher, XYZLut, destagger);
+ * default 0 or env OUSTER_B200_DEVICE (b200::set_device) */
+ob_status obh_set_device(int device);
+int obh_get_device(void);
+
 /* ---- SensorInfo / PacketFormat (types.h:109-1116, sensor_info.h:171-244) ---- */
 ob_status obh_sensor_create(const char* udp_profile_lidar, int header_type_fusa,
                             uint32_t pixels_per_column, uint32_t columns_per_frame,

@@ -48,7 +48,8 @@ class DecodeIO(C.Structure):
                 ("col_src", vp), ("hdr_src", vp),
                 ("fields", vp * OB_MAX_FIELDS),
                 ("timestamp", vp), ("measurement_id", vp), ("status", vp),
-                ("xyz", vp * OB_MAX_RETURNS), ("range_destaggered", vp * OB_MAX_RETURNS)]
+                ("xyz", vp * OB_MAX_RETURNS), ("range_destaggered", vp * OB_MAX_RETURNS),
+                ("lut", vp)]
 
 
 class DecodeBatch(C.Structure):
@@ -71,6 +72,7 @@ def _sig(name, restype, *argtypes):
 
 
 _sig("ob_abi_version", i32)
+_sig("ob_abi_sizeof", sz, C.c_char_p)
 _sig("ob_last_error", C.c_char_p)
 _sig("ob_device_count", i32)
 _sig("ob_kernel_launch_count", u64)

@@ -222,6 +222,17 @@ extern "C" {
 
 int ob_abi_version(void) { return OB_ABI_VERSION; }
 
+size_t ob_abi_sizeof(const char* name) {
+    if (!name) return 0;
+    const std::string n(name);
+    if (n == "ob_cloud_io") return sizeof(ob_cloud_io);
+    if (n == "ob_field_desc") return sizeof(ob_field_desc);
+    if (n == "ob_packet_layout") return sizeof(ob_packet_layout);
+    if (n == "ob_decode_io") return sizeof(ob_decode_io);
+    if (n == "ob_decode_batch") return sizeof(ob_decode_batch);
+    return 0;
+}
+
 const char* ob_last_error(void) { return g_last_error.c_str(); }
 
 int ob_device_count(void) {

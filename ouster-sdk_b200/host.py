@@ -16,6 +16,8 @@ def _sig(name, restype, *argtypes):
     f.restype, f.argtypes = restype, list(argtypes)
 
 
+_sig("obh_set_device", i32, i32)
+_sig("obh_get_device", i32)
 _sig("obh_sensor_create", i32, C.c_char_p, i32, u32, u32, u32, vp, u32, u64, C.c_char_p, u32, u32, PP(vp))
 _sig("obh_sensor_set_intrinsics", i32, vp, vp, sz, vp, sz, vp, vp, vp)
 _sig("obh_sensor_set_custom_fields", i32, vp, sz, PP(C.c_char_p), vp, vp, vp, vp, sz)
@@ -63,6 +65,15 @@ NP_TAG = {np.dtype(np.uint8): 1, np.dtype(np.uint16): 2, np.dtype(np.uint32): 3,
           np.dtype(np.uint64): 4, np.dtype(np.int8): 5, np.dtype(np.int16): 6,
           np.dtype(np.int32): 7, np.dtype(np.int64): 8, np.dtype(np.float32): 9,
           np.dtype(np.float64): 10}
+
+
+def set_device(device):
+    """CUDA device for this thread's FrameBatcher / host-mirror objects (b200::set_device)."""
+    check(lib.obh_set_device(int(device)))
+
+
+def get_device():
+    return lib.obh_get_device()
 
 
 def _as_array(ptr, dtype, shape):

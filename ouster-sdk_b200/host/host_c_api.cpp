@@ -61,6 +61,14 @@ size_t elem_bytes_of(const Field& f) {
 
 extern "C" {
 
+ob_status obh_set_device(int device) {
+    return guard([&] {
+        if (device < 0) throw std::invalid_argument("invalid CUDA device index");
+        b200::set_device(device);
+    });
+}
+int obh_get_device(void) { return b200::device(); }
+
 ob_status obh_sensor_create(const char* profile, int fusa, uint32_t h, uint32_t w, uint32_t cpp,
                             const int32_t* shifts, uint32_t init_id, uint64_t sn, const char* fw_rev,
                             uint32_t cw_first, uint32_t cw_second, obh_sensor** out) {

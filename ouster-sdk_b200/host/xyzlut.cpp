@@ -147,6 +147,38 @@ std::vector<Packet> frame_to_packets(const LidarFrame& frame, const PacketFormat
 
 }  // namespace impl
 
+Field destagger(const SensorInfo& info, const Field& field, bool inverse) {
+    Field result(field.tag(), field.shape());
+    const auto& shp = field.shape();
+    switch (field.tag()) {  // visit_field_2d: the arithmetic types only
+        case ChanFieldType::UINT8: case ChanFieldType::UINT16: case ChanFieldType::UINT32:
+        case ChanFieldType::UINT64: case ChanFieldType::INT8: case ChanFieldType::INT16:
+        case ChanFieldType::INT32: case ChanFieldType::INT64: case ChanFieldType::FLOAT32:
+        case ChanFieldType::FLOAT64:
+            break;
+        default:
+            return result;  // FLOAT16 / CHAR / ZONE_STATE: silently zero-filled in the reference
+    }
+    if (shp.size() != 2) return result;
+    if (info.format.pixel_shift_by_row.size() != shp[0])
+        throw std::invalid_argument{"image height does not match shifts size"};
+    impl::destagger_raw(field.element_size(), 1, field.get(), info.format.pixel_shift_by_row, shp[0],
+                        shp[1], inverse, result.get());
+    return result;
+}
+
+uint64_t column_timestamp_at_destaggered_pixel(size_t row, size_t col,
+                                               const std::vector<int>& pixel_shift_by_row,
+                                               const HeaderRef<const uint64_t>& column_timestamps) {
+    const size_t width = column_timestamps.size();
+    if (row >= pixel_shift_by_row.size() || col >= width)
+        throw std::invalid_argument("row or column is out of range");
+    const int w = static_cast<int>(width);
+    const int offset = (w + pixel_shift_by_row[row] % w) % w;  // int arithmetic, as the reference
+    const int staggered_col = (static_cast<int>(col) - offset + w) % w;
+    return column_timestamps[static_cast<size_t>(staggered_col)];
+}
+
 PointCloudXYZd cartesian(const ArrayRef<const uint32_t>& range, const XYZLut& lut) {
     if (range.cols() * range.rows() != lut.direction.rows())
         throw std::invalid_argument("unexpected image dimensions");

@@ -5,6 +5,7 @@
 // Prints "DROPIN OK" when every check passes.  Built and run by tests/test_gpu_cpp_dropin.py.
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <cstdlib>
 #include <random>
 #include <stdexcept>
@@ -100,6 +101,17 @@ int main() {
     for (size_t u = 0; u < h; ++u) {
         const int s = info->format.pixel_shift_by_row[u];
         for (size_t j = 0; j < w; ++j) CHECK(destag(u, (j + s) % w) == range(u, j));
+    }
+    {   // untyped Field form + timestamp mapping (tests/destagger_test.cpp:135-161)
+        Field fd = destagger(*info, scan.field(ChanField::RANGE));
+        CHECK(std::memcmp(fd.get(), destag.data(), h * w * 4) == 0);
+        for (size_t u = 0; u < h; u += 7)
+            for (size_t j = 0; j < w; j += 13) {
+                const int s = info->format.pixel_shift_by_row[u];
+                const size_t src_col = (j + w - static_cast<size_t>(s)) % w;
+                CHECK(column_timestamp_at_destaggered_pixel(u, j, info->format.pixel_shift_by_row,
+                                                            scan.timestamp()) == 1000 + src_col);
+            }
     }
     img_t<uint32_t> back = stagger<uint32_t>(*info, destag);
     for (size_t i = 0; i < h * w; ++i) CHECK(back(i) == range(i));

@@ -58,3 +58,15 @@ def test_argument_validation_messages_without_device():
         ob.XYZLutT.from_intrinsics(0, 4, 0.001, ident, ident, [0] * 4, [0] * 4)
     with pytest.raises(ValueError, match="unexpected frame dimensions"):
         ob.XYZLutT.from_intrinsics(8, 4, 0.001, ident, ident, [0] * 3, [0] * 4)
+
+
+def test_ctypes_struct_layouts_match_the_c_abi():
+    """The Python binding's structs must have exactly the C sizes (guards against ABI drift)."""
+    ob = graft.load_package()
+    capi = ob._capi
+    pairs = {"ob_cloud_io": capi.CloudIO, "ob_field_desc": capi.FieldDesc,
+             "ob_packet_layout": capi.PacketLayout, "ob_decode_io": capi.DecodeIO,
+             "ob_decode_batch": capi.DecodeBatch}
+    for name, cls in pairs.items():
+        assert capi.lib.ob_abi_sizeof(name.encode()) == ctypes.sizeof(cls), name
+    assert capi.lib.ob_abi_sizeof(b"nope") == 0
