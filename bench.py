@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="k1", choices=["k1", "k2"])
     ap.add_argument("--frames", type=int, default=64, help="frames per step (per GPU)")
+    ap.add_argument("--streams-per-gpu", type=int, default=1,
+                    help="k2: independent sensor streams (own LUT each) batched per launch per GPU; "
+                         "1 = BASELINE configs[2], 8 (x8 GPUs = 64 streams) = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="tuning aid: device-resident timing only")
     args = ap.parse_args()
@@ -192,7 +195,7 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if not os.environ.get("OB_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+            os.environ.pop("NCCL_DEBUG", None)   # keep stdout to the single JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     if args.workload == "k2":

@@ -88,7 +88,7 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
     lut = ob.XYZLutT.from_arrays(t_dir, t_off, H, W, device=local_rank)
     # independent sensor streams (BASELINE configs[3]): STREAMS_PER_GPU streams per rank, each with
     # its own LUT (stream i lives on GPU i mod G), frames of all streams batched into one launch
-    STREAMS_PER_GPU = 8
+    STREAMS_PER_GPU = max(1, min(int(getattr(args, 'streams_per_gpu', 1)), F))
     my_streams = [rank + world * i for i in range(STREAMS_PER_GPU)]
     stream_luts = [ob.XYZLutT.from_arrays(t_dir * (1.0 + 1e-3 * sid), t_off * (1.0 + 1e-3 * sid), H, W,
                                           device=local_rank) for sid in my_streams]
