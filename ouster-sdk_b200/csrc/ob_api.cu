@@ -46,7 +46,7 @@ static Tunables& tunables_mut(int device) {
         t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 256)));
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
         t.decode_stages = std::max(1, env_int("OB_DECODE_STAGES", 1));
-        t.decode_threads = std::min(1024, std::max(64, env_int("OB_DECODE_THREADS", 384)));
+        t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384)));
         t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
         t.decode_tile_packets = std::max(1, env_int("OB_DECODE_TILE_PACKETS", 2));
         t.force_fallback = env_int("OB_FORCE_FALLBACK", 0);
@@ -76,7 +76,7 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "cloud_threads") t.cloud_threads = std::min(256, std::max(32, value / 32 * 32));
     else if (n == "cloud_ctas_per_sm") t.cloud_ctas_per_sm = std::max(1, value);
     else if (n == "decode_stages") t.decode_stages = std::max(1, value);
-    else if (n == "decode_threads") t.decode_threads = std::min(1024, std::max(64, value / 32 * 32));
+    else if (n == "decode_threads") t.decode_threads = std::min(384, std::max(64, value / 32 * 32));
     else if (n == "decode_ctas_per_sm") t.decode_ctas_per_sm = std::max(1, value);
     else if (n == "decode_tile_packets") t.decode_tile_packets = std::max(1, value);
     else if (n == "force_fallback") t.force_fallback = value;

@@ -144,17 +144,22 @@ __device__ __forceinline__ double project1(uint32_t r, double d, double o) {
     return r == 0 ? 0.0 : __dadd_rn(__dmul_rn(static_cast<double>(r), d), o);
 }
 
-// Row loop of phase A for one field, specialised on the destination element size, on whether the
-// field straddles two aligned words, on whether it is a range image (destaggered copy) and on
-// whether the plain (staggered) image is requested.  ~12 instructions per pixel.
-template <int ES, bool NEED_B, bool RR, bool HAS_OUT>
+// Row loop of phase A for one field.  Compile-time specialisations remove every per-pixel branch:
+//   ES      destination element size (1, 2, 4)
+//   NEED_B  the field straddles two aligned 32-bit words
+//   SHIFTED the value needs the extra up/down shift (low-bandwidth profiles, custom tables)
+//   MODE    1 = plain image only, 2 = plain + destaggered range, 3 = destaggered range only
+//   FULL    every lane holds a present column (complete tile): no predication, no zero fill
+// The main loop handles 4 rows per trip with a single bounds test; all addresses advance by
+// loop-invariant strides.  ~9 instructions per pixel in the common case.
+template <int ES, bool NEED_B, bool SHIFTED, int MODE, bool FULL>
 __device__ __forceinline__ void decode_rows(const uint8_t* px0, unsigned cds, const DecodeParams::Plan& pl,
                                             bool col_valid, uint32_t zv, bool lane_on, uint8_t* out,
                                             size_t pix0, unsigned W, unsigned H, int warp, int nwarps,
                                             uint32_t* rdp, const DecodeParams& p) {
+    constexpr bool HAS_OUT = MODE != 3, RR = MODE != 1;
     const uint32_t lsh = pl.d > 0 ? static_cast<uint32_t>(pl.d) : 0u;
     const uint32_t rsh = pl.d < 0 ? static_cast<uint32_t>(-pl.d) : 0u;
-    // all addresses advance by loop-invariant strides
     const uint32_t* w = reinterpret_cast<const uint32_t*>(px0 + static_cast<size_t>(warp) * cds) + pl.wa;
     const unsigned wstep = static_cast<unsigned>(nwarps) * cds / 4u;
     uint8_t* o = HAS_OUT ? out + (static_cast<size_t>(warp) * W + pix0) * ES : nullptr;
@@ -162,22 +167,23 @@ __device__ __forceinline__ void decode_rows(const uint8_t* px0, unsigned cds, co
     uint32_t* rrow = RR ? rdp + static_cast<size_t>(warp) * W : nullptr;
     const size_t rstep = static_cast<size_t>(nwarps) * W;
     const int col = static_cast<int>(pix0), Wi = static_cast<int>(W);
-#pragma unroll 4
-    for (unsigned row = warp; row < H; row += nwarps) {
+    const bool has_shift = p.has_shift != 0;
+
+    auto body = [&](unsigned row) {
         const uint32_t a = w[0] & pl.ma;
         uint32_t v;
         if (NEED_B) v = __funnelshift_r(a, w[1] & pl.mb, pl.rs);
         else v = a >> pl.rs;
-        v = (v << lsh) >> rsh;
-        v = col_valid ? v : zv;
-        if (lane_on) {
+        if (SHIFTED) v = (v << lsh) >> rsh;
+        if (!FULL) v = col_valid ? v : zv;
+        if (FULL || lane_on) {
             if (HAS_OUT) {
                 if (ES == 4) *reinterpret_cast<uint32_t*>(o) = v;
                 else if (ES == 2) *reinterpret_cast<uint16_t*>(o) = static_cast<uint16_t>(v);
                 else *o = static_cast<uint8_t>(v);
             }
             if (RR) {
-                int dcol = col + (p.has_shift ? p.shift[row] : 0);
+                int dcol = col + (has_shift ? p.shift[row] : 0);
                 dcol = dcol >= Wi ? dcol - Wi : dcol;
                 rrow[dcol] = v;
             }
@@ -185,22 +191,47 @@ __device__ __forceinline__ void decode_rows(const uint8_t* px0, unsigned cds, co
         w += wstep;
         if (HAS_OUT) o += ostep;
         if (RR) rrow += rstep;
+    };
+    unsigned row = warp;
+    const unsigned nw = static_cast<unsigned>(nwarps);
+    for (; row + 3u * nw < H; row += 4u * nw) {
+        body(row);
+        body(row + nw);
+        body(row + 2u * nw);
+        body(row + 3u * nw);
     }
+    for (; row < H; row += nw) body(row);
 }
 
-template <int ES, bool NEED_B>
+template <int ES, bool NEED_B, bool SHIFTED, bool FULL>
+__device__ __forceinline__ void decode_rows_mode(bool has_out, bool has_rd, const uint8_t* px0, unsigned cds,
+                                                 const DecodeParams::Plan& pl, bool col_valid, uint32_t zv,
+                                                 bool lane_on, uint8_t* out, size_t pix0, unsigned W,
+                                                 unsigned H, int warp, int nwarps, uint32_t* rdp,
+                                                 const DecodeParams& p) {
+    if (has_out && has_rd)
+        decode_rows<ES, NEED_B, SHIFTED, 2, FULL>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+    else if (has_out)
+        decode_rows<ES, NEED_B, SHIFTED, 1, FULL>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+    else if (has_rd)
+        decode_rows<ES, NEED_B, SHIFTED, 3, FULL>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+}
+
+template <int ES, bool FULL>
 __device__ __forceinline__ void decode_rows_dispatch(bool has_out, bool has_rd, const uint8_t* px0,
                                                      unsigned cds, const DecodeParams::Plan& pl,
                                                      bool col_valid, uint32_t zv, bool lane_on,
                                                      uint8_t* out, size_t pix0, unsigned W, unsigned H,
                                                      int warp, int nwarps, uint32_t* rdp,
                                                      const DecodeParams& p) {
-    if (has_out && has_rd)
-        decode_rows<ES, NEED_B, true, true>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
-    else if (has_out)
-        decode_rows<ES, NEED_B, false, true>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
-    else if (has_rd)
-        decode_rows<ES, NEED_B, true, false>(px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+    const bool need_b = pl.mb != 0, shifted = pl.d != 0;
+    if (need_b) {
+        if (shifted) decode_rows_mode<ES, true, true, FULL>(has_out, has_rd, px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+        else decode_rows_mode<ES, true, false, FULL>(has_out, has_rd, px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+    } else {
+        if (shifted) decode_rows_mode<ES, false, true, FULL>(has_out, has_rd, px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+        else decode_rows_mode<ES, false, false, FULL>(has_out, has_rd, px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
+    }
 }
 
 // range of pixel (row, column offset `co`) straight from the staged packet bytes
@@ -214,8 +245,61 @@ __device__ __forceinline__ uint32_t range_from_stage(const uint8_t* st, int co, 
     return pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
 }
 
+// Phase B row walk of one thread: chunk position fixed, rows strided.  SIMPLE: both range fields
+// are `word & mask` (no straddle, no shift); BOTH: both returns requested and both pixels present.
+template <typename T, bool SIMPLE, bool BOTH>
+__device__ __forceinline__ void project_rows(const T* dir, const T* offs, T* xo0, T* xo1, size_t estep,
+                                             const uint32_t* wa, const uint32_t* wb, unsigned wstep,
+                                             const DecodeParams::Plan& pl0, const DecodeParams::Plan& pl1,
+                                             bool v0, bool v1, unsigned k0, unsigned row0,
+                                             unsigned rows_per_pass, unsigned H) {
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    constexpr int VN = 16 / sizeof(T);
+    auto rng = [](const uint32_t* w, const DecodeParams::Plan& pl, bool valid) -> uint32_t {
+        const uint32_t a = w[pl.wa] & pl.ma;
+        if (SIMPLE) return a;
+        const uint32_t b = pl.mb ? (w[pl.wa + 1] & pl.mb) : 0u;
+        uint32_t v = __funnelshift_r(a, b, pl.rs);
+        v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
+        return valid ? v : 0u;
+    };
+    // element e of the chunk belongs to the chunk's first pixel iff k0 + e < 3
+    bool first[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) first[e] = (k0 + e) < 3u;
+#pragma unroll 2
+    for (unsigned row = row0; row < H; row += rows_per_pass) {
+        const V dv = *reinterpret_cast<const V*>(dir);
+        const V ov = *reinterpret_cast<const V*>(offs);
+        const T* de = reinterpret_cast<const T*>(&dv);
+        const T* oe = reinterpret_cast<const T*>(&ov);
+        if (BOTH || xo0 != nullptr) {
+            const uint32_t ra = rng(wa, pl0, v0), rb = rng(wb, pl0, v1);
+            V outv;
+            T* o2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o2[e] = project1(first[e] ? ra : rb, de[e], oe[e]);
+            *reinterpret_cast<V*>(xo0) = outv;
+            xo0 += estep;
+        }
+        if (BOTH || xo1 != nullptr) {
+            const uint32_t ra = rng(wa, pl1, v0), rb = rng(wb, pl1, v1);
+            V outv;
+            T* o2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o2[e] = project1(first[e] ? ra : rb, de[e], oe[e]);
+            *reinterpret_cast<V*>(xo1) = outv;
+            xo1 += estep;
+        }
+        wa += wstep;
+        wb += wstep;
+        dir += estep;
+        offs += estep;
+    }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ DecodeParams p) {
+__global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ DecodeParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DecodeLayout& L = p.L;
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -402,10 +486,11 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
                 if (pl.fast && es <= 4) {
                     const uint32_t zv = (fd.zero_pattern & 0xffffu) | ((fd.zero_pattern & 0xffffu) << 16);
                     const bool ho = out != nullptr, hr = rdp != nullptr;
-                    if (pl.mb != 0) {
-                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
-                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
-                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                    const bool full = regular && (cg + 1) * 32u <= tc;
+                    if (full) {
+                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
+                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
                     } else {
                         if (es == 4) decode_rows_dispatch<4, false>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
                         else if (es == 2) decode_rows_dispatch<2, false>(ho, hr, px0, cds, pl, col_valid, zv, lane_on, out, pix0, L.W, L.H, warp, nwarps, rdp, p);
@@ -440,10 +525,9 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
             T* xo0 = static_cast<T*>(fr.xyz[0]);
             T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
             if (p.vec_ok && (tc % 4u) == 0 && p.plan_ranges_fast) {
-                using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
                 const unsigned nvr = 3u * tc / VN;  // 16-byte chunks per row segment
                 // every thread owns one chunk position q of the row segment and walks down the rows:
-                // pixel indices, column offsets and masks are loop invariants
+                // pixel indices, column offsets, masks and element->pixel selects are loop invariants
                 const unsigned rows_per_pass = static_cast<unsigned>(nthreads) / nvr;
                 if (rows_per_pass > 0 && static_cast<unsigned>(tid) < rows_per_pass * nvr) {
                     const unsigned row0 = static_cast<unsigned>(tid) / nvr;
@@ -458,41 +542,17 @@ __global__ void __launch_bounds__(1024) decode_kernel(const __grid_constant__ De
                     const uint32_t* wa0 = reinterpret_cast<const uint32_t*>(st + (v0 ? co0 : 0) + static_cast<size_t>(row0) * cds);
                     const uint32_t* wb0 = reinterpret_cast<const uint32_t*>(st + (v1 ? co1 : 0) + static_cast<size_t>(row0) * cds);
                     const unsigned wstep = rows_per_pass * cds / 4u;
-                    size_t ebase = (static_cast<size_t>(row0) * L.W + j0) * 3 + static_cast<size_t>(q) * VN;
+                    const size_t ebase = (static_cast<size_t>(row0) * L.W + j0) * 3 + static_cast<size_t>(q) * VN;
                     const size_t estep = static_cast<size_t>(rows_per_pass) * L.W * 3;
-                    auto rng = [](const uint32_t* w, const DecodeParams::Plan& pl, bool valid) -> uint32_t {
-                        const uint32_t a = w[pl.wa] & pl.ma;
-                        const uint32_t b = pl.mb ? (w[pl.wa + 1] & pl.mb) : 0u;
-                        uint32_t v = __funnelshift_r(a, b, pl.rs);
-                        v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
-                        return valid ? v : 0u;
-                    };
-#pragma unroll 2
-                    for (unsigned row = row0; row < L.H; row += rows_per_pass) {
-                        const V dv = *reinterpret_cast<const V*>(dir + ebase);
-                        const V ov = *reinterpret_cast<const V*>(offs + ebase);
-                        const T* de = reinterpret_cast<const T*>(&dv);
-                        const T* oe = reinterpret_cast<const T*>(&ov);
-                        if (xo0 != nullptr) {
-                            const uint32_t ra = rng(wa0, pl0, v0), rb = rng(wb0, pl0, v1);
-                            V outv;
-                            T* o2 = reinterpret_cast<T*>(&outv);
-#pragma unroll
-                            for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
-                            *reinterpret_cast<V*>(xo0 + ebase) = outv;
-                        }
-                        if (xo1 != nullptr) {
-                            const uint32_t ra = rng(wa0, pl1, v0), rb = rng(wb0, pl1, v1);
-                            V outv;
-                            T* o2 = reinterpret_cast<T*>(&outv);
-#pragma unroll
-                            for (int e = 0; e < VN; ++e) o2[e] = project1((k0 + e) >= 3u ? rb : ra, de[e], oe[e]);
-                            *reinterpret_cast<V*>(xo1 + ebase) = outv;
-                        }
-                        wa0 += wstep;
-                        wb0 += wstep;
-                        ebase += estep;
-                    }
+                    const bool simple = (pl0.mb | pl1.mb | pl0.rs | pl1.rs) == 0 && pl0.d == 0 && pl1.d == 0;
+                    const bool both = xo0 != nullptr && xo1 != nullptr;
+                    if (simple && v0 && v1 && both)
+                        project_rows<T, true, true>(dir + ebase, offs + ebase, xo0 + ebase, xo1 + ebase, estep,
+                                                    wa0, wb0, wstep, pl0, pl1, true, true, k0, row0, rows_per_pass, L.H);
+                    else
+                        project_rows<T, false, false>(dir + ebase, offs + ebase, xo0 ? xo0 + ebase : nullptr,
+                                                      xo1 ? xo1 + ebase : nullptr, estep, wa0, wb0, wstep, pl0, pl1,
+                                                      v0, v1, k0, row0, rows_per_pass, L.H);
                 }
             } else {
                 for (unsigned idx = tid; idx < L.H * tc; idx += nthreads) {

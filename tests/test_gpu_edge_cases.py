@@ -114,9 +114,9 @@ def test_decode_unaligned_wire_layout_and_wide_fields(ob):
         pass
     src = orc.Frame(pf, with_window=False, extra_fields=[("WIDE", orc.UINT64)])
     rs = np.random.default_rng(5)
-    for n in ("RANGE", "SIGNAL", "FLAGS"):
-        a = src.field(n)
-        a[...] = (rs.integers(0, 1 << 32, size=a.shape, dtype=np.uint64) & np.uint64(pf.value_mask(n))).astype(a.dtype)
+    # WIDE covers the whole 7-byte pixel and is encoded last (name order), so it defines the wire
+    # bytes; the narrower fields decode overlapping views of it
+    src.field("WIDE")[...] = rs.integers(0, 1 << 56, size=(8, 64), dtype=np.uint64)
     src.measurement_id[:] = np.arange(64)
     src.status[:] = 1
     src.packet_timestamp[:] = 7
@@ -143,6 +143,7 @@ def test_decode_unaligned_wire_layout_and_wide_fields(ob):
     st.sync()
     for n, a in outs.items():
         assert np.array_equal(a, ref.field(n)), n
-    assert np.any(outs["WIDE"] > (1 << 40))
+    assert np.array_equal(outs["WIDE"], src.field("WIDE")) and np.any(outs["WIDE"] > (1 << 40))
+    assert np.array_equal(outs["RANGE"], (src.field("WIDE") & np.uint64(0x7ffff)).astype(np.uint32))
     assert np.array_equal(io["xyz"][0], orc.cartesian(ref.field("RANGE"), d, o))
     assert np.array_equal(io["range_destaggered"][0], orc.destagger(ref.field("RANGE"), sh))

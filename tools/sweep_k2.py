@@ -26,7 +26,7 @@ def step():
     dec.decode_batch(F, t_pk, n_slots, psz, n_slots * psz, fields, lut=lut, pixel_shift_by_row=k2.SHIFTS,
                      xyz=xyz, range_destaggered=rd, stream=st)
 rows = []
-for tp, stg, th, cta in itertools.product([1, 2], [1, 2, 3], [256, 384, 512, 768, 1024], [1, 2, 3, 4, 5, 6]):
+for tp, stg, th, cta in itertools.product([1, 2], [1, 2, 3], [192, 256, 320, 384], [1, 2, 3, 4]):
     smem = 5120 + stg * 33152 * tp
     if smem * cta > 227 * 1024 or th * cta > 2048:
         continue
