@@ -10,3 +10,4 @@ from .core import (Decoder, Stream, XYZLut, XYZLutFloat, XYZLutT, cartesian, des
 from .host import get_device, set_device  # noqa: F401,E402
 from .host import FrameBatcher, LidarFrame, LidarScan, ScanBatcher, SensorInfo, frame_to_packets  # noqa: F401,E402
 from . import sharding  # noqa: F401,E402
+from . import pyapi  # noqa: F401,E402

@@ -128,3 +128,20 @@ def random_frame(pf, seed, with_window=True, frame_id=700):
             vals = rs.integers(0, mask + 1 if mask < (1 << 63) else (1 << 63), size=a.shape, dtype=np.uint64) & np.uint64(mask)
             a[...] = vals.astype(a.dtype)
     return f
+
+
+# ---- BASELINE configs[0]: default OS1-64 1024x64 sensor (sensor_info.cpp:163-222, data_format.cpp:79-126)
+def default_os1_64(w=1024):
+    top = [16.611, 16.084, 15.557, 15.029, 14.502, 13.975, 13.447, 12.920, 12.393, 11.865, 11.338, 10.811,
+           10.283, 9.756, 9.229, 8.701, 8.174, 7.646, 7.119, 6.592, 6.064, 5.537, 5.010, 4.482, 3.955, 3.428,
+           2.900, 2.373, 1.846, 1.318, 0.791, 0.264]
+    alt = np.array(top + [-a for a in reversed(top)])
+    az = np.tile(np.array([3.164, 1.055, -1.055, -3.164]), 16)
+    unit = {512: 3, 1024: 6, 2048: 12, 4096: 24}[w]
+    shifts = np.tile(np.array([3, 2, 1, 0], np.int32) * unit, 16)
+    b2l = np.eye(4)
+    b2l[0, 3] = 15.806
+    l2s = np.diag([-1.0, -1.0, 1.0, 1.0])
+    l2s[2, 3] = 36.18
+    return {"h": 64, "w": w, "beam_altitude_angles": alt, "beam_azimuth_angles": az,
+            "pixel_shift_by_row": shifts, "beam_to_lidar_transform": b2l, "lidar_to_sensor_transform": l2s}

@@ -1,0 +1,101 @@
+"""The reference's own Python tests for this path, restated against the drop-in module
+(python/tests/test_destagger.py:12-114, python/tests/test_xyzlut.py:119-136) on the 'legacy-2.0'
+fixture (OS-2-32-U0_v2.0.0_1024x10)."""
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as graft
+from tests.helpers import GOLDEN, load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def core():
+    graft.build()
+    ob = graft.load_package()
+    assert ob.device_count() > 0
+    return ob.pyapi
+
+
+@pytest.fixture(scope="module")
+def meta_frame(core):
+    meta, packets = load_fixture("OS-2-32-U0_v2.0.0_1024x10")
+    info = core.SensorInfo.from_meta(meta)
+    scan = core.LidarScan(info)
+    batch = core.ScanBatcher(info)
+    done = [batch(p, 77, scan) for p in packets]
+    assert done[-1]
+    return info, scan, meta
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16,
+                                   np.int32, np.int64, np.float32, np.float64])
+def test_destagger_type_good(core, meta_frame, dtype):
+    info = meta_frame[0]
+    assert core.destagger(info, np.zeros((info.h, info.w), dtype)).dtype == dtype
+    assert core.destagger(info, np.zeros((info.h, info.w, 2), dtype)).dtype == dtype
+
+
+@pytest.mark.parametrize("shape", [(32, 1024), (32, 1024, 1), (32, 1024, 10)])
+def test_destagger_shape_good(core, meta_frame, shape):
+    info = meta_frame[0]
+    assert core.destagger(info, np.zeros(shape)).shape == shape
+    assert core.destagger(info, np.zeros(shape), inverse=True).shape == shape
+
+
+def test_destagger_shape_bad(core, meta_frame):
+    info = meta_frame[0]
+    h, w = info.h, info.w
+    for shape in [(0, w), (h, 0, 2), (h, w + 1), (h - 1, w), (h, w - 1, 1), (h + 1, w, 2)]:
+        with pytest.raises(ValueError):
+            core.destagger(info, np.zeros(shape))
+
+
+def test_destagger_inverse(core, meta_frame):
+    info = meta_frame[0]
+    a = np.arange(info.h * info.w).reshape((info.h, info.w))
+    assert np.array_equal(a, core.destagger(info, core.destagger(info, a, inverse=True)))
+    d = core.destagger(info, a)
+    assert np.array_equal(a, core.destagger(info, d, inverse=True))
+    assert np.array_equal(a, core.stagger(info, d))
+
+
+def test_destagger_xyz_and_correct(core, meta_frame):
+    info, scan, meta = meta_frame
+    xyz = core.XYZLut(info)(scan)
+    assert xyz.shape == (info.h, info.w, 3) and xyz.dtype == np.float64
+    assert core.destagger(info, xyz).shape == (info.h, info.w, 3)
+    rng = scan.field(core.ChanField.RANGE)
+    ref = np.stack([np.roll(rng[u], info.pixel_shift_by_row[u]) for u in range(info.h)])  # reference.py:158-161
+    assert np.array_equal(ref, core.destagger(info, rng))
+    near_ir = scan.field(core.ChanField.NEAR_IR)
+    stacked = np.repeat(near_ir[..., None], 5, axis=2)
+    ref_ir = np.stack([np.roll(near_ir[u], info.pixel_shift_by_row[u]) for u in range(info.h)])
+    out = core.destagger(info, stacked)
+    assert out.dtype == np.uint16 and np.array_equal(out, np.repeat(ref_ir[..., None], 5, axis=2))
+
+
+def test_xyzlut_vs_doc_formula(core, meta_frame):
+    """python/tests/test_xyzlut.py:119-136: XYZLut(info)(scan) allclose the manual's formula."""
+    info, scan, meta = meta_frame
+    rng = scan.field("RANGE").astype(np.float64)
+    h, w = info.h, info.w
+    n = np.hypot(info.beam_to_lidar_transform[0, 3], info.beam_to_lidar_transform[2, 3])
+    v = np.arange(w)
+    te = 2.0 * np.pi * (1.0 - v / w)
+    ta = -2.0 * np.pi * np.asarray(info.beam_azimuth_angles) / 360.0
+    phi = 2.0 * np.pi * np.asarray(info.beam_altitude_angles) / 360.0
+    b03, b23 = info.beam_to_lidar_transform[0, 3], info.beam_to_lidar_transform[2, 3]
+    x = (rng - n) * np.cos(te[None] + ta[:, None]) * np.cos(phi[:, None]) + b03 * np.cos(te[None])
+    y = (rng - n) * np.sin(te[None] + ta[:, None]) * np.cos(phi[:, None]) + b03 * np.sin(te[None])
+    z = (rng - n) * np.sin(phi[:, None]) + b23
+    ref = np.stack([x, y, z, np.ones_like(x)], -1) @ info.lidar_to_sensor_transform.T
+    ref = ref[..., :3] * 0.001
+    ref[rng == 0] = 0
+    assert np.allclose(core.XYZLut(info, use_extrinsics=False)(scan), ref)
+    assert np.allclose(core.XYZLutFloat(info, use_extrinsics=False)(scan), ref, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError, match="Image dimensions do not match lut."):
+        core.XYZLut(info)(np.zeros((h, w + 1), np.uint32))
