@@ -116,6 +116,15 @@ ob_status ob_cartesian(const ob_lut* lut, const uint32_t* range, size_t n_pixels
 ob_status ob_destagger(size_t elem_size, size_t k, const void* img, const int32_t* pixel_shift_by_row,
                        size_t n_shifts, size_t h, size_t w, int inverse, void* out, ob_stream* s);
 
+/* ---- per-column pose application ----
+ * replaces dewarp<T>(dewarped, points, poses)   ouster_core/include/ouster/core/pose_util.h:37-59
+ *          transform<T>(transformed, points, pose)  pose_util.h:118-131  (n_poses == 1)
+ * points/out: n_points x 3 of dtype, row-major, point i*n_poses + w uses pose w;
+ * poses: n_poses x 16 of dtype (row-major 4x4 each).  n_points must be a multiple of n_poses.
+ */
+ob_status ob_dewarp(ob_dtype dtype, const void* points, const void* poses, size_t n_points,
+                    size_t n_poses, void* out, ob_stream* s);
+
 /* ---- fused range -> (XYZ, destaggered range, destaggered XYZ), batched over frames ----
  * One launch performs, for every frame f and return r of the batch, what the reference does as
  * separate passes: lut(range) (xyzlut.h:139-150) and destagger<uint32_t>(range, shifts)

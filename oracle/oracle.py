@@ -137,6 +137,9 @@ def lib():
         getattr(L, n).argtypes = [vp, vp, vp, vp, sz]
         getattr(L, n).restype = None
     L.orc_make_xyz_lut.argtypes = [sz, sz, C.c_double, vp, vp, vp, sz, vp, sz, vp, vp]
+    for n in ("orc_dewarp_f64", "orc_dewarp_f32"):
+        getattr(L, n).argtypes = [vp, vp, vp, sz, sz]
+        getattr(L, n).restype = None
     L.orc_snapshot_hash.argtypes = [vp, sz, sz]
     L.orc_snapshot_hash.restype = u64
     _lib = L
@@ -380,6 +383,17 @@ def make_xyz_lut(w, h, range_unit, beam_to_lidar, transform, az_deg, alt_deg):
     if rc == -2:
         raise ValueError("unexpected frame dimensions")
     return d, o
+
+
+def dewarp(points, poses):
+    """dewarp<T>(points (H,W,3)|(N,3), poses (W,4,4)|(W,16)) -- pose_util.h:37-59."""
+    pts = np.ascontiguousarray(points)
+    ps = np.ascontiguousarray(poses, dtype=pts.dtype).reshape(-1, 16)
+    out = np.empty_like(pts)
+    n = pts.size // 3
+    name = {np.dtype(np.float32): "orc_dewarp_f32", np.dtype(np.float64): "orc_dewarp_f64"}[pts.dtype]
+    getattr(lib(), name)(_ptr(out), _ptr(pts), _ptr(ps), n, ps.shape[0])
+    return out
 
 
 def snapshot_hash(a):

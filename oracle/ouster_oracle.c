@@ -1089,6 +1089,28 @@ int orc_make_xyz_lut(size_t w, size_t h, double range_unit, const double* b2l, c
     return 0;
 }
 
+/* dewarp<T> -- pose_util.h:37-59 (transform<T> is the W == 1 case, :118-131) */
+#define ORC_DEWARP_BODY(T)                                                              \
+    for (size_t wv = 0; wv < w; ++wv) {                                                 \
+        const T* m = poses + wv * 16;                                                   \
+        const size_t hh = n / w;                                                        \
+        for (size_t i = 0; i < hh; ++i) {                                               \
+            const size_t ix = i * w + wv;                                               \
+            const T x = pts[ix * 3], y = pts[ix * 3 + 1], z = pts[ix * 3 + 2];         \
+            for (int r = 0; r < 3; ++r) {                                               \
+                const T a = m[r * 4] * x, b = m[r * 4 + 1] * y, c = m[r * 4 + 2] * z;  \
+                out[ix * 3 + r] = (a + (b + c)) + m[r * 4 + 3];                         \
+            }                                                                           \
+        }                                                                               \
+    }
+
+void orc_dewarp_f64(double* out, const double* pts, const double* poses, size_t n, size_t w) {
+    ORC_DEWARP_BODY(double)
+}
+void orc_dewarp_f32(float* out, const float* pts, const float* poses, size_t n, size_t w) {
+    ORC_DEWARP_BODY(float)
+}
+
 /* matrix_hash -- tests/frame_batcher_test.cpp:595-606 (libstdc++ std::hash<int> = identity) */
 uint64_t orc_snapshot_hash(const void* data, size_t n, size_t elem_size) {
     uint64_t seed = 0;

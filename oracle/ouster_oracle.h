@@ -187,6 +187,13 @@ int orc_make_xyz_lut(size_t w, size_t h, double range_unit, const double* beam_t
                      const double* transform /*4x4 rm*/, const double* az_deg, size_t n_az,
                      const double* alt_deg, size_t n_alt, double* direction, double* offset);
 
+/* ---- dewarp / transform -- ouster_core/include/ouster/core/pose_util.h:37-59, 118-131 ----
+ * out[i*W + w] = R_w * p[i*W + w] + t_w, poses = W x 16 (row-major 4x4 each); n = H*W points.
+ * The 3-term dot products are summed as x0 + (x1 + x2) (Eigen's redux_novec_unroller split for
+ * length 3); the reference's own test only pins this to rtol 1e-5 (python/tests/test_pose_util.py:334-360). */
+void orc_dewarp_f64(double* out, const double* pts, const double* poses, size_t n, size_t w);
+void orc_dewarp_f32(float* out, const float* pts, const float* poses, size_t n, size_t w);
+
 /* std::hash-combine snapshot of a field, tests/frame_batcher_test.cpp:595-606 */
 uint64_t orc_snapshot_hash(const void* data, size_t n, size_t elem_size);
 

@@ -93,6 +93,7 @@ _sig("ob_lut_device_ptrs", i32, vp, C.POINTER(vp), C.POINTER(vp))
 _sig("ob_lut_destroy", i32, vp)
 _sig("ob_cartesian", i32, vp, vp, sz, vp, vp)
 _sig("ob_destagger", i32, sz, sz, vp, vp, sz, sz, sz, i32, vp, vp)
+_sig("ob_dewarp", i32, i32, vp, vp, sz, sz, vp, vp)
 _sig("ob_scan_to_cloud", i32, vp, vp, sz, C.POINTER(CloudIO), vp)
 if hasattr(lib, "ob_decoder_create"):
     _sig("ob_decoder_create", i32, C.POINTER(PacketLayout), C.POINTER(FieldDesc), sz, i32,

@@ -280,6 +280,43 @@ def destagger(img, pixel_shift_by_row, inverse=False, out=None, stream=None, dev
     return out
 
 
+def dewarp(points, poses, out=None, stream=None, device=0):
+    """dewarp(points (H, W, 3), poses (W, 4, 4)) -> (H, W, 3): per-column pose application
+    (python/src/cpp/client/processing.cpp:132-161; pose_util.h:37-59).  float32 or float64."""
+    st = _stream(stream, device)
+    dt = _np_dtype(points)
+    if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("points must be float32 or float64")
+    if not _is_torch(poses):
+        poses = np.ascontiguousarray(poses, dt)
+    n_points = _numel(points) // 3
+    n_poses = _numel(poses) // 16
+    if len(points.shape) == 3 and points.shape[1] != n_poses:
+        raise RuntimeError("Number of points per set must match number of poses")
+    own = out is None
+    if own:
+        if _is_torch(points):
+            import torch
+            out = torch.empty_like(points)
+        else:
+            points = np.ascontiguousarray(points)
+            out = np.empty_like(points)
+    status = lib.ob_dewarp(_capi.OB_F64 if dt == np.float64 else _capi.OB_F32, _ptr(points), _ptr(poses),
+                           n_points, n_poses, _ptr(out), st.h)
+    if status == _capi.OB_RUNTIME_ERROR:
+        raise RuntimeError(lib.ob_last_error().decode())
+    check(status)
+    if own and not (_is_torch(out) and out.is_cuda):
+        st.sync()
+    return out
+
+
+def transform(points, pose, out=None, stream=None, device=0):
+    """transform(points (..., 3), pose (4, 4)): one pose for every point (pose_util.h:118-131)."""
+    pose = pose if _is_torch(pose) else np.ascontiguousarray(pose, _np_dtype(points)).reshape(1, 16)
+    return dewarp(points, pose, out=out, stream=stream, device=device)
+
+
 def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None,
                   xyz_destaggered=None, stream=None):
     """Fused batch: rng is [F, R, H, W] uint32; outputs [F, R, H*W, 3] (xyz), [F, R, H, W]

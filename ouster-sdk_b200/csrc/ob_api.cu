@@ -541,6 +541,37 @@ ob_status ob_cartesian(const ob_lut* lut, const uint32_t* range, size_t n_pixels
     return ob_scan_to_cloud(lut, nullptr, 0, &io, s);
 }
 
+ob_status ob_dewarp(ob_dtype dtype, const void* points, const void* poses, size_t n_points,
+                    size_t n_poses, void* out, ob_stream* s) {
+    if (!s) return fail(OB_INVALID_ARGUMENT, "null stream");
+    if (dtype != OB_F32 && dtype != OB_F64) return fail(OB_INVALID_ARGUMENT, "unknown dtype");
+    if (n_points == 0) return OB_OK;
+    if (!points || !poses || !out) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (n_poses == 0 || n_points % n_poses != 0)
+        return fail(OB_RUNTIME_ERROR, "Number of points per set must match number of poses");
+    ob_status rs = require_device(s->device);
+    if (rs != OB_OK) return rs;
+    const size_t esz = dtype == OB_F64 ? 8 : 4;
+    Staging stg(s->st);
+    const void *dp = nullptr, *dq = nullptr;
+    void* dout = nullptr;
+    cudaError_t e = stg.in(points, n_points * 3 * esz, &dp);
+    if (e == cudaSuccess) e = stg.in(poses, n_poses * 16 * esz, &dq);
+    if (e == cudaSuccess) e = stg.out(out, n_points * 3 * esz, &dout);
+    if (e != cudaSuccess) return fail_cuda(e, "stage dewarp buffers");
+    const size_t H = n_points / n_poses;
+    if (dtype == OB_F64)
+        e = launch_dewarp<double>(static_cast<const double*>(dp), static_cast<const double*>(dq),
+                                  static_cast<double*>(dout), H, n_poses, s->st);
+    else
+        e = launch_dewarp<float>(static_cast<const float*>(dp), static_cast<const float*>(dq),
+                                 static_cast<float*>(dout), H, n_poses, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp launch");
+    e = stg.flush();
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp D2H");
+    return OB_OK;
+}
+
 ob_status ob_destagger(size_t elem_size, size_t k, const void* img, const int32_t* shifts,
                        size_t n_shifts, size_t h, size_t w, int inverse, void* out, ob_stream* s) {
     if (!s) return fail(OB_INVALID_ARGUMENT, "null stream");

@@ -425,6 +425,61 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// dewarp / transform: out[i*W + w] = R_w * p[i*W + w] + t_w  (pose_util.h:37-59, 118-131).
+// A CTA stages the 3x4 parts of 128 consecutive column poses in shared memory and sweeps a band of
+// rows; lane = column, so point loads/stores are contiguous 384-byte runs per warp.
+// Products are rounded separately and summed as x0 + (x1 + x2), then + t (no FMA contraction).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float madd3(float a0, float b0, float a1, float b1, float a2, float b2, float t) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2))), t);
+}
+__device__ __forceinline__ double madd3(double a0, double b0, double a1, double b1, double a2, double b2, double t) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a0, b0), __dadd_rn(__dmul_rn(a1, b1), __dmul_rn(a2, b2))), t);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dewarp_kernel(const T* __restrict__ pts, const T* __restrict__ poses,
+                                                     T* __restrict__ out, unsigned long long H,
+                                                     unsigned long long W, unsigned rows_per_block) {
+    __shared__ T sp[128 * 12];
+    const unsigned long long c0 = static_cast<unsigned long long>(blockIdx.x) * 128ull;
+    const unsigned ncol = static_cast<unsigned>(min(128ull, W - c0));
+    for (unsigned i = threadIdx.x; i < ncol * 12u; i += blockDim.x)
+        sp[i] = poses[(c0 + i / 12u) * 16ull + (i % 12u)];
+    __syncthreads();
+    const unsigned lc = threadIdx.x & 127u;          // column inside the block
+    const unsigned rsub = threadIdx.x >> 7;           // 2 rows in flight per 256 threads
+    if (lc >= ncol) return;
+    const T* m = sp + lc * 12u;
+    const unsigned long long r0 = static_cast<unsigned long long>(blockIdx.y) * rows_per_block;
+    const unsigned long long r1 = min(H, r0 + rows_per_block);
+    for (unsigned long long row = r0 + rsub; row < r1; row += 2) {
+        const unsigned long long ix = (row * W + c0 + lc) * 3ull;
+        const T x = pts[ix], y = pts[ix + 1], z = pts[ix + 2];
+        out[ix] = madd3(m[0], x, m[1], y, m[2], z, m[3]);
+        out[ix + 1] = madd3(m[4], x, m[5], y, m[6], z, m[7]);
+        out[ix + 2] = madd3(m[8], x, m[9], y, m[10], z, m[11]);
+    }
+}
+
+template <typename T>
+cudaError_t launch_dewarp(const T* pts, const T* poses, T* out, size_t H, size_t W, cudaStream_t st) {
+    if (H == 0 || W == 0) return cudaSuccess;
+    const unsigned col_blocks = static_cast<unsigned>((W + 127) / 128);
+    // enough row bands to fill the machine, at least 8 rows each
+    unsigned bands = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(H / 8 + 1, 2368 / std::max(1u, col_blocks) + 1)));
+    unsigned rows_per_block = static_cast<unsigned>((H + bands - 1) / bands);
+    bands = static_cast<unsigned>((H + rows_per_block - 1) / rows_per_block);
+    if (bands > 65535) return cudaErrorInvalidValue;
+    dim3 grid(col_blocks, bands);
+    dewarp_kernel<T><<<grid, 256, 0, st>>>(pts, poses, out, H, W, rows_per_block);
+    count_launch();
+    return cudaGetLastError();
+}
+template cudaError_t launch_dewarp<float>(const float*, const float*, float*, size_t, size_t, cudaStream_t);
+template cudaError_t launch_dewarp<double>(const double*, const double*, double*, size_t, size_t, cudaStream_t);
+
 template cudaError_t launch_cloud<float>(const CloudArgs<float>&, int, cudaStream_t);
 template cudaError_t launch_cloud<double>(const CloudArgs<double>&, int, cudaStream_t);
 

@@ -45,6 +45,9 @@ struct CloudArgs {
 template <typename T>
 cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st);
 
+template <typename T>
+cudaError_t launch_dewarp(const T* pts, const T* poses, T* out, size_t H, size_t W, cudaStream_t st);
+
 cudaError_t launch_destagger(size_t elem_size, size_t k, const void* img, const uint16_t* shift_host,
                              size_t h, size_t w, void* out, int device, cudaStream_t st);
 

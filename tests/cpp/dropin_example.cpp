@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ouster/core/lidar_scan.h"  // deprecated forwarding header
+#include "ouster/core/pose_util.h"
 #include "ouster/core/xyzlut.h"
 
 using namespace ouster::sdk::core;
@@ -130,6 +131,25 @@ int main() {
             cartesian(ArrayRef<const uint32_t>(small), lut);
         },
         "unexpected image dimensions");
+
+    // ---- dewarp: per-column poses (python/tests/test_pose_util.py:334-360 known answer) ----
+    {
+        MatrixX16R<double> poses(4, 16);
+        const double pose[16] = {1, 0, 0, 1, 0, 1, 0, -2, 0, 0, 1, 3, 0, 0, 0, 1};
+        for (int w2 = 0; w2 < 4; ++w2)
+            for (int k = 0; k < 16; ++k) poses(w2, k) = pose[k];
+        PointCloudXYZd pts(8, 3);
+        for (int i = 0; i < 8; ++i) {
+            pts(i, 0) = i - 3;
+            pts(i, 1) = i + 1;
+            pts(i, 2) = i + 2;
+        }
+        PointCloudXYZd dw = dewarp<double>(pts, poses);
+        for (int i = 0; i < 8; ++i)
+            CHECK(dw(i, 0) == pts(i, 0) + 1 && dw(i, 1) == pts(i, 1) - 2 && dw(i, 2) == pts(i, 2) + 3);
+        PointCloudXYZd tr = transform<double>(pts, pose);
+        CHECK(tr == dw);
+    }
 
     // ---- frame_to_packets -> ScanBatcher -> LidarScan round trip ----
     PacketFormat pf(*info);

@@ -1,0 +1,63 @@
+"""Next-row: per-column pose application.  Known answers are the reference's own
+(python/tests/test_pose_util.py:300-360, rtol 1e-5); GPU vs oracle is bit-exact."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as graft
+from oracle import oracle as orc
+
+
+def _ref_cases():
+    poses = np.array([[1, 0, 0, 1, 0, 1, 0, -2, 0, 0, 1, 3, 0, 0, 0, 1] for _ in range(4)], np.float64)
+    points = np.array([[i - 3, i + 1, i + 2] for i in range(8)], np.float64).reshape(2, 4, 3)
+    expected = np.array([[[-2, -1, 5], [-1, 0, 6], [0, 1, 7], [1, 2, 8]],
+                         [[2, 3, 9], [3, 4, 10], [4, 5, 11], [5, 6, 12]]], np.float64)
+    pts2 = np.arange(1, 25, dtype=np.float64).reshape(2, 4, 3)
+    tf = np.array([[0.866, -0.5, 0.0, 1.0], [0.5, 0.866, 0.0, 2.0], [0.0, 0.0, 1.0, -1.0], [0, 0, 0, 1.0]])
+    exp2 = np.array([[[0.866, 4.232, 2], [1.964, 8.33, 5], [3.062, 12.428, 8], [4.16, 16.526, 11]],
+                     [[5.258, 20.624, 14], [6.356, 24.722, 17], [7.454, 28.82, 20], [8.552, 32.918, 23]]])
+    return poses, points, expected, pts2, tf, exp2
+
+
+def test_oracle_dewarp_known_answers():
+    poses, points, expected, pts2, tf, exp2 = _ref_cases()
+    np.testing.assert_allclose(orc.dewarp(points, poses), expected, rtol=1e-5, atol=1e-8)
+    np.testing.assert_almost_equal(orc.dewarp(pts2.reshape(-1, 3), tf.reshape(1, 16)).reshape(2, 4, 3), exp2, decimal=5)
+
+
+@pytest.fixture(scope="module")
+def ob():
+    graft.build()
+    m = graft.load_package()
+    assert m.device_count() > 0
+    return m
+
+
+@pytest.mark.gpu
+def test_gpu_dewarp_known_answers(ob):
+    poses, points, expected, pts2, tf, exp2 = _ref_cases()
+    got = ob.dewarp(points, poses.reshape(4, 4, 4))
+    assert got.shape == (2, 4, 3)
+    np.testing.assert_allclose(got, expected, rtol=1e-5, atol=1e-8)
+    np.testing.assert_almost_equal(ob.transform(pts2, tf), exp2, decimal=5)
+    with pytest.raises(RuntimeError, match="Number of points per set must match number of poses"):
+        ob.dewarp(np.zeros((2, 5, 3)), poses.reshape(4, 4, 4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w", [(128, 2048), (64, 1024), (7, 130), (1, 1)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gpu_dewarp_matches_oracle(ob, h, w, dtype):
+    rs = np.random.default_rng(h * w)
+    pts = (rs.random((h, w, 3)) * 100 - 50).astype(dtype)
+    ang = rs.random(w) * 2 * np.pi
+    poses = np.zeros((w, 4, 4), dtype)
+    poses[:, 0, 0], poses[:, 0, 1] = np.cos(ang), -np.sin(ang)
+    poses[:, 1, 0], poses[:, 1, 1] = np.sin(ang), np.cos(ang)
+    poses[:, 2, 2] = 1
+    poses[:, 3, 3] = 1
+    poses[:, :3, 3] = rs.random((w, 3)) * 10
+    got = ob.dewarp(pts, poses)
+    assert np.array_equal(got, orc.dewarp(pts, poses))
+    ref = np.einsum("wij,hwj->hwi", poses[:, :3, :3].astype(np.float64), pts.astype(np.float64)) + poses[None, :, :3, 3]
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-4 if dtype == np.float32 else 1e-9)
