@@ -314,7 +314,10 @@ def dewarp(points, poses, out=None, stream=None, device=0):
 def transform(points, pose, out=None, stream=None, device=0):
     """transform(points (..., 3), pose (4, 4)): one pose for every point (pose_util.h:118-131)."""
     pose = pose if _is_torch(pose) else np.ascontiguousarray(pose, _np_dtype(points)).reshape(1, 16)
-    return dewarp(points, pose, out=out, stream=stream, device=device)
+    shape = tuple(points.shape)
+    flat = points.reshape(-1, 3)
+    res = dewarp(flat, pose, out=None if out is None else out.reshape(-1, 3), stream=stream, device=device)
+    return res.reshape(shape)
 
 
 def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None,
