@@ -45,10 +45,11 @@ static Tunables& tunables_mut(int device) {
         t.cloud_stages = std::max(2, env_int("OB_CLOUD_STAGES", 4));
         t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 256)));
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
+        t.cloud_frames_per_lut = env_int("OB_CLOUD_FRAMES_PER_LUT", 4);
         t.decode_stages = std::max(1, env_int("OB_DECODE_STAGES", 1));
         t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384)));
         t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
-        t.decode_tile_packets = std::max(1, env_int("OB_DECODE_TILE_PACKETS", 2));
+        t.decode_tile_packets = std::max(0, env_int("OB_DECODE_TILE_PACKETS", 0));  // 0 = auto
         t.force_fallback = env_int("OB_FORCE_FALLBACK", 0);
         int sm = 148;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
@@ -75,10 +76,11 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "cloud_stages") t.cloud_stages = std::max(2, value);
     else if (n == "cloud_threads") t.cloud_threads = std::min(256, std::max(32, value / 32 * 32));
     else if (n == "cloud_ctas_per_sm") t.cloud_ctas_per_sm = std::max(1, value);
+    else if (n == "cloud_frames_per_lut") t.cloud_frames_per_lut = value;
     else if (n == "decode_stages") t.decode_stages = std::max(1, value);
     else if (n == "decode_threads") t.decode_threads = std::min(384, std::max(64, value / 32 * 32));
     else if (n == "decode_ctas_per_sm") t.decode_ctas_per_sm = std::max(1, value);
-    else if (n == "decode_tile_packets") t.decode_tile_packets = std::max(1, value);
+    else if (n == "decode_tile_packets") t.decode_tile_packets = std::max(0, value);
     else if (n == "force_fallback") t.force_fallback = value;
     else return false;
     return true;

@@ -39,6 +39,7 @@ struct CloudParams {
     T* xd;
     unsigned long long range_fs, range_rs, xyz_fs, xyz_rs, rd_fs, rd_rs, xd_fs, xd_rs;
     int H, W, TW, tiles_per_row, stages;
+    int fb;                    // frames that share one staged LUT tile (v2 kernel), 1 = v1 kernel
     unsigned n_frames, n_tiles, stage_bytes;
     unsigned short shift[kMaxRows];
 };
@@ -305,6 +306,223 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
     if (tid == 0) bulk_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: LUT-stationary variant for batches.  A CTA keeps the direction/offset slices of one
+// (row, column chunk) in shared memory (double buffered) and streams the range slices of FB
+// consecutive frames through the ring, so the LUT is read from L2 once per FB frames instead of
+// once per frame (the v1 kernel is L2-throughput bound on those re-reads).  The projection writes
+// into a per-stage output buffer; everything else (TMA in, TMA out, shuffle realignment) is as v1.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int R>
+__global__ void __launch_bounds__(256) cloud_tma_kernel_v2(const __grid_constant__ CloudParams<T> p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // S range barriers
+    uint64_t* lutbar = reinterpret_cast<uint64_t*>(smem + 64);  // 2 LUT barriers
+    uint8_t* lut0 = smem + 128;
+    const int tid = threadIdx.x;
+    const int S = p.stages;
+    const int FB = p.fb;
+    const unsigned lut_bytes_full = 3u * p.TW * sizeof(T);
+    const unsigned lut_buf = 2u * lut_bytes_full;          // dir | off
+    uint8_t* stage0 = lut0 + 2u * lut_buf;
+    const unsigned rng_bytes_full = R * 4u * p.TW;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_init(&lutbar[0], 1);
+        mbar_init(&lutbar[1], 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    // super tile = (frame block, row, chunk); p.n_tiles counts super tiles here
+    const unsigned first = blockIdx.x;
+    const unsigned n_super = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned n_units = n_super * FB;
+
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (tid == 0) {
+        pol_keep = policy_evict_last();
+        pol_stream = policy_evict_first();
+    }
+    auto super_coord = [&](unsigned si) {  // -> tile coordinates with f = first frame of the block
+        TileCoord tc = tile_coord(p, first + si * gridDim.x);
+        tc.f *= FB;
+        return tc;
+    };
+    auto issue_lut = [&](unsigned si) {  // thread 0
+        const TileCoord tc = super_coord(si);
+        uint8_t* lb = lut0 + (si & 1u) * lut_buf;
+        const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
+        const unsigned lut_b = 3u * tc.tw * sizeof(T);
+        mbar_expect_tx(&lutbar[si & 1u], 2u * lut_b);
+        bulk_g2s_hint(lb, p.dir + px * 3, lut_b, &lutbar[si & 1u], pol_keep);
+        bulk_g2s_hint(lb + lut_bytes_full, p.off + px * 3, lut_b, &lutbar[si & 1u], pol_keep);
+    };
+    auto issue_range = [&](unsigned k) {  // thread 0
+        const unsigned si = k / FB, j = k - si * FB;
+        const TileCoord tc = super_coord(si);
+        const int s = k % S;
+        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+        const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
+        const unsigned rng_b = 4u * tc.tw;
+        mbar_expect_tx(&full[s], R * rng_b);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            bulk_g2s_hint(st + r * 4u * p.TW, p.range + (tc.f + j) * p.range_fs + r * p.range_rs + px,
+                          rng_b, &full[s], pol_stream);
+    };
+
+    if (tid == 0 && n_units > 0) {
+        issue_lut(0);
+        const unsigned pre = min(n_units, static_cast<unsigned>(S));
+        for (unsigned k = 0; k < pre; ++k) issue_range(k);
+    }
+
+    for (unsigned k = 0; k < n_units; ++k) {
+        const int s = k % S;
+        const unsigned si = k / FB, j = k - si * FB;
+        if (tid == 0) {
+            if (k >= 1 && (k - 1 + S) < n_units) {  // refill the stage unit k-1 used
+                bulk_wait_read<0>();
+                issue_range(k - 1 + S);
+            }
+            // first unit of a super tile: prefetch the next LUT slice into the other buffer
+            // (its previous user, super tile si-1, finished behind the last __syncthreads)
+            if (j == 0 && si + 1 < n_super) issue_lut(si + 1);
+        }
+        TileCoord tc = super_coord(si);
+        tc.f += j;
+        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+        const T* dir_s = reinterpret_cast<const T*>(lut0 + (si & 1u) * lut_buf);
+        const T* off_s = reinterpret_cast<const T*>(lut0 + (si & 1u) * lut_buf + lut_bytes_full);
+        uint32_t* rng_s = reinterpret_cast<uint32_t*>(st);
+        T* out_s = reinterpret_cast<T*>(st + rng_bytes_full);  // R buffers of 3*TW scalars
+
+        mbar_wait(&full[s], (k / S) & 1);
+        if (j == 0) mbar_wait(&lutbar[si & 1u], (si >> 1) & 1u);
+
+        const int sh = (p.rd != nullptr || p.xd != nullptr) ? p.shift[tc.row] : 0;
+        const int q = sh & 3;
+        const int n_groups = tc.tw >> 2;
+
+        if (p.rd != nullptr && q != 0) {  // destaggered range, unaligned shift: warp-shuffle realignment
+            const int lane = tid & 31;
+            const int nv = n_groups;
+            const int base_col = tc.c0 + sh - q;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(rng_s + r * p.TW);
+                uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + static_cast<size_t>(tc.row) * p.W;
+                for (int m0 = (tid >> 5) * 32; m0 <= nv; m0 += blockDim.x) {
+                    const int m = m0 + lane;
+                    uint4 b = make_uint4(0, 0, 0, 0);
+                    if (m < nv) b = s4[m];
+                    uint4 a;
+                    a.x = __shfl_up_sync(0xffffffffu, b.x, 1);
+                    a.y = __shfl_up_sync(0xffffffffu, b.y, 1);
+                    a.z = __shfl_up_sync(0xffffffffu, b.z, 1);
+                    a.w = __shfl_up_sync(0xffffffffu, b.w, 1);
+                    if (lane == 0) a = (m > 0 && m <= nv) ? s4[m - 1] : make_uint4(0, 0, 0, 0);
+                    if (m > nv) continue;
+                    uint4 o;
+                    if (q == 1) o = make_uint4(a.w, b.x, b.y, b.z);
+                    else if (q == 2) o = make_uint4(a.z, a.w, b.x, b.y);
+                    else o = make_uint4(a.y, a.z, a.w, b.x);
+                    int col = base_col + 4 * m;
+                    col = col >= p.W ? col - p.W : col;
+                    col = col >= p.W ? col - p.W : col;
+                    uint32_t* dst = drow + col;
+                    if (m == 0) {
+                        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+                        for (int e = q; e < 4; ++e) stg_stream(dst + e, ov[e]);
+                    } else if (m == nv) {
+                        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+                        for (int e = 0; e < q; ++e) stg_stream(dst + e, ov[e]);
+                    } else {
+                        stg_stream(reinterpret_cast<uint4*>(dst), o);
+                    }
+                }
+            }
+        }
+
+        // ---- projection: LUT buffer (read only) x range slice -> per-stage output buffers ----
+        for (int g = tid; g < n_groups; g += blockDim.x) {
+            T d[12], o[12];
+            lds12(dir_s + 12 * g, d);
+            lds12(off_s + 12 * g, o);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint4 rr = reinterpret_cast<const uint4*>(rng_s + r * p.TW)[g];
+                const uint32_t rv[4] = {rr.x, rr.y, rr.z, rr.w};
+                T out[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) out[i] = project(rv[i / 3], d[i], o[i]);
+                sts12(out_s + static_cast<size_t>(r) * 3u * p.TW + 12 * g, out);
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+
+        bool thread_path_xd = false;
+        if (tid == 0) {
+            const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
+            if (p.xyz != nullptr) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    bulk_s2g(p.xyz + tc.f * p.xyz_fs + r * p.xyz_rs + px * 3,
+                             out_s + static_cast<size_t>(r) * 3u * p.TW, 3u * tc.tw * sizeof(T));
+            }
+            if (q == 0 && (p.rd != nullptr || p.xd != nullptr)) {
+                int d0 = tc.c0 + sh;
+                d0 = d0 >= p.W ? d0 - p.W : d0;
+                const int n1 = min(tc.tw, p.W - d0);
+                const size_t rowpx = static_cast<size_t>(tc.row) * p.W;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (p.rd != nullptr) {
+                        uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + rowpx;
+                        const uint32_t* src = rng_s + r * p.TW;
+                        bulk_s2g(drow + d0, src, 4u * n1);
+                        if (n1 < tc.tw) bulk_s2g(drow, src + n1, 4u * (tc.tw - n1));
+                    }
+                    if (p.xd != nullptr) {
+                        T* drow = p.xd + tc.f * p.xd_fs + r * p.xd_rs + rowpx * 3;
+                        const T* src = out_s + static_cast<size_t>(r) * 3u * p.TW;
+                        bulk_s2g(drow + static_cast<size_t>(d0) * 3, src, 3u * n1 * sizeof(T));
+                        if (n1 < tc.tw)
+                            bulk_s2g(drow, src + static_cast<size_t>(n1) * 3, 3u * (tc.tw - n1) * sizeof(T));
+                    }
+                }
+            }
+            bulk_commit();
+        }
+        if (p.xd != nullptr && q != 0) {  // destaggered XYZ, unaligned shift: coalesced word copies
+            thread_path_xd = true;
+            constexpr int WPE = sizeof(T) / 4;
+            const int row_words = p.W * 3 * WPE;
+            const int n_words = tc.tw * 3 * WPE;
+            int d0 = tc.c0 + sh;
+            d0 = d0 >= p.W ? d0 - p.W : d0;
+            const int dst0 = d0 * 3 * WPE;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                uint32_t* drow = reinterpret_cast<uint32_t*>(
+                    p.xd + tc.f * p.xd_fs + r * p.xd_rs + static_cast<size_t>(tc.row) * p.W * 3);
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(out_s + static_cast<size_t>(r) * 3u * p.TW);
+                for (int i = tid; i < n_words; i += blockDim.x) {
+                    int dw = dst0 + i;
+                    dw = dw >= row_words ? dw - row_words : dw;
+                    stg_stream(drow + dw, src[i]);
+                }
+            }
+        }
+        if (thread_path_xd) __syncthreads();
+    }
+    if (tid == 0) bulk_wait<0>();
+}
+
 // Generic kernel: any width / alignment / stride.  One pixel per thread, grid-stride.
 template <typename T>
 __global__ void cloud_generic_kernel(const __grid_constant__ CloudParams<T> p, int n_returns) {
@@ -386,6 +604,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
 
     if (!fast) {
         p.TW = 0;
+        p.fb = 1;
         p.tiles_per_row = 0;
         p.stages = 0;
         p.n_tiles = 0;
@@ -410,15 +629,42 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     p.TW = TW;
     p.tiles_per_row = (a.W + TW - 1) / TW;
     p.stages = tn.cloud_stages;
+    // LUT-stationary variant: FB = largest divisor of n_frames not above the tunable (>= 2)
+    int fb = 1;
+    if (need_lut && tn.cloud_frames_per_lut >= 2)
+        for (int c = std::min<int>(tn.cloud_frames_per_lut, static_cast<int>(a.n_frames)); c >= 2; --c)
+            if (a.n_frames % static_cast<unsigned>(c) == 0) {
+                fb = c;
+                break;
+            }
+    p.fb = fb;
+    cudaError_t e;
+    int grid;
+    size_t smem;
+    if (fb >= 2) {
+        p.stages = std::max(2, tn.cloud_stages - 1);
+        p.n_tiles = static_cast<unsigned>(a.H) * p.tiles_per_row * (a.n_frames / fb);  // super tiles
+        p.stage_bytes = static_cast<unsigned>(a.n_returns) * 4u * TW +
+                        static_cast<unsigned>(a.n_returns) * 3u * TW * static_cast<unsigned>(sizeof(T));
+        p.stage_bytes = (p.stage_bytes + 127u) & ~127u;
+        smem = 128 + 2u * (2u * 3u * TW * sizeof(T)) + static_cast<size_t>(p.stages) * p.stage_bytes;
+        grid = static_cast<int>(
+            std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm));
+        auto kern2 = a.n_returns == 2 ? cloud_tma_kernel_v2<T, 2> : cloud_tma_kernel_v2<T, 1>;
+        e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        kern2<<<std::max(grid, 1), tn.cloud_threads, smem, st>>>(p);
+        count_launch();
+        return cudaGetLastError();
+    }
     p.n_tiles = static_cast<unsigned>(a.H) * p.tiles_per_row * a.n_frames;
     p.stage_bytes = 2u * 3u * TW * sizeof(T) + static_cast<unsigned>(a.n_returns) * 4u * TW;
     p.stage_bytes = (p.stage_bytes + 127u) & ~127u;
-    const size_t smem = 128 + static_cast<size_t>(p.stages) * p.stage_bytes;
-    const int grid = static_cast<int>(
+    smem = 128 + static_cast<size_t>(p.stages) * p.stage_bytes;
+    grid = static_cast<int>(
         std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm));
     auto kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2> : cloud_tma_kernel<T, 1>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     kern<<<std::max(grid, 1), tn.cloud_threads, smem, st>>>(p);
     count_launch();

@@ -26,8 +26,8 @@
 
 namespace ob {
 
-constexpr int kMaxTileCols = 64;
-constexpr int kMaxStages = 8;
+constexpr int kMaxTileCols = 128;
+constexpr int kMaxStages = 4;
 
 struct DecodeParams {
     DecodeLayout L;
@@ -588,11 +588,19 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
     p.lut_dir = a.lut_dir;
     p.lut_off = a.lut_off;
     p.n_frames = a.n_frames;
-    p.P = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(std::max(tn.decode_tile_packets, 1)), 64 / L.cpp));
+    p.pkt_stride_s = (L.packet_size + 16 + 15) & ~15u;  // +16: slack for trailing 8-byte field reads
+    if (tn.decode_tile_packets > 0) {
+        p.P = static_cast<uint32_t>(tn.decode_tile_packets);
+    } else {
+        // auto: as many packets as fit a ~68 KB stage (3 CTAs per SM), power of two, at least 32 columns
+        p.P = 1;
+        while (p.P * 2 * p.pkt_stride_s <= 68u * 1024u && p.P * 2 * L.cpp <= static_cast<uint32_t>(kMaxTileCols))
+            p.P *= 2;
+    }
+    p.P = std::max<uint32_t>(1, std::min<uint32_t>(p.P, static_cast<uint32_t>(kMaxTileCols) / L.cpp));
     p.TC = p.P * L.cpp;
     p.tiles_per_frame = (L.W + p.TC - 1) / p.TC;
     p.n_tiles = p.tiles_per_frame * a.n_frames;
-    p.pkt_stride_s = (L.packet_size + 16 + 15) & ~15u;  // +16: slack for trailing 8-byte field reads
     p.stage_bytes = (p.P * p.pkt_stride_s + 127) & ~127u;
     p.stages = std::min(std::max(tn.decode_stages, 1), kMaxStages);
     const bool word_aligned = (L.packet_header_size % 4 == 0) && (L.col_header_size % 4 == 0) &&

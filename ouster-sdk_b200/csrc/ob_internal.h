@@ -17,6 +17,7 @@ struct Tunables {
     int cloud_stages;      // TMA ring depth
     int cloud_threads;     // threads per CTA
     int cloud_ctas_per_sm; // persistent CTAs per SM
+    int cloud_frames_per_lut;  // frames sharing a staged LUT tile (K1 v2); < 2 disables v2
     int decode_stages;
     int decode_threads;
     int decode_ctas_per_sm;
