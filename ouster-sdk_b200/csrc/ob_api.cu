@@ -45,7 +45,7 @@ static Tunables& tunables_mut(int device) {
         t.cloud_stages = std::max(2, env_int("OB_CLOUD_STAGES", 4));
         t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 256)));
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
-        t.cloud_frames_per_lut = env_int("OB_CLOUD_FRAMES_PER_LUT", 4);
+        t.cloud_frames_per_lut = env_int("OB_CLOUD_FRAMES_PER_LUT", 0);
         t.decode_stages = std::max(1, env_int("OB_DECODE_STAGES", 1));
         t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384)));
         t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
