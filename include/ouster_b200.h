@@ -189,8 +189,10 @@ ob_status ob_decoder_destroy(ob_decoder* dec);
  * col_src[j] (host, w entries) = slot*columns_per_packet + column index of the packet column whose
  *   pixel data lands in frame column j, or -1: column j is zero-filled (missing / invalid / dropped).
  *   NULL means the identity map (slot j/cpp, column j%cpp): a complete in-order frame.
- * hdr_src: same for the per-column headers (timestamp/measurement_id/status); NULL = col_src.
- *   (They differ only when block parsing meets non-consecutive measurement ids, parsing.cpp:647-653.)
+ * The optional device copies of the column headers (timestamp / measurement_id / status) are decoded
+ *   from the same packet column as the pixels (col_src).  FrameBatcher writes the LidarFrame's own
+ *   header arrays on the host, exactly like the reference, including the corner case where block
+ *   parsing meets non-consecutive measurement ids (parsing.cpp:647-653).
  * fields[i]: h x w row-major image of fields[i].elem_size bytes for decoder field i; NULL = skip.
  * Fused consumers (all optional): with lut != NULL, xyz[r] / range_destaggered[r] receive the same
  * products as ob_scan_to_cloud for the range field(s) tagged with range_return = r.
@@ -199,7 +201,6 @@ typedef struct ob_decode_io {
     const uint8_t* packets;
     size_t n_slots, packet_stride;
     const int32_t* col_src;
-    const int32_t* hdr_src;
     void* fields[OB_MAX_FIELDS];
     uint64_t* timestamp;      /* w */
     uint16_t* measurement_id; /* w */

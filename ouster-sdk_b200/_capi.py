@@ -45,7 +45,7 @@ class PacketLayout(C.Structure):
 
 class DecodeIO(C.Structure):
     _fields_ = [("packets", vp), ("n_slots", sz), ("packet_stride", sz),
-                ("col_src", vp), ("hdr_src", vp),
+                ("col_src", vp),
                 ("fields", vp * OB_MAX_FIELDS),
                 ("timestamp", vp), ("measurement_id", vp), ("status", vp),
                 ("xyz", vp * OB_MAX_RETURNS), ("range_destaggered", vp * OB_MAX_RETURNS),

@@ -83,7 +83,6 @@ struct DecodeFrame {  // one per frame of a batched launch, lives in device memo
     uint32_t n_slots;
     uint32_t flags;          // bit0: identity column map
     const int32_t* col_src;  // device, W entries (unused when identity)
-    const int32_t* hdr_src;  // device, W entries
     void* fields[OB_MAX_FIELDS];
     uint64_t* timestamp;
     uint16_t* measurement_id;
