@@ -160,35 +160,47 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
         roundtrip = ok
         dev0 = ([xyz[r][0].cpu().numpy() for r in range(R)], [rd[r][0].cpu().numpy().view(np.uint32) for r in range(R)])
 
-    # ---- e2e: host packets -> product FrameBatcher -> host LidarFrame + fused cloud ----
+    # ---- e2e: page-locked host packets -> product FramePipeline (FrameBatcher host state machine,
+    #      3 frames in flight) -> host LidarFrame fields + fused cloud, every frame H2D + D2H ----
     ob.set_device(local_rank)
-    batcher = ob.FrameBatcher(si)
-    batcher.set_fused_cloud(lut, SHIFTS)
-    frame = ob.LidarFrame(si)
-    e2e_frames = min(F, 16)
-
+    pipe = ob.FramePipeline(si, depth=3, lut=frame_luts[0], pixel_shift_by_row=SHIFTS)
+    e2e_frames = 2 * F
+    pin_pool = ob.pinned_empty((e2e_frames,) + pool.shape[1:], np.uint8)
+    pin_pool[:F] = pool
+    pin_pool[F:] = pool
     host_ts = 10 + np.arange(n_slots, dtype=np.uint64)
 
-    def e2e_step():
-        n_done = 0
+    def stamp_ids(base):   # distinct, increasing frame ids so that no packet is dropped as "old frame"
         for i in range(e2e_frames):
-            used, done = batcher.batch_burst(pool[i % F], host_ts, frame)   # 128 packets -> 1 frame
-            n_done += int(done and used == n_slots)
-        return n_done
+            fid = base + i
+            pin_pool[i, :, 2] = fid & 0xff
+            pin_pool[i, :, 3] = (fid >> 8) & 0xff
 
-    # distinct, increasing frame ids so that no packet is dropped as "old frame"
-    for i in range(F):
-        fid = 1000 + i
-        pool[i, :, 2] = fid & 0xff
-        pool[i, :, 3] = (fid >> 8) & 0xff
-    e2e_step()
-    for i in range(F):  # fresh ids for the timed pass
-        fid = 3000 + i
-        pool[i, :, 2] = fid & 0xff
-        pool[i, :, 3] = (fid >> 8) & 0xff
+    def e2e_step(check=False):
+        n_done, ok = 0, True
+        def retire(slot):
+            nonlocal n_done, ok
+            if check and n_done == 0:   # frame 0 of the pool: fields == source frame, cloud == device path
+                for f in dec.fields:
+                    ok &= bool(np.array_equal(slot.frame.field(f["name"]), src_frames[0].field(f["name"])))
+                for r in range(R):
+                    ok &= bool(np.array_equal(slot.xyz[r], xyz[r][0].cpu().numpy().reshape(-1, 3)))
+                    ok &= bool(np.array_equal(slot.range_destaggered[r], rd[r][0].cpu().numpy().view(np.uint32)))
+            n_done += 1
+        for i in range(e2e_frames):
+            used, slot = pipe.push_burst(pin_pool[i], host_ts)   # 128 packets -> 1 frame
+            if slot is not None:
+                retire(slot)
+        while (slot := pipe.drain()) is not None:
+            retire(slot)
+        return n_done, ok
+
+    stamp_ids(1000)
+    _, e2e_ok = e2e_step(check=True)
+    stamp_ids(3000)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    done = e2e_step()
+    done, _ = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -248,8 +260,9 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
         "e2e": {"value": e2e_val, "unit": "Mpoints/s",
                 "h2d_bytes_per_step": int(e2e_frames * n_slots * psz),
                 "d2h_bytes_per_step": int(e2e_frames * (field_bytes + R * H * W * 16)),
-                "frames": e2e_frames, "frames_completed": int(done),
-                "path": "FrameBatcher.batch() per packet (host state machine) + fused GPU launch per frame"},
+                "frames": e2e_frames, "frames_completed": int(done), "matches_device_path": bool(e2e_ok),
+                "path": "FramePipeline.push_burst (FrameBatcher host state machine per packet, zero-copy "
+                        "upload from page-locked bursts, 3 frames in flight) + one fused launch per frame"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "parity_vs_oracle": parity,

@@ -26,6 +26,7 @@
 #include "ouster/core/visibility.h"
 
 struct ob_decoder;
+struct ob_decode_job;
 struct ob_stream;
 struct ob_lut;
 
@@ -279,6 +280,24 @@ class OUSTER_API_CLASS FrameBatcher {
     OUSTER_API_FUNCTION void set_headers_only(bool on);
     /// Kernel launches issued by this batcher.
     OUSTER_API_FUNCTION size_t gpu_launches() const;
+    /// Feed `n` packets laid out `stride` bytes apart (host_timestamps[i] belongs to packet i) until
+    /// a frame completes; returns the number of packets consumed.  When the burst lies in
+    /// page-locked (cudaHostAlloc / cudaHostRegister) or device memory the copy engine reads the
+    /// packets where they are (no staging memcpy); the memory may be reused as soon as the call returns.
+    OUSTER_API_FUNCTION size_t batch_burst(const uint8_t* packets, size_t n, size_t stride, size_t size,
+                                           const uint64_t* host_timestamps, LidarFrame& lidar_frame,
+                                           bool& complete);
+    /// Frames in flight.  1 (default): batch() returns true with the frame materialised, like the
+    /// reference.  n >= 2: batch() returns true as soon as the frame's GPU pass is *submitted*; the
+    /// caller batches the next frame into another LidarFrame (and FusedCloud) meanwhile and calls
+    /// wait(frame) before reading pixel fields / fused outputs.  Column and packet headers are
+    /// host-written and valid immediately.  A frame must outlive its wait().  See FramePipeline
+    /// (frame_pipeline.h) for a ready-made ring of frames.
+    OUSTER_API_FUNCTION void set_pipeline_depth(size_t n);
+    OUSTER_API_FUNCTION size_t pipeline_depth() const;
+    /// Block until the GPU pass that fills lidar_frame has landed (no-op when none is pending).
+    OUSTER_API_FUNCTION void wait(const LidarFrame& lidar_frame);
+    OUSTER_API_FUNCTION void wait_all();
 
    private:
     struct CachedPacket {
@@ -305,6 +324,7 @@ class OUSTER_API_CLASS FrameBatcher {
     FusedCloud* fused_{nullptr};
     bool headers_only_{false};
     size_t launches_{0};
+    int n_returns_{0};
 
     bool batch_impl(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f);
     void cache_packet(const uint8_t* buf, size_t size, uint64_t host_ts);
@@ -316,6 +336,9 @@ class OUSTER_API_CLASS FrameBatcher {
     bool batch_with_caching(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f);
     bool check_frame_complete(const LidarFrame& f) const;
     void decode_staged(LidarFrame& f);
+    std::vector<std::string> ensure_decoder(LidarFrame& f);
+    void upload_runs(LidarFrame& f);
+    void settle_user_uploads();
 };
 
 /// Deprecated spellings kept by the reference (lidar_frame.h:1157-1160).

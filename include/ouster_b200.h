@@ -240,6 +240,38 @@ typedef struct ob_decode_batch {
 ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* batch, const ob_lut* lut,
                               const int32_t* pixel_shift_by_row, size_t n_shifts, ob_stream* s);
 
+/* ---------------------------------------------------------------------------------------------
+ * Decode job: ob_decode_frames for ONE frame with persistent device buffers and asynchronous
+ * completion, so that a caller (FrameBatcher) can overlap the host state machine of frame k+1 with
+ * the H2D / kernel / D2H of frame k.  Replaces the same reference code as ob_decode_frames
+ * (lidar_frame.cpp:1422-1528 + finalize :1905-1922); what is new is only the pipelining.
+ *
+ *   upload(): enqueue the H2D (or D2D) of `count` packets, `src_stride` bytes apart, into packet
+ *             slots [first_slot, first_slot+count) of the job.  Page-locked sources are read by
+ *             DMA directly -- no bounce copy; uploads_done() blocks until every enqueued upload has
+ *             left the source memory.  An upload at first_slot 0 begins a new frame.
+ *   submit(): launch the fused decode over slots [0, io->n_slots) (io->packets and
+ *             io->packet_stride are ignored) and enqueue the D2H of every host output in `io`;
+ *             device output pointers are written in place.  Outputs are valid after wait().
+ *             submit() on a busy job waits for the previous submission first.
+ * A job is bound to one stream; jobs on different streams overlap (H2D of one with D2H of another).
+ * Not thread-safe; one job = one frame in flight.
+ */
+typedef struct ob_decode_job ob_decode_job;
+ob_status ob_decode_job_create(const ob_decoder* dec, size_t reserve_slots, ob_stream* s,
+                               ob_decode_job** out);
+ob_status ob_decode_job_upload(ob_decode_job* job, const uint8_t* src, size_t src_stride,
+                               size_t first_slot, size_t count);
+ob_status ob_decode_job_uploads_done(ob_decode_job* job);
+ob_status ob_decode_job_submit(ob_decode_job* job, const ob_decode_io* io, const ob_lut* lut,
+                               const int32_t* pixel_shift_by_row, size_t n_shifts);
+ob_status ob_decode_job_wait(ob_decode_job* job);
+int ob_decode_job_busy(const ob_decode_job* job); /* 1 while a submission has not been waited for */
+ob_status ob_decode_job_destroy(ob_decode_job* job);
+
+/* 0: pageable host memory (or unknown), 1: page-locked host memory, 2: device / managed memory */
+int ob_pointer_kind(const void* p);
+
 #ifdef __cplusplus
 }
 #endif

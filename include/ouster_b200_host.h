@@ -101,7 +101,30 @@ ob_status obh_batcher_set_fused(obh_batcher* b, ob_lut* lut /* borrowed; NULL de
                                 const int32_t* pixel_shift_by_row, size_t n_shifts);
 ob_status obh_batcher_fused_outputs(obh_batcher* b, int ret, void** xyz, size_t* xyz_bytes,
                                     uint32_t** range_destaggered);
+/* FrameBatcher::set_pipeline_depth / wait (frame == NULL: wait_all) -- see lidar_frame.h */
+ob_status obh_batcher_set_pipeline_depth(obh_batcher* b, size_t n);
+ob_status obh_batcher_wait(obh_batcher* b, obh_frame* frame);
 ob_status obh_batcher_destroy(obh_batcher* b);
+
+/* ---- FramePipeline (include/ouster/core/frame_pipeline.h): ring of frames, `depth` in flight ---- */
+typedef struct obh_pipeline obh_pipeline;
+typedef struct obh_slot {
+    obh_frame* frame;  /* borrowed view of the finished slot's LidarFrame; NULL = no frame finished.
+                          Valid until the next slot is returned. */
+    void* xyz[2];      /* fused cloud of the slot (NULL when not requested) */
+    uint32_t* range_destaggered[2];
+    size_t xyz_bytes;
+} obh_slot;
+ob_status obh_pipeline_create(const obh_sensor* s, size_t depth, ob_lut* lut /* nullable, borrowed */,
+                              const int32_t* pixel_shift_by_row, size_t n_shifts, obh_pipeline** out);
+ob_status obh_pipeline_push_burst(obh_pipeline* p, const uint8_t* packets, size_t n, size_t stride,
+                                  size_t size, const uint64_t* host_timestamps, size_t* consumed,
+                                  obh_slot* done);
+ob_status obh_pipeline_drain(obh_pipeline* p, obh_slot* done);
+size_t obh_pipeline_in_flight(const obh_pipeline* p);
+size_t obh_pipeline_gpu_launches(const obh_pipeline* p);
+size_t obh_pipeline_dropped_packets(const obh_pipeline* p);
+ob_status obh_pipeline_destroy(obh_pipeline* p);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,7 @@
 // ob_api_decode.cu -- C-ABI glue of the packet-decode path (ob_decoder_*, ob_decode_frames).
+#include <algorithm>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "ob_api_common.h"
@@ -342,6 +344,286 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
     e = stg.flush();
     if (e != cudaSuccess) return fail_cuda(e, "decode D2H");
     return OB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// decode job
+// ---------------------------------------------------------------------------------------------
+struct ob_decode_job {
+    const ob_decoder* dec;
+    ob_stream* s;
+    cudaStream_t st;
+    int device;
+    size_t stride;             // bytes per packet slot on the device (multiple of 16)
+    uint8_t* d_pk{nullptr};    // packet slots
+    size_t cap_slots{0};
+    size_t up_slots{0};        // highest uploaded slot + 1
+    uint8_t* d_out{nullptr};   // output slab (fields, headers, xyz, destaggered ranges)
+    size_t out_bytes{0};
+    int32_t* d_colsrc{nullptr};
+    int32_t* h_colsrc{nullptr};     // pinned
+    DecodeFrame* d_frame{nullptr};
+    DecodeFrame* h_frame{nullptr};  // pinned
+    cudaEvent_t ev_up{nullptr}, ev_done{nullptr};
+    bool up_pending{false}, busy{false};
+};
+
+static cudaError_t job_reserve(ob_decode_job* j, size_t slots) {
+    if (slots <= j->cap_slots) return cudaSuccess;
+    const size_t cap = std::max(slots, j->cap_slots ? j->cap_slots * 2 : static_cast<size_t>(16));
+    uint8_t* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap * j->stride + 16);
+    if (e != cudaSuccess) return e;
+    if (j->d_pk) {  // rare: more packets than the frame was sized for (duplicates, retransmits)
+        e = cudaStreamSynchronize(j->st);
+        if (e == cudaSuccess && j->up_slots)
+            e = cudaMemcpy(p, j->d_pk, j->up_slots * j->stride, cudaMemcpyDeviceToDevice);
+        cudaFree(j->d_pk);
+        if (e != cudaSuccess) {
+            cudaFree(p);
+            j->d_pk = nullptr;
+            j->cap_slots = 0;
+            return e;
+        }
+    }
+    j->d_pk = p;
+    j->cap_slots = cap;
+    return cudaSuccess;
+}
+
+ob_status ob_decode_job_create(const ob_decoder* dec, size_t reserve_slots, ob_stream* s,
+                               ob_decode_job** out) {
+    if (!dec || !s || !out) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    const int device = stream_device(s);
+    if (device != dec->device) return fail(OB_INVALID_ARGUMENT, "decoder and stream are on different devices");
+    ob_status rs = require_device(device);
+    if (rs != OB_OK) return rs;
+    std::unique_ptr<ob_decode_job> j(new ob_decode_job);
+    j->dec = dec;
+    j->s = s;
+    j->st = stream_handle(s);
+    j->device = device;
+    j->stride = (static_cast<size_t>(dec->L.packet_size) + 15) & ~static_cast<size_t>(15);
+    cudaError_t e = cudaEventCreateWithFlags(&j->ev_up, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&j->d_colsrc, static_cast<size_t>(dec->L.W) * 4);
+    if (e == cudaSuccess) e = cudaHostAlloc(&j->h_colsrc, static_cast<size_t>(dec->L.W) * 4, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&j->d_frame, sizeof(DecodeFrame));
+    if (e == cudaSuccess) e = cudaHostAlloc(&j->h_frame, sizeof(DecodeFrame), cudaHostAllocDefault);
+    if (e == cudaSuccess && reserve_slots) e = job_reserve(j.get(), reserve_slots);
+    if (e != cudaSuccess) {
+        ob_decode_job_destroy(j.release());
+        return fail_cuda(e, "decode job allocation");
+    }
+    *out = j.release();
+    return OB_OK;
+}
+
+ob_status ob_decode_job_destroy(ob_decode_job* j) {
+    if (!j) return OB_OK;
+    cudaSetDevice(j->device);
+    cudaStreamSynchronize(j->st);
+    if (j->ev_up) cudaEventDestroy(j->ev_up);
+    if (j->ev_done) cudaEventDestroy(j->ev_done);
+    cudaFree(j->d_pk);
+    cudaFree(j->d_out);
+    cudaFree(j->d_colsrc);
+    cudaFree(j->d_frame);
+    if (j->h_colsrc) cudaFreeHost(j->h_colsrc);
+    if (j->h_frame) cudaFreeHost(j->h_frame);
+    delete j;
+    return OB_OK;
+}
+
+int ob_decode_job_busy(const ob_decode_job* j) { return j && j->busy ? 1 : 0; }
+
+ob_status ob_decode_job_upload(ob_decode_job* j, const uint8_t* src, size_t src_stride,
+                               size_t first_slot, size_t count) {
+    if (!j || (count && !src)) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (count == 0) return OB_OK;
+    const size_t psize = j->dec->L.packet_size;
+    if (count > 1 && src_stride < psize)
+        return fail(OB_INVALID_ARGUMENT, "packet_stride smaller than the lidar packet size");
+    if (first_slot + count > (1u << 20)) return fail(OB_INVALID_ARGUMENT, "too many packet slots");
+    ob_status rs = require_device(j->device);
+    if (rs != OB_OK) return rs;
+    if (j->busy) {  // the previous frame still reads the slots
+        rs = ob_decode_job_wait(j);
+        if (rs != OB_OK) return rs;
+    }
+    cudaError_t e = job_reserve(j, first_slot + count);
+    if (e != cudaSuccess) return fail_cuda(e, "decode job packet slots");
+    uint8_t* dst = j->d_pk + first_slot * j->stride;
+    if (count == 1 || src_stride == j->stride)
+        e = cudaMemcpyAsync(dst, src, (count - 1) * j->stride + psize, cudaMemcpyDefault, j->st);
+    else
+        e = cudaMemcpy2DAsync(dst, j->stride, src, src_stride, psize, count, cudaMemcpyDefault, j->st);
+    if (e != cudaSuccess) return fail_cuda(e, "packet upload");
+    e = cudaEventRecord(j->ev_up, j->st);
+    if (e != cudaSuccess) return fail_cuda(e, "packet upload event");
+    j->up_pending = true;
+    // an upload at slot 0 begins a new frame: slots of the previous one are no longer valid
+    j->up_slots = first_slot == 0 ? count : std::max(j->up_slots, first_slot + count);
+    return OB_OK;
+}
+
+ob_status ob_decode_job_uploads_done(ob_decode_job* j) {
+    if (!j) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (!j->up_pending) return OB_OK;
+    cudaError_t e = cudaEventSynchronize(j->ev_up);
+    j->up_pending = false;
+    if (e != cudaSuccess) return fail_cuda(e, "packet upload");
+    return OB_OK;
+}
+
+ob_status ob_decode_job_wait(ob_decode_job* j) {
+    if (!j) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (!j->busy) return OB_OK;
+    cudaError_t e = cudaEventSynchronize(j->ev_done);
+    j->busy = false;
+    j->up_pending = false;
+    if (e != cudaSuccess) return fail_cuda(e, "decode job");
+    return OB_OK;
+}
+
+ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const ob_lut* lut,
+                               const int32_t* shifts, size_t n_shifts) {
+    if (!j || !io) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    const DecodeLayout& L = j->dec->L;
+    ob_status rs = require_device(j->device);
+    if (rs != OB_OK) return rs;
+    if (io->n_slots > j->up_slots) return fail(OB_INVALID_ARGUMENT, "n_slots exceeds the uploaded packet slots");
+    const ob_lut* use_lut = io->lut ? io->lut : lut;
+    const void *ldir = nullptr, *loff = nullptr;
+    int ldtype = OB_F32;
+    if (use_lut) {
+        size_t lh, lw;
+        int ldev;
+        lut_view(use_lut, &ldir, &loff, &ldtype, &lh, &lw, &ldev);
+        if (lh != L.H || lw != L.W) return fail(OB_INVALID_ARGUMENT, "unexpected image dimensions");
+        if (ldev != j->device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
+    }
+    std::vector<uint16_t> sh;
+    if (shifts) {
+        if (n_shifts != L.H) return fail(OB_INVALID_ARGUMENT, "image height does not match shifts size");
+        if (L.H > static_cast<uint32_t>(kMaxRows))
+            return fail(OB_INVALID_ARGUMENT, "fused destagger supports at most 512 rows");
+        reduce_shifts(shifts, L.H, L.W, 0, sh);
+    }
+    for (int r = 0; r < OB_MAX_RETURNS; ++r) {
+        if (io->xyz[r] && !use_lut) return fail(OB_INVALID_ARGUMENT, "xyz output requested without a lut");
+        if (io->range_destaggered[r] && !shifts)
+            return fail(OB_INVALID_ARGUMENT, "image height does not match shifts size");
+    }
+    if (j->busy) {  // the previous submission still owns h_frame / h_colsrc / the slab
+        rs = ob_decode_job_wait(j);
+        if (rs != OB_OK) return rs;
+    }
+
+    // ---- outputs: device pointers in place, host pointers through the slab + D2H ----
+    const size_t n_px = static_cast<size_t>(L.H) * L.W;
+    struct Out {
+        void* user;
+        size_t bytes;
+        void** slot;  // where the device pointer goes
+        bool host;
+        size_t off;
+    };
+    DecodeFrame f;
+    std::memset(&f, 0, sizeof(f));
+    Out outs[OB_MAX_FIELDS + 3 + 2 * OB_MAX_RETURNS];
+    size_t n_out = 0;
+    void* fld[OB_MAX_FIELDS] = {};
+    void *ts = nullptr, *mid = nullptr, *stt = nullptr, *xyz[OB_MAX_RETURNS] = {}, *rd[OB_MAX_RETURNS] = {};
+    auto add = [&](void* user, size_t bytes, void** slot) {
+        if (user) outs[n_out++] = Out{user, bytes, slot, false, 0};
+    };
+    for (uint32_t k = 0; k < L.n_fields; ++k) add(io->fields[k], n_px * L.fields[k].elem_size, &fld[k]);
+    add(io->timestamp, static_cast<size_t>(L.W) * 8, &ts);
+    add(io->measurement_id, static_cast<size_t>(L.W) * 2, &mid);
+    add(io->status, static_cast<size_t>(L.W) * 4, &stt);
+    for (int r = 0; r < OB_MAX_RETURNS; ++r) {
+        add(io->xyz[r], n_px * 3 * (ldtype == OB_F64 ? 8 : 4), &xyz[r]);
+        add(io->range_destaggered[r], n_px * 4, &rd[r]);
+    }
+    size_t need = 0;
+    for (size_t i = 0; i < n_out; ++i) {
+        outs[i].host = !is_device_ptr(outs[i].user);
+        if (outs[i].host) {
+            outs[i].off = need;
+            need += (outs[i].bytes + 255) & ~static_cast<size_t>(255);
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    if (need > j->out_bytes) {  // job is idle here
+        cudaFree(j->d_out);
+        j->d_out = nullptr;
+        j->out_bytes = 0;
+        e = cudaMalloc(&j->d_out, need);
+        if (e != cudaSuccess) return fail_cuda(e, "decode job output slab");
+        j->out_bytes = need;
+    }
+    for (size_t i = 0; i < n_out; ++i) *outs[i].slot = outs[i].host ? j->d_out + outs[i].off : outs[i].user;
+
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    bool vec_ok = !use_lut || (al16(ldir) && al16(loff));
+    f.packets = j->d_pk;
+    f.packet_stride = j->stride;
+    f.n_slots = static_cast<uint32_t>(io->n_slots);
+    f.flags = 0;
+    if (!io->col_src) f.flags |= 1u;
+    if (L.packet_size % 16 == 0) f.flags |= 2u;  // slots are 16-byte aligned by construction
+    if (io->col_src) {
+        std::memcpy(j->h_colsrc, io->col_src, static_cast<size_t>(L.W) * 4);
+        e = cudaMemcpyAsync(j->d_colsrc, j->h_colsrc, static_cast<size_t>(L.W) * 4, cudaMemcpyHostToDevice, j->st);
+        if (e != cudaSuccess) return fail_cuda(e, "stage column map");
+        f.col_src = j->d_colsrc;
+    }
+    for (uint32_t k = 0; k < L.n_fields; ++k) f.fields[k] = fld[k];
+    f.timestamp = static_cast<uint64_t*>(ts);
+    f.measurement_id = static_cast<uint16_t*>(mid);
+    f.status = static_cast<uint32_t*>(stt);
+    for (int r = 0; r < OB_MAX_RETURNS; ++r) {
+        f.xyz[r] = xyz[r];
+        f.rd[r] = static_cast<uint32_t*>(rd[r]);
+        if (xyz[r] && !al16(xyz[r])) vec_ok = false;
+    }
+    *j->h_frame = f;
+    e = cudaMemcpyAsync(j->d_frame, j->h_frame, sizeof(DecodeFrame), cudaMemcpyHostToDevice, j->st);
+    if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
+    DecodeLaunch a;
+    a.layout_host = &L;
+    a.frames_dev = j->d_frame;
+    a.n_frames = 1;
+    a.lut_dir = ldir;
+    a.lut_off = loff;
+    a.lut_dtype = ldtype;
+    a.shift_host = shifts ? sh.data() : nullptr;
+    a.vec_ok = vec_ok;
+    e = launch_decode(a, j->device, j->st);
+    if (e != cudaSuccess) return fail_cuda(e, "decode launch");
+    for (size_t i = 0; i < n_out; ++i) {
+        if (!outs[i].host) continue;
+        e = cudaMemcpyAsync(outs[i].user, j->d_out + outs[i].off, outs[i].bytes, cudaMemcpyDeviceToHost, j->st);
+        if (e != cudaSuccess) return fail_cuda(e, "decode D2H");
+    }
+    e = cudaEventRecord(j->ev_done, j->st);
+    if (e != cudaSuccess) return fail_cuda(e, "decode job event");
+    j->busy = true;
+    return OB_OK;
+}
+
+int ob_pointer_kind(const void* p) {
+    if (!p) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (at.type == cudaMemoryTypeHost) return 1;
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return 2;
+    return 0;
 }
 
 }  // extern "C"

@@ -56,7 +56,23 @@ _sig("obh_batcher_set_max_cache_size", i32, vp, sz)
 _sig("obh_batcher_set_fused", i32, vp, vp, vp, sz)
 _sig("obh_batcher_set_headers_only", i32, vp, i32)
 _sig("obh_batcher_fused_outputs", i32, vp, i32, PP(vp), PP(sz), PP(vp))
+_sig("obh_batcher_set_pipeline_depth", i32, vp, sz)
+_sig("obh_batcher_wait", i32, vp, vp)
 _sig("obh_batcher_destroy", i32, vp)
+
+
+class Slot(C.Structure):
+    """obh_slot (include/ouster_b200_host.h)."""
+    _fields_ = [("frame", vp), ("xyz", vp * 2), ("range_destaggered", vp * 2), ("xyz_bytes", sz)]
+
+
+_sig("obh_pipeline_create", i32, vp, sz, vp, vp, sz, PP(vp))
+_sig("obh_pipeline_push_burst", i32, vp, vp, sz, sz, sz, vp, PP(sz), PP(Slot))
+_sig("obh_pipeline_drain", i32, vp, PP(Slot))
+_sig("obh_pipeline_in_flight", sz, vp)
+_sig("obh_pipeline_gpu_launches", sz, vp)
+_sig("obh_pipeline_dropped_packets", sz, vp)
+_sig("obh_pipeline_destroy", i32, vp)
 
 # ChanFieldType tags (chanfield.h:111-128)
 TAG_NP = {1: np.uint8, 2: np.uint16, 3: np.uint32, 4: np.uint64, 5: np.int8, 6: np.int16,
@@ -198,9 +214,14 @@ class SensorInfo:
 class LidarFrame:
     """LidarFrame / LidarScan: named row-major fields + per-column / per-packet headers (host)."""
 
-    def __init__(self, info):
-        hd = vp()
-        check(lib.obh_frame_create(info._h, C.byref(hd)))
+    def __init__(self, info, _borrowed=None):
+        if _borrowed is None:
+            hd = vp()
+            check(lib.obh_frame_create(info._h, C.byref(hd)))
+            self._owned = True
+        else:  # view of a frame owned by a FramePipeline slot
+            hd = vp(_borrowed)
+            self._owned = False
         self._h, self.info = hd, info
         ts, mid, st, pts, af = vp(), vp(), vp(), vp(), vp()
         w, h, npk = sz(), sz(), sz()
@@ -257,12 +278,12 @@ class LidarFrame:
         lib.obh_frame_set_status(self._h, frame_status, shutdown_countdown, shot_limiting_countdown)
 
     def __del__(self):
-        if getattr(self, "_h", None) and lib is not None:
+        if getattr(self, "_h", None) and getattr(self, "_owned", False) and lib is not None:
             try:
                 lib.obh_frame_destroy(self._h)
             except Exception:
                 pass
-            self._h = None
+        self._h = None
 
 
 def frame_to_packets(frame, info, init_id=0, prod_sn=0):
@@ -336,6 +357,14 @@ class FrameBatcher:
         check(lib.obh_batcher_set_fused(self._h, lut._h if lut is not None else None,
                                         sh.ctypes.data if sh is not None else None, n))
 
+    def set_pipeline_depth(self, n):
+        """n >= 2: batch() returns True once the frame's GPU pass is submitted; wait(frame) before
+        reading pixel fields (FrameBatcher::set_pipeline_depth, lidar_frame.h)."""
+        check(lib.obh_batcher_set_pipeline_depth(self._h, int(n)))
+
+    def wait(self, frame=None):
+        check(lib.obh_batcher_wait(self._h, frame._h if frame is not None else None))
+
     def fused_outputs(self, ret):
         xyz, nb, rd = vp(), sz(), vp()
         check(lib.obh_batcher_fused_outputs(self._h, ret, C.byref(xyz), C.byref(nb), C.byref(rd)))
@@ -350,6 +379,90 @@ class FrameBatcher:
         if getattr(self, "_h", None) and lib is not None:
             try:
                 lib.obh_batcher_destroy(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class FinishedSlot:
+    """A finished FramePipeline slot: .frame (LidarFrame view), .xyz[r], .range_destaggered[r].
+    Valid until the pipeline returns its next slot; the views are built on first access."""
+
+    def __init__(self, info, slot, dtype):
+        self._info, self._dtype = info, np.dtype(dtype)
+        self._frame_h, self._xyz_p = slot.frame, (slot.xyz[0], slot.xyz[1])
+        self._rd_p, self._nb = (slot.range_destaggered[0], slot.range_destaggered[1]), slot.xyz_bytes
+        self._frame = self._xyz = self._rd = None
+
+    @property
+    def frame(self):
+        if self._frame is None:
+            self._frame = LidarFrame(self._info, _borrowed=self._frame_h)
+        return self._frame
+
+    @property
+    def xyz(self):
+        if self._xyz is None:
+            n = self._nb // self._dtype.itemsize
+            self._xyz = [(_as_array(p, self._dtype, (n // 3, 3)) if p else None) for p in self._xyz_p]
+        return self._xyz
+
+    @property
+    def range_destaggered(self):
+        if self._rd is None:
+            hw = (self._info.h, self._info.w)
+            self._rd = [(_as_array(p, np.uint32, hw) if p else None) for p in self._rd_p]
+        return self._rd
+
+
+class FramePipeline:
+    """Ring of LidarFrames with `depth` frames in flight on the GPU (frame_pipeline.h): the host
+    state machine of frame k+1 overlaps the H2D / fused kernel / D2H of frame k."""
+
+    def __init__(self, info, depth=3, lut=None, pixel_shift_by_row=None):
+        sh, n = None, 0
+        if pixel_shift_by_row is not None:
+            sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
+            n = sh.size
+        hd = vp()
+        check(lib.obh_pipeline_create(info._h, int(depth), lut._h if lut is not None else None,
+                                      sh.ctypes.data if sh is not None else None, n, C.byref(hd)))
+        self._h, self.info, self._lut = hd, info, lut
+        self._dtype = lut.dtype if lut is not None else np.float32
+
+    def _wrap(self, slot):
+        return FinishedSlot(self.info, slot, self._dtype) if slot.frame else None
+
+    def push_burst(self, packets, host_timestamps):
+        """Feed a [n, packet_size] uint8 burst; returns (packets consumed, FinishedSlot or None)."""
+        ts = np.ascontiguousarray(host_timestamps, np.uint64)
+        used, slot = sz(0), Slot()
+        check(lib.obh_pipeline_push_burst(self._h, packets.ctypes.data, packets.shape[0], packets.strides[0],
+                                          packets.shape[1], ts.ctypes.data, C.byref(used), C.byref(slot)))
+        return used.value, self._wrap(slot)
+
+    def drain(self):
+        """Oldest frame still in flight (waited for), or None."""
+        slot = Slot()
+        check(lib.obh_pipeline_drain(self._h, C.byref(slot)))
+        return self._wrap(slot)
+
+    @property
+    def in_flight(self):
+        return lib.obh_pipeline_in_flight(self._h)
+
+    @property
+    def gpu_launches(self):
+        return lib.obh_pipeline_gpu_launches(self._h)
+
+    @property
+    def dropped_packets(self):
+        return lib.obh_pipeline_dropped_packets(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and lib is not None:
+            try:
+                lib.obh_pipeline_destroy(self._h)
             except Exception:
                 pass
             self._h = None

@@ -22,45 +22,85 @@ namespace ouster {
 namespace sdk {
 namespace core {
 
+// One frame in flight: an ob_decode_job (device packet slots + output slab + events) on its own
+// stream, and a page-locked bounce buffer for packets that arrive in pageable memory.
 struct FrameBatcher::Staging {
-    uint8_t* pinned{nullptr};
-    size_t capacity{0};  // packets
-    size_t stride{0};    // bytes per slot (multiple of 16)
-    size_t n_slots{0};
+    struct Job {
+        ob_decode_job* job{nullptr};
+        ob_stream* stream{nullptr};
+        uint8_t* bounce{nullptr};
+        size_t bounce_cap{0};  // packets
+        bool bounce_cuda{false};
+        const LidarFrame* owner{nullptr};  // frame whose outputs the job is writing
+        bool user_uploads{false};          // uploads that read caller memory are in flight
+    };
+    // pending upload: `count` packets, src_stride apart, into slots [first, first+count)
+    struct Run {
+        const uint8_t* src;
+        size_t src_stride, first, count;
+        bool user;  // reads caller-owned (page-locked / device) memory
+    };
+    std::vector<Job> jobs;
+    size_t cur{0};
+    size_t depth{1};
+    size_t stride{0};   // bytes per slot (multiple of 16)
+    size_t n_slots{0};  // packets accepted into the frame in flight
+    std::vector<Run> runs;
     std::vector<int32_t> col_src;
+    // the burst being fed (batch_burst): zero-copy window when its memory is DMA-able
+    const uint8_t* burst_begin{nullptr};
+    const uint8_t* burst_end{nullptr};
+    size_t burst_stride{0};
     ob_decoder* dec{nullptr};
     std::string signature;
-    std::vector<std::string> field_names;
-    std::vector<size_t> field_bytes;
     int device{0};
 
-    bool pinned_is_cuda{false};
-
     ~Staging() {
-        release();
+        for (Job& j : jobs) {
+            if (j.job) ob_decode_job_destroy(j.job);
+            if (j.stream) ob_stream_destroy(j.stream);
+            if (j.bounce) {
+                if (j.bounce_cuda) ob_host_free(j.bounce);
+                else std::free(j.bounce);
+            }
+        }
         if (dec) ob_decoder_destroy(dec);
     }
-    void release() {
-        if (!pinned) return;
-        if (pinned_is_cuda) ob_host_free(pinned);
-        else std::free(pinned);
-        pinned = nullptr;
-    }
-    void reserve(size_t packets) {
-        if (packets <= capacity) return;
-        size_t cap = std::max<size_t>(packets, capacity ? capacity * 2 : 16);
+    Job& job() { return jobs[cur]; }
+    void reserve_bounce(size_t packets) {
+        Job& j = job();
+        if (packets <= j.bounce_cap) return;
+        const size_t cap = std::max<size_t>(packets, j.bounce_cap ? j.bounce_cap * 2 : 16);
         void* p = nullptr;
-        // pinned memory when a device exists; plain memory keeps the header-only mode usable
+        // pinned memory when a device exists; plain memory keeps the host state machine usable
         // on machines without one (decode itself still fails loudly there)
         const bool cuda = ob_device_count() > 0;
         if (cuda) b200::check(ob_host_alloc(cap * stride, &p));
         else p = std::malloc(cap * stride);
         if (!p) throw std::runtime_error("out of memory staging lidar packets");
-        if (pinned) std::memcpy(p, pinned, n_slots * stride);
-        release();
-        pinned = static_cast<uint8_t*>(p);
-        pinned_is_cuda = cuda;
-        capacity = cap;
+        if (j.bounce) {
+            // pending runs may point into the old block
+            for (Run& r : runs)
+                if (!r.user) r.src = static_cast<uint8_t*>(p) + (r.src - j.bounce);
+            std::memcpy(p, j.bounce, j.bounce_cap * stride);
+            if (j.bounce_cuda) ob_host_free(j.bounce);
+            else std::free(j.bounce);
+        }
+        j.bounce = static_cast<uint8_t*>(p);
+        j.bounce_cuda = cuda;
+        j.bounce_cap = cap;
+    }
+    void add_run(const uint8_t* src, size_t src_stride, size_t slot, bool user) {
+        if (!runs.empty()) {
+            Run& r = runs.back();
+            if (r.user == user && r.first + r.count == slot &&
+                (r.count == 1 || r.src_stride == src_stride) && r.src + r.count * src_stride == src) {
+                r.src_stride = src_stride;
+                r.count++;
+                return;
+            }
+        }
+        runs.push_back(Run{src, src_stride, slot, 1, user});
     }
 };
 
@@ -75,11 +115,17 @@ FrameBatcher::FrameBatcher(const std::shared_ptr<SensorInfo>& info)
     stg_->stride = (pf.lidar_packet_size + 15) & ~static_cast<size_t>(15);
     stg_->col_src.assign(info->format.columns_per_frame, -1);
     stg_->device = b200::device();
+    stg_->jobs.resize(1);
 }
 
 FrameBatcher::FrameBatcher(const SensorInfo& info) : FrameBatcher(std::make_shared<SensorInfo>(info)) {}
 
-FrameBatcher::~FrameBatcher() = default;
+FrameBatcher::~FrameBatcher() {
+    try {
+        wait_all();
+    } catch (...) {
+    }
+}
 
 size_t FrameBatcher::batched_packets() const { return batched_lidar_packets_; }
 size_t FrameBatcher::dropped_packets() const { return dropped_packets_; }
@@ -98,8 +144,46 @@ void FrameBatcher::reset() {
     next_valid_m_id_ = 0;
     batched_lidar_packets_ = 0;
     cache_.clear();
+    settle_user_uploads();
     stg_->n_slots = 0;
+    stg_->runs.clear();
     std::fill(stg_->col_src.begin(), stg_->col_src.end(), -1);
+}
+
+void FrameBatcher::set_pipeline_depth(size_t n) {
+    if (n == 0) n = 1;
+    wait_all();
+    if (stg_->n_slots != 0 && n != stg_->depth)
+        throw std::logic_error("set_pipeline_depth: a frame is being batched; call between frames or after reset()");
+    stg_->depth = n;
+    if (stg_->jobs.size() < n) stg_->jobs.resize(n);
+    if (stg_->cur >= n) stg_->cur = 0;
+}
+size_t FrameBatcher::pipeline_depth() const { return stg_->depth; }
+
+void FrameBatcher::wait(const LidarFrame& f) {
+    for (Staging::Job& j : stg_->jobs)
+        if (j.owner == &f && j.job) {
+            j.owner = nullptr;
+            b200::check(ob_decode_job_wait(j.job));
+        }
+}
+
+void FrameBatcher::wait_all() {
+    for (Staging::Job& j : stg_->jobs)
+        if (j.job) {
+            j.owner = nullptr;
+            b200::check(ob_decode_job_wait(j.job));
+        }
+}
+
+// uploads that read caller memory must have left it before control returns to the caller
+void FrameBatcher::settle_user_uploads() {
+    for (Staging::Job& j : stg_->jobs)
+        if (j.user_uploads && j.job) {
+            j.user_uploads = false;
+            b200::check(ob_decode_job_uploads_done(j.job));
+        }
 }
 
 void FrameBatcher::cache_packet(const uint8_t* buf, size_t size, uint64_t host_ts) {
@@ -137,8 +221,18 @@ void FrameBatcher::start_frame(int64_t f_id, const uint8_t* packet_buf, LidarFra
     f.shutdown_countdown = static_cast<uint8_t>(pf.countdown_thermal_shutdown(packet_buf));
     f.shot_limiting_countdown = static_cast<uint8_t>(pf.countdown_shot_limiting(packet_buf));
     f.sensor_info = sensor_info_;
-    stg_->n_slots = 0;
-    std::fill(stg_->col_src.begin(), stg_->col_src.end(), -1);
+    Staging& s = *stg_;
+    // a frame object that is still the target of an earlier submission must land first
+    wait(f);
+    // next job of the ring; its previous frame (depth frames ago) must have completed
+    if (s.depth > 1) s.cur = (s.cur + 1) % s.depth;
+    if (s.job().job) {
+        s.job().owner = nullptr;
+        b200::check(ob_decode_job_wait(s.job().job));
+    }
+    s.n_slots = 0;
+    s.runs.clear();
+    std::fill(s.col_src.begin(), s.col_src.end(), -1);
 }
 
 void FrameBatcher::batch_lidar_packet(const uint8_t* packet_buf, uint64_t host_ts, LidarFrame& f) {
@@ -150,11 +244,20 @@ void FrameBatcher::batch_lidar_packet(const uint8_t* packet_buf, uint64_t host_t
         f.alert_flags()[packet_id] = pf.alert_flags(packet_buf);
     }
 
-    // stage the wire bytes
+    // stage the wire bytes: packets of a DMA-able burst are uploaded from where they are,
+    // anything else goes through the page-locked bounce buffer of the job
     Staging& s = *stg_;
-    s.reserve(s.n_slots + 1);
     const size_t slot = s.n_slots++;
-    std::memcpy(s.pinned + slot * s.stride, packet_buf, pf.lidar_packet_size);
+    if (!headers_only_) {
+        if (packet_buf >= s.burst_begin && packet_buf < s.burst_end) {
+            s.add_run(packet_buf, s.burst_stride, slot, true);
+        } else {
+            s.reserve_bounce(slot + 1);
+            uint8_t* dst = s.job().bounce + slot * s.stride;
+            std::memcpy(dst, packet_buf, pf.lidar_packet_size);
+            s.add_run(dst, s.stride, slot, false);
+        }
+    }
     const int32_t src0 = static_cast<int32_t>(slot) * cpp;
 
     // block path preconditions (lidar_frame.cpp:1542-1567)
@@ -237,15 +340,18 @@ void FrameBatcher::finalize_frame(LidarFrame& f) {
     batched_lidar_packets_ = 0;
 }
 
-void FrameBatcher::flush(LidarFrame& f) { decode_staged(f); }
+void FrameBatcher::flush(LidarFrame& f) {
+    decode_staged(f);
+    wait(f);
+}
 
 void FrameBatcher::set_headers_only(bool on) { headers_only_ = on; }
 
-void FrameBatcher::decode_staged(LidarFrame& f) {
+// (Re)build the device decode table for the fields this frame shares with the profile
+// (foreach_channel_field: profile order, only fields the frame has; impl/lidar_frame_impl.h:367-375)
+// and make sure the current job exists.  Returns the names of the decoded fields, in table order.
+std::vector<std::string> FrameBatcher::ensure_decoder(LidarFrame& f) {
     Staging& s = *stg_;
-    if (headers_only_) return;
-    // (re)build the device decode table for the fields this frame shares with the profile
-    // (foreach_channel_field: profile order, only fields the frame has; impl/lidar_frame_impl.h:367-375)
     std::string sig;
     std::vector<std::string> names;
     std::vector<ob_field_desc> descs;
@@ -274,7 +380,14 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
                std::to_string(info.mask) + ":" + std::to_string(info.shift) + ";";
     }
     if (descs.size() > OB_MAX_FIELDS) throw std::invalid_argument("too many fields to decode");
+    n_returns_ = 0;
+    for (const auto& d : descs) n_returns_ = std::max(n_returns_, d.range_return + 1);
     if (!s.dec || sig != s.signature) {
+        wait_all();
+        for (Staging::Job& j : s.jobs) {  // jobs are bound to the decoder
+            if (j.job) ob_decode_job_destroy(j.job);
+            j.job = nullptr;
+        }
         if (s.dec) ob_decoder_destroy(s.dec);
         s.dec = nullptr;
         ob_packet_layout L{};
@@ -302,13 +415,39 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
         b200::check(ob_decoder_create(&L, descs.data(), descs.size(), s.device, &s.dec));
         s.signature = sig;
     }
+    Staging::Job& j = s.job();
+    if (!j.stream) b200::check(ob_stream_create(s.device, &j.stream));
+    if (!j.job) b200::check(ob_decode_job_create(s.dec, expected_lidar_packets_, j.stream, &j.job));
+    return names;
+}
+
+// enqueue the H2D of every packet accepted since the last call
+void FrameBatcher::upload_runs(LidarFrame& f) {
+    Staging& s = *stg_;
+    if (s.runs.empty() || headers_only_) {
+        s.runs.clear();
+        return;
+    }
+    ensure_decoder(f);
+    Staging::Job& j = s.job();
+    for (const Staging::Run& r : s.runs) {
+        b200::check(ob_decode_job_upload(j.job, r.src, r.src_stride, r.first, r.count));
+        if (r.user) j.user_uploads = true;
+    }
+    s.runs.clear();
+}
+
+void FrameBatcher::decode_staged(LidarFrame& f) {
+    Staging& s = *stg_;
+    if (headers_only_) return;
+    const std::vector<std::string> names = ensure_decoder(f);
+    upload_runs(f);
+    Staging::Job& j = s.job();
 
     ob_decode_io io{};
-    io.packets = s.pinned;
     io.n_slots = s.n_slots;
-    io.packet_stride = s.stride;
     bool identity = s.n_slots * static_cast<size_t>(pf.columns_per_packet) >= f.w;
-    for (size_t j = 0; j < f.w && identity; ++j) identity = s.col_src[j] == static_cast<int32_t>(j);
+    for (size_t c = 0; c < f.w && identity; ++c) identity = s.col_src[c] == static_cast<int32_t>(c);
     io.col_src = identity ? nullptr : s.col_src.data();
     for (size_t i = 0; i < names.size(); ++i) io.fields[i] = f.field(names[i]).get();
 
@@ -318,9 +457,7 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
     if (fused_ && fused_->lut) {
         lut = fused_->lut.get();
         const size_t n = f.h * f.w;
-        int n_ret = 0;
-        for (const auto& d : descs) n_ret = std::max(n_ret, d.range_return + 1);
-        for (int r = 0; r < n_ret; ++r) {
+        for (int r = 0; r < n_returns_; ++r) {
             const size_t xb = n * 3 * (fused_->lut_is_f64 ? 8 : 4);
             if (fused_->xyz[r].size() != xb) fused_->xyz[r].resize(xb);
             io.xyz[r] = fused_->xyz[r].data();
@@ -335,10 +472,60 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
         }
     }
     if (names.empty() && !lut) return;
-    ob_stream* st = b200::thread_stream();
-    b200::check(ob_decode_frames(s.dec, &io, 1, lut, shifts, n_shifts, st));
-    b200::check(ob_stream_sync(st));
+    b200::check(ob_decode_job_submit(j.job, &io, lut, shifts, n_shifts));
+    j.owner = &f;
     launches_++;
+    if (s.depth <= 1) {  // synchronous: the frame is materialised when batch() returns true
+        j.owner = nullptr;
+        j.user_uploads = false;
+        b200::check(ob_decode_job_wait(j.job));
+    }
+}
+
+size_t FrameBatcher::batch_burst(const uint8_t* packets, size_t n, size_t stride, size_t size,
+                                 const uint64_t* host_timestamps, LidarFrame& f, bool& complete) {
+    complete = false;
+    if (n == 0) return 0;
+    if (!packets || !host_timestamps) throw std::invalid_argument("null pointer");
+    if (n > 1 && stride < size) throw std::invalid_argument("packet stride smaller than the packet size");
+    Staging& s = *stg_;
+    // page-locked or device memory can be read by the copy engine where it lies
+    const bool dma = !headers_only_ && ob_pointer_kind(packets) != 0 &&
+                     ob_pointer_kind(packets + (n - 1) * stride + size - 1) != 0;
+    if (dma) {
+        s.burst_begin = packets;
+        s.burst_end = packets + (n - 1) * stride + size;
+        s.burst_stride = stride;
+    }
+    struct Window {  // the zero-copy window never outlives this call
+        Staging& s;
+        FrameBatcher& b;
+        LidarFrame& f;
+        bool ok{false};
+        ~Window() {
+            s.burst_begin = s.burst_end = nullptr;
+            if (!ok) {  // unwinding: drop pending reads of caller memory
+                s.runs.erase(std::remove_if(s.runs.begin(), s.runs.end(),
+                                            [](const Staging::Run& r) { return r.user; }),
+                             s.runs.end());
+                try {
+                    b.settle_user_uploads();
+                } catch (...) {
+                }
+            }
+        }
+    } window{s, *this, f};
+    size_t i = 0;
+    for (; i < n && !complete; ++i) complete = batch_impl(packets + i * stride, size, host_timestamps[i], f);
+    if (dma) {
+        // packets of a frame that is still open: upload now, the caller may reuse its memory
+        bool user_pending = false;
+        for (const Staging::Run& r : s.runs) user_pending |= r.user;
+        if (user_pending) upload_runs(f);
+        settle_user_uploads();
+    }
+    window.ok = true;
+    return i;
 }
 
 bool FrameBatcher::batch_with_caching(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f) {

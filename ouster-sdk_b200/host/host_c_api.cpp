@@ -4,6 +4,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "ouster/core/frame_pipeline.h"
 #include "ouster/core/lidar_frame.h"
 #include "ouster/core/xyzlut.h"
 #include "ouster_b200_host.h"
@@ -20,7 +21,10 @@ struct obh_sensor {
     bool custom{false};
 };
 struct obh_frame {
-    LidarFrame frame;
+    LidarFrame own;              // storage of frames created through obh_frame_create
+    LidarFrame* borrowed{nullptr};  // pipeline slots expose their frames without owning them
+    LidarFrame& ref() { return borrowed ? *borrowed : own; }
+    const LidarFrame& ref() const { return borrowed ? *borrowed : own; }
 };
 struct obh_batcher {
     std::unique_ptr<FrameBatcher> b;
@@ -202,9 +206,9 @@ ob_status obh_frame_create(const obh_sensor* s, obh_frame** out) {
             LidarFrameFieldTypes ft;
             for (auto it = s->pf->begin(); it != s->pf->end(); ++it)
                 ft.emplace_back(it->first, it->second.first);
-            f->frame = LidarFrame(s->info, ft);
+            f->own = LidarFrame(s->info, ft);
         } else {
-            f->frame = LidarFrame(s->info);
+            f->own = LidarFrame(s->info);
         }
         *out = f.release();
     });
@@ -215,17 +219,17 @@ ob_status obh_frame_add_field(obh_frame* f, const char* name, int32_t tag, size_
         if (!f || !name) throw std::invalid_argument("null pointer");
         std::vector<size_t> ed;
         if (extra > 1) ed.push_back(extra);
-        f->frame.add_field(name, static_cast<ChanFieldType>(tag), ed);
+        f->ref().add_field(name, static_cast<ChanFieldType>(tag), ed);
     });
 }
 
-size_t obh_frame_n_fields(const obh_frame* f) { return f ? f->frame.fields().size() : 0; }
+size_t obh_frame_n_fields(const obh_frame* f) { return f ? f->ref().fields().size() : 0; }
 
 ob_status obh_frame_field_at(obh_frame* f, size_t i, char* name, size_t cap, int32_t* tag,
                              size_t* elem_bytes, void** data) {
     return guard([&] {
-        if (!f || i >= f->frame.fields().size()) throw std::invalid_argument("field index out of range");
-        auto it = f->frame.fields().begin();
+        if (!f || i >= f->ref().fields().size()) throw std::invalid_argument("field index out of range");
+        auto it = f->ref().fields().begin();
         std::advance(it, static_cast<std::ptrdiff_t>(i));
         copy_name(it->first, name, cap);
         if (tag) *tag = static_cast<int32_t>(it->second.tag());
@@ -237,7 +241,7 @@ ob_status obh_frame_field_at(obh_frame* f, size_t i, char* name, size_t cap, int
 ob_status obh_frame_field(obh_frame* f, const char* name, int32_t* tag, size_t* elem_bytes, void** data) {
     return guard([&] {
         if (!f || !name) throw std::invalid_argument("null pointer");
-        Field& fld = f->frame.field(name);
+        Field& fld = f->ref().field(name);
         if (tag) *tag = static_cast<int32_t>(fld.tag());
         if (elem_bytes) *elem_bytes = elem_bytes_of(fld);
         if (data) *data = fld.get();
@@ -248,7 +252,7 @@ ob_status obh_frame_headers(obh_frame* f, uint64_t** ts, uint16_t** mid, uint32_
                             uint64_t** pts, uint8_t** af, size_t* w, size_t* h, size_t* np) {
     return guard([&] {
         if (!f) throw std::invalid_argument("null pointer");
-        LidarFrame& fr = f->frame;
+        LidarFrame& fr = f->ref();
         if (ts) *ts = fr.timestamp().data();
         if (mid) *mid = fr.measurement_id().data();
         if (st) *st = fr.status().data();
@@ -260,17 +264,17 @@ ob_status obh_frame_headers(obh_frame* f, uint64_t** ts, uint16_t** mid, uint32_
     });
 }
 
-int64_t obh_frame_get_frame_id(const obh_frame* f) { return f->frame.frame_id; }
-void obh_frame_set_frame_id(obh_frame* f, int64_t id) { f->frame.frame_id = id; }
+int64_t obh_frame_get_frame_id(const obh_frame* f) { return f->ref().frame_id; }
+void obh_frame_set_frame_id(obh_frame* f, int64_t id) { f->ref().frame_id = id; }
 uint64_t obh_frame_get_status(const obh_frame* f, uint8_t* sc, uint8_t* slc) {
-    if (sc) *sc = f->frame.shutdown_countdown;
-    if (slc) *slc = f->frame.shot_limiting_countdown;
-    return f->frame.frame_status;
+    if (sc) *sc = f->ref().shutdown_countdown;
+    if (slc) *slc = f->ref().shot_limiting_countdown;
+    return f->ref().frame_status;
 }
 void obh_frame_set_status(obh_frame* f, uint64_t st, uint8_t sc, uint8_t slc) {
-    f->frame.frame_status = st;
-    f->frame.shutdown_countdown = sc;
-    f->frame.shot_limiting_countdown = slc;
+    f->ref().frame_status = st;
+    f->ref().shutdown_countdown = sc;
+    f->ref().shot_limiting_countdown = slc;
 }
 ob_status obh_frame_destroy(obh_frame* f) {
     delete f;
@@ -281,7 +285,7 @@ ob_status obh_frame_to_packets(const obh_frame* f, const obh_sensor* s, uint32_t
                                uint64_t prod_sn, uint8_t* out, uint64_t* host_ts, size_t* n_out) {
     return guard([&] {
         if (!f || !s || !out || !n_out) throw std::invalid_argument("null pointer");
-        auto packets = impl::frame_to_packets(f->frame, *s->pf, init_id, prod_sn);
+        auto packets = impl::frame_to_packets(f->ref(), *s->pf, init_id, prod_sn);
         const size_t psz = s->pf->lidar_packet_size;
         for (size_t i = 0; i < packets.size(); ++i) {
             std::memcpy(out + i * psz, packets[i].buf.data(), psz);
@@ -306,7 +310,7 @@ ob_status obh_batcher_batch(obh_batcher* b, const uint8_t* packet, size_t size, 
                             obh_frame* frame, int* complete) {
     return guard([&] {
         if (!b || !packet || !frame) throw std::invalid_argument("null pointer");
-        const bool done = b->b->batch(packet, size, ts, frame->frame);
+        const bool done = b->b->batch(packet, size, ts, frame->ref());
         if (complete) *complete = done ? 1 : 0;
     });
 }
@@ -316,16 +320,15 @@ ob_status obh_batcher_batch_burst(obh_batcher* b, const uint8_t* packets, size_t
                                   size_t* consumed, int* complete) {
     return guard([&] {
         if (!b || !packets || !frame || !ts) throw std::invalid_argument("null pointer");
-        size_t i = 0;
         bool done = false;
-        for (; i < n && !done; ++i) done = b->b->batch(packets + i * stride, size, ts[i], frame->frame);
-        if (consumed) *consumed = i;
+        const size_t used = b->b->batch_burst(packets, n, stride, size, ts, frame->ref(), done);
+        if (consumed) *consumed = used;
         if (complete) *complete = done ? 1 : 0;
     });
 }
 
 ob_status obh_batcher_flush(obh_batcher* b, obh_frame* frame) {
-    return guard([&] { b->b->flush(frame->frame); });
+    return guard([&] { b->b->flush(frame->ref()); });
 }
 ob_status obh_batcher_reset(obh_batcher* b) {
     return guard([&] { b->b->reset(); });
@@ -373,8 +376,92 @@ ob_status obh_batcher_fused_outputs(obh_batcher* b, int ret, void** xyz, size_t*
     });
 }
 
+ob_status obh_batcher_set_pipeline_depth(obh_batcher* b, size_t n) {
+    return guard([&] { b->b->set_pipeline_depth(n); });
+}
+ob_status obh_batcher_wait(obh_batcher* b, obh_frame* frame) {
+    return guard([&] {
+        if (frame) b->b->wait(frame->ref());
+        else b->b->wait_all();
+    });
+}
+
 ob_status obh_batcher_destroy(obh_batcher* b) {
     delete b;
+    return OB_OK;
+}
+
+// ---- FramePipeline ----
+struct obh_pipeline {
+    std::unique_ptr<FramePipeline> p;
+    std::vector<std::pair<const FramePipeline::Slot*, std::unique_ptr<obh_frame>>> views;
+    obh_frame* view(const FramePipeline::Slot* s) {
+        for (auto& v : views)
+            if (v.first == s) return v.second.get();
+        auto f = std::make_unique<obh_frame>();
+        f->borrowed = const_cast<LidarFrame*>(&s->frame);
+        views.emplace_back(s, std::move(f));
+        return views.back().second.get();
+    }
+};
+
+static void fill_slot_out(obh_pipeline* p, const FramePipeline::Slot* s, obh_slot* out) {
+    std::memset(out, 0, sizeof(*out));
+    if (!s) return;
+    out->frame = p->view(s);
+    for (int r = 0; r < 2; ++r) {
+        out->xyz[r] = s->cloud.xyz[r].size() ? const_cast<uint8_t*>(s->cloud.xyz[r].data()) : nullptr;
+        out->range_destaggered[r] =
+            s->cloud.range_destaggered[r].size()
+                ? reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(s->cloud.range_destaggered[r].data()))
+                : nullptr;
+    }
+    out->xyz_bytes = s->cloud.xyz[0].size();
+}
+
+ob_status obh_pipeline_create(const obh_sensor* s, size_t depth, ob_lut* lut,
+                              const int32_t* shifts, size_t n_shifts, obh_pipeline** out) {
+    return guard([&] {
+        if (!s || !out) throw std::invalid_argument("null pointer");
+        if (s->custom) throw std::invalid_argument("FramePipeline does not support custom profiles yet");
+        FusedCloud proto;
+        if (lut) {
+            int dtype = OB_F32;
+            ob_lut_info(lut, nullptr, nullptr, &dtype, nullptr);
+            proto.lut = std::shared_ptr<ob_lut>(lut, [](ob_lut*) {});  // borrowed
+            proto.lut_is_f64 = dtype == OB_F64;
+            if (shifts) proto.pixel_shift_by_row.assign(shifts, shifts + n_shifts);
+        }
+        auto p = std::make_unique<obh_pipeline>();
+        p->p = std::make_unique<FramePipeline>(s->info, depth, lut ? &proto : nullptr);
+        *out = p.release();
+    });
+}
+
+ob_status obh_pipeline_push_burst(obh_pipeline* p, const uint8_t* packets, size_t n, size_t stride,
+                                  size_t size, const uint64_t* ts, size_t* consumed, obh_slot* done) {
+    return guard([&] {
+        if (!p || !packets || !ts || !done) throw std::invalid_argument("null pointer");
+        const FramePipeline::Slot* s = nullptr;
+        const size_t used = p->p->push_burst(packets, n, stride, size, ts, &s);
+        if (consumed) *consumed = used;
+        fill_slot_out(p, s, done);
+    });
+}
+
+ob_status obh_pipeline_drain(obh_pipeline* p, obh_slot* done) {
+    return guard([&] {
+        if (!p || !done) throw std::invalid_argument("null pointer");
+        fill_slot_out(p, p->p->drain(), done);
+    });
+}
+
+size_t obh_pipeline_in_flight(const obh_pipeline* p) { return p ? p->p->in_flight() : 0; }
+size_t obh_pipeline_gpu_launches(const obh_pipeline* p) { return p ? p->p->batcher().gpu_launches() : 0; }
+size_t obh_pipeline_dropped_packets(const obh_pipeline* p) { return p ? p->p->batcher().dropped_packets() : 0; }
+
+ob_status obh_pipeline_destroy(obh_pipeline* p) {
+    delete p;
     return OB_OK;
 }
 
