@@ -199,10 +199,15 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
     _, e2e_ok = e2e_step(check=True)
     stamp_ids(3000)
     torch.cuda.synchronize()
+    st0 = pipe.stats()
     t0 = time.perf_counter()
     done, _ = e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    st1 = pipe.stats()
+    host_ms = {k[:-2] + "_ms_per_frame": (st1[k] - st0[k]) * 1e3 / e2e_frames
+               for k in ("burst_s", "upload_wait_s", "submit_s", "wait_s")}
+    host_ms["total_ms_per_frame"] = e2e_s * 1e3 / e2e_frames
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -261,6 +266,7 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
                 "h2d_bytes_per_step": int(e2e_frames * n_slots * psz),
                 "d2h_bytes_per_step": int(e2e_frames * (field_bytes + R * H * W * 16)),
                 "frames": e2e_frames, "frames_completed": int(done), "matches_device_path": bool(e2e_ok),
+                "host_thread": host_ms,
                 "path": "FramePipeline.push_burst (FrameBatcher host state machine per packet, zero-copy "
                         "upload from page-locked bursts, 3 frames in flight) + one fused launch per frame"},
         "gpu_launches": int(launches),

@@ -70,6 +70,10 @@ class OUSTER_API_CLASS HostBuffer {
     size_t size() const { return n_; }
     OUSTER_API_FUNCTION void resize(size_t bytes);  ///< contents are zeroed
     OUSTER_API_FUNCTION bool operator==(const HostBuffer& o) const;
+    /// Zero-initialised buffers of the given sizes laid out back to back (256-byte aligned) in ONE
+    /// block, so that a device->host transfer of all of them is a single copy (ob_decode_job_submit
+    /// merges outputs that are adjacent in memory).  Each buffer keeps the block alive.
+    OUSTER_API_FUNCTION static std::vector<HostBuffer> carve(const std::vector<size_t>& sizes);
 
    private:
     void release();
@@ -77,6 +81,7 @@ class OUSTER_API_CLASS HostBuffer {
     size_t n_{0};
     size_t cap_{0};
     bool pinned_{false};
+    std::shared_ptr<void> arena_;  ///< set when p_ lies inside a block shared with other buffers
 };
 
 /// Typed dense buffer (field.h:828+).  Zero-initialised like the reference's calloc (field.cpp:254).
@@ -84,6 +89,8 @@ class OUSTER_API_CLASS Field {
    public:
     Field() = default;
     Field(ChanFieldType tag, const std::vector<size_t>& shape);
+    /// adopts `storage` (resized to the field's byte size when it does not match)
+    Field(ChanFieldType tag, const std::vector<size_t>& shape, HostBuffer&& storage);
     ChanFieldType tag() const { return tag_; }
     const std::vector<size_t>& shape() const { return shape_; }
     size_t element_size() const { return field_type_size(tag_); }
@@ -201,6 +208,7 @@ class OUSTER_API_CLASS LidarFrame {
    private:
     Field& checked(const std::string& name, ChanFieldType tag);
     void init_headers(size_t columns_per_packet);
+    std::vector<size_t> field_shape(FieldClass field_class, const std::vector<size_t>& extra_dims) const;
     std::map<std::string, Field> fields_;
     std::map<std::string, FieldClass> field_class_;
     std::vector<uint64_t> timestamp_;
@@ -240,6 +248,9 @@ struct OUSTER_API_CLASS FusedCloud {
     std::vector<int> pixel_shift_by_row;   ///< empty: no destaggered range
     HostBuffer xyz[2];                     ///< (h*w) x 3 of float|double per return, staggered order
     HostBuffer range_destaggered[2];       ///< h x w uint32 per return
+    /// (Re)allocate the outputs of n_returns returns for an h x w frame in one page-locked block;
+    /// no-op when they already have the right sizes.  FrameBatcher calls this before each launch.
+    OUSTER_API_FUNCTION void reserve(size_t h, size_t w, int n_returns);
     const float* xyz_f32(int r) const { return reinterpret_cast<const float*>(xyz[r].data()); }
     const double* xyz_f64(int r) const { return reinterpret_cast<const double*>(xyz[r].data()); }
     const uint32_t* rd(int r) const { return reinterpret_cast<const uint32_t*>(range_destaggered[r].data()); }
@@ -280,6 +291,15 @@ class OUSTER_API_CLASS FrameBatcher {
     OUSTER_API_FUNCTION void set_headers_only(bool on);
     /// Kernel launches issued by this batcher.
     OUSTER_API_FUNCTION size_t gpu_launches() const;
+    /// Cumulative host-side time of the calling thread, by phase (nanoseconds).  ns_burst is the
+    /// total spent inside batch_burst(); ns_upload_wait (waiting for zero-copy uploads to leave the
+    /// caller's memory) and ns_submit (decode table, launch, D2H enqueue) are parts of it; ns_wait
+    /// is time blocked on finished GPU passes (wait(), ring reuse, synchronous mode).
+    struct Stats {
+        uint64_t ns_burst{0}, ns_upload_wait{0}, ns_submit{0}, ns_wait{0};
+        size_t frames{0};
+    };
+    OUSTER_API_FUNCTION const Stats& stats() const;
     /// Feed `n` packets laid out `stride` bytes apart (host_timestamps[i] belongs to packet i) until
     /// a frame completes; returns the number of packets consumed.  When the burst lies in
     /// page-locked (cudaHostAlloc / cudaHostRegister) or device memory the copy engine reads the
@@ -325,6 +345,7 @@ class OUSTER_API_CLASS FrameBatcher {
     bool headers_only_{false};
     size_t launches_{0};
     int n_returns_{0};
+    Stats stats_;
 
     bool batch_impl(const uint8_t* buf, size_t size, uint64_t host_ts, LidarFrame& f);
     void cache_packet(const uint8_t* buf, size_t size, uint64_t host_ts);

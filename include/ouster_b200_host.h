@@ -121,6 +121,8 @@ ob_status obh_pipeline_push_burst(obh_pipeline* p, const uint8_t* packets, size_
                                   size_t size, const uint64_t* host_timestamps, size_t* consumed,
                                   obh_slot* done);
 ob_status obh_pipeline_drain(obh_pipeline* p, obh_slot* done);
+/* FrameBatcher::Stats of the pipeline's batcher: ns_burst, ns_upload_wait, ns_submit, ns_wait, frames */
+ob_status obh_pipeline_stats(const obh_pipeline* p, uint64_t* out5);
 size_t obh_pipeline_in_flight(const obh_pipeline* p);
 size_t obh_pipeline_gpu_launches(const obh_pipeline* p);
 size_t obh_pipeline_dropped_packets(const obh_pipeline* p);

@@ -547,13 +547,26 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
         add(io->xyz[r], n_px * 3 * (ldtype == OB_F64 ? 8 : 4), &xyz[r]);
         add(io->range_destaggered[r], n_px * 4, &rd[r]);
     }
-    size_t need = 0;
+    // host outputs take slab space in ADDRESS order; buffers that are adjacent in host memory
+    // (HostBuffer::carve) stay adjacent in the slab, so their D2H is one copy
+    size_t order[OB_MAX_FIELDS + 3 + 2 * OB_MAX_RETURNS];
+    size_t n_host = 0;
     for (size_t i = 0; i < n_out; ++i) {
         outs[i].host = !is_device_ptr(outs[i].user);
-        if (outs[i].host) {
-            outs[i].off = need;
-            need += (outs[i].bytes + 255) & ~static_cast<size_t>(255);
-        }
+        if (outs[i].host) order[n_host++] = i;
+    }
+    std::sort(order, order + n_host, [&](size_t a, size_t b) {
+        return reinterpret_cast<uintptr_t>(outs[a].user) < reinterpret_cast<uintptr_t>(outs[b].user);
+    });
+    size_t need = 0;
+    for (size_t k = 0; k < n_host; ++k) {
+        Out& o = outs[order[k]];
+        const bool adjacent = k > 0 && static_cast<uint8_t*>(outs[order[k - 1]].user) + outs[order[k - 1]].bytes ==
+                                           static_cast<uint8_t*>(o.user) &&
+                              (need % 16) == 0;
+        if (!adjacent) need = (need + 255) & ~static_cast<size_t>(255);
+        o.off = need;
+        need += o.bytes;
     }
     cudaError_t e = cudaSuccess;
     if (need > j->out_bytes) {  // job is idle here
@@ -603,10 +616,17 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
     a.vec_ok = vec_ok;
     e = launch_decode(a, j->device, j->st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
-    for (size_t i = 0; i < n_out; ++i) {
-        if (!outs[i].host) continue;
-        e = cudaMemcpyAsync(outs[i].user, j->d_out + outs[i].off, outs[i].bytes, cudaMemcpyDeviceToHost, j->st);
+    for (size_t k = 0; k < n_host;) {  // one D2H per run of outputs contiguous on both sides
+        const Out& first = outs[order[k]];
+        size_t bytes = first.bytes, m = k + 1;
+        while (m < n_host && outs[order[m]].off == first.off + bytes &&
+               static_cast<uint8_t*>(outs[order[m]].user) == static_cast<uint8_t*>(first.user) + bytes) {
+            bytes += outs[order[m]].bytes;
+            ++m;
+        }
+        e = cudaMemcpyAsync(first.user, j->d_out + first.off, bytes, cudaMemcpyDeviceToHost, j->st);
         if (e != cudaSuccess) return fail_cuda(e, "decode D2H");
+        k = m;
     }
     e = cudaEventRecord(j->ev_done, j->st);
     if (e != cudaSuccess) return fail_cuda(e, "decode job event");

@@ -69,6 +69,7 @@ class Slot(C.Structure):
 _sig("obh_pipeline_create", i32, vp, sz, vp, vp, sz, PP(vp))
 _sig("obh_pipeline_push_burst", i32, vp, vp, sz, sz, sz, vp, PP(sz), PP(Slot))
 _sig("obh_pipeline_drain", i32, vp, PP(Slot))
+_sig("obh_pipeline_stats", i32, vp, vp)
 _sig("obh_pipeline_in_flight", sz, vp)
 _sig("obh_pipeline_gpu_launches", sz, vp)
 _sig("obh_pipeline_dropped_packets", sz, vp)
@@ -450,6 +451,13 @@ class FramePipeline:
     @property
     def in_flight(self):
         return lib.obh_pipeline_in_flight(self._h)
+
+    def stats(self):
+        """Cumulative host-thread time by phase (FrameBatcher::Stats), seconds."""
+        a = np.zeros(5, np.uint64)
+        check(lib.obh_pipeline_stats(self._h, a.ctypes.data))
+        return {"burst_s": a[0] * 1e-9, "upload_wait_s": a[1] * 1e-9, "submit_s": a[2] * 1e-9,
+                "wait_s": a[3] * 1e-9, "frames": int(a[4])}
 
     @property
     def gpu_launches(self):

@@ -10,6 +10,7 @@
 // Device side, when the frame is finalized: decode of every field of every pixel + zero fill
 // (+ optional destagger and XYZ), reading the staged packets once.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -21,6 +22,21 @@
 namespace ouster {
 namespace sdk {
 namespace core {
+
+namespace {
+constexpr size_t kUploadChunk = 32;  // packets per early upload of a zero-copy burst (~1 MB)
+inline uint64_t now_ns() {
+    return static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                     std::chrono::steady_clock::now().time_since_epoch())
+                                     .count());
+}
+struct ScopedNs {  // adds the lifetime of the object to a counter
+    uint64_t& acc;
+    uint64_t t0;
+    explicit ScopedNs(uint64_t& a) : acc(a), t0(now_ns()) {}
+    ~ScopedNs() { acc += now_ns() - t0; }
+};
+}  // namespace
 
 // One frame in flight: an ob_decode_job (device packet slots + output slab + events) on its own
 // stream, and a page-locked bounce buffer for packets that arrive in pageable memory.
@@ -130,6 +146,7 @@ FrameBatcher::~FrameBatcher() {
 size_t FrameBatcher::batched_packets() const { return batched_lidar_packets_; }
 size_t FrameBatcher::dropped_packets() const { return dropped_packets_; }
 size_t FrameBatcher::gpu_launches() const { return launches_; }
+const FrameBatcher::Stats& FrameBatcher::stats() const { return stats_; }
 void FrameBatcher::set_fused_cloud(FusedCloud* cloud) { fused_ = cloud; }
 
 void FrameBatcher::set_max_cache_size(size_t n) {
@@ -153,7 +170,7 @@ void FrameBatcher::reset() {
 void FrameBatcher::set_pipeline_depth(size_t n) {
     if (n == 0) n = 1;
     wait_all();
-    if (stg_->n_slots != 0 && n != stg_->depth)
+    if (batched_lidar_packets_ != 0 && n != stg_->depth)
         throw std::logic_error("set_pipeline_depth: a frame is being batched; call between frames or after reset()");
     stg_->depth = n;
     if (stg_->jobs.size() < n) stg_->jobs.resize(n);
@@ -162,6 +179,7 @@ void FrameBatcher::set_pipeline_depth(size_t n) {
 size_t FrameBatcher::pipeline_depth() const { return stg_->depth; }
 
 void FrameBatcher::wait(const LidarFrame& f) {
+    ScopedNs t(stats_.ns_wait);
     for (Staging::Job& j : stg_->jobs)
         if (j.owner == &f && j.job) {
             j.owner = nullptr;
@@ -170,6 +188,7 @@ void FrameBatcher::wait(const LidarFrame& f) {
 }
 
 void FrameBatcher::wait_all() {
+    ScopedNs t(stats_.ns_wait);
     for (Staging::Job& j : stg_->jobs)
         if (j.job) {
             j.owner = nullptr;
@@ -179,6 +198,7 @@ void FrameBatcher::wait_all() {
 
 // uploads that read caller memory must have left it before control returns to the caller
 void FrameBatcher::settle_user_uploads() {
+    ScopedNs t(stats_.ns_upload_wait);
     for (Staging::Job& j : stg_->jobs)
         if (j.user_uploads && j.job) {
             j.user_uploads = false;
@@ -227,6 +247,7 @@ void FrameBatcher::start_frame(int64_t f_id, const uint8_t* packet_buf, LidarFra
     // next job of the ring; its previous frame (depth frames ago) must have completed
     if (s.depth > 1) s.cur = (s.cur + 1) % s.depth;
     if (s.job().job) {
+        ScopedNs t(stats_.ns_wait);
         s.job().owner = nullptr;
         b200::check(ob_decode_job_wait(s.job().job));
     }
@@ -428,7 +449,7 @@ void FrameBatcher::upload_runs(LidarFrame& f) {
         s.runs.clear();
         return;
     }
-    ensure_decoder(f);
+    if (!s.job().job) ensure_decoder(f);
     Staging::Job& j = s.job();
     for (const Staging::Run& r : s.runs) {
         b200::check(ob_decode_job_upload(j.job, r.src, r.src_stride, r.first, r.count));
@@ -440,6 +461,7 @@ void FrameBatcher::upload_runs(LidarFrame& f) {
 void FrameBatcher::decode_staged(LidarFrame& f) {
     Staging& s = *stg_;
     if (headers_only_) return;
+    ScopedNs t_submit(stats_.ns_submit);
     const std::vector<std::string> names = ensure_decoder(f);
     upload_runs(f);
     Staging::Job& j = s.job();
@@ -456,15 +478,11 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
     size_t n_shifts = 0;
     if (fused_ && fused_->lut) {
         lut = fused_->lut.get();
-        const size_t n = f.h * f.w;
+        fused_->reserve(f.h, f.w, n_returns_);
         for (int r = 0; r < n_returns_; ++r) {
-            const size_t xb = n * 3 * (fused_->lut_is_f64 ? 8 : 4);
-            if (fused_->xyz[r].size() != xb) fused_->xyz[r].resize(xb);
             io.xyz[r] = fused_->xyz[r].data();
-            if (!fused_->pixel_shift_by_row.empty()) {
-                if (fused_->range_destaggered[r].size() != n * 4) fused_->range_destaggered[r].resize(n * 4);
+            if (!fused_->pixel_shift_by_row.empty())
                 io.range_destaggered[r] = reinterpret_cast<uint32_t*>(fused_->range_destaggered[r].data());
-            }
         }
         if (!fused_->pixel_shift_by_row.empty()) {
             shifts = fused_->pixel_shift_by_row.data();
@@ -475,7 +493,9 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
     b200::check(ob_decode_job_submit(j.job, &io, lut, shifts, n_shifts));
     j.owner = &f;
     launches_++;
-    if (s.depth <= 1) {  // synchronous: the frame is materialised when batch() returns true
+    stats_.frames++;
+    if (s.depth <= 1) {
+        ScopedNs t(stats_.ns_wait);  // synchronous: the frame is materialised when batch() returns true
         j.owner = nullptr;
         j.user_uploads = false;
         b200::check(ob_decode_job_wait(j.job));
@@ -486,6 +506,7 @@ size_t FrameBatcher::batch_burst(const uint8_t* packets, size_t n, size_t stride
                                  const uint64_t* host_timestamps, LidarFrame& f, bool& complete) {
     complete = false;
     if (n == 0) return 0;
+    ScopedNs t_total(stats_.ns_burst);
     if (!packets || !host_timestamps) throw std::invalid_argument("null pointer");
     if (n > 1 && stride < size) throw std::invalid_argument("packet stride smaller than the packet size");
     Staging& s = *stg_;
@@ -516,7 +537,12 @@ size_t FrameBatcher::batch_burst(const uint8_t* packets, size_t n, size_t stride
         }
     } window{s, *this, f};
     size_t i = 0;
-    for (; i < n && !complete; ++i) complete = batch_impl(packets + i * stride, size, host_timestamps[i], f);
+    for (; i < n && !complete; ++i) {
+        complete = batch_impl(packets + i * stride, size, host_timestamps[i], f);
+        // start the DMA of what has been accepted so far: it overlaps the parsing of the rest
+        if (dma && !complete && s.runs.size() == 1 && s.runs[0].user && s.runs[0].count >= kUploadChunk)
+            upload_runs(f);
+    }
     if (dma) {
         // packets of a frame that is still open: upload now, the caller may reuse its memory
         bool user_pending = false;

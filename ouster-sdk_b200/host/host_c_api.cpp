@@ -456,6 +456,17 @@ ob_status obh_pipeline_drain(obh_pipeline* p, obh_slot* done) {
     });
 }
 
+ob_status obh_pipeline_stats(const obh_pipeline* p, uint64_t* out5) {
+    return guard([&] {
+        if (!p || !out5) throw std::invalid_argument("null pointer");
+        const FrameBatcher::Stats& st = p->p->batcher().stats();
+        out5[0] = st.ns_burst;
+        out5[1] = st.ns_upload_wait;
+        out5[2] = st.ns_submit;
+        out5[3] = st.ns_wait;
+        out5[4] = st.frames;
+    });
+}
 size_t obh_pipeline_in_flight(const obh_pipeline* p) { return p ? p->p->in_flight() : 0; }
 size_t obh_pipeline_gpu_launches(const obh_pipeline* p) { return p ? p->p->batcher().gpu_launches() : 0; }
 size_t obh_pipeline_dropped_packets(const obh_pipeline* p) { return p ? p->p->batcher().dropped_packets() : 0; }

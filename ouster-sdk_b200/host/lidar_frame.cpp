@@ -70,7 +70,8 @@ HostBuffer::HostBuffer(const HostBuffer& o) {
     resize(o.n_);
     if (o.n_) std::memcpy(p_, o.p_, o.n_);
 }
-HostBuffer::HostBuffer(HostBuffer&& o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_), pinned_(o.pinned_) {
+HostBuffer::HostBuffer(HostBuffer&& o) noexcept
+    : p_(o.p_), n_(o.n_), cap_(o.cap_), pinned_(o.pinned_), arena_(std::move(o.arena_)) {
     o.p_ = nullptr;
     o.n_ = o.cap_ = 0;
 }
@@ -88,6 +89,7 @@ HostBuffer& HostBuffer::operator=(HostBuffer&& o) noexcept {
         n_ = o.n_;
         cap_ = o.cap_;
         pinned_ = o.pinned_;
+        arena_ = std::move(o.arena_);
         o.p_ = nullptr;
         o.n_ = o.cap_ = 0;
     }
@@ -95,9 +97,34 @@ HostBuffer& HostBuffer::operator=(HostBuffer&& o) noexcept {
 }
 HostBuffer::~HostBuffer() { release(); }
 void HostBuffer::release() {
-    pool().give_back(p_, cap_, pinned_);
+    if (arena_) arena_.reset();  // the shared block goes back to the pool with its last user
+    else pool().give_back(p_, cap_, pinned_);
     p_ = nullptr;
     n_ = cap_ = 0;
+}
+
+std::vector<HostBuffer> HostBuffer::carve(const std::vector<size_t>& sizes) {
+    auto align = [](size_t n) { return (n + 255) & ~static_cast<size_t>(255); };
+    size_t total = 0;
+    for (size_t n : sizes) total += align(n);
+    std::vector<HostBuffer> out(sizes.size());
+    if (total == 0) return out;
+    size_t cap = 0;
+    bool pinned = false;
+    void* block = pool().acquire(total, &cap, &pinned);
+    std::memset(block, 0, total);
+    std::shared_ptr<void> arena(block, [cap, pinned](void* p) { pool().give_back(p, cap, pinned); });
+    size_t off = 0;
+    for (size_t i = 0; i < sizes.size(); ++i) {
+        if (sizes[i] == 0) continue;
+        out[i].p_ = static_cast<uint8_t*>(block) + off;
+        out[i].n_ = sizes[i];
+        out[i].cap_ = align(sizes[i]);
+        out[i].pinned_ = pinned;
+        out[i].arena_ = arena;
+        off += align(sizes[i]);
+    }
+    return out;
 }
 void HostBuffer::resize(size_t bytes) {
     if (bytes > cap_ || p_ == nullptr) {
@@ -117,6 +144,13 @@ Field::Field(ChanFieldType tag, const std::vector<size_t>& shape) : tag_(tag), s
     size_t n = field_type_size(tag);
     for (size_t d : shape) n *= d;
     buf_.resize(n);
+}
+
+Field::Field(ChanFieldType tag, const std::vector<size_t>& shape, HostBuffer&& storage)
+    : tag_(tag), shape_(shape), buf_(std::move(storage)) {
+    size_t n = field_type_size(tag);
+    for (size_t d : shape) n *= d;
+    if (buf_.size() != n) buf_.resize(n);
 }
 
 void Field::set_zero() {
@@ -233,7 +267,22 @@ LidarFrame::LidarFrame(size_t h_, size_t w_, const LidarFrameFieldTypes& field_t
                        size_t columns_per_packet)
     : w(w_), h(h_) {
     init_headers(columns_per_packet);
-    for (const auto& ft : field_types) add_field(ft);
+    // the initial fields share one page-locked block (see HostBuffer::carve)
+    std::vector<std::vector<size_t>> shapes;
+    std::vector<size_t> sizes;
+    for (const auto& ft : field_types) {
+        shapes.push_back(field_shape(ft.field_class, ft.extra_dims));
+        size_t n = field_type_size(ft.element_type);
+        for (size_t d : shapes.back()) n *= d;
+        sizes.push_back(n);
+    }
+    std::vector<HostBuffer> bufs = HostBuffer::carve(sizes);
+    for (size_t i = 0; i < field_types.size(); ++i) {
+        const FieldType& ft = field_types[i];
+        if (has_field(ft.name)) throw std::invalid_argument("Duplicated field '" + ft.name + "'");
+        field_class_[ft.name] = ft.field_class;
+        fields_.emplace(ft.name, Field(ft.element_type, shapes[i], std::move(bufs[i])));
+    }
 }
 
 LidarFrame::LidarFrame(size_t h_, size_t w_, UDPProfileLidar profile, size_t columns_per_packet)
@@ -281,6 +330,11 @@ Field& LidarFrame::checked(const std::string& name, ChanFieldType tag) {
 Field& LidarFrame::add_field(const std::string& name, ChanFieldType type,
                              const std::vector<size_t>& extra_dims, FieldClass field_class) {
     if (has_field(name)) throw std::invalid_argument("Duplicated field '" + name + "'");
+    field_class_[name] = field_class;
+    return fields_.emplace(name, Field(type, field_shape(field_class, extra_dims))).first->second;
+}
+
+std::vector<size_t> LidarFrame::field_shape(FieldClass field_class, const std::vector<size_t>& extra_dims) const {
     std::vector<size_t> shape;
     switch (field_class) {
         case FieldClass::PIXEL_FIELD: shape = {h, w}; break;
@@ -289,8 +343,29 @@ Field& LidarFrame::add_field(const std::string& name, ChanFieldType type,
         default: break;
     }
     shape.insert(shape.end(), extra_dims.begin(), extra_dims.end());
-    field_class_[name] = field_class;
-    return fields_.emplace(name, Field(type, shape)).first->second;
+    return shape;
+}
+
+void FusedCloud::reserve(size_t fh, size_t fw, int n_returns) {
+    const size_t n = fh * fw;
+    const size_t xb = n * 3 * (lut_is_f64 ? 8 : 4);
+    const size_t rb = pixel_shift_by_row.empty() ? 0 : n * 4;
+    bool ok = true;
+    for (int r = 0; r < 2; ++r) {
+        const bool on = r < n_returns;
+        ok &= xyz[r].size() == (on ? xb : 0) && range_destaggered[r].size() == (on ? rb : 0);
+    }
+    if (ok) return;
+    std::vector<size_t> sizes;
+    for (int r = 0; r < 2; ++r) {
+        sizes.push_back(r < n_returns ? xb : 0);
+        sizes.push_back(r < n_returns ? rb : 0);
+    }
+    std::vector<HostBuffer> bufs = HostBuffer::carve(sizes);
+    for (int r = 0; r < 2; ++r) {
+        xyz[r] = std::move(bufs[2 * r]);
+        range_destaggered[r] = std::move(bufs[2 * r + 1]);
+    }
 }
 
 Field& LidarFrame::add_field(const FieldType& t) {

@@ -206,7 +206,7 @@ def test_decode_job_c_abi_device_outputs(ob):
     lib.ob_decode_job_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     for f in ("ob_decode_job_uploads_done", "ob_decode_job_wait", "ob_decode_job_destroy", "ob_decode_job_busy"):
         getattr(lib, f).argtypes = [C.c_void_p]
-    check(lib.ob_decode_job_create(dec._h, 4, st._h, C.byref(job)))     # reserve < needed: grows
+    check(lib.ob_decode_job_create(dec._h, 4, st.h, C.byref(job)))     # reserve < needed: grows
     half = pk.shape[0] // 2
     check(lib.ob_decode_job_upload(job, pk.ctypes.data, pk.strides[0], 0, half))
     check(lib.ob_decode_job_upload(job, pk[half:].ctypes.data, pk.strides[0], half, pk.shape[0] - half))
