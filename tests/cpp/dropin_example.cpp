@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "ouster/core/frame_pipeline.h"
 #include "ouster/core/lidar_scan.h"  // deprecated forwarding header
 #include "ouster/core/pose_util.h"
 #include "ouster/core/xyzlut.h"
@@ -170,6 +171,30 @@ int main() {
             batcher.batch(packets[0], wrong);
         },
         "unexpected frame dimensions");
+
+    // ---- B200 extension: FramePipeline keeps several frames in flight ----
+    {
+        FusedCloud proto;
+        XYZLutT<float> flut(*info);
+        proto.lut = flut.device_lut();
+        proto.pixel_shift_by_row = info->format.pixel_shift_by_row;
+        FramePipeline pipe(info, 2, &proto);
+        size_t finished = 0;
+        auto verify = [&](const FramePipeline::Slot* s, int64_t want_id) {
+            CHECK(s->frame.frame_id == want_id);
+            CHECK(s->frame.field(ChanField::RANGE) == scan.field(ChanField::RANGE));
+            PointCloudXYZf want = flut(scan.field<uint32_t>(ChanField::RANGE));
+            CHECK(std::memcmp(want.data(), s->cloud.xyz_f32(0), sizeof(float) * 3 * h * w) == 0);
+            ++finished;
+        };
+        for (int k = 0; k < 5; ++k) {
+            scan.frame_id = 800 + k;
+            for (const Packet& p : impl::frame_to_packets(scan, pf, 0, 0))
+                if (const FramePipeline::Slot* s = pipe.push(p)) verify(s, 800 + static_cast<int64_t>(finished));
+        }
+        while (const FramePipeline::Slot* s = pipe.drain()) verify(s, 800 + static_cast<int64_t>(finished));
+        CHECK(finished == 5);
+    }
 
     std::printf("DROPIN OK launches=%zu\n", batcher.gpu_launches());
     return 0;
