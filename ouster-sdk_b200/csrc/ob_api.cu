@@ -50,6 +50,8 @@ static Tunables& tunables_mut(int device) {
         t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384)));
         t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
         t.decode_tile_packets = std::max(0, env_int("OB_DECODE_TILE_PACKETS", 0));  // 0 = auto
+        t.decode_prefetch = env_int("OB_DECODE_PREFETCH", 0);
+        t.decode_runtime_plans = env_int("OB_DECODE_RUNTIME_PLANS", 0);
         t.force_fallback = env_int("OB_FORCE_FALLBACK", 0);
         int sm = 148;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
@@ -81,6 +83,8 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "decode_threads") t.decode_threads = std::min(384, std::max(64, value / 32 * 32));
     else if (n == "decode_ctas_per_sm") t.decode_ctas_per_sm = std::max(1, value);
     else if (n == "decode_tile_packets") t.decode_tile_packets = std::max(0, value);
+    else if (n == "decode_prefetch") t.decode_prefetch = value;
+    else if (n == "decode_runtime_plans") t.decode_runtime_plans = value ? 1 : 0;
     else if (n == "force_fallback") t.force_fallback = value;
     else return false;
     return true;

@@ -20,6 +20,7 @@
 // are bulk-copied; irregular groups are gathered column by column by the threads.
 #include <algorithm>
 #include <type_traits>
+#include <utility>
 
 #include "ob_internal.h"
 #include "ob_ptx.cuh"
@@ -46,6 +47,10 @@ struct DecodeParams {
     int32_t cpp_shift;          // log2(columns_per_packet) or -1
     uint32_t range_field[OB_MAX_RETURNS];  // index of the range field of each return
     uint32_t plan_ranges_fast;  // the range fields have 32-bit plans
+    uint32_t prefetch;          // L2 prefetch of the next tile (Tunables::decode_prefetch)
+    uint32_t layout_id;         // > 0: compile-time pixel layout (see PxLayout); 0: runtime plans
+    signed char slot_field[16]; // layout slot -> index into fields[] (or -1: field not in the frame)
+    uint32_t layout_all;        // every slot of the layout is a decoder field
     struct Plan {        // per-field extraction plan, precomputed on the host (see make_plan)
         uint32_t wa;     // aligned 32-bit word (from the pixel start) holding the field's LSB
         uint32_t ma, mb; // masks of that word and the next one
@@ -158,6 +163,9 @@ __device__ __forceinline__ void decode_rows(const uint8_t* px0, unsigned cds, co
                                             size_t pix0, unsigned W, unsigned H, int warp, int nwarps,
                                             uint32_t* rdp, const DecodeParams& p) {
     constexpr bool HAS_OUT = MODE != 3, RR = MODE != 1;
+    // output pointers come from the frame table (generic): tell the compiler they are global memory
+    if (HAS_OUT) __builtin_assume(__isGlobal(out));
+    if (RR) __builtin_assume(__isGlobal(rdp));
     const uint32_t lsh = pl.d > 0 ? static_cast<uint32_t>(pl.d) : 0u;
     const uint32_t rsh = pl.d < 0 ? static_cast<uint32_t>(-pl.d) : 0u;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(px0 + static_cast<size_t>(warp) * cds) + pl.wa;
@@ -267,10 +275,20 @@ __device__ __forceinline__ void project_rows(const T* dir, const T* offs, T* xo0
     bool first[VN];
 #pragma unroll
     for (int e = 0; e < VN; ++e) first[e] = (k0 + e) < 3u;
+    __builtin_assume(__isGlobal(dir));
+    __builtin_assume(__isGlobal(offs));
+    if (BOTH || xo0 != nullptr) __builtin_assume(__isGlobal(xo0));
+    if (BOTH || xo1 != nullptr) __builtin_assume(__isGlobal(xo1));
+    // software pipeline: the LUT chunk of the next row is in flight while this row is computed
+    V dv = *reinterpret_cast<const V*>(dir);
+    V ov = *reinterpret_cast<const V*>(offs);
 #pragma unroll 2
     for (unsigned row = row0; row < H; row += rows_per_pass) {
-        const V dv = *reinterpret_cast<const V*>(dir);
-        const V ov = *reinterpret_cast<const V*>(offs);
+        V dvn = dv, ovn = ov;
+        if (row + rows_per_pass < H) {
+            dvn = *reinterpret_cast<const V*>(dir + estep);
+            ovn = *reinterpret_cast<const V*>(offs + estep);
+        }
         const T* de = reinterpret_cast<const T*>(&dv);
         const T* oe = reinterpret_cast<const T*>(&ov);
         if (BOTH || xo0 != nullptr) {
@@ -295,7 +313,156 @@ __device__ __forceinline__ void project_rows(const T* dir, const T* offs, T* xo0
         wb += wstep;
         dir += estep;
         offs += estep;
+        dv = dvn;
+        ov = ovn;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compile-time pixel layouts.  The channel-data block of the standard profiles is a fixed bit
+// field (parsing.cpp:170-363); with the layout known at compile time a pixel is read once
+// (cds/4 LDS) and every field is one or two ALU instructions and one store -- no per-field pass,
+// no per-field branches.  A slot is (first bit, width, up-shift, destination element size, return
+// whose range image it is or -1); names do not matter, so profiles that only rename a slot
+// (NEAR_IR / ZONE_MASK) share a layout.  launch_decode() matches the decoder's runtime field
+// table against these slots; anything else (custom profiles, RAW32_WORDn, RGB, wider
+// destinations) keeps the runtime-plan path above.
+// ---------------------------------------------------------------------------------------------
+struct PxSlot {
+    unsigned short lsb;
+    unsigned char bits, up, es;
+    signed char ret;
+};
+constexpr int kMaxSlots = 16;
+template <int L>
+struct PxLayout;
+template <>
+struct PxLayout<1> {  // 16-byte dual-return pixel: RNG19_RFL8_SIG16_NIR16_DUAL, ..._ZONE16_DUAL
+    static constexpr int cds = 16, n = 10;
+    static constexpr PxSlot s[n] = {{0, 19, 0, 4, 0},  {19, 5, 0, 1, -1},  {24, 8, 0, 1, -1}, {32, 19, 0, 4, 1},
+                                    {51, 5, 0, 1, -1}, {56, 8, 0, 1, -1},  {64, 16, 0, 2, -1}, {80, 16, 0, 2, -1},
+                                    {96, 16, 0, 2, -1}, {120, 8, 0, 1, -1}};
+};
+template <>
+struct PxLayout<2> {  // 12-byte single-return pixel: RNG19_RFL8_SIG16_NIR16 (+ _ZONE16)
+    static constexpr int cds = 12, n = 8;
+    static constexpr PxSlot s[n] = {{0, 19, 0, 4, 0},   {19, 5, 0, 1, -1},  {32, 8, 0, 1, -1}, {40, 8, 0, 1, -1},
+                                    {48, 16, 0, 2, -1}, {64, 16, 0, 2, -1}, {80, 16, 0, 2, -1}, {88, 8, 0, 1, -1}};
+};
+template <>
+struct PxLayout<3> {  // 4-byte low-data-rate pixel: RNG15_RFL8_NIR8, RNG15_RFL8_WIN8
+    static constexpr int cds = 4, n = 5;
+    static constexpr PxSlot s[n] = {{0, 15, 3, 4, 0}, {15, 1, 0, 1, -1}, {16, 8, 0, 1, -1}, {24, 8, 4, 2, -1},
+                                    {24, 8, 0, 1, -1}};
+};
+template <>
+struct PxLayout<4> {  // 8-byte low-data-rate dual pixel: (FUSA_)RNG15_RFL8_NIR8_DUAL, RNG15_RFL8_NIR8_ZONE16
+    static constexpr int cds = 8, n = 9;
+    static constexpr PxSlot s[n] = {{0, 15, 3, 4, 0},  {15, 1, 0, 1, -1}, {16, 8, 0, 1, -1}, {24, 8, 4, 2, -1},
+                                    {32, 15, 3, 4, 1}, {47, 1, 0, 1, -1}, {48, 8, 0, 1, -1}, {56, 8, 0, 1, -1},
+                                    {32, 16, 0, 2, -1}};
+};
+template <>
+struct PxLayout<5> {  // LEGACY 12-byte pixel
+    static constexpr int cds = 12, n = 5;
+    static constexpr PxSlot s[n] = {{0, 20, 0, 4, 0}, {28, 4, 0, 1, -1}, {32, 8, 0, 1, -1}, {48, 16, 0, 2, -1},
+                                    {64, 16, 0, 2, -1}};
+};
+
+template <int L, int I>
+__device__ __forceinline__ uint32_t slot_value(const uint32_t (&w)[PxLayout<L>::cds / 4]) {
+    constexpr PxSlot sl = PxLayout<L>::s[I];
+    constexpr int wi = sl.lsb / 32, bo = sl.lsb % 32;
+    constexpr uint32_t mask = sl.bits >= 32 ? 0xffffffffu : ((1u << sl.bits) - 1u);
+    uint32_t v;
+    if constexpr (bo + sl.bits <= 32) {
+        v = w[wi];
+        if constexpr (bo != 0) v >>= bo;
+        if constexpr (bo + sl.bits != 32) v &= mask;
+    } else {
+        v = __funnelshift_r(w[wi], w[wi + 1], bo) & mask;
+    }
+    if constexpr (sl.up != 0) v <<= sl.up;
+    return v;
+}
+
+// ALL: every slot of the layout has an output image and every range slot a destaggered image
+// (the default LidarFrame of the profile with a fused cloud) -> no null tests in the row loop.
+template <int L, int I, bool FULL, bool ALL>
+__device__ __forceinline__ void slot_store(const uint32_t (&w)[PxLayout<L>::cds / 4], uint8_t* const (&outp)[kMaxSlots],
+                                           uint32_t* const (&rdp)[2], unsigned pix, unsigned rdpix,
+                                           bool col_valid, bool lane_on) {
+    constexpr PxSlot sl = PxLayout<L>::s[I];
+    uint8_t* o = outp[I];
+    uint32_t* r = nullptr;
+    if constexpr (sl.ret >= 0) r = rdp[sl.ret];
+    if (ALL || o != nullptr || r != nullptr) {  // uniform per tile
+        uint32_t v = slot_value<L, I>(w);
+        if (!FULL) v = col_valid ? v : 0u;
+        if (FULL || lane_on) {
+            if (ALL || o != nullptr) {
+                __builtin_assume(__isGlobal(o));
+                if constexpr (sl.es == 4) reinterpret_cast<uint32_t*>(o)[pix] = v;
+                else if constexpr (sl.es == 2) reinterpret_cast<uint16_t*>(o)[pix] = static_cast<uint16_t>(v);
+                else o[pix] = static_cast<uint8_t>(v);
+            }
+            if constexpr (sl.ret >= 0) {
+                if (ALL || r != nullptr) {
+                    __builtin_assume(__isGlobal(r));
+                    r[rdpix] = v;
+                }
+            }
+        }
+    }
+}
+
+template <int L, bool FULL, bool ALL, int... I>
+__device__ __forceinline__ void store_all(const uint32_t (&w)[PxLayout<L>::cds / 4], uint8_t* const (&outp)[kMaxSlots],
+                                          uint32_t* const (&rdp)[2], unsigned pix, unsigned rdpix, bool col_valid,
+                                          bool lane_on, std::integer_sequence<int, I...>) {
+    (slot_store<L, I, FULL, ALL>(w, outp, rdp, pix, rdpix, col_valid, lane_on), ...);
+}
+
+// Phase A with a compile-time layout: lane = frame column, warps stride the rows, all fields of a
+// pixel from registers.
+template <int L, bool FULL, bool ALL>
+__device__ __forceinline__ void decode_static(const uint8_t* px0, bool col_valid, bool lane_on,
+                                              uint8_t* const (&outp)[kMaxSlots], uint32_t* const (&rdp)[2],
+                                              unsigned col, unsigned W, unsigned H, int warp, int nwarps,
+                                              const DecodeParams& p) {
+    constexpr int NW = PxLayout<L>::cds / 4;
+    const bool has_rd = ALL || rdp[0] != nullptr || rdp[1] != nullptr;
+    const bool has_shift = p.has_shift != 0;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(px0) + static_cast<unsigned>(warp) * NW;
+    const unsigned wstep = static_cast<unsigned>(nwarps) * NW;
+    unsigned pix = static_cast<unsigned>(warp) * W + col;
+    const unsigned pstep = static_cast<unsigned>(nwarps) * W;
+#pragma unroll 2
+    for (unsigned row = warp; row < H; row += nwarps) {
+        uint32_t w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = wp[i];
+        unsigned rdpix = pix;
+        if (has_rd) {
+            unsigned dcol = col + (has_shift ? p.shift[row] : 0u);
+            dcol = dcol >= W ? dcol - W : dcol;
+            rdpix = pix - col + dcol;
+        }
+        store_all<L, FULL, ALL>(w, outp, rdp, pix, rdpix, col_valid, lane_on,
+                                std::make_integer_sequence<int, PxLayout<L>::n>{});
+        wp += wstep;
+        pix += pstep;
+    }
+}
+
+template <int L>
+__device__ __forceinline__ void decode_static_tile(bool full, bool all, const uint8_t* px0, bool col_valid,
+                                                   bool lane_on, uint8_t* const (&outp)[kMaxSlots],
+                                                   uint32_t* const (&rdp)[2], unsigned col, unsigned W, unsigned H,
+                                                   int warp, int nwarps, const DecodeParams& p) {
+    if (full && all) decode_static<L, true, true>(px0, true, true, outp, rdp, col, W, H, warp, nwarps, p);
+    else if (full) decode_static<L, true, false>(px0, true, true, outp, rdp, col, W, H, warp, nwarps, p);
+    else decode_static<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, warp, nwarps, p);
 }
 
 template <typename T>
@@ -397,6 +564,23 @@ __global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ 
         }
     };
 
+    // Warm L2 with the packets of a later tile (regular tiles only): with one stage per CTA the TMA
+    // of tile k+S is issued only after tile k is consumed; having the bytes in L2 by then takes the
+    // DRAM latency out of the mbarrier wait.
+    auto prefetch_tile = [&](unsigned k, bool keep) {
+        unsigned f, j0, tc;
+        tile_of(k, f, j0, tc);
+        const DecodeFrame& fr = p.frames[f];
+        if ((fr.flags & 3u) != 3u || (tc % L.cpp) != 0 || (j0 + tc) / L.cpp > fr.n_slots) return;
+        const unsigned slot0 = j0 / L.cpp, n_groups = tc / L.cpp;
+        const uint64_t pol = keep ? policy_evict_last() : 0;
+        for (unsigned g = 0; g < n_groups; ++g) {
+            const uint8_t* src = fr.packets + static_cast<size_t>(slot0 + g) * fr.packet_stride;
+            if (keep) bulk_prefetch_l2_hint(src, L.packet_size, pol);
+            else bulk_prefetch_l2(src, L.packet_size);
+        }
+    };
+
     if (tid == 0) {
         const unsigned pre = min(n_my, static_cast<unsigned>(S));
         for (unsigned k = 0; k < pre; ++k) issue(k);
@@ -416,6 +600,7 @@ __global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ 
 
         mbar_wait(&full[s], (k / S) & 1);
         const bool regular = c.regular != 0;
+        if (p.prefetch == 1 && tid == 32 && (k + S) < n_my) prefetch_tile(k + S, true);
 
         // ---- irregular groups: gather the columns with ordinary loads ----
         if (!regular) {
@@ -475,6 +660,26 @@ __global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ 
             const bool col_valid = co >= 0;
             const uint8_t* px0 = st + (col_valid ? co : col_offset(tt));
             const size_t pix0 = static_cast<size_t>(j0) + tt;
+            if (p.layout_id != 0) {
+                uint8_t* outp[kMaxSlots];
+#pragma unroll
+                for (int i = 0; i < kMaxSlots; ++i)
+                    outp[i] = p.slot_field[i] >= 0 ? static_cast<uint8_t*>(fr.fields[p.slot_field[i]]) : nullptr;
+                uint32_t* rdp2[2] = {fr.rd[0], fr.rd[1]};
+                const bool full = regular && (cg + 1) * 32u <= tc;
+                const unsigned col = static_cast<unsigned>(pix0);
+                const bool all = p.layout_all != 0 && (p.n_returns < 1 || rdp2[0] != nullptr) &&
+                                 (p.n_returns < 2 || rdp2[1] != nullptr) && fr.fields[0] != nullptr &&
+                                 p.n_returns > 0;
+                switch (p.layout_id) {
+                    case 1: decode_static_tile<1>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
+                    case 2: decode_static_tile<2>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
+                    case 3: decode_static_tile<3>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
+                    case 4: decode_static_tile<4>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
+                    default: decode_static_tile<5>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
+                }
+                continue;
+            }
             for (unsigned fi = 0; fi < L.n_fields; ++fi) {
                 const DecodeField& fd = L.fields[fi];
                 uint8_t* out = static_cast<uint8_t*>(fr.fields[fi]);
@@ -512,6 +717,8 @@ __global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ 
                 }
             }
         }
+
+        if (p.prefetch == 2 && tid == 32 && (k + S) < n_my) prefetch_tile(k + S, false);
 
         // ---- phase B: XYZ; lane = 16-byte chunk of a row segment, ranges re-read from the stage ----
         const void* lut_dir_f = fr.lut_dir != nullptr ? fr.lut_dir : p.lut_dir;
@@ -642,6 +849,47 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
         }
         p.plan[i] = pl;
     }
+    // ---- compile-time layout match: every runtime field must land on a distinct slot ----
+    p.layout_id = 0;
+    p.layout_all = 0;
+    for (int i = 0; i < kMaxSlots; ++i) p.slot_field[i] = -1;
+    if (word_aligned && !tn.decode_runtime_plans && static_cast<uint64_t>(L.H) * L.W < (1ull << 30)) {
+        auto try_layout = [&](int id, const PxSlot* slots, int n_slots, uint32_t cds) {
+            if (p.layout_id != 0 || L.channel_data_size != cds || L.n_fields == 0) return;
+            signed char map[kMaxSlots];
+            for (int i = 0; i < kMaxSlots; ++i) map[i] = -1;
+            for (uint32_t i = 0; i < L.n_fields; ++i) {
+                const DecodeField& f = L.fields[i];
+                if (f.mask == 0 || f.zero_pattern != 0) return;
+                const int tz = __builtin_ctzll(f.mask);
+                const uint64_t core = f.mask >> tz;
+                if ((core & (core + 1)) != 0) return;  // not a contiguous bit field
+                const int bits = __builtin_popcountll(core);
+                const int up = tz - f.shift;
+                const uint32_t lsb = f.offset * 8u + static_cast<uint32_t>(tz);
+                int hit = -1;
+                for (int j = 0; j < n_slots; ++j) {
+                    const PxSlot& sl = slots[j];
+                    if (sl.bits != 0 && sl.lsb == lsb && sl.bits == bits && sl.up == up && sl.es == f.elem_size &&
+                        sl.ret == f.range_return && map[j] < 0) {
+                        hit = j;
+                        break;
+                    }
+                }
+                if (hit < 0) return;
+                map[hit] = static_cast<signed char>(i);
+            }
+            p.layout_id = static_cast<uint32_t>(id);
+            p.layout_all = 1;
+            for (int i = 0; i < kMaxSlots; ++i) p.slot_field[i] = map[i];
+            for (int j = 0; j < n_slots; ++j) p.layout_all &= map[j] >= 0 ? 1u : 0u;
+        };
+        try_layout(1, PxLayout<1>::s, PxLayout<1>::n, PxLayout<1>::cds);
+        try_layout(2, PxLayout<2>::s, PxLayout<2>::n, PxLayout<2>::cds);
+        try_layout(3, PxLayout<3>::s, PxLayout<3>::n, PxLayout<3>::cds);
+        try_layout(4, PxLayout<4>::s, PxLayout<4>::n, PxLayout<4>::cds);
+        try_layout(5, PxLayout<5>::s, PxLayout<5>::n, PxLayout<5>::cds);
+    }
     p.cpp_shift = -1;
     for (int b = 0; b < 8; ++b)
         if ((1u << b) == L.cpp) p.cpp_shift = b;
@@ -654,6 +902,7 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
             if (!p.plan[i].fast) p.plan_ranges_fast = 0;
         }
     }
+    p.prefetch = static_cast<uint32_t>(std::max(0, tn.decode_prefetch));
     p.vec_ok = (L.W % 4 == 0) ? 1 : 0;  // caller (ob_decode_frames) also checks pointer alignment
     p.has_shift = a.shift_host != nullptr ? 1 : 0;
     for (int i = 0; i < kMaxRows; ++i)

@@ -65,6 +65,15 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_s
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// warm L2 with a region that a later bulk copy will read (no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2_hint(const void* gmem_src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(gmem_src), "r"(bytes),
+                 "l"(policy)
+                 : "memory");
+}
 // shared -> global (bulk group completion)
 __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),

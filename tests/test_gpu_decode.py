@@ -103,8 +103,17 @@ PROFILE_CASES = [
 ]
 
 
+@pytest.fixture(params=["static_layouts", "runtime_plans"])
+def plans(ob, request):
+    """K2 has two phase-A code paths: compile-time pixel layouts for the standard profiles and
+    runtime extraction plans for everything else; run the parity cases through both."""
+    ob.set_tunable("decode_runtime_plans", int(request.param == "runtime_plans"))
+    yield request.param
+    ob.set_tunable("decode_runtime_plans", 0)
+
+
 @pytest.mark.parametrize("profile,header,h,w", PROFILE_CASES)
-def test_random_frame_roundtrip_all_profiles(ob, profile, header, h, w):
+def test_random_frame_roundtrip_all_profiles(ob, plans, profile, header, h, w):
     """frame -> frame_to_packets -> GPU decode == frame (tests/packet_format_test.cpp:218-326)."""
     pf = oracle_pf(profile, h, w, 16, header)
     src = random_frame(pf, seed=0xdeadbeef % (1 << 31))
@@ -123,7 +132,36 @@ def test_random_frame_roundtrip_all_profiles(ob, profile, header, h, w):
         assert np.array_equal(io["xyz"][1], orc.cartesian(src.field("RANGE2"), d, o))
 
 
-def test_fault_injection_matches_oracle_batcher(ob):
+@pytest.mark.parametrize("keep", [("RANGE",), ("RANGE2", "SIGNAL", "WINDOW"), ("FLAGS", "NEAR_IR")])
+def test_subset_of_fields_other_images_untouched(ob, plans, keep):
+    """a frame that carries only some profile fields: those decode, nothing else is written"""
+    pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", 64, 512)
+    src = random_frame(pf, seed=21)
+    packets, _ = orc.frame_to_packets(src, pf)
+    layout, fields = decoder_desc_from_oracle(pf, src)
+    fields = [f for f in fields if f["name"] in keep]
+    dec = ob.Decoder(layout, fields)
+    outs = {f["name"]: np.full((64, 512), 0xAB, src.field(f["name"]).dtype) for f in fields}
+    d, o = random_lut(64 * 512, 4)
+    lut = ob.XYZLutT.from_arrays(d, o, 64, 512)
+    n_ret = 1 + int("RANGE2" in keep)
+    io = {"packets": np.ascontiguousarray(packets), "n_slots": len(packets), "packet_stride": packets.shape[1],
+          "col_src": None, "fields": outs}
+    has_r0 = "RANGE" in keep
+    if has_r0 or "RANGE2" in keep:
+        io["xyz"] = [np.full((64 * 512, 3), 9, np.float32) if (r == 0 and has_r0) or (r == 1 and "RANGE2" in keep)
+                     else None for r in range(n_ret)]
+    st = ob.Stream(0)
+    dec.decode([io], lut=lut, stream=st)
+    st.sync()
+    for name, a in outs.items():
+        assert np.array_equal(a, src.field(name)), name
+    for r, nm in enumerate(("RANGE", "RANGE2")[:n_ret]):
+        if io.get("xyz") and io["xyz"][r] is not None:
+            assert np.array_equal(io["xyz"][r], orc.cartesian(src.field(nm), d, o)), nm
+
+
+def test_fault_injection_matches_oracle_batcher(ob, plans):
     """dropped packet, invalidated columns, swapped packets, duplicate packet
     (tests/frame_batcher_test.cpp:119-170, 208-259)."""
     pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", 128, 1024)

@@ -26,11 +26,16 @@ def step():
     dec.decode_batch(F, t_pk, n_slots, psz, n_slots * psz, fields, lut=lut, pixel_shift_by_row=k2.SHIFTS,
                      xyz=xyz, range_destaggered=rd, stream=st)
 rows = []
-for tp, stg, th, cta in itertools.product([1, 2], [1, 2, 3], [192, 256, 320, 384], [1, 2, 3, 4]):
+PF = [int(x) for x in os.environ.get("SWEEP_PREFETCH", "2").split(",")]
+GEOM = list(itertools.product([1, 2], [1, 2, 3], [192, 256, 320, 384], [1, 2, 3, 4]))
+if os.environ.get("SWEEP_QUICK"):
+    GEOM = [(2, 1, 384, 3), (2, 1, 320, 3), (1, 2, 384, 3), (2, 1, 256, 3)]
+for (tp, stg, th, cta), pf in itertools.product(GEOM, PF):
     smem = 5120 + stg * 33152 * tp
     if smem * cta > 227 * 1024 or th * cta > 2048:
         continue
-    for k, v in (("decode_tile_packets", tp), ("decode_stages", stg), ("decode_threads", th), ("decode_ctas_per_sm", cta)):
+    for k, v in (("decode_tile_packets", tp), ("decode_stages", stg), ("decode_threads", th),
+                 ("decode_ctas_per_sm", cta), ("decode_prefetch", pf)):
         ob.set_tunable(k, v)
     try:
         for _ in range(2):
@@ -48,7 +53,8 @@ for tp, stg, th, cta in itertools.product([1, 2], [1, 2, 3], [192, 256, 320, 384
         print("fail", stg, th, cta, ex)
         continue
     gbps = k2.K2_BYTES_PER_FRAME_F32 * F / (ms * 1e-3) / 1e9
-    rows.append({"tile_packets": tp, "stages": stg, "threads": th, "ctas": cta, "ms": ms, "gbps": gbps, "frac": gbps / peak})
+    rows.append({"tile_packets": tp, "stages": stg, "threads": th, "ctas": cta, "prefetch": pf, "ms": ms,
+                 "gbps": gbps, "frac": gbps / peak})
 rows.sort(key=lambda r: -r["gbps"])
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/sweep_k2.json", "w"), indent=0)
