@@ -27,6 +27,18 @@ static DecodeField to_dev(const ob_field_desc& f) {
     return d;
 }
 
+// Frames of independent sensor streams carry their own LUTs.  The frame table is only a work list
+// (every entry holds its own output pointers), so it may be reordered freely: keeping the frames
+// of one LUT together lets each 6-12 MB table stay L2-resident while its frames are processed.
+static void group_by_lut(std::vector<DecodeFrame>& frames) {
+    bool any = false;
+    for (const DecodeFrame& f : frames) any |= f.lut_dir != nullptr;
+    if (!any) return;
+    std::stable_sort(frames.begin(), frames.end(), [](const DecodeFrame& a, const DecodeFrame& b) {
+        return reinterpret_cast<uintptr_t>(a.lut_dir) < reinterpret_cast<uintptr_t>(b.lut_dir);
+    });
+}
+
 extern "C" {
 
 ob_status ob_decoder_create(const ob_packet_layout* layout, const ob_field_desc* fields,
@@ -194,6 +206,7 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
             }
         }
     }
+    group_by_lut(hf);
     void* fdev = nullptr;
     cudaError_t e = stg.scratch(n_frames * sizeof(DecodeFrame), &fdev);
     if (e != cudaSuccess) return fail_cuda(e, "frame table alloc");
@@ -325,6 +338,7 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
             if (drd[r]) d.rd[r] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(drd[r]) + f * b->rd_frame_stride);
         }
     }
+    group_by_lut(hf);
     void* fdev = nullptr;
     e = stg.scratch(F * sizeof(DecodeFrame), &fdev);
     if (e != cudaSuccess) return fail_cuda(e, "frame table alloc");

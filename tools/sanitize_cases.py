@@ -81,4 +81,47 @@ for profile, hh, ww in (("RNG19_RFL8_SIG16_NIR16_DUAL", 16, 128), ("LEGACY", 16,
             assert np.array_equal(io["xyz"][0], orc.cartesian(ref.field("RANGE"), d, o))
             assert np.array_equal(io["range_destaggered"][0], orc.destagger(ref.field("RANGE"), shifts))
 print("K2 ok")
+
+# K2 through the runtime-plan phase A as well (the loop above took the compile-time layouts where
+# one exists), then the pipelined host path: decode jobs, zero-copy bursts, frames in flight
+ob.set_tunable("decode_runtime_plans", 1)
+pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", 16, 128)
+src = random_frame(pf, seed=6)
+pk, ts = orc.frame_to_packets(src, pf)
+layout, fields = decoder_desc_from_oracle(pf, src)
+dec = ob.Decoder(layout, fields)
+outs = {f["name"]: np.zeros(src.field(f["name"]).shape, src.field(f["name"]).dtype) for f in fields}
+dec.decode([{"packets": np.ascontiguousarray(pk), "n_slots": len(pk), "packet_stride": pk.shape[1],
+             "col_src": None, "fields": outs}], stream=st)
+st.sync()
+for n, a in outs.items():
+    assert np.array_equal(a, src.field(n)), n
+ob.set_tunable("decode_runtime_plans", 0)
+print("K2 runtime plans ok")
+
+si = ob.SensorInfo("RNG19_RFL8_SIG16_NIR16_DUAL", 16, 128, fw_rev="v3.2.1")
+d, o = random_lut(16 * 128, 5)
+lut = ob.XYZLutT.from_arrays(d, o, 16, 128)
+shifts = (np.arange(16, dtype=np.int32) * 3) % 17
+pipe = ob.FramePipeline(si, depth=2, lut=lut, pixel_shift_by_row=shifts)
+buf = ob.pinned_empty(pk.shape, np.uint8)
+want = []
+got = []
+for k in range(4):
+    f = random_frame(pf, seed=30 + k, frame_id=900 + k)
+    p, t = orc.frame_to_packets(f, pf)
+    want.append(f)
+    buf[...] = p
+    used, slot = pipe.push_burst(buf, t)
+    assert used == len(p)
+    if slot is not None:
+        got.append((slot.frame.field("RANGE").copy(), slot.xyz[0].copy(), slot.range_destaggered[1].copy()))
+while (slot := pipe.drain()) is not None:
+    got.append((slot.frame.field("RANGE").copy(), slot.xyz[0].copy(), slot.range_destaggered[1].copy()))
+assert len(got) == 4
+for f, (r, x, rd2) in zip(want, got):
+    assert np.array_equal(r, f.field("RANGE"))
+    assert np.array_equal(x, orc.cartesian(f.field("RANGE"), d, o))
+    assert np.array_equal(rd2, orc.destagger(f.field("RANGE2"), shifts))
+print("pipeline ok")
 print("SANITIZE CASES OK")
