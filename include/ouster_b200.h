@@ -128,7 +128,8 @@ ob_status ob_dewarp(ob_dtype dtype, const void* points, const void* poses, size_
 /* ---- fused range -> (XYZ, destaggered range, destaggered XYZ), batched over frames ----
  * One launch performs, for every frame f and return r of the batch, what the reference does as
  * separate passes: lut(range) (xyzlut.h:139-150) and destagger<uint32_t>(range, shifts)
- * (impl/lidar_frame_impl.h:825-834), optionally destagger<T,3>(xyz) (:849-860).
+ * (impl/lidar_frame_impl.h:825-834), optionally destagger<T,3>(xyz) (:849-860) and
+ * dewarp<T>(xyz, poses) (pose_util.h:37-59).
  * Layout: element (f, r, ...) of an array lives at base + f*frame_stride + r*return_stride
  * (strides in ELEMENTS of that array's scalar type).  NULL outputs are skipped.
  */
@@ -143,6 +144,13 @@ typedef struct ob_cloud_io {
     size_t rd_frame_stride, rd_return_stride;
     void* xyz_destaggered;
     size_t xd_frame_stride, xd_return_stride;
+    /* optional per-column poses, n_frames x w x 16 scalars of the LUT dtype (row-major 4x4 per
+     * column, the layout of LidarFrame::body_to_world cast to T): when set, every XYZ output is
+     * dewarp<T>(lut(range), poses) (pose_util.h:37-59) -- point (row, col) becomes R_col*p + t_col,
+     * zero-range points included (they land on t_col) -- at no extra pass over memory.
+     * poses_frame_stride in scalars; 0 = the same w x 16 block for every frame. */
+    const void* poses;
+    size_t poses_frame_stride;
 } ob_cloud_io;
 
 ob_status ob_scan_to_cloud(const ob_lut* lut, const int32_t* pixel_shift_by_row /* h, host */,

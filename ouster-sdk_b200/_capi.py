@@ -27,7 +27,8 @@ class CloudIO(C.Structure):
                 ("range", vp), ("range_frame_stride", sz), ("range_return_stride", sz),
                 ("xyz", vp), ("xyz_frame_stride", sz), ("xyz_return_stride", sz),
                 ("range_destaggered", vp), ("rd_frame_stride", sz), ("rd_return_stride", sz),
-                ("xyz_destaggered", vp), ("xd_frame_stride", sz), ("xd_return_stride", sz)]
+                ("xyz_destaggered", vp), ("xd_frame_stride", sz), ("xd_return_stride", sz),
+                ("poses", vp), ("poses_frame_stride", sz)]
 
 
 class FieldDesc(C.Structure):

@@ -321,9 +321,11 @@ def transform(points, pose, out=None, stream=None, device=0):
 
 
 def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None,
-                  xyz_destaggered=None, stream=None):
+                  xyz_destaggered=None, stream=None, poses=None):
     """Fused batch: rng is [F, R, H, W] uint32; outputs [F, R, H*W, 3] (xyz), [F, R, H, W]
-    (range_destaggered), [F, R, H, W, 3] (xyz_destaggered).  Asynchronous on `stream`."""
+    (range_destaggered), [F, R, H, W, 3] (xyz_destaggered).  `poses` ([W, 4, 4] shared by all
+    frames or [F, W, 4, 4], LUT dtype, e.g. LidarScan.body_to_world) fuses dewarp(xyz, poses) into
+    the same pass.  Asynchronous on `stream`."""
     st = _stream(stream, lut.device)
     F, R, H, W = tuple(rng.shape)
     io = CloudIO()
@@ -336,6 +338,16 @@ def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None
         io.range_destaggered, io.rd_frame_stride, io.rd_return_stride = _ptr(range_destaggered), R * n, n
     if xyz_destaggered is not None:
         io.xyz_destaggered, io.xd_frame_stride, io.xd_return_stride = _ptr(xyz_destaggered), R * n * 3, n * 3
+    if poses is not None:
+        if _np_dtype(poses) != lut.dtype:
+            raise ValueError("poses must have the dtype of the lut")
+        pn = _numel(poses)
+        if pn == W * 16:
+            io.poses, io.poses_frame_stride = _ptr(poses), 0
+        elif pn == F * W * 16:
+            io.poses, io.poses_frame_stride = _ptr(poses), W * 16
+        else:
+            raise ValueError("poses must be [W, 4, 4] or [F, W, 4, 4]")
     sh, nsh = None, 0
     if pixel_shift_by_row is not None:
         sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)

@@ -45,7 +45,10 @@ static Tunables& tunables_mut(int device) {
         t.cloud_stages = std::max(2, env_int("OB_CLOUD_STAGES", 4));
         t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 256)));
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
-        t.cloud_frames_per_lut = env_int("OB_CLOUD_FRAMES_PER_LUT", 0);
+        t.cloud_pose_tw = std::max(16, env_int("OB_CLOUD_POSE_TW", 256));
+        t.cloud_store_lag = env_int("OB_CLOUD_STORE_LAG", 1);
+        t.cloud_pose_stages = std::max(2, env_int("OB_CLOUD_POSE_STAGES", 2));
+        t.cloud_pose_ctas_per_sm = std::max(1, env_int("OB_CLOUD_POSE_CTAS_PER_SM", 5));
         t.decode_stages = std::max(1, env_int("OB_DECODE_STAGES", 1));
         t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384)));
         t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
@@ -78,7 +81,10 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "cloud_stages") t.cloud_stages = std::max(2, value);
     else if (n == "cloud_threads") t.cloud_threads = std::min(256, std::max(32, value / 32 * 32));
     else if (n == "cloud_ctas_per_sm") t.cloud_ctas_per_sm = std::max(1, value);
-    else if (n == "cloud_frames_per_lut") t.cloud_frames_per_lut = value;
+    else if (n == "cloud_pose_tw") t.cloud_pose_tw = std::max(16, value / 4 * 4);
+    else if (n == "cloud_store_lag") t.cloud_store_lag = value ? 1 : 0;
+    else if (n == "cloud_pose_stages") t.cloud_pose_stages = std::max(2, value);
+    else if (n == "cloud_pose_ctas_per_sm") t.cloud_pose_ctas_per_sm = std::max(1, value);
     else if (n == "decode_stages") t.decode_stages = std::max(1, value);
     else if (n == "decode_threads") t.decode_threads = std::min(384, std::max(64, value / 32 * 32));
     else if (n == "decode_ctas_per_sm") t.decode_ctas_per_sm = std::max(1, value);
@@ -500,6 +506,13 @@ static ob_status scan_to_cloud_t(const ob_lut* lut, const uint16_t* shift, const
         if (e != cudaSuccess) return fail_cuda(e, "stage xyz_destaggered");
         a.xd = static_cast<T*>(dout);
     }
+    if (io->poses) {
+        const size_t pn = static_cast<size_t>(lut->w) * 16;
+        e = stg.in(io->poses, ((F - 1) * io->poses_frame_stride + pn) * sizeof(T), &din);
+        if (e != cudaSuccess) return fail_cuda(e, "stage poses");
+        a.poses = static_cast<const T*>(din);
+        a.poses_fs = io->poses_frame_stride;
+    }
     e = launch_cloud<T>(a, s->device, s->st);
     if (e != cudaSuccess) return fail_cuda(e, "scan_to_cloud launch");
     e = stg.flush();
@@ -524,6 +537,8 @@ ob_status ob_scan_to_cloud(const ob_lut* lut, const int32_t* shifts, size_t n_sh
             return fail(OB_INVALID_ARGUMENT, "fused destagger supports at most 512 rows");
     }
     if (lut->w > 65535) return fail(OB_INVALID_ARGUMENT, "frame width exceeds 65535 columns");
+    if (io->poses && !io->xyz && !io->xyz_destaggered)
+        return fail(OB_INVALID_ARGUMENT, "poses given without an xyz output");
     ob_status rs = require_device(s->device);
     if (rs != OB_OK) return rs;
     if (lut->device != s->device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");

@@ -4,6 +4,7 @@
 // What it replaces (reference paths relative to /root/reference):
 //   impl::cartesianT<T>        ouster_core/include/ouster/core/impl/cartesian.h:36-66
 //   destagger_into<T> (2-D/N-D) ouster_core/include/ouster/core/impl/lidar_frame_impl.h:733-811
+//   dewarp<T> after the projection (optional, fused)  ouster_core/include/ouster/core/pose_util.h:37-59
 //
 // Design (HBM-bound streaming kernel, no tensor cores -- there is no contraction here):
 //   * persistent CTAs, interleaved tile schedule; a tile = TW consecutive pixels of one row of
@@ -29,6 +30,8 @@
 
 namespace ob {
 
+constexpr int kPoseRows = 32;  // rows per work item of the pose-fused variant
+
 template <typename T>
 struct CloudParams {
     const T* dir;
@@ -38,8 +41,11 @@ struct CloudParams {
     uint32_t* rd;
     T* xd;
     unsigned long long range_fs, range_rs, xyz_fs, xyz_rs, rd_fs, rd_rs, xd_fs, xd_rs;
+    const T* poses;            // optional: n_frames x W x 16 (row-major 4x4 per column), dewarp fused
+    unsigned long long poses_fs;
     int H, W, TW, tiles_per_row, stages;
-    int fb;                    // frames that share one staged LUT tile (v2 kernel), 1 = v1 kernel
+    int RT, row_blocks;        // rows per work item (1, or kPoseRows with poses) and ceil(H / RT)
+    int store_lag;             // tiles between a stage's bulk stores and its refill (0 or 1)
     unsigned n_frames, n_tiles, stage_bytes;
     unsigned short shift[kMaxRows];
 };
@@ -94,6 +100,21 @@ __device__ __forceinline__ void sts12(T* s, const T (&v)[12]) {
     }
 }
 
+// 4 consecutive T values via 16-byte shared-memory accesses
+template <typename T>
+__device__ __forceinline__ void lds4(const T* s, T (&v)[4]) {
+    using V = typename Vec<T>::type;
+    constexpr int NV = 4 / Vec<T>::N;
+    const V* p = reinterpret_cast<const V*>(s);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        V x = p[i];
+        const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+        for (int j = 0; j < Vec<T>::N; ++j) v[i * Vec<T>::N + j] = e[j];
+    }
+}
+
 struct TileCoord {
     unsigned f;
     int row, c0, tw;
@@ -102,35 +123,60 @@ struct TileCoord {
 template <typename T>
 __device__ __forceinline__ TileCoord tile_coord(const CloudParams<T>& p, unsigned t) {
     TileCoord tc;
-    const unsigned per_frame = static_cast<unsigned>(p.H) * p.tiles_per_row;
+    const unsigned per_frame = static_cast<unsigned>(p.row_blocks) * p.tiles_per_row;
     tc.f = t / per_frame;
     const unsigned rem = t - tc.f * per_frame;
-    tc.row = rem / p.tiles_per_row;
-    tc.c0 = (rem - tc.row * p.tiles_per_row) * p.TW;
+    const unsigned rb = rem / p.tiles_per_row;
+    tc.row = static_cast<int>(rb) * p.RT;  // first row of the tile
+    tc.c0 = (rem - rb * p.tiles_per_row) * p.TW;
     tc.tw = min(p.TW, p.W - tc.c0);
     return tc;
 }
 
-template <typename T, int R>
+// pose of one column applied to one point: R*p + t with every product rounded on its own and the
+// sum taken as x0 + (x1 + x2), then + t (pose_util.h:37-59; same helper as the stand-alone dewarp)
+__device__ __forceinline__ float pose_row(const float* m, float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fadd_rn(__fmul_rn(m[1], y), __fmul_rn(m[2], z))), m[3]);
+}
+__device__ __forceinline__ double pose_row(const double* m, double x, double y, double z) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dadd_rn(__dmul_rn(m[1], y), __dmul_rn(m[2], z))), m[3]);
+}
+
+// POSE: the variant with per-column poses (dewarp fused after the projection).  Work is handed out
+// in items of RPI consecutive rows of one column range; a CTA streams the rows of an item through
+// the usual ring while the item's pose slice (16 scalars per column, one bulk copy) stays in a
+// double-buffered side buffer, so poses cost one L2 read per RPI rows.
+template <typename T, int R, bool POSE>
 __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ CloudParams<T> p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    uint8_t* stage0 = smem + 128;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // S stage barriers
+    uint64_t* pose_bar = reinterpret_cast<uint64_t*>(smem + 64);  // pose-slice barrier
+    // pose slice of the current item: raw (16 scalars per column, as it lies in memory) and the
+    // 12 planes [element][column] the projection loop reads with conflict-free 16-byte loads
+    const unsigned pose_raw_bytes = POSE ? 16u * p.TW * static_cast<unsigned>(sizeof(T)) : 0u;
+    const unsigned pose_soa_bytes = POSE ? 12u * p.TW * static_cast<unsigned>(sizeof(T)) : 0u;
+    uint8_t* pose_raw = smem + 128;
+    T* pose_soa = reinterpret_cast<T*>(pose_raw + pose_raw_bytes);
+    uint8_t* stage0 = pose_raw + pose_raw_bytes + pose_soa_bytes;
 
     const int tid = threadIdx.x;
     const int S = p.stages;
     const bool need_lut = (p.xyz != nullptr) || (p.xd != nullptr);
     const unsigned lut_bytes_full = 3u * p.TW * sizeof(T);
+    const unsigned RPI = POSE ? static_cast<unsigned>(p.RT) : 1u;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        if (POSE) mbar_init(pose_bar, 1);
         mbar_fence_init();
         fence_proxy_async();
     }
     __syncthreads();
 
+    // tiles of this CTA: item (first + j * grid), rows 0..RPI-1 of it in order
     const unsigned first = blockIdx.x;
-    const unsigned n_my = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned n_items_my = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned n_my = n_items_my * RPI;
 
     uint64_t pol_keep = 0, pol_stream = 0;
     if (tid == 0) {
@@ -138,10 +184,28 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
         pol_stream = policy_evict_first();
     }
 
+    auto coord = [&](unsigned k) {
+        TileCoord tc = tile_coord(p, first + (k / RPI) * gridDim.x);
+        if (POSE) tc.row += static_cast<int>(k % RPI);
+        return tc;
+    };
+
     auto issue_load = [&](unsigned k) {  // thread 0 only
-        const TileCoord tc = tile_coord(p, first + k * gridDim.x);
+        const TileCoord tc = coord(k);
         const int s = k % S;
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+        if (POSE && (k % RPI) == 0) {
+            // first row of an item: its pose slice.  The raw buffer is free: the previous item
+            // re-laid it out at its first row, more than S tiles ago (RPI > S).
+            const unsigned pb = 16u * tc.tw * static_cast<unsigned>(sizeof(T));
+            mbar_expect_tx(pose_bar, pb);
+            bulk_g2s_hint(pose_raw, p.poses + tc.f * p.poses_fs + static_cast<size_t>(tc.c0) * 16, pb,
+                          pose_bar, pol_keep);
+        }
+        if (tc.row >= p.H) {  // item overhangs the last rows: empty tile
+            mbar_expect_tx(&full[s], 0);
+            return;
+        }
         const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
         const unsigned lut_b = 3u * tc.tw * sizeof(T);
         const unsigned rng_b = 4u * tc.tw;
@@ -165,18 +229,40 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
 
     for (unsigned k = 0; k < n_my; ++k) {
         const int s = k % S;
-        // refill the stage tile k-1 used: its bulk stores must have finished READING smem
-        if (tid == 0 && k >= 1 && (k - 1 + S) < n_my) {
-            bulk_wait_read<0>();
-            issue_load(k - 1 + S);
+        // refill a stage whose bulk stores have finished READING smem.  lag 0: the stage of tile
+        // k-1 (its stores were issued a moment ago: thread 0 eats their read latency every tile);
+        // lag 1: the stage of tile k-2, whose stores have had a whole tile time to drain.
+        if (tid == 0) {
+            if (p.store_lag == 0) {
+                if (k >= 1 && (k - 1 + S) < n_my) {
+                    bulk_wait_read<0>();
+                    issue_load(k - 1 + S);
+                }
+            } else if (k >= 2 && (k - 2 + S) < n_my) {
+                bulk_wait_read<1>();
+                issue_load(k - 2 + S);
+            }
         }
-        const TileCoord tc = tile_coord(p, first + k * gridDim.x);
+        const TileCoord tc = coord(k);
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
         T* dir_s = reinterpret_cast<T*>(st);
         T* off_s = reinterpret_cast<T*>(st + lut_bytes_full);
         uint32_t* rng_s = reinterpret_cast<uint32_t*>(st + 2 * lut_bytes_full);
 
         mbar_wait(&full[s], (k / S) & 1);
+        if (POSE && (k % RPI) == 0) {  // new item: rows 0..2 of every column pose -> planes
+            mbar_wait(pose_bar, (k / RPI) & 1u);
+            const T* raw = reinterpret_cast<const T*>(pose_raw);
+            for (int idx = tid; idx < tc.tw * 12; idx += blockDim.x) {
+                const int col = idx / 12, e = idx - col * 12;
+                pose_soa[e * p.TW + col] = raw[col * 16 + e];
+            }
+            __syncthreads();
+        }
+        if (POSE && tc.row >= p.H) {
+            __syncthreads();
+            continue;
+        }
 
         const int sh = (p.rd != nullptr || p.xd != nullptr) ? p.shift[tc.row] : 0;
         const int q = sh & 3;
@@ -223,25 +309,50 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
             }
         }
 
-        // ---- projection, in place ----
-        if (need_lut) {
+        // ---- projection (and pose), in place ----
+        if (need_lut && !POSE) {
             for (int g = tid; g < n_groups; g += blockDim.x) {
                 T d[12], o[12];
                 lds12(dir_s + 12 * g, d);
                 lds12(off_s + 12 * g, o);
-                uint4 rr[R];
+                uint4 rv4[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    rr[r] = reinterpret_cast<const uint4*>(rng_s + r * p.TW)[g];
+                for (int r = 0; r < R; ++r) rv4[r] = reinterpret_cast<const uint4*>(rng_s + r * p.TW)[g];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const uint32_t rv[4] = {rr[r].x, rr[r].y, rr[r].z, rr[r].w};
+                    const uint32_t rv[4] = {rv4[r].x, rv4[r].y, rv4[r].z, rv4[r].w};
                     T out[12];
 #pragma unroll
                     for (int i = 0; i < 12; ++i) out[i] = project(rv[i / 3], d[i], o[i]);
                     sts12((r == 0 ? dir_s : off_s) + 12 * g, out);
                 }
             }
+        }
+        if (need_lut && POSE) {
+            // one pixel per thread: the pose math is a long dependent chain, so thread-level
+            // parallelism matters more than vector width here (scalar accesses at strides of 1 and
+            // 3 words are bank-conflict free)
+            for (int j = tid; j < tc.tw; j += blockDim.x) {
+                T d[3], o[3], m[12];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    d[c] = dir_s[3 * j + c];
+                    o[c] = off_s[3 * j + c];
+                }
+#pragma unroll
+                for (int e = 0; e < 12; ++e) m[e] = pose_soa[e * p.TW + j];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t rv = rng_s[r * p.TW + j];
+                    const T x = project(rv, d[0], o[0]), y = project(rv, d[1], o[1]), z = project(rv, d[2], o[2]);
+                    T* dst = (r == 0 ? dir_s : off_s) + 3 * j;
+                    dst[0] = pose_row(m, x, y, z);
+                    dst[1] = pose_row(m + 4, x, y, z);
+                    dst[2] = pose_row(m + 8, x, y, z);
+                }
+            }
+        }
+        if (need_lut) {
             fence_proxy_async();
         }
         __syncthreads();
@@ -306,223 +417,6 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
     if (tid == 0) bulk_wait<0>();
 }
 
-// ---------------------------------------------------------------------------------------------
-// v2: LUT-stationary variant for batches.  A CTA keeps the direction/offset slices of one
-// (row, column chunk) in shared memory (double buffered) and streams the range slices of FB
-// consecutive frames through the ring, so the LUT is read from L2 once per FB frames instead of
-// once per frame (the v1 kernel is L2-throughput bound on those re-reads).  The projection writes
-// into a per-stage output buffer; everything else (TMA in, TMA out, shuffle realignment) is as v1.
-// ---------------------------------------------------------------------------------------------
-template <typename T, int R>
-__global__ void __launch_bounds__(256) cloud_tma_kernel_v2(const __grid_constant__ CloudParams<T> p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // S range barriers
-    uint64_t* lutbar = reinterpret_cast<uint64_t*>(smem + 64);  // 2 LUT barriers
-    uint8_t* lut0 = smem + 128;
-    const int tid = threadIdx.x;
-    const int S = p.stages;
-    const int FB = p.fb;
-    const unsigned lut_bytes_full = 3u * p.TW * sizeof(T);
-    const unsigned lut_buf = 2u * lut_bytes_full;          // dir | off
-    uint8_t* stage0 = lut0 + 2u * lut_buf;
-    const unsigned rng_bytes_full = R * 4u * p.TW;
-
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
-        mbar_init(&lutbar[0], 1);
-        mbar_init(&lutbar[1], 1);
-        mbar_fence_init();
-        fence_proxy_async();
-    }
-    __syncthreads();
-
-    // super tile = (frame block, row, chunk); p.n_tiles counts super tiles here
-    const unsigned first = blockIdx.x;
-    const unsigned n_super = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
-    const unsigned n_units = n_super * FB;
-
-    uint64_t pol_keep = 0, pol_stream = 0;
-    if (tid == 0) {
-        pol_keep = policy_evict_last();
-        pol_stream = policy_evict_first();
-    }
-    auto super_coord = [&](unsigned si) {  // -> tile coordinates with f = first frame of the block
-        TileCoord tc = tile_coord(p, first + si * gridDim.x);
-        tc.f *= FB;
-        return tc;
-    };
-    auto issue_lut = [&](unsigned si) {  // thread 0
-        const TileCoord tc = super_coord(si);
-        uint8_t* lb = lut0 + (si & 1u) * lut_buf;
-        const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
-        const unsigned lut_b = 3u * tc.tw * sizeof(T);
-        mbar_expect_tx(&lutbar[si & 1u], 2u * lut_b);
-        bulk_g2s_hint(lb, p.dir + px * 3, lut_b, &lutbar[si & 1u], pol_keep);
-        bulk_g2s_hint(lb + lut_bytes_full, p.off + px * 3, lut_b, &lutbar[si & 1u], pol_keep);
-    };
-    auto issue_range = [&](unsigned k) {  // thread 0
-        const unsigned si = k / FB, j = k - si * FB;
-        const TileCoord tc = super_coord(si);
-        const int s = k % S;
-        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
-        const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
-        const unsigned rng_b = 4u * tc.tw;
-        mbar_expect_tx(&full[s], R * rng_b);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            bulk_g2s_hint(st + r * 4u * p.TW, p.range + (tc.f + j) * p.range_fs + r * p.range_rs + px,
-                          rng_b, &full[s], pol_stream);
-    };
-
-    if (tid == 0 && n_units > 0) {
-        issue_lut(0);
-        const unsigned pre = min(n_units, static_cast<unsigned>(S));
-        for (unsigned k = 0; k < pre; ++k) issue_range(k);
-    }
-
-    for (unsigned k = 0; k < n_units; ++k) {
-        const int s = k % S;
-        const unsigned si = k / FB, j = k - si * FB;
-        if (tid == 0) {
-            if (k >= 1 && (k - 1 + S) < n_units) {  // refill the stage unit k-1 used
-                bulk_wait_read<0>();
-                issue_range(k - 1 + S);
-            }
-            // first unit of a super tile: prefetch the next LUT slice into the other buffer
-            // (its previous user, super tile si-1, finished behind the last __syncthreads)
-            if (j == 0 && si + 1 < n_super) issue_lut(si + 1);
-        }
-        TileCoord tc = super_coord(si);
-        tc.f += j;
-        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
-        const T* dir_s = reinterpret_cast<const T*>(lut0 + (si & 1u) * lut_buf);
-        const T* off_s = reinterpret_cast<const T*>(lut0 + (si & 1u) * lut_buf + lut_bytes_full);
-        uint32_t* rng_s = reinterpret_cast<uint32_t*>(st);
-        T* out_s = reinterpret_cast<T*>(st + rng_bytes_full);  // R buffers of 3*TW scalars
-
-        mbar_wait(&full[s], (k / S) & 1);
-        if (j == 0) mbar_wait(&lutbar[si & 1u], (si >> 1) & 1u);
-
-        const int sh = (p.rd != nullptr || p.xd != nullptr) ? p.shift[tc.row] : 0;
-        const int q = sh & 3;
-        const int n_groups = tc.tw >> 2;
-
-        if (p.rd != nullptr && q != 0) {  // destaggered range, unaligned shift: warp-shuffle realignment
-            const int lane = tid & 31;
-            const int nv = n_groups;
-            const int base_col = tc.c0 + sh - q;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(rng_s + r * p.TW);
-                uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + static_cast<size_t>(tc.row) * p.W;
-                for (int m0 = (tid >> 5) * 32; m0 <= nv; m0 += blockDim.x) {
-                    const int m = m0 + lane;
-                    uint4 b = make_uint4(0, 0, 0, 0);
-                    if (m < nv) b = s4[m];
-                    uint4 a;
-                    a.x = __shfl_up_sync(0xffffffffu, b.x, 1);
-                    a.y = __shfl_up_sync(0xffffffffu, b.y, 1);
-                    a.z = __shfl_up_sync(0xffffffffu, b.z, 1);
-                    a.w = __shfl_up_sync(0xffffffffu, b.w, 1);
-                    if (lane == 0) a = (m > 0 && m <= nv) ? s4[m - 1] : make_uint4(0, 0, 0, 0);
-                    if (m > nv) continue;
-                    uint4 o;
-                    if (q == 1) o = make_uint4(a.w, b.x, b.y, b.z);
-                    else if (q == 2) o = make_uint4(a.z, a.w, b.x, b.y);
-                    else o = make_uint4(a.y, a.z, a.w, b.x);
-                    int col = base_col + 4 * m;
-                    col = col >= p.W ? col - p.W : col;
-                    col = col >= p.W ? col - p.W : col;
-                    uint32_t* dst = drow + col;
-                    if (m == 0) {
-                        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
-                        for (int e = q; e < 4; ++e) stg_stream(dst + e, ov[e]);
-                    } else if (m == nv) {
-                        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
-                        for (int e = 0; e < q; ++e) stg_stream(dst + e, ov[e]);
-                    } else {
-                        stg_stream(reinterpret_cast<uint4*>(dst), o);
-                    }
-                }
-            }
-        }
-
-        // ---- projection: LUT buffer (read only) x range slice -> per-stage output buffers ----
-        for (int g = tid; g < n_groups; g += blockDim.x) {
-            T d[12], o[12];
-            lds12(dir_s + 12 * g, d);
-            lds12(off_s + 12 * g, o);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint4 rr = reinterpret_cast<const uint4*>(rng_s + r * p.TW)[g];
-                const uint32_t rv[4] = {rr.x, rr.y, rr.z, rr.w};
-                T out[12];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) out[i] = project(rv[i / 3], d[i], o[i]);
-                sts12(out_s + static_cast<size_t>(r) * 3u * p.TW + 12 * g, out);
-            }
-        }
-        fence_proxy_async();
-        __syncthreads();
-
-        bool thread_path_xd = false;
-        if (tid == 0) {
-            const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
-            if (p.xyz != nullptr) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    bulk_s2g(p.xyz + tc.f * p.xyz_fs + r * p.xyz_rs + px * 3,
-                             out_s + static_cast<size_t>(r) * 3u * p.TW, 3u * tc.tw * sizeof(T));
-            }
-            if (q == 0 && (p.rd != nullptr || p.xd != nullptr)) {
-                int d0 = tc.c0 + sh;
-                d0 = d0 >= p.W ? d0 - p.W : d0;
-                const int n1 = min(tc.tw, p.W - d0);
-                const size_t rowpx = static_cast<size_t>(tc.row) * p.W;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (p.rd != nullptr) {
-                        uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + rowpx;
-                        const uint32_t* src = rng_s + r * p.TW;
-                        bulk_s2g(drow + d0, src, 4u * n1);
-                        if (n1 < tc.tw) bulk_s2g(drow, src + n1, 4u * (tc.tw - n1));
-                    }
-                    if (p.xd != nullptr) {
-                        T* drow = p.xd + tc.f * p.xd_fs + r * p.xd_rs + rowpx * 3;
-                        const T* src = out_s + static_cast<size_t>(r) * 3u * p.TW;
-                        bulk_s2g(drow + static_cast<size_t>(d0) * 3, src, 3u * n1 * sizeof(T));
-                        if (n1 < tc.tw)
-                            bulk_s2g(drow, src + static_cast<size_t>(n1) * 3, 3u * (tc.tw - n1) * sizeof(T));
-                    }
-                }
-            }
-            bulk_commit();
-        }
-        if (p.xd != nullptr && q != 0) {  // destaggered XYZ, unaligned shift: coalesced word copies
-            thread_path_xd = true;
-            constexpr int WPE = sizeof(T) / 4;
-            const int row_words = p.W * 3 * WPE;
-            const int n_words = tc.tw * 3 * WPE;
-            int d0 = tc.c0 + sh;
-            d0 = d0 >= p.W ? d0 - p.W : d0;
-            const int dst0 = d0 * 3 * WPE;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                uint32_t* drow = reinterpret_cast<uint32_t*>(
-                    p.xd + tc.f * p.xd_fs + r * p.xd_rs + static_cast<size_t>(tc.row) * p.W * 3);
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(out_s + static_cast<size_t>(r) * 3u * p.TW);
-                for (int i = tid; i < n_words; i += blockDim.x) {
-                    int dw = dst0 + i;
-                    dw = dw >= row_words ? dw - row_words : dw;
-                    stg_stream(drow + dw, src[i]);
-                }
-            }
-        }
-        if (thread_path_xd) __syncthreads();
-    }
-    if (tid == 0) bulk_wait<0>();
-}
-
 // Generic kernel: any width / alignment / stride.  One pixel per thread, grid-stride.
 template <typename T>
 __global__ void cloud_generic_kernel(const __grid_constant__ CloudParams<T> p, int n_returns) {
@@ -552,11 +446,20 @@ __global__ void cloud_generic_kernel(const __grid_constant__ CloudParams<T> p, i
             const uint32_t rv = p.range[f * p.range_fs + r * p.range_rs + px];
             if (p.rd != nullptr) p.rd[f * p.rd_fs + r * p.rd_rs + dpx] = rv;
             if (p.xyz != nullptr || p.xd != nullptr) {
+                T v[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = project(rv, d[c], o[c]);
+                if (p.poses != nullptr) {
+                    const T* m = p.poses + f * p.poses_fs + static_cast<size_t>(col) * 16;
+                    const T x = v[0], y = v[1], z = v[2];
+                    v[0] = pose_row(m, x, y, z);
+                    v[1] = pose_row(m + 4, x, y, z);
+                    v[2] = pose_row(m + 8, x, y, z);
+                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const T v = project(rv, d[c], o[c]);
-                    if (p.xyz != nullptr) p.xyz[f * p.xyz_fs + r * p.xyz_rs + px * 3 + c] = v;
-                    if (p.xd != nullptr) p.xd[f * p.xd_fs + r * p.xd_rs + dpx * 3 + c] = v;
+                    if (p.xyz != nullptr) p.xyz[f * p.xyz_fs + r * p.xyz_rs + px * 3 + c] = v[c];
+                    if (p.xd != nullptr) p.xd[f * p.xd_fs + r * p.xd_rs + dpx * 3 + c] = v[c];
                 }
             }
         }
@@ -602,9 +505,15 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     if (a.n_returns < 1 || a.n_returns > 2) return cudaErrorInvalidValue;
     if ((a.rd != nullptr || a.xd != nullptr) && a.H > kMaxRows) return cudaErrorInvalidValue;
 
+    if (a.poses) fast = fast && aligned16(a.poses) && a.poses_fs % t4 == 0;
+    p.poses = a.poses;
+    p.poses_fs = a.poses_fs;
+    p.store_lag = 0;
+    p.RT = 1;
+    p.row_blocks = a.H;
+
     if (!fast) {
         p.TW = 0;
-        p.fb = 1;
         p.tiles_per_row = 0;
         p.stages = 0;
         p.n_tiles = 0;
@@ -618,53 +527,38 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
         return cudaGetLastError();
     }
 
-    int TW = tn.cloud_tw;
+    const bool pose = a.poses != nullptr && need_lut;
+    int TW = pose ? tn.cloud_pose_tw : tn.cloud_tw;
     if (sizeof(T) == 8) TW = std::max(4, TW / 2 / 4 * 4);
     TW = std::min(TW, a.W);
     TW = std::max(4, TW / 4 * 4);
+    const int RT = pose ? std::min(kPoseRows, std::max(8, a.H)) : 1;
+    const int row_blocks = (a.H + RT - 1) / RT;
     // small launches: shrink tiles until every SM has work for a few CTAs
     const unsigned want_tiles = static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm * 2;
-    while (TW > 128 && static_cast<unsigned>(a.H) * ((a.W + TW - 1) / TW) * a.n_frames < want_tiles)
+    while (TW > 128 && static_cast<unsigned>(row_blocks) * ((a.W + TW - 1) / TW) * a.n_frames < want_tiles)
         TW = std::max(128, TW / 2 / 4 * 4);
     p.TW = TW;
+    p.RT = RT;
+    p.row_blocks = row_blocks;
     p.tiles_per_row = (a.W + TW - 1) / TW;
-    p.stages = tn.cloud_stages;
-    // LUT-stationary variant: FB = largest divisor of n_frames not above the tunable (>= 2)
-    int fb = 1;
-    if (need_lut && tn.cloud_frames_per_lut >= 2)
-        for (int c = std::min<int>(tn.cloud_frames_per_lut, static_cast<int>(a.n_frames)); c >= 2; --c)
-            if (a.n_frames % static_cast<unsigned>(c) == 0) {
-                fb = c;
-                break;
-            }
-    p.fb = fb;
-    cudaError_t e;
-    int grid;
-    size_t smem;
-    if (fb >= 2) {
-        p.stages = std::max(2, tn.cloud_stages - 1);
-        p.n_tiles = static_cast<unsigned>(a.H) * p.tiles_per_row * (a.n_frames / fb);  // super tiles
-        p.stage_bytes = static_cast<unsigned>(a.n_returns) * 4u * TW +
-                        static_cast<unsigned>(a.n_returns) * 3u * TW * static_cast<unsigned>(sizeof(T));
-        p.stage_bytes = (p.stage_bytes + 127u) & ~127u;
-        smem = 128 + 2u * (2u * 3u * TW * sizeof(T)) + static_cast<size_t>(p.stages) * p.stage_bytes;
-        grid = static_cast<int>(
-            std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm));
-        auto kern2 = a.n_returns == 2 ? cloud_tma_kernel_v2<T, 2> : cloud_tma_kernel_v2<T, 1>;
-        e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        kern2<<<std::max(grid, 1), tn.cloud_threads, smem, st>>>(p);
-        count_launch();
-        return cudaGetLastError();
-    }
-    p.n_tiles = static_cast<unsigned>(a.H) * p.tiles_per_row * a.n_frames;
+    p.stages = pose ? tn.cloud_pose_stages : tn.cloud_stages;
+    p.store_lag = tn.cloud_store_lag ? 1 : 0;
+    if (pose) p.stages = std::max(2, std::min(p.stages, RT - 1));  // the pose double buffer relies on RPI > stages
+    p.n_tiles = static_cast<unsigned>(row_blocks) * p.tiles_per_row * a.n_frames;  // work items
     p.stage_bytes = 2u * 3u * TW * sizeof(T) + static_cast<unsigned>(a.n_returns) * 4u * TW;
     p.stage_bytes = (p.stage_bytes + 127u) & ~127u;
-    smem = 128 + static_cast<size_t>(p.stages) * p.stage_bytes;
-    grid = static_cast<int>(
-        std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm));
-    auto kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2> : cloud_tma_kernel<T, 1>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    const size_t pose_bytes = pose ? (16u + 12u) * TW * sizeof(T) : 0u;  // raw slice + 12 planes
+    const size_t smem = 128 + pose_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
+    if (smem > 227u * 1024u) return cudaErrorInvalidValue;
+    const int ctas = std::max<int>(
+        1, std::min<size_t>(pose ? tn.cloud_pose_ctas_per_sm : tn.cloud_ctas_per_sm, (227u * 1024u) / smem));
+    const int grid =
+        static_cast<int>(std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * ctas));
+    void (*kern)(CloudParams<T>);
+    if (pose) kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2, true> : cloud_tma_kernel<T, 1, true>;
+    else kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2, false> : cloud_tma_kernel<T, 1, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     kern<<<std::max(grid, 1), tn.cloud_threads, smem, st>>>(p);
     count_launch();

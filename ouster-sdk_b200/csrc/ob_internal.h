@@ -17,7 +17,9 @@ struct Tunables {
     int cloud_stages;      // TMA ring depth
     int cloud_threads;     // threads per CTA
     int cloud_ctas_per_sm; // persistent CTAs per SM
-    int cloud_frames_per_lut;  // frames sharing a staged LUT tile (K1 v2); < 2 disables v2
+    int cloud_pose_tw;     // pixels per row of a tile of the pose-fused variant
+    int cloud_pose_stages, cloud_pose_ctas_per_sm;
+    int cloud_store_lag;   // 1: refill the stage of tile k-2 instead of k-1 (hides the store drain)
     int decode_stages;
     int decode_threads;
     int decode_ctas_per_sm;
@@ -43,6 +45,8 @@ struct CloudArgs {
     int H, W, n_returns;
     uint32_t n_frames;
     const uint16_t* shift;  // H entries, already reduced to [0, W) (host memory); may be null if no rd/xd
+    const T* poses{nullptr};  // optional per-column poses: n_frames x W x 16 (device), fused dewarp
+    size_t poses_fs{0};
 };
 
 template <typename T>

@@ -61,3 +61,70 @@ def test_gpu_dewarp_matches_oracle(ob, h, w, dtype):
     assert np.array_equal(got, orc.dewarp(pts, poses))
     ref = np.einsum("wij,hwj->hwi", poses[:, :3, :3].astype(np.float64), pts.astype(np.float64)) + poses[None, :, :3, 3]
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-4 if dtype == np.float32 else 1e-9)
+
+
+def _random_poses(w, dtype, seed, frames=None):
+    rs = np.random.default_rng(seed)
+    n = w if frames is None else frames * w
+    ang = rs.random(n) * 2 * np.pi
+    poses = np.zeros((n, 4, 4), dtype)
+    poses[:, 0, 0], poses[:, 0, 1] = np.cos(ang), -np.sin(ang)
+    poses[:, 1, 0], poses[:, 1, 1] = np.sin(ang), np.cos(ang)
+    poses[:, 2, 2] = 1
+    poses[:, 3, 3] = 1
+    poses[:, :3, 3] = rs.random((n, 3)) * 10
+    return poses if frames is None else poses.reshape(frames, w, 4, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w,returns,frames", [(128, 2048, 2, 3), (64, 1024, 1, 2), (20, 516, 2, 2), (7, 130, 1, 1)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("per_frame", [False, True])
+def test_fused_projection_and_dewarp_matches_two_passes(ob, h, w, returns, frames, dtype, per_frame):
+    """scan_to_cloud(poses=...) == dewarp(cartesian(range), poses) of the oracle, bit for bit,
+    for the staggered and the destaggered cloud (pose_util.h:37-59 after impl/cartesian.h:36-66).
+    (20,516) has rows that do not fill the last 8-row tile; (7,130) takes the generic kernel."""
+    from tests.helpers import random_lut, random_range
+    rng = np.stack([np.stack([random_range(h, w, 10 * f + r) for r in range(returns)]) for f in range(frames)])
+    d, o = random_lut(h * w, 2, dtype)
+    lut = ob.XYZLutT.from_arrays(d, o, h, w)
+    poses = _random_poses(w, dtype, 5, frames if per_frame else None)
+    # negative shifts only on power-of-two widths (DESIGN.md section 8: the reference's size_t modulo)
+    lo = -30 if (w & (w - 1)) == 0 else 0
+    shifts = np.random.default_rng(3).integers(lo, 31, h).astype(np.int32)
+    xyz = np.zeros((frames, returns, h * w, 3), dtype)
+    xd = np.zeros((frames, returns, h, w, 3), dtype)
+    rd = np.zeros((frames, returns, h, w), np.uint32)
+    st = ob.Stream(0)
+    ob.scan_to_cloud(lut, shifts, rng, xyz=xyz, range_destaggered=rd, xyz_destaggered=xd, stream=st, poses=poses)
+    st.sync()
+    for f in range(frames):
+        pf = poses[f] if per_frame else poses
+        for r in range(returns):
+            want = orc.dewarp(orc.cartesian(rng[f, r], d, o).reshape(h, w, 3), pf)
+            assert np.array_equal(xyz[f, r].reshape(h, w, 3), want), (f, r)
+            assert np.array_equal(xd[f, r], orc.destagger(want, shifts)), (f, r)
+            assert np.array_equal(rd[f, r], orc.destagger(rng[f, r], shifts)), (f, r)
+    # zero-range points land on the column translation, as dewarp() of a zero point does
+    zr = rng[0, 0] == 0
+    if zr.any():
+        p0 = poses[0] if per_frame else poses
+        cols = np.nonzero(zr)[1]
+        assert np.array_equal(xyz[0, 0].reshape(h, w, 3)[zr], p0[cols, :3, 3])
+
+
+@pytest.mark.gpu
+def test_fused_dewarp_argument_errors(ob):
+    from tests.helpers import random_lut, random_range
+    h, w = 16, 64
+    d, o = random_lut(h * w, 2)
+    lut = ob.XYZLutT.from_arrays(d, o, h, w)
+    rng = random_range(h, w, 1).reshape(1, 1, h, w)
+    with pytest.raises(ValueError, match="dtype of the lut"):
+        ob.scan_to_cloud(lut, None, rng, xyz=np.zeros((1, 1, h * w, 3), np.float32), poses=np.zeros((w, 4, 4)))
+    with pytest.raises(ValueError, match="poses must be"):
+        ob.scan_to_cloud(lut, None, rng, xyz=np.zeros((1, 1, h * w, 3), np.float32),
+                         poses=np.zeros((w - 1, 4, 4), np.float32))
+    with pytest.raises(ValueError, match="without an xyz output"):
+        ob.scan_to_cloud(lut, np.zeros(h, np.int32), rng, range_destaggered=np.zeros((1, 1, h, w), np.uint32),
+                         poses=np.zeros((w, 4, 4), np.float32))

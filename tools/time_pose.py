@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""K1 with fused per-column poses vs the two-pass form (K1, then ob_dewarp over the cloud):
+128x2048 dual return, 64 frames per launch, device-resident (run under gpurun)."""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as graft
+import bench
+ob = graft.load_package()
+F, H, W, R = 64, bench.H, bench.W, bench.R
+dev = torch.device("cuda", 0)
+rng = torch.from_numpy(bench.synth_pool(F).view(np.int32)).to(dev)
+d, o = bench.synth_lut()
+lut = ob.XYZLutT.from_arrays(torch.from_numpy(d).to(dev), torch.from_numpy(o).to(dev), H, W)
+xyz = torch.empty((F, R, H * W, 3), dtype=torch.float32, device=dev)
+xyz2 = torch.empty_like(xyz)
+rd = torch.empty((F, R, H, W), dtype=torch.int32, device=dev)
+rs = np.random.default_rng(1)
+poses = np.tile(np.eye(4, dtype=np.float32), (F, W, 1, 1))
+poses[..., :3, 3] = rs.random((F, W, 3))
+t_pose = torch.from_numpy(poses).to(dev)
+st = ob.Stream(0, cuda_stream=torch.cuda.current_stream().cuda_stream)
+peak, _ = bench.measured_peaks()
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+def plain():
+    ob.scan_to_cloud(lut, bench.SHIFTS, rng, xyz=xyz, range_destaggered=rd, stream=st)
+def fused():
+    ob.scan_to_cloud(lut, bench.SHIFTS, rng, xyz=xyz, range_destaggered=rd, stream=st, poses=t_pose)
+def two_pass():
+    ob.scan_to_cloud(lut, bench.SHIFTS, rng, xyz=xyz2, range_destaggered=rd, stream=st)
+    for f in range(F):   # both returns of a frame in one dewarp launch: (R*H, W, 3) points, W poses
+        ob.dewarp(xyz2[f].view(R * H, W, 3), t_pose[f], out=xyz2[f].view(R * H, W, 3), stream=st)
+
+out = {}
+sweep = []
+for tw in (128, 256, 512):
+    for stg in (2, 3, 4):
+        for cta in (3, 4, 5, 6, 8):
+            for th in (128, 256):
+                for k, v in (("cloud_pose_tw", tw), ("cloud_pose_stages", stg), ("cloud_pose_ctas_per_sm", cta),
+                             ("cloud_threads", th)):
+                    ob.set_tunable(k, v)
+                try:
+                    sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": timeit(fused, n=5)})
+                except Exception as ex:
+                    sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "error": str(ex)[:80]})
+ok = sorted([r for r in sweep if "ms" in r], key=lambda r: r["ms"])
+out["sweep_best"] = ok[:6]
+out["sweep_worst"] = ok[-1]
+best = ok[0]
+for k, v in (("cloud_pose_tw", best["tw"]), ("cloud_pose_stages", best["stages"]),
+             ("cloud_pose_ctas_per_sm", best["ctas"]), ("cloud_threads", best["threads"])):
+    ob.set_tunable(k, v)
+out["fused_tw_best_ms"] = timeit(fused)
+ob.set_tunable("cloud_threads", 256)
+out["plain_ms"] = timeit(plain)
+try:
+    out["two_pass_ms"] = timeit(two_pass, n=3)
+    fused(); torch.cuda.synchronize()
+    out["fused_equals_two_pass"] = bool(torch.equal(xyz, xyz2))
+except Exception as ex:  # dewarp(out=, stream=) not available: report the fused numbers only
+    out["two_pass_error"] = str(ex)[:200]
+pts = F * H * W * R
+alg = bench.K1_BYTES_PER_FRAME_F32 * F + F * W * 64
+for k in list(out):
+    if k.endswith("_ms") and isinstance(out[k], float):
+        out[k.replace("_ms", "_gpts")] = pts / out[k] / 1e6
+out["fused_frac_of_peak"] = alg / (min(v for k, v in out.items() if k.startswith("fused_tw") and k.endswith("_ms")) * 1e-3) / 1e9 / peak
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/time_pose.json", "w"), indent=1)
+print(json.dumps(out, indent=1))
