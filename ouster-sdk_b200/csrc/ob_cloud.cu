@@ -142,47 +142,52 @@ __device__ __forceinline__ double pose_row(const double* m, double x, double y, 
     return __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dadd_rn(__dmul_rn(m[1], y), __dmul_rn(m[2], z))), m[3]);
 }
 
+// Warp-specialised: warp 0 is the copy warp -- one thread issues every TMA load and store of the
+// CTA and does the tile bookkeeping (integer divisions, expect_tx, store-drain waits) -- while the
+// other warps only compute.  The two sides meet through mbarriers: full[s] (bytes of tile k have
+// landed in stage s) and done[s] (every compute thread is finished with stage s, results in
+// place).  The copy thread's serial work therefore overlaps the compute of the following tiles
+// instead of sitting between two __syncthreads of every tile.
+//
 // POSE: the variant with per-column poses (dewarp fused after the projection).  Work is handed out
 // in items of RPI consecutive rows of one column range; a CTA streams the rows of an item through
-// the usual ring while the item's pose slice (16 scalars per column, one bulk copy) stays in a
-// double-buffered side buffer, so poses cost one L2 read per RPI rows.
+// the ring while the item's pose slice (16 scalars per column, one bulk copy) is re-laid out once
+// into 12 planes [element][column], so poses cost one L2 read per RPI rows.
 template <typename T, int R, bool POSE>
-__global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ CloudParams<T> p) {
+__global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ CloudParams<T> p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // S stage barriers
-    uint64_t* pose_bar = reinterpret_cast<uint64_t*>(smem + 64);  // pose-slice barrier
-    // pose slice of the current item: raw (16 scalars per column, as it lies in memory) and the
-    // 12 planes [element][column] the projection loop reads with conflict-free 16-byte loads
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // [kMaxStagesK1] loads landed
+    uint64_t* done = reinterpret_cast<uint64_t*>(smem + 64);      // [kMaxStagesK1] compute finished
+    uint64_t* pose_bar = reinterpret_cast<uint64_t*>(smem + 128);  // pose slice landed
     const unsigned pose_raw_bytes = POSE ? 16u * p.TW * static_cast<unsigned>(sizeof(T)) : 0u;
     const unsigned pose_soa_bytes = POSE ? 12u * p.TW * static_cast<unsigned>(sizeof(T)) : 0u;
-    uint8_t* pose_raw = smem + 128;
+    uint8_t* pose_raw = smem + 256;
     T* pose_soa = reinterpret_cast<T*>(pose_raw + pose_raw_bytes);
     uint8_t* stage0 = pose_raw + pose_raw_bytes + pose_soa_bytes;
 
     const int tid = threadIdx.x;
+    const int nct = static_cast<int>(blockDim.x) - 32;  // compute threads
+    const int ctid = tid - 32;                          // index among them (< 0: copy warp)
     const int S = p.stages;
     const bool need_lut = (p.xyz != nullptr) || (p.xd != nullptr);
     const unsigned lut_bytes_full = 3u * p.TW * sizeof(T);
     const unsigned RPI = POSE ? static_cast<unsigned>(p.RT) : 1u;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&done[s], static_cast<uint32_t>(nct));
+        }
         if (POSE) mbar_init(pose_bar, 1);
         mbar_fence_init();
         fence_proxy_async();
     }
-    __syncthreads();
+    __syncthreads();  // the only CTA-wide barrier
 
     // tiles of this CTA: item (first + j * grid), rows 0..RPI-1 of it in order
     const unsigned first = blockIdx.x;
     const unsigned n_items_my = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
     const unsigned n_my = n_items_my * RPI;
-
-    uint64_t pol_keep = 0, pol_stream = 0;
-    if (tid == 0) {
-        pol_keep = policy_evict_last();
-        pol_stream = policy_evict_first();
-    }
 
     auto coord = [&](unsigned k) {
         TileCoord tc = tile_coord(p, first + (k / RPI) * gridDim.x);
@@ -190,59 +195,105 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
         return tc;
     };
 
-    auto issue_load = [&](unsigned k) {  // thread 0 only
-        const TileCoord tc = coord(k);
-        const int s = k % S;
-        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
-        if (POSE && (k % RPI) == 0) {
-            // first row of an item: its pose slice.  The raw buffer is free: the previous item
-            // re-laid it out at its first row, more than S tiles ago (RPI > S).
-            const unsigned pb = 16u * tc.tw * static_cast<unsigned>(sizeof(T));
-            mbar_expect_tx(pose_bar, pb);
-            bulk_g2s_hint(pose_raw, p.poses + tc.f * p.poses_fs + static_cast<size_t>(tc.c0) * 16, pb,
-                          pose_bar, pol_keep);
-        }
-        if (tc.row >= p.H) {  // item overhangs the last rows: empty tile
-            mbar_expect_tx(&full[s], 0);
-            return;
-        }
-        const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
-        const unsigned lut_b = 3u * tc.tw * sizeof(T);
-        const unsigned rng_b = 4u * tc.tw;
-        mbar_expect_tx(&full[s], (need_lut ? 2u * lut_b : 0u) + R * rng_b);
-        if (need_lut) {
-            bulk_g2s_hint(st, p.dir + px * 3, lut_b, &full[s], pol_keep);
-            bulk_g2s_hint(st + lut_bytes_full, p.off + px * 3, lut_b, &full[s], pol_keep);
-        }
+    // =============================== copy warp ===============================
+    if (ctid < 0) {
+        if (tid != 0) return;
+        const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+        auto issue_load = [&](unsigned k) {
+            const TileCoord tc = coord(k);
+            const int s = k % S;
+            uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+            if (POSE && (k % RPI) == 0) {
+                // first row of an item: its pose slice.  The raw buffer is free: the compute warps
+                // re-laid the previous slice out at that item's first row, and this load is only
+                // issued after they have finished a later tile of it (RPI > S).
+                const unsigned pb = 16u * tc.tw * static_cast<unsigned>(sizeof(T));
+                mbar_expect_tx(pose_bar, pb);
+                bulk_g2s_hint(pose_raw, p.poses + tc.f * p.poses_fs + static_cast<size_t>(tc.c0) * 16, pb,
+                              pose_bar, pol_keep);
+            }
+            if (tc.row >= p.H) {  // item overhangs the last rows: empty tile
+                mbar_expect_tx(&full[s], 0);
+                return;
+            }
+            const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
+            const unsigned lut_b = 3u * tc.tw * sizeof(T);
+            const unsigned rng_b = 4u * tc.tw;
+            mbar_expect_tx(&full[s], (need_lut ? 2u * lut_b : 0u) + R * rng_b);
+            if (need_lut) {
+                bulk_g2s_hint(st, p.dir + px * 3, lut_b, &full[s], pol_keep);
+                bulk_g2s_hint(st + lut_bytes_full, p.off + px * 3, lut_b, &full[s], pol_keep);
+            }
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            bulk_g2s_hint(st + 2 * lut_bytes_full + r * 4u * p.TW,
-                          p.range + tc.f * p.range_fs + r * p.range_rs + px, rng_b, &full[s],
-                          pol_stream);
-        }
-    };
-
-    if (tid == 0) {
+            for (int r = 0; r < R; ++r) {
+                bulk_g2s_hint(st + 2 * lut_bytes_full + r * 4u * p.TW,
+                              p.range + tc.f * p.range_fs + r * p.range_rs + px, rng_b, &full[s],
+                              pol_stream);
+            }
+        };
         const unsigned pre = min(n_my, static_cast<unsigned>(S));
         for (unsigned k = 0; k < pre; ++k) issue_load(k);
-    }
-
-    for (unsigned k = 0; k < n_my; ++k) {
-        const int s = k % S;
-        // refill a stage whose bulk stores have finished READING smem.  lag 0: the stage of tile
-        // k-1 (its stores were issued a moment ago: thread 0 eats their read latency every tile);
-        // lag 1: the stage of tile k-2, whose stores have had a whole tile time to drain.
-        if (tid == 0) {
-            if (p.store_lag == 0) {
-                if (k >= 1 && (k - 1 + S) < n_my) {
-                    bulk_wait_read<0>();
-                    issue_load(k - 1 + S);
+        const unsigned lag = p.store_lag ? 1u : 0u;
+        for (unsigned k = 0; k < n_my; ++k) {
+            const int s = k % S;
+            const TileCoord tc = coord(k);
+            mbar_wait(&done[s], (k / S) & 1);  // results of tile k are in place
+            if (tc.row < p.H) {
+                uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+                const T* dir_s = reinterpret_cast<const T*>(st);
+                const T* off_s = reinterpret_cast<const T*>(st + lut_bytes_full);
+                const uint32_t* rng_s = reinterpret_cast<const uint32_t*>(st + 2 * lut_bytes_full);
+                const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
+                if (p.xyz != nullptr) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        bulk_s2g(p.xyz + tc.f * p.xyz_fs + r * p.xyz_rs + px * 3, r == 0 ? dir_s : off_s,
+                                 3u * tc.tw * sizeof(T));
                 }
-            } else if (k >= 2 && (k - 2 + S) < n_my) {
-                bulk_wait_read<1>();
-                issue_load(k - 2 + S);
+                const bool want_d = p.rd != nullptr || p.xd != nullptr;
+                const int sh = want_d ? p.shift[tc.row] : 0;
+                if ((sh & 3) == 0 && want_d) {  // 16-byte aligned rotation: straight from the stage
+                    int d0 = tc.c0 + sh;
+                    d0 = d0 >= p.W ? d0 - p.W : d0;
+                    const int n1 = min(tc.tw, p.W - d0);
+                    const size_t rowpx = static_cast<size_t>(tc.row) * p.W;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (p.rd != nullptr) {
+                            uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + rowpx;
+                            const uint32_t* src = rng_s + r * p.TW;
+                            bulk_s2g(drow + d0, src, 4u * n1);
+                            if (n1 < tc.tw) bulk_s2g(drow, src + n1, 4u * (tc.tw - n1));
+                        }
+                        if (p.xd != nullptr) {
+                            T* drow = p.xd + tc.f * p.xd_fs + r * p.xd_rs + rowpx * 3;
+                            const T* src = r == 0 ? dir_s : off_s;
+                            bulk_s2g(drow + static_cast<size_t>(d0) * 3, src, 3u * n1 * sizeof(T));
+                            if (n1 < tc.tw)
+                                bulk_s2g(drow, src + static_cast<size_t>(n1) * 3,
+                                         3u * (tc.tw - n1) * sizeof(T));
+                        }
+                    }
+                }
+            }
+            bulk_commit();  // one group per tile (possibly empty) keeps the wait arithmetic uniform
+            // refill a stage whose bulk stores have finished READING smem: lag 0 = this tile's
+            // (wait for the stores just issued), lag 1 = the previous tile's (had a tile time to drain)
+            if (k >= lag && (k - lag + S) < n_my) {
+                if (lag == 0) bulk_wait_read<0>();
+                else bulk_wait_read<1>();
+                issue_load(k - lag + S);
             }
         }
+        bulk_wait<0>();
+        return;
+    }
+
+    // ============================== compute warps ==============================
+    const int lane = tid & 31;
+    const int cwarp = ctid >> 5;
+    for (unsigned k = 0; k < n_my; ++k) {
+        const int s = k % S;
         const TileCoord tc = coord(k);
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
         T* dir_s = reinterpret_cast<T*>(st);
@@ -253,14 +304,15 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
         if (POSE && (k % RPI) == 0) {  // new item: rows 0..2 of every column pose -> planes
             mbar_wait(pose_bar, (k / RPI) & 1u);
             const T* raw = reinterpret_cast<const T*>(pose_raw);
-            for (int idx = tid; idx < tc.tw * 12; idx += blockDim.x) {
+            named_barrier_sync(1, nct);  // nobody still reads the planes of the previous item
+            for (int idx = ctid; idx < tc.tw * 12; idx += nct) {
                 const int col = idx / 12, e = idx - col * 12;
                 pose_soa[e * p.TW + col] = raw[col * 16 + e];
             }
-            __syncthreads();
+            named_barrier_sync(1, nct);
         }
         if (POSE && tc.row >= p.H) {
-            __syncthreads();
+            mbar_arrive(&done[s]);
             continue;
         }
 
@@ -270,14 +322,13 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
 
         // ---- destaggered range, unaligned row shift: warp-shuffle realignment ----
         if (p.rd != nullptr && q != 0) {
-            const int lane = tid & 31;
             const int nv = n_groups;  // source vectors; dest vectors m = 0..nv (edges partial)
             const int base_col = tc.c0 + sh - q;  // multiple of 4
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const uint4* s4 = reinterpret_cast<const uint4*>(rng_s + r * p.TW);
                 uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + static_cast<size_t>(tc.row) * p.W;
-                for (int m0 = (tid >> 5) * 32; m0 <= nv; m0 += blockDim.x) {
+                for (int m0 = cwarp * 32; m0 <= nv; m0 += nct) {
                     const int m = m0 + lane;
                     uint4 b = make_uint4(0, 0, 0, 0);
                     if (m < nv) b = s4[m];
@@ -311,7 +362,7 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
 
         // ---- projection (and pose), in place ----
         if (need_lut && !POSE) {
-            for (int g = tid; g < n_groups; g += blockDim.x) {
+            for (int g = ctid; g < n_groups; g += nct) {
                 T d[12], o[12];
                 lds12(dir_s + 12 * g, d);
                 lds12(off_s + 12 * g, o);
@@ -332,7 +383,7 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
             // one pixel per thread: the pose math is a long dependent chain, so thread-level
             // parallelism matters more than vector width here (scalar accesses at strides of 1 and
             // 3 words are bank-conflict free)
-            for (int j = tid; j < tc.tw; j += blockDim.x) {
+            for (int j = ctid; j < tc.tw; j += nct) {
                 T d[3], o[3], m[12];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -352,48 +403,10 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
                 }
             }
         }
-        if (need_lut) {
-            fence_proxy_async();
-        }
-        __syncthreads();
 
-        bool thread_path_xd = false;
-        if (tid == 0) {
-            const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
-            if (p.xyz != nullptr) {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    bulk_s2g(p.xyz + tc.f * p.xyz_fs + r * p.xyz_rs + px * 3,
-                             r == 0 ? dir_s : off_s, 3u * tc.tw * sizeof(T));
-            }
-            if (q == 0 && (p.rd != nullptr || p.xd != nullptr)) {
-                int d0 = tc.c0 + sh;
-                d0 = d0 >= p.W ? d0 - p.W : d0;
-                const int n1 = min(tc.tw, p.W - d0);
-                const size_t rowpx = static_cast<size_t>(tc.row) * p.W;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (p.rd != nullptr) {
-                        uint32_t* drow = p.rd + tc.f * p.rd_fs + r * p.rd_rs + rowpx;
-                        const uint32_t* src = rng_s + r * p.TW;
-                        bulk_s2g(drow + d0, src, 4u * n1);
-                        if (n1 < tc.tw) bulk_s2g(drow, src + n1, 4u * (tc.tw - n1));
-                    }
-                    if (p.xd != nullptr) {
-                        T* drow = p.xd + tc.f * p.xd_fs + r * p.xd_rs + rowpx * 3;
-                        const T* src = r == 0 ? dir_s : off_s;
-                        bulk_s2g(drow + static_cast<size_t>(d0) * 3, src, 3u * n1 * sizeof(T));
-                        if (n1 < tc.tw)
-                            bulk_s2g(drow, src + static_cast<size_t>(n1) * 3,
-                                     3u * (tc.tw - n1) * sizeof(T));
-                    }
-                }
-            }
-            bulk_commit();
-        }
         // ---- destaggered XYZ, unaligned row shift: coalesced 32-bit word copies ----
         if (p.xd != nullptr && q != 0) {
-            thread_path_xd = true;
+            named_barrier_sync(1, nct);  // every compute thread's results are in the stage
             constexpr int WPE = sizeof(T) / 4;  // 32-bit words per scalar
             const int row_words = p.W * 3 * WPE;
             const int n_words = tc.tw * 3 * WPE;
@@ -405,16 +418,16 @@ __global__ void __launch_bounds__(256) cloud_tma_kernel(const __grid_constant__ 
                 uint32_t* drow = reinterpret_cast<uint32_t*>(
                     p.xd + tc.f * p.xd_fs + r * p.xd_rs + static_cast<size_t>(tc.row) * p.W * 3);
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(r == 0 ? dir_s : off_s);
-                for (int i = tid; i < n_words; i += blockDim.x) {
+                for (int i = ctid; i < n_words; i += nct) {
                     int dw = dst0 + i;
                     dw = dw >= row_words ? dw - row_words : dw;
                     stg_stream(drow + dw, src[i]);
                 }
             }
         }
-        if (thread_path_xd) __syncthreads();  // stage may be refilled next iteration
+        if (need_lut) fence_proxy_async();  // generic-proxy results -> visible to the TMA stores
+        mbar_arrive(&done[s]);
     }
-    if (tid == 0) bulk_wait<0>();
 }
 
 // Generic kernel: any width / alignment / stride.  One pixel per thread, grid-stride.
@@ -549,7 +562,8 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     p.stage_bytes = 2u * 3u * TW * sizeof(T) + static_cast<unsigned>(a.n_returns) * 4u * TW;
     p.stage_bytes = (p.stage_bytes + 127u) & ~127u;
     const size_t pose_bytes = pose ? (16u + 12u) * TW * sizeof(T) : 0u;  // raw slice + 12 planes
-    const size_t smem = 128 + pose_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
+    if (p.stages > 8) p.stages = 8;  // barrier arrays hold 8 entries each
+    const size_t smem = 256 + pose_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
     if (smem > 227u * 1024u) return cudaErrorInvalidValue;
     const int ctas = std::max<int>(
         1, std::min<size_t>(pose ? tn.cloud_pose_ctas_per_sm : tn.cloud_ctas_per_sm, (227u * 1024u) / smem));
@@ -560,7 +574,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     else kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2, false> : cloud_tma_kernel<T, 1, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kern<<<std::max(grid, 1), tn.cloud_threads, smem, st>>>(p);
+    kern<<<std::max(grid, 1), tn.cloud_threads + 32, smem, st>>>(p);  // + the copy warp
     count_launch();
     return cudaGetLastError();
 }

@@ -36,6 +36,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// plain arrival (no transaction bytes): consumers signal "done with this stage"
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among a subset of the CTA's warps (id 1..15; count = participating threads, multiple of 32)
+__device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // ---- L2 cache policies for bulk copies ----
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;

@@ -1,3 +1,4 @@
+# full GPU regression + every bench line + the sweeps that feed profiles/ (run under gpurun)
 set -x
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 timeout 300 python bench.py 2>/dev/null | tail -1 > gpurun_out/bench_k1.json

@@ -18,15 +18,12 @@ rd = torch.empty((F, R, H, W), dtype=torch.int32, device=dev)
 st = ob.Stream(0, cuda_stream=torch.cuda.current_stream().cuda_stream)
 peak, _ = bench.measured_peaks()
 rows = []
-grid = list(itertools.product([1, 2, 4, 8, 16], [256, 512, 1024], [3, 4, 5], [2, 3, 4], [128, 256]))
-for fb, tw, stg, cta, th in grid:
-    if fb >= 2:
-        smem = 128 + 2 * (tw * 24) + (stg - 1) * (tw * 32)
-    else:
-        smem = 128 + stg * (tw * 32)
-    if smem * cta > 225 * 1024 or smem > 225 * 1024:
+grid = list(itertools.product([0, 1], [256, 512, 1024], [3, 4, 5, 6], [2, 3, 4, 6, 8], [64, 128, 256]))
+for lag, tw, stg, cta, th in grid:
+    smem = 256 + stg * (tw * 32)
+    if smem * cta > 225 * 1024 or smem > 225 * 1024 or (th + 32) * cta > 2048:
         continue
-    for k, v in (("cloud_frames_per_lut", fb), ("cloud_tw", tw), ("cloud_stages", stg), ("cloud_ctas_per_sm", cta), ("cloud_threads", th)):
+    for k, v in (("cloud_store_lag", lag), ("cloud_tw", tw), ("cloud_stages", stg), ("cloud_ctas_per_sm", cta), ("cloud_threads", th)):
         ob.set_tunable(k, v)
     try:
         for _ in range(2):
@@ -41,10 +38,10 @@ for fb, tw, stg, cta, th in grid:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
     except Exception as ex:
-        print("fail", fb, tw, stg, cta, th, ex)
+        print("fail", lag, tw, stg, cta, th, ex)
         continue
     gbps = bench.K1_BYTES_PER_FRAME_F32 * F / (ms * 1e-3) / 1e9
-    rows.append({"fb": fb, "tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": ms, "gbps": gbps, "frac": gbps / peak})
+    rows.append({"lag": lag, "tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": ms, "gbps": gbps, "frac": gbps / peak})
 rows.sort(key=lambda r: -r["gbps"])
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/sweep_k1.json", "w"), indent=0)

@@ -46,9 +46,9 @@ def two_pass():
 
 out = {}
 sweep = []
-for tw in (128, 256, 512):
+for tw in (256, 512):
     for stg in (2, 3, 4):
-        for cta in (3, 4, 5, 6, 8):
+        for cta in (3, 4, 6):
             for th in (128, 256):
                 for k, v in (("cloud_pose_tw", tw), ("cloud_pose_stages", stg), ("cloud_pose_ctas_per_sm", cta),
                              ("cloud_threads", th)):
@@ -67,6 +67,18 @@ for k, v in (("cloud_pose_tw", best["tw"]), ("cloud_pose_stages", best["stages"]
 out["fused_tw_best_ms"] = timeit(fused)
 ob.set_tunable("cloud_threads", 256)
 out["plain_ms"] = timeit(plain)
+for lag in (0, 1):
+    ob.set_tunable("cloud_store_lag", lag)
+    out[f"plain_lag{lag}_ms"] = timeit(plain)
+ob.set_tunable("cloud_store_lag", 1)
+plain_sweep = []
+for tw, stg, cta, th in ((512, 4, 3, 256), (512, 2, 4, 256), (512, 3, 4, 128), (256, 3, 6, 128), (256, 3, 6, 64), (1024, 2, 2, 256), (1024, 3, 2, 256)):
+    for k, v in (("cloud_tw", tw), ("cloud_stages", stg), ("cloud_ctas_per_sm", cta), ("cloud_threads", th)):
+        ob.set_tunable(k, v)
+    plain_sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": timeit(plain, n=5)})
+out["plain_sweep"] = plain_sweep
+for k, v in (("cloud_tw", 512), ("cloud_stages", 4), ("cloud_ctas_per_sm", 3), ("cloud_threads", 256)):
+    ob.set_tunable(k, v)
 try:
     out["two_pass_ms"] = timeit(two_pass, n=3)
     fused(); torch.cuda.synchronize()
