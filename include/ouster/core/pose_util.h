@@ -35,6 +35,29 @@ PointCloudXYZ<T> dewarp(const PointCloudXYZ<T>& points, const MatrixX16R<T>& pos
     return out;
 }
 
+/// dewarp(lut, range, poses) == dewarp(lut(range), poses) in ONE pass over memory (B200 extension:
+/// the fusion the reference asks for in impl/dewarp_impl.h:27-29): point (row, col) of the staggered
+/// cloud becomes R_col * p + t_col.  range is H x W, poses W x 16.
+template <typename T>
+PointCloudXYZ<T> dewarp(const XYZLutT<T>& lut, const ArrayRef<const uint32_t>& range,
+                        const MatrixX16R<T>& poses) {
+    const size_t n = static_cast<size_t>(lut.h) * lut.w;
+    if (static_cast<size_t>(range.rows()) * range.cols() != n)
+        throw std::invalid_argument("unexpected image dimensions");
+    if (poses.cols() != 16 || static_cast<size_t>(poses.rows()) != lut.w)
+        throw std::runtime_error("Number of points per set must match number of poses");
+    PointCloudXYZ<T> out(n, 3);
+    ob_cloud_io io{};
+    io.n_frames = 1;
+    io.n_returns = 1;
+    io.range = range.data();
+    io.xyz = out.data();
+    io.poses = poses.data();
+    b200::check(ob_scan_to_cloud(lut.device_lut().get(), nullptr, 0, &io, b200::thread_stream()));
+    b200::synchronize();
+    return out;
+}
+
 /// transform(points, pose): one 4x4 pose (16 values, row-major) for every point (pose_util.h:118-160).
 template <typename T>
 PointCloudXYZ<T> transform(const PointCloudXYZ<T>& points, const T* pose16) {

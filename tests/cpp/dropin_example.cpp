@@ -150,6 +150,14 @@ int main() {
             CHECK(dw(i, 0) == pts(i, 0) + 1 && dw(i, 1) == pts(i, 1) - 2 && dw(i, 2) == pts(i, 2) + 3);
         PointCloudXYZd tr = transform<double>(pts, pose);
         CHECK(tr == dw);
+        // one-pass form: projection and per-column pose in the same kernel
+        MatrixX16R<double> col_poses(w, 16);
+        for (size_t c = 0; c < w; ++c)
+            for (int k = 0; k < 16; ++k) col_poses(c, k) = pose[k] + (k % 4 == 3 && k < 12 ? 0.001 * c : 0.0);
+        auto range = scan.field<uint32_t>(ChanField::RANGE);
+        PointCloudXYZd two_pass = dewarp<double>(lut(range), col_poses);
+        PointCloudXYZd fused = dewarp<double>(lut, range, col_poses);
+        CHECK(fused == two_pass);
     }
 
     // ---- frame_to_packets -> ScanBatcher -> LidarScan round trip ----
