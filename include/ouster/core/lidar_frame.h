@@ -199,6 +199,20 @@ class OUSTER_API_CLASS LidarFrame {
     Header<uint8_t> alert_flags() { return {alert_flags_.data(), alert_flags_.size()}; }
     Header<const uint8_t> alert_flags() const { return {alert_flags_.data(), alert_flags_.size()}; }
 
+    /// Per-column poses, w x 4 x 4 doubles, identity on construction (lidar_frame.h:732-736,
+    /// lidar_frame.cpp:350-358); pose() is the deprecated spelling.
+    Field& body_to_world() { return body_to_world_; }
+    const Field& body_to_world() const { return body_to_world_; }
+    Field& pose() { return body_to_world_; }
+    const Field& pose() const { return body_to_world_; }
+    /// throw std::out_of_range("Column index out of range") (lidar_frame.cpp:959-980)
+    OUSTER_API_FUNCTION void set_column_pose(int index, const mat4d& pose);
+    OUSTER_API_FUNCTION mat4d get_column_pose(int index) const;
+    /// first / last column with status & 1; throw std::runtime_error("No valid columns in
+    /// LidarFrame") (lidar_frame.cpp:907-925)
+    OUSTER_API_FUNCTION int get_first_valid_column() const;
+    OUSTER_API_FUNCTION int get_last_valid_column() const;
+
     /// true when every column inside the window carries status & 1 (lidar_frame.cpp:421-446)
     OUSTER_API_FUNCTION bool complete(ColumnWindow window) const;
     OUSTER_API_FUNCTION bool complete() const;
@@ -216,6 +230,7 @@ class OUSTER_API_CLASS LidarFrame {
     std::vector<uint32_t> status_;
     std::vector<uint64_t> packet_timestamp_;
     std::vector<uint8_t> alert_flags_;
+    Field body_to_world_;
 };
 
 OUSTER_API_FUNCTION bool operator==(const LidarFrame& a, const LidarFrame& b);

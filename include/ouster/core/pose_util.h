@@ -2,9 +2,12 @@
 // (mirrors ouster_core/include/ouster/core/pose_util.h:24-160).  The loops run on the
 // GPU (ob_dewarp).
 #pragma once
+#include <cstring>
 #include <stdexcept>
+#include <vector>
 
 #include "ouster/core/b200_runtime.h"
+#include "ouster/core/lidar_frame.h"
 #include "ouster/core/typedefs.h"
 #include "ouster/core/xyzlut.h"
 
@@ -55,6 +58,44 @@ PointCloudXYZ<T> dewarp(const XYZLutT<T>& lut, const ArrayRef<const uint32_t>& r
     io.poses = poses.data();
     b200::check(ob_scan_to_cloud(lut.device_lut().get(), nullptr, 0, &io, b200::thread_stream()));
     b200::synchronize();
+    return out;
+}
+
+/// dewarp(lidar_frame, xyzlut, min_range, max_range) (pose_util.h:456-485, impl/dewarp_impl.h:22-76):
+/// world-frame points of the first return, columns between the first and last valid one in order,
+/// status == 0 columns skipped, min_range <= r <= max_range (metres), each point posed with its
+/// column's body_to_world.  Returns an n x 3 array (the reference's std::vector<Eigen::Vector3<T>>
+/// has the same memory layout).  One fused GPU pass (ob_dewarp_frame).  Optional per-point
+/// provenance like impl::dewarp_impl: column index and column timestamp.
+template <typename T>
+PointCloudXYZ<T> dewarp(const LidarFrame& lidar_frame, const XYZLutT<T>& xyzlut, double min_range,
+                        double max_range, std::vector<uint32_t>* col_idxs = nullptr,
+                        std::vector<uint64_t>* timestamps_ns = nullptr) {
+    auto range = lidar_frame.field<uint32_t>(ChanField::RANGE);
+    const size_t n = static_cast<size_t>(xyzlut.h) * xyzlut.w;
+    if (static_cast<size_t>(range.rows()) * range.cols() != n || lidar_frame.w != xyzlut.w)
+        throw std::invalid_argument("unexpected image dimensions");
+    PointCloudXYZ<T> all(n, 3);
+    std::vector<uint32_t> ci(col_idxs ? n : 0);
+    std::vector<uint64_t> ts(timestamps_ns ? n : 0);
+    ob_dewarp_frame_io io{};
+    io.range = range.data();
+    io.poses = lidar_frame.body_to_world().template get<double>();
+    io.status = lidar_frame.status().data();
+    io.timestamps = lidar_frame.timestamp().data();
+    io.min_range = min_range;
+    io.max_range = max_range;
+    io.points = all.data();
+    io.col_idx = col_idxs ? ci.data() : nullptr;
+    io.timestamps_out = timestamps_ns ? ts.data() : nullptr;
+    io.capacity = n;
+    size_t count = 0;
+    b200::check(ob_dewarp_frame(xyzlut.device_lut().get(), &io, &count, b200::thread_stream()));
+    PointCloudXYZ<T> out(count, 3);
+    if (count) std::memcpy(out.data(), all.data(), count * 3 * sizeof(T));
+    if (col_idxs) col_idxs->insert(col_idxs->end(), ci.begin(), ci.begin() + static_cast<std::ptrdiff_t>(count));
+    if (timestamps_ns)
+        timestamps_ns->insert(timestamps_ns->end(), ts.begin(), ts.begin() + static_cast<std::ptrdiff_t>(count));
     return out;
 }
 

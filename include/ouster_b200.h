@@ -50,7 +50,7 @@ typedef struct ob_decoder ob_decoder; /* device-resident PacketFormat decode tab
 /* ---- library ---- */
 int ob_abi_version(void);
 /* sizeof() of a public struct by name ("ob_cloud_io", "ob_field_desc", "ob_packet_layout",
- * "ob_decode_io", "ob_decode_batch"); 0 for unknown names.  Lets FFI bindings verify their layout. */
+ * "ob_decode_io", "ob_decode_batch", "ob_dewarp_frame_io"); 0 for unknown names.  Lets FFI bindings verify their layout. */
 size_t ob_abi_sizeof(const char* struct_name);
 const char* ob_last_error(void);
 /* number of visible CUDA devices (0 without a driver/GPU); never fails */
@@ -126,6 +126,32 @@ ob_status ob_destagger(size_t elem_size, size_t k, const void* img, const int32_
  */
 ob_status ob_dewarp(ob_dtype dtype, const void* points, const void* poses, size_t n_points,
                     size_t n_poses, void* out, ob_stream* s);
+
+/* ---- range image -> world-frame point list (projection + pose + range filter + compaction) ----
+ * replaces dewarp<T>(const LidarFrame&, const XYZLutT<T>&, min_range, max_range)
+ *                                                ouster_core/include/ouster/core/pose_util.h:456-485
+ *          impl::dewarp_impl (single frame)      ouster_core/include/ouster/core/impl/dewarp_impl.h:22-76
+ * Columns between the first and the last column with status bit 0 set are visited in order, columns
+ * whose status word is 0 are skipped, and inside a column the pixels with
+ * ceil(min_range*1e3) <= r <= floor(max_range*1e3) are emitted top to bottom as R_col*lut(r) + t_col
+ * (body_to_world cast to the LUT dtype) -- the reference's order and arithmetic, without
+ * materialising the full cloud first (the fusion its own note at dewarp_impl.h:27-29 asks for).
+ * The call returns after the point count is known (it synchronises the stream once); host
+ * outputs are final on return, device outputs after ob_stream_sync.
+ * error: "output capacity too small" when more than `capacity` points pass the filter.
+ */
+typedef struct ob_dewarp_frame_io {
+    const uint32_t* range;       /* h x w, staggered (the RANGE field) */
+    const double* poses;         /* w x 16: LidarFrame::body_to_world (row-major 4x4 per column) */
+    const uint32_t* status;      /* w: LidarFrame::status */
+    const uint64_t* timestamps;  /* w: LidarFrame::timestamp; only read when timestamps_out != NULL */
+    double min_range, max_range; /* metres */
+    void* points;                /* capacity x 3 of the LUT dtype */
+    uint32_t* col_idx;           /* optional: column of every point */
+    uint64_t* timestamps_out;    /* optional: column timestamp of every point */
+    size_t capacity;             /* in points; h*w always suffices */
+} ob_dewarp_frame_io;
+ob_status ob_dewarp_frame(const ob_lut* lut, const ob_dewarp_frame_io* io, size_t* n_points, ob_stream* s);
 
 /* ---- fused range -> (XYZ, destaggered range, destaggered XYZ), batched over frames ----
  * One launch performs, for every frame f and return r of the batch, what the reference does as

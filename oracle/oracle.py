@@ -140,6 +140,9 @@ def lib():
     for n in ("orc_dewarp_f64", "orc_dewarp_f32"):
         getattr(L, n).argtypes = [vp, vp, vp, sz, sz]
         getattr(L, n).restype = None
+    for n in ("orc_dewarp_frame_f64", "orc_dewarp_frame_f32"):
+        getattr(L, n).argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, sz, C.c_double, C.c_double]
+        getattr(L, n).restype = sz
     L.orc_snapshot_hash.argtypes = [vp, sz, sz]
     L.orc_snapshot_hash.restype = u64
     _lib = L
@@ -394,6 +397,25 @@ def dewarp(points, poses):
     name = {np.dtype(np.float32): "orc_dewarp_f32", np.dtype(np.float64): "orc_dewarp_f64"}[pts.dtype]
     getattr(lib(), name)(_ptr(out), _ptr(pts), _ptr(ps), n, ps.shape[0])
     return out
+
+
+def dewarp_frame(rng, direction, offset, poses, status, timestamps, min_range, max_range):
+    """dewarp<T>(LidarFrame, XYZLutT<T>, min_range, max_range) with provenance vectors --
+    impl/dewarp_impl.h:22-76.  Returns (points [n,3], col_idx [n] u32, timestamps_ns [n] u64)."""
+    rng = np.ascontiguousarray(rng, np.uint32)
+    h, w = rng.shape
+    d = np.ascontiguousarray(direction)
+    o = np.ascontiguousarray(offset, d.dtype)
+    ps = np.ascontiguousarray(poses, np.float64).reshape(w, 16)
+    st = np.ascontiguousarray(status, np.uint32)
+    ts = np.ascontiguousarray(timestamps, np.uint64)
+    out = np.empty((h * w, 3), d.dtype)
+    ci = np.empty(h * w, np.uint32)
+    to = np.empty(h * w, np.uint64)
+    name = {np.dtype(np.float32): "orc_dewarp_frame_f32", np.dtype(np.float64): "orc_dewarp_frame_f64"}[d.dtype]
+    n = getattr(lib(), name)(_ptr(out), _ptr(ci), _ptr(to), _ptr(rng), _ptr(d), _ptr(o), _ptr(ps), _ptr(st),
+                             _ptr(ts), h, w, float(min_range), float(max_range))
+    return out[:n].copy(), ci[:n].copy(), to[:n].copy()
 
 
 def snapshot_hash(a):

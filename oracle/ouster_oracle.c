@@ -1111,6 +1111,66 @@ void orc_dewarp_f32(float* out, const float* pts, const float* poses, size_t n, 
     ORC_DEWARP_BODY(float)
 }
 
+/* dewarp(LidarFrame, XYZLutT<T>, min_range, max_range) -- impl/dewarp_impl.h:22-76 (single frame):
+ * cartesian of the whole range image, then, column by column between the first and last column
+ * whose status has bit 0 set (lidar_frame.cpp:907-925), skipping columns whose status word is 0,
+ * every pixel with min_r <= r <= max_r is posed with the column's body_to_world (cast to T) and
+ * appended; optional per-point column index and column timestamp.  Returns the point count. */
+#define ORC_DEWARP_FRAME_BODY(T, CART)                                                    \
+    const size_t n = h * w;                                                               \
+    T* pts = (T*)malloc(n * 3 * sizeof(T));                                               \
+    if (!pts) return 0;                                                                   \
+    CART(pts, range, dir, off, n);                                                        \
+    const uint32_t min_r = (uint32_t)ceil(min_range * 1e3);                               \
+    const uint32_t max_r = (uint32_t)floor(max_range * 1e3);                              \
+    long start_col = -1, stop_col = -1;                                                   \
+    for (size_t i = 0; i < w; ++i)                                                        \
+        if ((status[i] & 1u) > 0) {                                                       \
+            start_col = (long)i;                                                          \
+            break;                                                                        \
+        }                                                                                 \
+    for (long i = (long)w - 1; i >= 0; --i)                                               \
+        if ((status[i] & 1u) > 0) {                                                       \
+            stop_col = i;                                                                 \
+            break;                                                                        \
+        }                                                                                 \
+    size_t count = 0;                                                                     \
+    if (start_col >= 0 && stop_col >= start_col) {                                        \
+        for (long x = start_col; x <= stop_col; ++x) {                                    \
+            if (status[x] == 0) continue;                                                 \
+            T m[12];                                                                      \
+            for (int k = 0; k < 12; ++k) m[k] = (T)poses[(size_t)x * 16 + (size_t)k];     \
+            for (size_t y = 0; y < h; ++y) {                                              \
+                const uint32_t r = range[y * w + (size_t)x];                              \
+                if (r >= min_r && r <= max_r) {                                           \
+                    const T* p = pts + (y * w + (size_t)x) * 3;                           \
+                    for (int c = 0; c < 3; ++c) {                                         \
+                        const T a = m[c * 4] * p[0], b = m[c * 4 + 1] * p[1], cc = m[c * 4 + 2] * p[2]; \
+                        out[count * 3 + (size_t)c] = (a + (b + cc)) + m[c * 4 + 3];       \
+                    }                                                                     \
+                    if (col_idx) col_idx[count] = (uint32_t)x;                            \
+                    if (ts_out) ts_out[count] = timestamps[x];                            \
+                    ++count;                                                              \
+                }                                                                         \
+            }                                                                             \
+        }                                                                                 \
+    }                                                                                     \
+    free(pts);                                                                            \
+    return count;
+
+size_t orc_dewarp_frame_f64(double* out, uint32_t* col_idx, uint64_t* ts_out, const uint32_t* range,
+                            const double* dir, const double* off, const double* poses,
+                            const uint32_t* status, const uint64_t* timestamps, size_t h, size_t w,
+                            double min_range, double max_range) {
+    ORC_DEWARP_FRAME_BODY(double, orc_cartesian_f64)
+}
+size_t orc_dewarp_frame_f32(float* out, uint32_t* col_idx, uint64_t* ts_out, const uint32_t* range,
+                            const float* dir, const float* off, const double* poses,
+                            const uint32_t* status, const uint64_t* timestamps, size_t h, size_t w,
+                            double min_range, double max_range) {
+    ORC_DEWARP_FRAME_BODY(float, orc_cartesian_f32)
+}
+
 /* matrix_hash -- tests/frame_batcher_test.cpp:595-606 (libstdc++ std::hash<int> = identity) */
 uint64_t orc_snapshot_hash(const void* data, size_t n, size_t elem_size) {
     uint64_t seed = 0;

@@ -194,6 +194,18 @@ int orc_make_xyz_lut(size_t w, size_t h, double range_unit, const double* beam_t
 void orc_dewarp_f64(double* out, const double* pts, const double* poses, size_t n, size_t w);
 void orc_dewarp_f32(float* out, const float* pts, const float* poses, size_t n, size_t w);
 
+/* dewarp<T>(LidarFrame, XYZLutT<T>, min_range, max_range) -- pose_util.h:456-485 ->
+ * impl::dewarp_impl, impl/dewarp_impl.h:22-76.  out holds up to h*w points; col_idx / ts_out may be
+ * NULL.  poses = LidarFrame::body_to_world (w x 16 doubles).  Returns the number of points. */
+size_t orc_dewarp_frame_f64(double* out, uint32_t* col_idx, uint64_t* ts_out, const uint32_t* range,
+                            const double* dir, const double* off, const double* poses,
+                            const uint32_t* status, const uint64_t* timestamps, size_t h, size_t w,
+                            double min_range, double max_range);
+size_t orc_dewarp_frame_f32(float* out, uint32_t* col_idx, uint64_t* ts_out, const uint32_t* range,
+                            const float* dir, const float* off, const double* poses,
+                            const uint32_t* status, const uint64_t* timestamps, size_t h, size_t w,
+                            double min_range, double max_range);
+
 /* std::hash-combine snapshot of a field, tests/frame_batcher_test.cpp:595-606 */
 uint64_t orc_snapshot_hash(const void* data, size_t n, size_t elem_size);
 

@@ -31,6 +31,12 @@ class CloudIO(C.Structure):
                 ("poses", vp), ("poses_frame_stride", sz)]
 
 
+class DewarpFrameIO(C.Structure):
+    _fields_ = [("range", vp), ("poses", vp), ("status", vp), ("timestamps", vp),
+                ("min_range", C.c_double), ("max_range", C.c_double),
+                ("points", vp), ("col_idx", vp), ("timestamps_out", vp), ("capacity", sz)]
+
+
 class FieldDesc(C.Structure):
     _fields_ = [("offset", u32), ("elem_size", u32), ("mask", u64), ("shift", C.c_int32),
                 ("range_return", C.c_int32), ("zero_pattern", u32), ("reserved", u32)]
@@ -96,6 +102,7 @@ _sig("ob_cartesian", i32, vp, vp, sz, vp, vp)
 _sig("ob_destagger", i32, sz, sz, vp, vp, sz, sz, sz, i32, vp, vp)
 _sig("ob_dewarp", i32, i32, vp, vp, sz, sz, vp, vp)
 _sig("ob_scan_to_cloud", i32, vp, vp, sz, C.POINTER(CloudIO), vp)
+_sig("ob_dewarp_frame", i32, vp, C.POINTER(DewarpFrameIO), C.POINTER(sz), vp)
 if hasattr(lib, "ob_decoder_create"):
     _sig("ob_decoder_create", i32, C.POINTER(PacketLayout), C.POINTER(FieldDesc), sz, i32,
          C.POINTER(vp))

@@ -311,6 +311,44 @@ def dewarp(points, poses, out=None, stream=None, device=0):
     return out
 
 
+def dewarp_frame(lut, rng, poses, status, timestamps=None, min_range=0.0, max_range=float("inf"),
+                 provenance=False, stream=None):
+    """dewarp(lidar_frame, xyzlut, min_range, max_range) (pose_util.h:456-485): project the range
+    image, apply each column's body_to_world pose, keep the points with min_range <= r <= max_range
+    (metres) of the columns between the first and last valid one, in column-major order.
+    Returns points [n, 3] (LUT dtype); with provenance=True also (col_idx u32 [n], timestamps u64 [n]).
+    One fused GPU pass: nothing but the surviving points is written."""
+    from ._capi import DewarpFrameIO
+    st = _stream(stream, lut.device)
+    n_px = lut.h * lut.w
+    if _numel(rng) != n_px:
+        raise ValueError("unexpected image dimensions")
+    if max_range == float("inf"):
+        max_range = 4294967.295
+    rng = rng if _is_torch(rng) else np.ascontiguousarray(rng, np.uint32)
+    poses = poses if _is_torch(poses) else np.ascontiguousarray(poses, np.float64)
+    status = status if _is_torch(status) else np.ascontiguousarray(status, np.uint32)
+    if _numel(poses) != lut.w * 16 or _numel(status) != lut.w:
+        raise ValueError("poses must be [W, 4, 4] and status [W]")
+    io = DewarpFrameIO()
+    io.range, io.poses, io.status = _ptr(rng), _ptr(poses), _ptr(status)
+    io.min_range, io.max_range = float(min_range), float(max_range)
+    pts = np.empty((n_px, 3), lut.dtype)
+    io.points, io.capacity = pts.ctypes.data, n_px
+    ci = ts_out = None
+    if provenance:
+        if timestamps is None:
+            raise ValueError("provenance needs the column timestamps")
+        timestamps = timestamps if _is_torch(timestamps) else np.ascontiguousarray(timestamps, np.uint64)
+        ci, ts_out = np.empty(n_px, np.uint32), np.empty(n_px, np.uint64)
+        io.timestamps, io.col_idx, io.timestamps_out = _ptr(timestamps), ci.ctypes.data, ts_out.ctypes.data
+    n = C.c_size_t(0)
+    check(lib.ob_dewarp_frame(lut._h, C.byref(io), C.byref(n), st.h))
+    if provenance:
+        return pts[:n.value], ci[:n.value], ts_out[:n.value]
+    return pts[:n.value]
+
+
 def transform(points, pose, out=None, stream=None, device=0):
     """transform(points (..., 3), pose (4, 4)): one pose for every point (pose_util.h:118-131)."""
     pose = pose if _is_torch(pose) else np.ascontiguousarray(pose, _np_dtype(points)).reshape(1, 16)

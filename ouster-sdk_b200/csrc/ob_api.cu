@@ -242,6 +242,7 @@ size_t ob_abi_sizeof(const char* name) {
     if (n == "ob_packet_layout") return sizeof(ob_packet_layout);
     if (n == "ob_decode_io") return sizeof(ob_decode_io);
     if (n == "ob_decode_batch") return sizeof(ob_decode_batch);
+    if (n == "ob_dewarp_frame_io") return sizeof(ob_dewarp_frame_io);
     return 0;
 }
 
@@ -590,6 +591,85 @@ ob_status ob_dewarp(ob_dtype dtype, const void* points, const void* poses, size_
     if (e != cudaSuccess) return fail_cuda(e, "dewarp launch");
     e = stg.flush();
     if (e != cudaSuccess) return fail_cuda(e, "dewarp D2H");
+    return OB_OK;
+}
+
+ob_status ob_dewarp_frame(const ob_lut* lut, const ob_dewarp_frame_io* io, size_t* n_points, ob_stream* s) {
+    if (!lut || !io || !n_points || !s) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    *n_points = 0;
+    if (!io->range || !io->poses || !io->status || !io->points)
+        return fail(OB_INVALID_ARGUMENT, "null range / poses / status / points");
+    if (io->timestamps_out && !io->timestamps)
+        return fail(OB_INVALID_ARGUMENT, "timestamps_out requested without column timestamps");
+    ob_status rs = require_device(s->device);
+    if (rs != OB_OK) return rs;
+    if (lut->device != s->device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
+    const size_t h = lut->h, w = lut->w, n_px = h * w;
+    const size_t esz = dtype_size(lut->dtype);
+    // same conversions as the reference (dewarp_impl.h:34-35); NaN / negative limits select nothing
+    const double lo = std::ceil(io->min_range * 1e3), hi = std::floor(io->max_range * 1e3);
+    if (!(lo <= 4294967295.0) || !(hi >= 0.0) || !(lo <= hi)) return OB_OK;
+    DewarpFrameArgs a;
+    a.min_r = lo <= 0.0 ? 0u : static_cast<uint32_t>(lo);
+    a.max_r = hi >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(hi);
+    a.H = static_cast<unsigned>(h);
+    a.W = static_cast<unsigned>(w);
+    a.dtype = lut->dtype;
+    a.dir = lut->dir;
+    a.off = lut->off;
+    Staging stg(s->st);
+    const void* d = nullptr;
+    cudaError_t e = stg.in(io->range, n_px * 4, &d);
+    if (e != cudaSuccess) return fail_cuda(e, "stage range");
+    a.range = static_cast<const uint32_t*>(d);
+    e = stg.in(io->poses, w * 16 * sizeof(double), &d);
+    if (e != cudaSuccess) return fail_cuda(e, "stage poses");
+    a.poses = static_cast<const double*>(d);
+    e = stg.in(io->status, w * 4, &d);
+    if (e != cudaSuccess) return fail_cuda(e, "stage status");
+    a.status = static_cast<const uint32_t*>(d);
+    a.timestamps = nullptr;
+    if (io->timestamps_out) {
+        e = stg.in(io->timestamps, w * 8, &d);
+        if (e != cudaSuccess) return fail_cuda(e, "stage timestamps");
+        a.timestamps = static_cast<const uint64_t*>(d);
+    }
+    e = stg.scratch(dewarp_frame_scratch_bytes(a.H, a.W), &a.scratch);
+    if (e != cudaSuccess) return fail_cuda(e, "scratch alloc");
+    e = launch_dewarp_frame_count(a, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame count launch");
+    unsigned long long total = 0;
+    e = cudaMemcpyAsync(&total, dewarp_frame_total_ptr(a), sizeof(total), cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame count");
+    if (total > io->capacity) return fail(OB_INVALID_ARGUMENT, "output capacity too small");
+    if (total == 0) return OB_OK;
+    // outputs: device pointers in place, host pointers through scratch sized to the real count
+    void* o = nullptr;
+    e = stg.out(io->points, total * 3 * esz, &o);
+    if (e != cudaSuccess) return fail_cuda(e, "stage points");
+    a.points = o;
+    a.col_idx = nullptr;
+    a.ts_out = nullptr;
+    if (io->col_idx) {
+        e = stg.out(io->col_idx, total * 4, &o);
+        if (e != cudaSuccess) return fail_cuda(e, "stage col_idx");
+        a.col_idx = static_cast<uint32_t*>(o);
+    }
+    if (io->timestamps_out) {
+        e = stg.out(io->timestamps_out, total * 8, &o);
+        if (e != cudaSuccess) return fail_cuda(e, "stage timestamps_out");
+        a.ts_out = static_cast<uint64_t*>(o);
+    }
+    e = launch_dewarp_frame_emit(a, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame emit launch");
+    e = stg.flush();
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame D2H");
+    if (!is_device_ptr(io->points)) {
+        e = cudaStreamSynchronize(s->st);
+        if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame");
+    }
+    *n_points = static_cast<size_t>(total);
     return OB_OK;
 }
 

@@ -64,6 +64,27 @@ cudaError_t launch_make_lut(size_t w, size_t h, double range_unit, const double*
                             cudaStream_t st);
 cudaError_t launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t st);
 
+// ---- K3: range -> posed, filtered, compacted point list (ob_dewarp_frame.cu) ----
+struct DewarpFrameArgs {  // all pointers are device memory
+    const uint32_t* range;       // H x W
+    const void* dir;             // LUT tables of `dtype`
+    const void* off;
+    const double* poses;         // W x 16
+    const uint32_t* status;      // W
+    const uint64_t* timestamps;  // W, may be null when ts_out is null
+    unsigned H, W;
+    uint32_t min_r, max_r;
+    int dtype;
+    void* scratch;               // dewarp_frame_scratch_bytes(H, W)
+    void* points;                // capacity x 3 of dtype
+    uint32_t* col_idx;           // nullable
+    uint64_t* ts_out;            // nullable
+};
+size_t dewarp_frame_scratch_bytes(unsigned H, unsigned W);
+cudaError_t launch_dewarp_frame_count(const DewarpFrameArgs& a, cudaStream_t st);  // counts + offsets
+const unsigned long long* dewarp_frame_total_ptr(const DewarpFrameArgs& a);         // device pointer
+cudaError_t launch_dewarp_frame_emit(const DewarpFrameArgs& a, cudaStream_t st);
+
 // ---- decode ----
 struct DecodeField {  // device-side copy of ob_field_desc, pre-digested
     uint32_t offset;

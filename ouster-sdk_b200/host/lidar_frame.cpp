@@ -261,6 +261,34 @@ void LidarFrame::init_headers(size_t columns_per_packet) {
     const size_t np = columns_per_packet ? w / columns_per_packet : 0;
     packet_timestamp_.assign(np, 0);
     alert_flags_.assign(np, 0);
+    body_to_world_ = Field(ChanFieldType::FLOAT64, {w, 4, 4});
+    double* p = body_to_world_.get<double>();
+    for (size_t c = 0; c < w; ++c)
+        for (int i = 0; i < 4; ++i) p[c * 16 + static_cast<size_t>(i) * 5] = 1.0;  // identity
+}
+
+void LidarFrame::set_column_pose(int index, const mat4d& pose) {
+    if (index < 0 || index >= static_cast<int>(w)) throw std::out_of_range("Column index out of range");
+    std::memcpy(body_to_world_.get<double>() + static_cast<size_t>(index) * 16, pose.data(), 16 * sizeof(double));
+}
+
+mat4d LidarFrame::get_column_pose(int index) const {
+    if (index < 0 || index >= static_cast<int>(w)) throw std::out_of_range("Column index out of range");
+    mat4d out;
+    std::memcpy(out.m.data(), body_to_world_.get<double>() + static_cast<size_t>(index) * 16, 16 * sizeof(double));
+    return out;
+}
+
+int LidarFrame::get_first_valid_column() const {
+    for (size_t i = 0; i < status_.size(); ++i)
+        if ((status_[i] & 1u) > 0) return static_cast<int>(i);
+    throw std::runtime_error("No valid columns in LidarFrame");
+}
+
+int LidarFrame::get_last_valid_column() const {
+    for (int i = static_cast<int>(status_.size()) - 1; i >= 0; --i)
+        if ((status_[static_cast<size_t>(i)] & 1u) > 0) return i;
+    throw std::runtime_error("No valid columns in LidarFrame");
 }
 
 LidarFrame::LidarFrame(size_t h_, size_t w_, const LidarFrameFieldTypes& field_types,
@@ -424,7 +452,7 @@ bool LidarFrame::equals(const LidarFrame& o) const {
            shot_limiting_countdown == o.shot_limiting_countdown && fields_ == o.fields_ &&
            timestamp_ == o.timestamp_ && measurement_id_ == o.measurement_id_ &&
            status_ == o.status_ && packet_timestamp_ == o.packet_timestamp_ &&
-           alert_flags_ == o.alert_flags_;
+           alert_flags_ == o.alert_flags_ && body_to_world_ == o.body_to_world_;  // lidar_frame.cpp:1016
 }
 
 bool operator==(const LidarFrame& a, const LidarFrame& b) { return a.equals(b); }

@@ -158,6 +158,32 @@ int main() {
         PointCloudXYZd two_pass = dewarp<double>(lut(range), col_poses);
         PointCloudXYZd fused = dewarp<double>(lut, range, col_poses);
         CHECK(fused == two_pass);
+        // dewarp(frame, lut, min, max): posed, range-filtered, compacted points of the valid columns
+        LidarScan posed(scan);
+        for (size_t c = 0; c < w; ++c) {
+            mat4d m = mat4d::Identity();
+            m(0, 3) = 0.5 * c;
+            posed.set_column_pose(static_cast<int>(c), m);
+            posed.status()[c] = (c % 7 == 3) ? 0u : 1u;
+        }
+        CHECK(posed.get_column_pose(2)(0, 3) == 1.0 && posed.get_first_valid_column() == 0);
+        std::vector<uint32_t> cols;
+        PointCloudXYZd world = dewarp<double>(posed, lut, 0.3, 50.0, &cols);
+        PointCloudXYZd cloud = lut(range);
+        size_t k = 0;
+        for (size_t c = 0; c < w; ++c) {
+            if (c % 7 == 3) continue;
+            for (size_t r = 0; r < h; ++r) {
+                const uint32_t rv = range(r, c);
+                if (rv < 300 || rv > 50000) continue;
+                CHECK(k < static_cast<size_t>(world.rows()) && cols[k] == c);
+                CHECK(world(k, 0) == cloud(r * w + c, 0) + 0.5 * c && world(k, 1) == cloud(r * w + c, 1));
+                ++k;
+            }
+        }
+        CHECK(k == static_cast<size_t>(world.rows()) && k > 0);
+        expect_throw<std::out_of_range>([&] { posed.set_column_pose(-1, mat4d::Identity()); },
+                                        "Column index out of range");
     }
 
     // ---- frame_to_packets -> ScanBatcher -> LidarScan round trip ----

@@ -66,7 +66,7 @@ def test_ctypes_struct_layouts_match_the_c_abi():
     capi = ob._capi
     pairs = {"ob_cloud_io": capi.CloudIO, "ob_field_desc": capi.FieldDesc,
              "ob_packet_layout": capi.PacketLayout, "ob_decode_io": capi.DecodeIO,
-             "ob_decode_batch": capi.DecodeBatch}
+             "ob_decode_batch": capi.DecodeBatch, "ob_dewarp_frame_io": capi.DewarpFrameIO}
     for name, cls in pairs.items():
         assert capi.lib.ob_abi_sizeof(name.encode()) == ctypes.sizeof(cls), name
     assert capi.lib.ob_abi_sizeof(b"nope") == 0

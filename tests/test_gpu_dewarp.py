@@ -128,3 +128,35 @@ def test_fused_dewarp_argument_errors(ob):
     with pytest.raises(ValueError, match="without an xyz output"):
         ob.scan_to_cloud(lut, np.zeros(h, np.int32), rng, range_destaggered=np.zeros((1, 1, h, w), np.uint32),
                          poses=np.zeros((w, 4, 4), np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w", [(128, 2048), (64, 1024), (20, 516), (5, 33)])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_dewarp_frame_matches_reference_loop(ob, h, w, dtype):
+    """dewarp(LidarFrame, lut, min_range, max_range) (pose_util.h:456-485, impl/dewarp_impl.h:22-76):
+    same points, same order, same provenance as the oracle's restatement of the reference loop."""
+    from tests.helpers import random_lut, random_range
+    rs = np.random.default_rng(h + w)
+    rng = random_range(h, w, 7, p_zero=0.3, max_range=60000)
+    d, o = random_lut(h * w, 2, dtype)
+    lut = ob.XYZLutT.from_arrays(d, o, h, w)
+    poses = _random_poses(w, np.float64, 9)
+    status = np.ones(w, np.uint32)
+    status[: w // 10] = 0                       # leading invalid columns: before the first valid one
+    status[rs.integers(w // 10, w, w // 8)] = 0  # holes: skipped
+    status[w // 2] = 2                          # non-zero word without the valid bit: still visited
+    status[-3:] = 0                             # trailing invalid columns
+    ts = (1000 + 17 * np.arange(w)).astype(np.uint64)
+    for lo, hi in ((0.5, 30.0), (0.0, 100.0), (10.0, 10.5), (50.0, 40.0)):
+        want_p, want_c, want_t = orc.dewarp_frame(rng, d, o, poses, status, ts, lo, hi)
+        got_p, got_c, got_t = ob.dewarp_frame(lut, rng, poses, status, ts, lo, hi, provenance=True)
+        assert got_p.shape == want_p.shape, (lo, hi)
+        assert np.array_equal(got_p, want_p), (lo, hi)
+        assert np.array_equal(got_c, want_c) and np.array_equal(got_t, want_t)
+        assert np.array_equal(ob.dewarp_frame(lut, rng, poses, status, None, lo, hi), want_p)
+    # no valid column at all -> empty (get_first_valid_column throws in the reference, :44-49)
+    none = np.zeros(w, np.uint32)
+    none[3] = 2
+    assert ob.dewarp_frame(lut, rng, poses, none, ts, 0.5, 30.0).shape == (0, 3)
+    assert orc.dewarp_frame(rng, d, o, poses, none, ts, 0.5, 30.0)[0].shape == (0, 3)
