@@ -77,3 +77,26 @@ def destagger(info, fields, inverse=False):
 
 def stagger(info, fields):
     return destagger(info, fields, True)
+
+
+def _floating(a, what):
+    a = np.asarray(a)
+    if a.dtype.kind != "f":
+        raise TypeError(f"{what} must be floating-point arrays")
+    return a
+
+
+def dewarp(points, poses):
+    """core.dewarp(points (H, W, 3), poses (W, 4, 4)) -> (H, W, 3) (processing.cpp:132-161, 300-310):
+    float32 points stay float32, anything else is computed in float64; TypeError for non-floating
+    input, RuntimeError when W differs."""
+    p, q = _floating(points, "points and poses"), _floating(poses, "points and poses")
+    dt = np.float32 if p.dtype == np.float32 else np.float64
+    return _c.dewarp(np.ascontiguousarray(p, dt), np.ascontiguousarray(q, dt))
+
+
+def transform(points, pose):
+    """core.transform(points (..., 3), pose (4, 4)) (processing.cpp:312-329)."""
+    p, q = _floating(points, "points and pose"), _floating(pose, "points and pose")
+    dt = np.float32 if p.dtype == np.float32 else np.float64
+    return _c.transform(np.ascontiguousarray(p, dt), np.ascontiguousarray(q, dt))

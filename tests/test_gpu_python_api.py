@@ -99,3 +99,19 @@ def test_xyzlut_vs_doc_formula(core, meta_frame):
     assert np.allclose(core.XYZLutFloat(info, use_extrinsics=False)(scan), ref, rtol=1e-5, atol=1e-5)
     with pytest.raises(ValueError, match="Image dimensions do not match lut."):
         core.XYZLut(info)(np.zeros((h, w + 1), np.uint32))
+
+
+def test_pyapi_dewarp_transform_dispatch(core):
+    """python/tests/test_pose_util.py:300-360: dtype dispatch and error types of dewarp/transform"""
+    poses = np.tile(np.eye(4), (4, 1, 1))
+    poses[:, :3, 3] = [1, -2, 3]
+    pts = np.array([[i - 3, i + 1, i + 2] for i in range(8)], np.float64).reshape(2, 4, 3)
+    out = core.dewarp(pts, poses)
+    assert out.dtype == np.float64 and np.array_equal(out, pts + [1, -2, 3])
+    out32 = core.dewarp(pts.astype(np.float32), poses)
+    assert out32.dtype == np.float32 and np.array_equal(out32, (pts + [1, -2, 3]).astype(np.float32))
+    assert np.array_equal(core.transform(pts, poses[0]), pts + [1, -2, 3])
+    with pytest.raises(TypeError, match="floating-point"):
+        core.dewarp(pts.astype(np.int32), poses)
+    with pytest.raises(RuntimeError, match="Number of points per set must match number of poses"):
+        core.dewarp(np.zeros((2, 5, 3)), poses)

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""K3 (ob_dewarp_frame) on one 128x2048 frame: device-resident and host-to-host time vs the
+oracle's restatement of the reference loop on one host core (run under gpurun)."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as graft
+import bench
+from oracle import oracle as orc
+ob = graft.load_package()
+H, W = bench.H, bench.W
+dev = torch.device("cuda", 0)
+rng = bench.synth_pool(1)[0, 0].copy()
+rng[rng > 0] = rng[rng > 0] % 60000 + 1
+d, o = bench.synth_lut()
+lut = ob.XYZLutT.from_arrays(torch.from_numpy(d).to(dev), torch.from_numpy(o).to(dev), H, W)
+poses = np.tile(np.eye(4), (W, 1, 1)); poses[:, :3, 3] = np.random.default_rng(1).random((W, 3))
+status = np.ones(W, np.uint32); ts = np.arange(W, dtype=np.uint64)
+t_rng, t_pose = torch.from_numpy(rng.view(np.int32)).to(dev), torch.from_numpy(poses).to(dev)
+t_st, t_ts = torch.from_numpy(status.view(np.int32)).to(dev), torch.from_numpy(ts.view(np.int64)).to(dev)
+st = ob.Stream(0, cuda_stream=torch.cuda.current_stream().cuda_stream)
+
+def best(fn, n=20):
+    fn(); fn()
+    t = []
+    for _ in range(n):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); t.append(time.perf_counter() - t0)
+    return min(t)
+
+out = {}
+n_host = len(ob.dewarp_frame(lut, rng, poses, status, ts, 0.5, 50.0))
+out["points"] = n_host
+out["host_to_host_ms"] = best(lambda: ob.dewarp_frame(lut, rng, poses, status, ts, 0.5, 50.0, stream=st)) * 1e3
+out["device_inputs_ms"] = best(lambda: ob.dewarp_frame(lut, t_rng, t_pose, t_st, t_ts, 0.5, 50.0, stream=st)) * 1e3
+t0 = time.perf_counter(); want = orc.dewarp_frame(rng, d, o, poses, status, ts, 0.5, 50.0)[0]; out["cpu_1thread_ms"] = (time.perf_counter() - t0) * 1e3
+out["matches_oracle"] = bool(np.array_equal(want, ob.dewarp_frame(lut, rng, poses, status, ts, 0.5, 50.0)))
+out["speedup_host_to_host"] = out["cpu_1thread_ms"] / out["host_to_host_ms"]
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/time_dewarp_frame.json", "w"), indent=1)
+print(json.dumps(out))
