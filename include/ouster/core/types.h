@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <optional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -133,6 +134,16 @@ class OUSTER_API_CLASS PacketFormat {
     }
 
     OUSTER_API_FUNCTION uint64_t calculate_crc(const uint8_t* buffer, size_t buffer_size) const;
+    /// CRC64 stored in the last 8 bytes of the packet; empty for LEGACY and FUSA packets, which
+    /// carry none (parsing.cpp:1219-1228).
+    std::optional<uint64_t> crc(const uint8_t* buffer, size_t buffer_size) const {
+        if (udp_profile_lidar == UDPProfileLidar::LEGACY ||
+            udp_profile_lidar == UDPProfileLidar::FUSA_RNG15_RFL8_NIR8_DUAL || header_type == HeaderType::FUSA)
+            return std::nullopt;
+        uint64_t v = 0;
+        for (int i = 7; i >= 0; --i) v = (v << 8) | buffer[buffer_size - 8 + static_cast<size_t>(i)];
+        return v;
+    }
     OUSTER_API_FUNCTION int frame_id_difference(uint32_t current, uint32_t other) const;
 
     /// Replace the channel-field table (the effect add_custom_profile() has on a profile,

@@ -274,3 +274,21 @@ def test_batcher_argument_errors(ob):
         b.set_max_cache_size(0)
     with pytest.raises(ValueError, match="Unknown lidar udp profile"):
         ob.SensorInfo("NOT_A_PROFILE", 16, 256)
+
+
+def test_cpp_headers_host_only_example():
+    """tests/cpp/host_only_example.cpp: the replacement headers' host-only surface (PacketFormat
+    geometry / CRC, LidarFrame fields + column poses, frame_to_packets, the FrameBatcher state
+    machine in header-only mode) compiled with plain g++ and run on the CPU."""
+    import subprocess
+    import __graft_entry__ as graft
+    graft.build()
+    root = graft.ROOT
+    lib_dir = os.path.join(root, "ouster-sdk_b200", "lib")
+    exe = os.path.join(root, "tests", "cpp", "host_only_example.bin")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "host_only_example.cpp"), "-L", lib_dir,
+                           "-louster_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "HOST OK" in out.stdout
