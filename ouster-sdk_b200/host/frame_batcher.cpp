@@ -258,7 +258,16 @@ void FrameBatcher::start_frame(int64_t f_id, const uint8_t* packet_buf, LidarFra
 
 void FrameBatcher::batch_lidar_packet(const uint8_t* packet_buf, uint64_t host_ts, LidarFrame& f) {
     const int cpp = pf.columns_per_packet;
-    const uint16_t first_m_id = pf.col_measurement_id(pf.nth_col(0, packet_buf));
+    // column header getters, inlined: the decode infos are copied once per call so that the 8-byte
+    // load / mask / shift of FieldDecodeInfo::get sits in this loop instead of behind a call
+    const FieldDecodeInfo i_ts = pf.col_timestamp_info(), i_mid = pf.col_measurement_id_info(),
+                          i_st = pf.col_status_info();
+    const size_t col0 = pf.packet_header_size, col_size = pf.col_size;
+    auto nth_col = [&](int i) { return packet_buf + col0 + static_cast<size_t>(i) * col_size; };
+    auto col_mid = [&](const uint8_t* c) { return i_mid.get<uint16_t>(c); };
+    auto col_st = [&](const uint8_t* c) { return i_st.get<uint32_t>(c); };
+    auto col_ts = [&](const uint8_t* c) { return i_ts.get<uint64_t>(c); };
+    const uint16_t first_m_id = col_mid(nth_col(0));
     const uint16_t packet_id = static_cast<uint16_t>(first_m_id / cpp);
     if (packet_id < f.packet_timestamp().rows()) {
         f.packet_timestamp()[packet_id] = host_ts;
@@ -284,11 +293,11 @@ void FrameBatcher::batch_lidar_packet(const uint8_t* packet_buf, uint64_t host_t
     // block path preconditions (lidar_frame.cpp:1542-1567)
     int block = pf.block_parsable();
     for (int icol = 0; icol < cpp && block; icol++) {
-        const uint8_t* col = pf.nth_col(icol, packet_buf);
-        if (!(pf.col_status(col) & 0x01) || pf.col_measurement_id(col) >= f.w) block = 0;
+        const uint8_t* col = nth_col(icol);
+        if (!(col_st(col) & 0x01) || col_mid(col) >= f.w) block = 0;
     }
     for (int icol = 0; icol < cpp && block; icol += block) {
-        if (static_cast<size_t>(pf.col_measurement_id(pf.nth_col(icol, packet_buf))) + block > f.w)
+        if (static_cast<size_t>(col_mid(nth_col(icol))) + block > f.w)
             block = 0;
     }
 
@@ -310,29 +319,29 @@ void FrameBatcher::batch_lidar_packet(const uint8_t* packet_buf, uint64_t host_t
             next_valid_m_id_ = static_cast<uint16_t>(first_m_id + cpp);
         }
         for (int icol = 0; icol < cpp; icol++) {
-            const uint8_t* col = pf.nth_col(icol, packet_buf);
-            const uint16_t m_id = pf.col_measurement_id(col);
+            const uint8_t* col = nth_col(icol);
+            const uint16_t m_id = col_mid(col);
             measurement_id[m_id] = m_id;
-            timestamp[m_id] = pf.col_timestamp(col);
-            status[m_id] = pf.col_status(col);
+            timestamp[m_id] = col_ts(col);
+            status[m_id] = col_st(col);
         }
         // block_field places a group at the measurement id of its first column (parsing.cpp:647-653)
         for (int icol = 0; icol < cpp; icol += block) {
-            const uint16_t m0 = pf.col_measurement_id(pf.nth_col(icol, packet_buf));
+            const uint16_t m0 = col_mid(nth_col(icol));
             for (int x = 0; x < block; ++x) s.col_src[m0 + x] = src0 + icol + x;
         }
     } else {  // parse_by_col, lidar_frame.cpp:1422-1466
         for (int icol = 0; icol < cpp; icol++) {
-            const uint8_t* col = pf.nth_col(icol, packet_buf);
-            const uint16_t m_id = pf.col_measurement_id(col);
-            const uint32_t st = pf.col_status(col);
+            const uint8_t* col = nth_col(icol);
+            const uint16_t m_id = col_mid(col);
+            const uint32_t st = col_st(col);
             if (m_id >= f.w) continue;
             if (!(st & 0x01)) continue;
             if (m_id >= next_valid_m_id_) {
                 zero_gap(next_valid_m_id_, m_id);
                 next_valid_m_id_ = static_cast<uint16_t>(m_id + 1);
             }
-            timestamp[m_id] = pf.col_timestamp(col);
+            timestamp[m_id] = col_ts(col);
             measurement_id[m_id] = m_id;
             status[m_id] = st;
             s.col_src[m_id] = src0 + icol;
