@@ -202,6 +202,7 @@ def main():
         return
 
     numa_cores = bind_to_gpu_numa(local_rank) if world > 1 else 0
+    args.numa_cores = numa_cores
     import torch
     import __graft_entry__ as graft
     graft.build()

@@ -255,7 +255,8 @@ def run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measure
                    "frames_per_stream_per_step": F // STREAMS_PER_GPU,
                    "parallelism": f"{STREAMS_PER_GPU * world} independent sensor streams, stream i -> GPU i mod {world}, "
                                   "own LUT per stream, one fused launch per GPU per step, no data-path collective",
-                   "l2_policy": f"{F * K2_BYTES_PER_FRAME_F32 / 1e6:.0f} MB touched per step > 126 MB L2"},
+                   "l2_policy": f"{F * K2_BYTES_PER_FRAME_F32 / 1e6:.0f} MB touched per step > 126 MB L2",
+                   "numa_bound_cores_per_rank": getattr(args, "numa_cores", 0)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                      "kernel": "decode_kernel<float>",
