@@ -428,17 +428,17 @@ __device__ __forceinline__ void store_all(const uint32_t (&w)[PxLayout<L>::cds /
 template <int L, bool FULL, bool ALL>
 __device__ __forceinline__ void decode_static(const uint8_t* px0, bool col_valid, bool lane_on,
                                               uint8_t* const (&outp)[kMaxSlots], uint32_t* const (&rdp)[2],
-                                              unsigned col, unsigned W, unsigned H, int warp, int nwarps,
+                                              unsigned col, unsigned W, unsigned H, unsigned row0, unsigned rstep,
                                               const DecodeParams& p) {
     constexpr int NW = PxLayout<L>::cds / 4;
     const bool has_rd = ALL || rdp[0] != nullptr || rdp[1] != nullptr;
     const bool has_shift = p.has_shift != 0;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(px0) + static_cast<unsigned>(warp) * NW;
-    const unsigned wstep = static_cast<unsigned>(nwarps) * NW;
-    unsigned pix = static_cast<unsigned>(warp) * W + col;
-    const unsigned pstep = static_cast<unsigned>(nwarps) * W;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(px0) + row0 * NW;
+    const unsigned wstep = rstep * NW;
+    unsigned pix = row0 * W + col;
+    const unsigned pstep = rstep * W;
 #pragma unroll 2
-    for (unsigned row = warp; row < H; row += nwarps) {
+    for (unsigned row = row0; row < H; row += rstep) {
         uint32_t w[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) w[i] = wp[i];
@@ -459,10 +459,10 @@ template <int L>
 __device__ __forceinline__ void decode_static_tile(bool full, bool all, const uint8_t* px0, bool col_valid,
                                                    bool lane_on, uint8_t* const (&outp)[kMaxSlots],
                                                    uint32_t* const (&rdp)[2], unsigned col, unsigned W, unsigned H,
-                                                   int warp, int nwarps, const DecodeParams& p) {
-    if (full && all) decode_static<L, true, true>(px0, true, true, outp, rdp, col, W, H, warp, nwarps, p);
-    else if (full) decode_static<L, true, false>(px0, true, true, outp, rdp, col, W, H, warp, nwarps, p);
-    else decode_static<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, warp, nwarps, p);
+                                                   unsigned row0, unsigned rstep, const DecodeParams& p) {
+    if (full && all) decode_static<L, true, true>(px0, true, true, outp, rdp, col, W, H, row0, rstep, p);
+    else if (full) decode_static<L, true, false>(px0, true, true, outp, rdp, col, W, H, row0, rstep, p);
+    else decode_static<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, row0, rstep, p);
 }
 
 template <typename T>
@@ -652,8 +652,12 @@ __global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ 
         }
 
         // ---- phase A: decode; lane = frame column, warp = row (strided), fields outermost ----
+        // narrow tiles (fewer than 32 columns) with a compile-time layout: a warp covers RW rows
+        // per instruction (lane = column + tc * sub-row) instead of leaving lanes idle
+        const unsigned RW = (p.layout_id != 0 && tc < 32u && (32u % tc) == 0u) ? 32u / tc : 1u;
         for (unsigned cg = 0; cg * 32 < tc; ++cg) {
-            const unsigned t = cg * 32 + lane;
+            const unsigned t = RW > 1 ? (static_cast<unsigned>(lane) % tc) : cg * 32 + lane;
+            const unsigned sub = RW > 1 ? static_cast<unsigned>(lane) / tc : 0u;
             const bool lane_on = t < tc;
             const unsigned tt = lane_on ? t : 0;
             const int co = regular ? col_offset(tt) : c.col_off[tt];
@@ -666,17 +670,18 @@ __global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ 
                 for (int i = 0; i < kMaxSlots; ++i)
                     outp[i] = p.slot_field[i] >= 0 ? static_cast<uint8_t*>(fr.fields[p.slot_field[i]]) : nullptr;
                 uint32_t* rdp2[2] = {fr.rd[0], fr.rd[1]};
-                const bool full = regular && (cg + 1) * 32u <= tc;
+                const bool full = regular && (RW > 1 || (cg + 1) * 32u <= tc);
                 const unsigned col = static_cast<unsigned>(pix0);
+                const unsigned row0 = static_cast<unsigned>(warp) * RW + sub, rstep = static_cast<unsigned>(nwarps) * RW;
                 const bool all = p.layout_all != 0 && (p.n_returns < 1 || rdp2[0] != nullptr) &&
                                  (p.n_returns < 2 || rdp2[1] != nullptr) && fr.fields[0] != nullptr &&
                                  p.n_returns > 0;
                 switch (p.layout_id) {
-                    case 1: decode_static_tile<1>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
-                    case 2: decode_static_tile<2>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
-                    case 3: decode_static_tile<3>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
-                    case 4: decode_static_tile<4>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
-                    default: decode_static_tile<5>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, warp, nwarps, p); break;
+                    case 1: decode_static_tile<1>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    case 2: decode_static_tile<2>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    case 3: decode_static_tile<3>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    case 4: decode_static_tile<4>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    default: decode_static_tile<5>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
                 }
                 continue;
             }

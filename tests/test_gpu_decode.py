@@ -103,13 +103,19 @@ PROFILE_CASES = [
 ]
 
 
-@pytest.fixture(params=["static_layouts", "runtime_plans"])
+@pytest.fixture(params=["static_layouts", "runtime_plans", "narrow_tiles"])
 def plans(ob, request):
     """K2 has two phase-A code paths: compile-time pixel layouts for the standard profiles and
-    runtime extraction plans for everything else; run the parity cases through both."""
+    runtime extraction plans for everything else; run the parity cases through both, and through
+    one-packet tiles (16 columns: a warp covers two rows per instruction) with a 2-stage ring."""
     ob.set_tunable("decode_runtime_plans", int(request.param == "runtime_plans"))
+    if request.param == "narrow_tiles":
+        ob.set_tunable("decode_tile_packets", 1)
+        ob.set_tunable("decode_stages", 2)
     yield request.param
     ob.set_tunable("decode_runtime_plans", 0)
+    ob.set_tunable("decode_tile_packets", 0)
+    ob.set_tunable("decode_stages", 1)
 
 
 @pytest.mark.parametrize("profile,header,h,w", PROFILE_CASES)
