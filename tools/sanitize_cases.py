@@ -34,7 +34,34 @@ for dtype in (np.float32, np.float64):
                     assert np.array_equal(xyz[f, r], want)
                     assert np.array_equal(rd[f, r], orc.destagger(rng[f, r], sh))
                     assert np.array_equal(xd[f, r], orc.destagger(want.reshape(h, w, 3), sh))
-print("K1 ok")
+# K1 with fused per-column poses (streamed rows + resident pose planes) and K3 (count/scan/emit)
+for dtype in (np.float32, np.float64):
+    hh, ww = 40, 256
+    rngp = np.stack([np.stack([random_range(hh, ww, 50 + 10 * f + r) for r in range(2)]) for f in range(2)])
+    d, o = random_lut(hh * ww, 4, dtype)
+    lut = ob.XYZLutT.from_arrays(d, o, hh, ww)
+    poses = np.tile(np.eye(4, dtype=dtype), (ww, 1, 1))
+    poses[:, :3, 3] = np.random.default_rng(2).random((ww, 3)).astype(dtype)
+    poses[:, 0, 1] = 0.25
+    sh = (np.arange(hh, dtype=np.int32) * 5) % 23
+    xyz = np.zeros((2, 2, hh * ww, 3), dtype)
+    xd = np.zeros((2, 2, hh, ww, 3), dtype)
+    ob.scan_to_cloud(lut, sh, rngp, xyz=xyz, xyz_destaggered=xd, stream=st, poses=poses)
+    st.sync()
+    for f in range(2):
+        for r in range(2):
+            want = orc.dewarp(orc.cartesian(rngp[f, r], d, o).reshape(hh, ww, 3), poses)
+            assert np.array_equal(xyz[f, r].reshape(hh, ww, 3), want)
+            assert np.array_equal(xd[f, r], orc.destagger(want, sh))
+    status = np.ones(ww, np.uint32)
+    status[:5] = 0
+    status[100] = 0
+    ts = np.arange(ww, dtype=np.uint64)
+    got = ob.dewarp_frame(lut, rngp[0, 0], poses.astype(np.float64), status, ts, 1.0, 300.0, provenance=True)
+    want = orc.dewarp_frame(rngp[0, 0], d, o, poses.astype(np.float64), status, ts, 1.0, 300.0)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+print("K1 ok (plain, posed), K3 ok")
 img = np.random.default_rng(1).integers(0, 255, (h, w), dtype=np.uint8)
 sh = np.arange(h, dtype=np.int32) - 5
 assert np.array_equal(ob.destagger(img, sh), orc.destagger(img, sh))
