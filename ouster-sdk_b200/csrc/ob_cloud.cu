@@ -292,17 +292,29 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
     // ============================== compute warps ==============================
     const int lane = tid & 31;
     const int cwarp = ctid >> 5;
+    // ring position, its phase, and the position inside the work item are carried along instead of
+    // being re-derived from k with integer divisions on every tile
+    int s = -1;
+    unsigned phase = 1, rr = RPI - 1, item = ~0u;
+    TileCoord item_tc{};
     for (unsigned k = 0; k < n_my; ++k) {
-        const int s = k % S;
-        const TileCoord tc = coord(k);
+        if (++s == S) s = 0;
+        if (s == 0) phase ^= 1u;
+        if (++rr == RPI) {
+            rr = 0;
+            ++item;
+            item_tc = tile_coord(p, first + item * gridDim.x);
+        }
+        TileCoord tc = item_tc;
+        tc.row += static_cast<int>(rr);
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
         T* dir_s = reinterpret_cast<T*>(st);
         T* off_s = reinterpret_cast<T*>(st + lut_bytes_full);
         uint32_t* rng_s = reinterpret_cast<uint32_t*>(st + 2 * lut_bytes_full);
 
-        mbar_wait(&full[s], (k / S) & 1);
-        if (POSE && (k % RPI) == 0) {  // new item: rows 0..2 of every column pose -> planes
-            mbar_wait(pose_bar, (k / RPI) & 1u);
+        mbar_wait(&full[s], phase);
+        if (POSE && rr == 0) {  // new item: rows 0..2 of every column pose -> planes
+            mbar_wait(pose_bar, item & 1u);
             const T* raw = reinterpret_cast<const T*>(pose_raw);
             named_barrier_sync(1, nct);  // nobody still reads the planes of the previous item
             for (int idx = ctid; idx < tc.tw * 12; idx += nct) {

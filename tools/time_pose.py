@@ -46,17 +46,15 @@ def two_pass():
 
 out = {}
 sweep = []
-for tw in (256, 512):
-    for stg in (2, 3, 4):
-        for cta in (3, 4, 6):
-            for th in (128, 256):
-                for k, v in (("cloud_pose_tw", tw), ("cloud_pose_stages", stg), ("cloud_pose_ctas_per_sm", cta),
-                             ("cloud_threads", th)):
-                    ob.set_tunable(k, v)
-                try:
-                    sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": timeit(fused, n=5)})
-                except Exception as ex:
-                    sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "error": str(ex)[:80]})
+for tw, stg, cta, th in ((256, 3, 6, 128), (256, 3, 4, 128), (256, 4, 4, 128), (256, 3, 6, 64), (512, 3, 3, 128),
+                         (512, 3, 3, 256), (128, 3, 8, 64)):
+    for k, v in (("cloud_pose_tw", tw), ("cloud_pose_stages", stg), ("cloud_pose_ctas_per_sm", cta),
+                 ("cloud_threads", th)):
+        ob.set_tunable(k, v)
+    try:
+        sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": timeit(fused, n=5)})
+    except Exception as ex:
+        sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "error": str(ex)[:80]})
 ok = sorted([r for r in sweep if "ms" in r], key=lambda r: r["ms"])
 out["sweep_best"] = ok[:6]
 out["sweep_worst"] = ok[-1]
@@ -65,7 +63,7 @@ for k, v in (("cloud_pose_tw", best["tw"]), ("cloud_pose_stages", best["stages"]
              ("cloud_pose_ctas_per_sm", best["ctas"]), ("cloud_threads", best["threads"])):
     ob.set_tunable(k, v)
 out["fused_tw_best_ms"] = timeit(fused)
-ob.set_tunable("cloud_threads", 256)
+ob.set_tunable("cloud_threads", 128)
 out["plain_ms"] = timeit(plain)
 for lag in (0, 1):
     ob.set_tunable("cloud_store_lag", lag)
@@ -77,7 +75,7 @@ for tw, stg, cta, th in ((512, 4, 3, 256), (512, 2, 4, 256), (512, 3, 4, 128), (
         ob.set_tunable(k, v)
     plain_sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": timeit(plain, n=5)})
 out["plain_sweep"] = plain_sweep
-for k, v in (("cloud_tw", 512), ("cloud_stages", 4), ("cloud_ctas_per_sm", 3), ("cloud_threads", 256)):
+for k, v in (("cloud_tw", 512), ("cloud_stages", 3), ("cloud_ctas_per_sm", 3), ("cloud_threads", 128)):
     ob.set_tunable(k, v)
 try:
     out["two_pass_ms"] = timeit(two_pass, n=3)
