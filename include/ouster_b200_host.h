@@ -65,6 +65,11 @@ ob_status obh_frame_field(obh_frame* f, const char* name, int32_t* ty_tag, size_
 ob_status obh_frame_headers(obh_frame* f, uint64_t** timestamp, uint16_t** measurement_id,
                             uint32_t** status, uint64_t** packet_timestamp, uint8_t** alert_flags,
                             size_t* w, size_t* h, size_t* n_packets);
+/* LidarFrame::body_to_world (lidar_frame.h:732-736): w x 4 x 4 doubles, identity on construction */
+ob_status obh_frame_body_to_world(obh_frame* f, double** poses);
+/* get_first_valid_column / get_last_valid_column (lidar_frame.cpp:907-925); returns 0 when no
+ * column has status bit 0 set (the C++ functions throw), else 1 */
+int obh_frame_valid_columns(const obh_frame* f, int* first, int* last);
 int64_t obh_frame_get_frame_id(const obh_frame* f);
 void obh_frame_set_frame_id(obh_frame* f, int64_t id);
 uint64_t obh_frame_get_status(const obh_frame* f, uint8_t* shutdown_countdown,

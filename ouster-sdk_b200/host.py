@@ -38,6 +38,8 @@ _sig("obh_frame_n_fields", sz, vp)
 _sig("obh_frame_field_at", i32, vp, sz, C.c_char_p, sz, PP(C.c_int32), PP(sz), PP(vp))
 _sig("obh_frame_field", i32, vp, C.c_char_p, PP(C.c_int32), PP(sz), PP(vp))
 _sig("obh_frame_headers", i32, vp, PP(vp), PP(vp), PP(vp), PP(vp), PP(vp), PP(sz), PP(sz), PP(sz))
+_sig("obh_frame_body_to_world", i32, vp, PP(vp))
+_sig("obh_frame_valid_columns", i32, vp, PP(i32), PP(i32))
 _sig("obh_frame_get_frame_id", i64, vp)
 _sig("obh_frame_set_frame_id", None, vp, i64)
 _sig("obh_frame_get_status", u64, vp, PP(C.c_uint8), PP(C.c_uint8))
@@ -234,6 +236,22 @@ class LidarFrame:
         self.status = _as_array(st.value, np.uint32, (self.w,))
         self.packet_timestamp = _as_array(pts.value, np.uint64, (self.n_packets,))
         self.alert_flags = _as_array(af.value, np.uint8, (self.n_packets,))
+        b2w = vp()
+        check(lib.obh_frame_body_to_world(hd, C.byref(b2w)))
+        self.body_to_world = _as_array(b2w.value, np.float64, (self.w, 4, 4))   # identity on construction
+        self.pose = self.body_to_world                                           # deprecated spelling
+
+    def get_first_valid_column(self):
+        a, b = i32(0), i32(0)
+        if not lib.obh_frame_valid_columns(self._h, C.byref(a), C.byref(b)):
+            raise RuntimeError("No valid columns in LidarFrame")
+        return a.value
+
+    def get_last_valid_column(self):
+        a, b = i32(0), i32(0)
+        if not lib.obh_frame_valid_columns(self._h, C.byref(a), C.byref(b)):
+            raise RuntimeError("No valid columns in LidarFrame")
+        return b.value
 
     def add_field(self, name, dtype, extra_dim=1):
         check(lib.obh_frame_add_field(self._h, name.encode(), NP_TAG[np.dtype(dtype)], extra_dim))

@@ -264,6 +264,24 @@ ob_status obh_frame_headers(obh_frame* f, uint64_t** ts, uint16_t** mid, uint32_
     });
 }
 
+ob_status obh_frame_body_to_world(obh_frame* f, double** poses) {
+    return guard([&] {
+        if (!f || !poses) throw std::invalid_argument("null pointer");
+        *poses = f->ref().body_to_world().get<double>();
+    });
+}
+
+int obh_frame_valid_columns(const obh_frame* f, int* first, int* last) {
+    try {
+        const int a = f->ref().get_first_valid_column(), b = f->ref().get_last_valid_column();
+        if (first) *first = a;
+        if (last) *last = b;
+        return 1;
+    } catch (const std::exception&) {
+        return 0;
+    }
+}
+
 int64_t obh_frame_get_frame_id(const obh_frame* f) { return f->ref().frame_id; }
 void obh_frame_set_frame_id(obh_frame* f, int64_t id) { f->ref().frame_id = id; }
 uint64_t obh_frame_get_status(const obh_frame* f, uint8_t* sc, uint8_t* slc) {

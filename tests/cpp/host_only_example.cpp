@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "ouster/core/frame_pipeline.h"
 #include "ouster/core/lidar_scan.h"
 
 using namespace ouster::sdk::core;
@@ -115,6 +116,24 @@ int main() {
     CHECK(column_timestamp_at_destaggered_pixel(2, 9, shifts, out.timestamp()) == out.timestamp()[4]);
     expect_throw<std::invalid_argument>(
         [&] { column_timestamp_at_destaggered_pixel(h, 0, shifts, out.timestamp()); }, "row or column is out of range");
+
+    // FramePipeline ring logic without a GPU (header-only batcher): frames come out in order,
+    // `depth` frames late, slots are recycled, drain() empties the ring
+    {
+        FramePipeline pipe(info, 2);
+        pipe.batcher().set_headers_only(true);
+        std::vector<int64_t> seen;
+        for (int k = 0; k < 7; ++k) {
+            scan.frame_id = 100 + k;
+            for (const Packet& p : impl::frame_to_packets(scan, pf, 9, 1234))
+                if (const FramePipeline::Slot* sl = pipe.push(p)) seen.push_back(sl->frame.frame_id);
+            CHECK(pipe.in_flight() == static_cast<size_t>(k < 2 ? k + 1 : 2));
+        }
+        CHECK(seen.size() == 5);
+        while (const FramePipeline::Slot* sl = pipe.drain()) seen.push_back(sl->frame.frame_id);
+        CHECK(seen.size() == 7 && pipe.in_flight() == 0);
+        for (int k = 0; k < 7; ++k) CHECK(seen[static_cast<size_t>(k)] == 100 + k);
+    }
 
     std::printf("HOST OK\n");
     return 0;

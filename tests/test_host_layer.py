@@ -292,3 +292,19 @@ def test_cpp_headers_host_only_example():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr + out.stdout
     assert "HOST OK" in out.stdout
+
+
+def test_python_frame_poses_and_valid_columns(ob):
+    """LidarScan.body_to_world / get_first|last_valid_column through the host C ABI (no GPU needed)."""
+    si = ob.SensorInfo("RNG19_RFL8_SIG16_NIR16", 16, 64)
+    fr = ob.LidarFrame(si)
+    assert fr.body_to_world.shape == (64, 4, 4) and np.array_equal(fr.body_to_world[5], np.eye(4))
+    fr.body_to_world[5, 0, 3] = 2.5
+    fr2 = ob.LidarFrame(si)
+    assert fr2.body_to_world[5, 0, 3] == 0.0 and fr.pose[5, 0, 3] == 2.5
+    with pytest.raises(RuntimeError, match="No valid columns in LidarFrame"):
+        fr.get_first_valid_column()
+    fr.status[3] = 1
+    fr.status[40] = 3
+    fr.status[50] = 2
+    assert fr.get_first_valid_column() == 3 and fr.get_last_valid_column() == 40
