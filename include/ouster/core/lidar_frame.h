@@ -213,6 +213,19 @@ class OUSTER_API_CLASS LidarFrame {
     OUSTER_API_FUNCTION int get_first_valid_column() const;
     OUSTER_API_FUNCTION int get_last_valid_column() const;
 
+    /// Host timestamp of the first / last / earliest / latest lidar packet that carries at least one
+    /// valid column (lidar_frame.cpp:643-790, lidar packets only -- IMU and zone packets are outside
+    /// this path).  The `_lidar_` spellings return 0 when there is none; the others throw
+    /// std::runtime_error("No valid packets in LidarFrame").
+    OUSTER_API_FUNCTION uint64_t get_first_valid_packet_timestamp() const;
+    OUSTER_API_FUNCTION uint64_t get_last_valid_packet_timestamp() const;
+    OUSTER_API_FUNCTION uint64_t get_min_valid_packet_timestamp() const;
+    OUSTER_API_FUNCTION uint64_t get_max_valid_packet_timestamp() const;
+    OUSTER_API_FUNCTION uint64_t get_first_valid_lidar_packet_timestamp() const;
+    OUSTER_API_FUNCTION uint64_t get_last_valid_lidar_packet_timestamp() const;
+    /// number of lidar packets per frame (lidar_frame.cpp:1008-1010)
+    size_t packet_count() const { return packet_timestamp_.size(); }
+
     /// true when every column inside the window carries status & 1 (lidar_frame.cpp:421-446)
     OUSTER_API_FUNCTION bool complete(ColumnWindow window) const;
     OUSTER_API_FUNCTION bool complete() const;

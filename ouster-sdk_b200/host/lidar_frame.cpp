@@ -279,6 +279,66 @@ mat4d LidarFrame::get_column_pose(int index) const {
     return out;
 }
 
+namespace {
+// mode 0: first, 1: last, 2: min, 3: max over the packets with at least one valid column
+bool valid_packet_ts(const LidarFrame& f, int mode, uint64_t* out) {
+    const auto status = f.status();
+    const auto pts = f.packet_timestamp();
+    const size_t np = pts.size();
+    if (np == 0) return false;
+    const size_t cpp = f.w / np;
+    bool have = false;
+    uint64_t t = 0;
+    for (size_t k = 0; k < np; ++k) {
+        const size_t i = mode == 1 ? np - 1 - k : k;
+        bool any = false;
+        for (size_t c = 0; c < cpp && !any; ++c) any = (status[i * cpp + c] & 1u) != 0;
+        if (!any) continue;
+        if (mode < 2) {
+            *out = pts[i];
+            return true;
+        }
+        t = !have ? pts[i] : (mode == 2 ? std::min(t, pts[i]) : std::max(t, pts[i]));
+        have = true;
+    }
+    *out = t;
+    return have;
+}
+uint64_t ts_or_throw(bool ok, uint64_t t) {
+    if (!ok) throw std::runtime_error("No valid packets in LidarFrame");
+    return t;
+}
+}  // namespace
+
+uint64_t LidarFrame::get_first_valid_packet_timestamp() const {
+    uint64_t t = 0;
+    const bool ok = valid_packet_ts(*this, 0, &t);  // sequenced before t is read
+    return ts_or_throw(ok, t);
+}
+uint64_t LidarFrame::get_last_valid_packet_timestamp() const {
+    uint64_t t = 0;
+    const bool ok = valid_packet_ts(*this, 1, &t);  // sequenced before t is read
+    return ts_or_throw(ok, t);
+}
+uint64_t LidarFrame::get_min_valid_packet_timestamp() const {
+    uint64_t t = 0;
+    const bool ok = valid_packet_ts(*this, 2, &t);  // sequenced before t is read
+    return ts_or_throw(ok, t);
+}
+uint64_t LidarFrame::get_max_valid_packet_timestamp() const {
+    uint64_t t = 0;
+    const bool ok = valid_packet_ts(*this, 3, &t);  // sequenced before t is read
+    return ts_or_throw(ok, t);
+}
+uint64_t LidarFrame::get_first_valid_lidar_packet_timestamp() const {
+    uint64_t t = 0;
+    return valid_packet_ts(*this, 0, &t) ? t : 0;
+}
+uint64_t LidarFrame::get_last_valid_lidar_packet_timestamp() const {
+    uint64_t t = 0;
+    return valid_packet_ts(*this, 1, &t) ? t : 0;
+}
+
 int LidarFrame::get_first_valid_column() const {
     for (size_t i = 0; i < status_.size(); ++i)
         if ((status_[i] & 1u) > 0) return static_cast<int>(i);

@@ -75,8 +75,19 @@ int main() {
     CHECK(scan.get_first_valid_column() == 1 && scan.get_last_valid_column() == static_cast<int>(w) - 2);
     scan.status()[0] = 1;
     scan.status()[w - 1] = 1;
+    // packet timestamps of the packets that carry valid columns (lidar_frame.cpp:643-790)
+    CHECK(scan.packet_count() == w / 16 && scan.get_first_valid_packet_timestamp() == 10);
+    CHECK(scan.get_last_valid_packet_timestamp() == 10 + w / 16 - 1 && scan.get_min_valid_packet_timestamp() == 10);
+    for (size_t c = 0; c < 16; ++c) scan.status()[c] = 0;  // first packet: no valid column left
+    scan.packet_timestamp()[5] = 3;                        // out-of-order host time
+    CHECK(scan.get_first_valid_lidar_packet_timestamp() == 11 && scan.get_min_valid_packet_timestamp() == 3);
+    CHECK(scan.get_max_valid_packet_timestamp() == 10 + w / 16 - 1);
+    for (size_t c = 0; c < 16; ++c) scan.status()[c] = 1;
+    scan.packet_timestamp()[5] = 15;
     {
         LidarScan empty(info);
+        expect_throw<std::runtime_error>([&] { empty.get_first_valid_packet_timestamp(); }, "No valid packets in LidarFrame");
+        CHECK(empty.get_last_valid_lidar_packet_timestamp() == 0);
         expect_throw<std::runtime_error>([&] { empty.get_first_valid_column(); }, "No valid columns in LidarFrame");
         LidarScan copy(scan);
         CHECK(copy == scan);
