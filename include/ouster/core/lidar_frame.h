@@ -183,7 +183,7 @@ class OUSTER_API_CLASS LidarFrame {
                                          FieldClass field_class = FieldClass::PIXEL_FIELD);
     OUSTER_API_FUNCTION Field& add_field(const FieldType& type);
     OUSTER_API_FUNCTION Field del_field(const std::string& name);
-    OUSTER_API_FUNCTION ChanFieldType field_type(const std::string& name) const;
+    OUSTER_API_FUNCTION FieldType field_type(const std::string& name) const;
     OUSTER_API_FUNCTION LidarFrameFieldTypes field_types() const;
     const std::map<std::string, Field>& fields() const { return fields_; }
     std::map<std::string, Field>& fields() { return fields_; }

@@ -470,19 +470,19 @@ Field LidarFrame::del_field(const std::string& name) {
     return out;
 }
 
-ChanFieldType LidarFrame::field_type(const std::string& name) const {
-    return has_field(name) ? fields_.at(name).tag() : ChanFieldType::VOID;
+// FieldType of one field: element type, trailing dimensions, class (lidar_frame.cpp:545-547)
+FieldType LidarFrame::field_type(const std::string& name) const {
+    const Field& f = field(name);  // throws std::invalid_argument("Invalid field for LidarFrame")
+    const auto& shp = f.shape();
+    const FieldClass fc = field_class_.count(name) ? field_class_.at(name) : FieldClass::PIXEL_FIELD;
+    const size_t base = fc == FieldClass::PIXEL_FIELD ? 2 : (fc == FieldClass::FRAME_FIELD ? 0 : 1);
+    std::vector<size_t> extra(shp.begin() + std::min(base, shp.size()), shp.end());
+    return FieldType(name, f.tag(), extra, fc);
 }
 
 LidarFrameFieldTypes LidarFrame::field_types() const {
     LidarFrameFieldTypes out;
-    for (const auto& kv : fields_) {
-        const auto& shp = kv.second.shape();
-        const FieldClass fc = field_class_.count(kv.first) ? field_class_.at(kv.first) : FieldClass::PIXEL_FIELD;
-        const size_t base = fc == FieldClass::PIXEL_FIELD ? 2 : (fc == FieldClass::FRAME_FIELD ? 0 : 1);
-        std::vector<size_t> extra(shp.begin() + std::min(base, shp.size()), shp.end());
-        out.emplace_back(kv.first, kv.second.tag(), extra, fc);
-    }
+    for (const auto& kv : fields_) out.push_back(field_type(kv.first));
     return out;
 }
 

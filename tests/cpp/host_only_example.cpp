@@ -60,6 +60,9 @@ int main() {
     for (size_t p = 0; p < w / 16; ++p) scan.packet_timestamp()[p] = 10 + p;
     scan.frame_id = 41;
     expect_throw<std::invalid_argument>([&] { scan.field<uint16_t>(ChanField::RANGE); }, "Accessed field at wrong type");
+    CHECK(scan.field_type(ChanField::RANGE) == FieldType(ChanField::RANGE, ChanFieldType::UINT32));
+    CHECK(scan.field_types().size() == scan.fields().size());
+    expect_throw<std::invalid_argument>([&] { scan.field_type("NOPE"); }, "Invalid field for LidarFrame");
     expect_throw<std::invalid_argument>([&] { scan.add_field(ChanField::RANGE, ChanFieldType::UINT32); }, "Duplicated field");
 
     // per-column poses: identity on construction, round trip, bounds (lidar_frame.cpp:350-358, 959-980)
