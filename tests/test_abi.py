@@ -70,3 +70,20 @@ def test_ctypes_struct_layouts_match_the_c_abi():
     for name, cls in pairs.items():
         assert capi.lib.ob_abi_sizeof(name.encode()) == ctypes.sizeof(cls), name
     assert capi.lib.ob_abi_sizeof(b"nope") == 0
+
+
+def test_c_headers_are_plain_c99(tmp_path):
+    """include/ouster_b200.h and include/ouster_b200_host.h are a C ABI: a C99 translation unit that
+    includes both compiles with -pedantic, links against the library and runs (no CUDA call)."""
+    import subprocess
+    graft.build()
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "ouster_b200.h"\n#include "ouster_b200_host.h"\n'
+                   "int main(void) { ob_cloud_io io; ob_decode_io d; ob_dewarp_frame_io w; obh_slot s;\n"
+                   "  (void)io; (void)d; (void)w; (void)s; return ob_abi_version() == OB_ABI_VERSION ? 0 : 1; }\n")
+    lib_dir = os.path.join(graft.ROOT, "ouster-sdk_b200", "lib")
+    exe = tmp_path / "cabi"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I",
+                           os.path.join(graft.ROOT, "include"), str(src), "-L", lib_dir, "-louster_b200",
+                           f"-Wl,-rpath,{lib_dir}", "-o", str(exe)])
+    assert subprocess.run([str(exe)]).returncode == 0
