@@ -43,14 +43,14 @@ static Tunables& tunables_mut(int device) {
         Tunables t;
         t.cloud_tw = env_int("OB_CLOUD_TW", 512);
         t.cloud_stages = std::max(2, env_int("OB_CLOUD_STAGES", 3));
-        t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 128)));  // compute threads
+        t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 128) / 32 * 32));  // compute threads
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
         t.cloud_pose_tw = std::max(16, env_int("OB_CLOUD_POSE_TW", 256));
         t.cloud_store_lag = env_int("OB_CLOUD_STORE_LAG", 1);
         t.cloud_pose_stages = std::max(2, env_int("OB_CLOUD_POSE_STAGES", 3));
         t.cloud_pose_ctas_per_sm = std::max(1, env_int("OB_CLOUD_POSE_CTAS_PER_SM", 6));
         t.decode_stages = std::max(1, env_int("OB_DECODE_STAGES", 1));
-        t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384)));
+        t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384) / 32 * 32));
         t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
         t.decode_tile_packets = std::max(0, env_int("OB_DECODE_TILE_PACKETS", 0));  // 0 = auto
         t.decode_prefetch = env_int("OB_DECODE_PREFETCH", 0);
