@@ -60,7 +60,8 @@ uint64_t ob_kernel_launch_count(void);
 /* tuning hook (launch geometry and code-path selection only, never results): cloud_tw, cloud_stages,
  * cloud_threads (compute threads; a copy warp is added), cloud_ctas_per_sm, cloud_store_lag,
  * cloud_pose_tw, cloud_pose_stages, cloud_pose_ctas_per_sm, decode_stages, decode_threads,
- * decode_ctas_per_sm, decode_tile_packets, decode_prefetch, decode_runtime_plans, force_fallback.
+ * decode_ctas_per_sm, decode_tile_packets, decode_prefetch, decode_runtime_plans, force_generic (K1: generic GPU kernel
+ * instead of the TMA one).
  * Defaults come from OB_* environment variables of the same (upper-case) names. */
 ob_status ob_set_tunable(int device, const char* name, int value);
 

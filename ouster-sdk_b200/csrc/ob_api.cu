@@ -55,7 +55,7 @@ static Tunables& tunables_mut(int device) {
         t.decode_tile_packets = std::max(0, env_int("OB_DECODE_TILE_PACKETS", 0));  // 0 = auto
         t.decode_prefetch = env_int("OB_DECODE_PREFETCH", 0);
         t.decode_runtime_plans = env_int("OB_DECODE_RUNTIME_PLANS", 0);
-        t.force_fallback = env_int("OB_FORCE_FALLBACK", 0);
+        t.force_generic = env_int("OB_FORCE_GENERIC", 0);
         int sm = 148;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
             cudaGetLastError();
@@ -91,7 +91,7 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "decode_tile_packets") t.decode_tile_packets = std::max(0, value);
     else if (n == "decode_prefetch") t.decode_prefetch = value;
     else if (n == "decode_runtime_plans") t.decode_runtime_plans = value ? 1 : 0;
-    else if (n == "force_fallback") t.force_fallback = value;
+    else if (n == "force_generic") t.force_generic = value;
     else return false;
     return true;
 }

@@ -521,7 +521,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     const bool need_lut = a.xyz != nullptr || a.xd != nullptr;
     // element-stride alignment so that every tile slice is 16-byte aligned
     const size_t t4 = 16 / sizeof(T);  // T elements per 16 bytes
-    bool fast = !tn.force_fallback && (a.W % 4 == 0) && a.H <= kMaxRows && aligned16(a.range) &&
+    bool fast = !tn.force_generic && (a.W % 4 == 0) && a.H <= kMaxRows && aligned16(a.range) &&
                 a.range_fs % 4 == 0 && a.range_rs % 4 == 0;
     if (need_lut) fast = fast && aligned16(a.dir) && aligned16(a.off);
     if (a.xyz) fast = fast && aligned16(a.xyz) && a.xyz_fs % t4 == 0 && a.xyz_rs % t4 == 0;

@@ -26,7 +26,7 @@ struct Tunables {
     int decode_tile_packets;  // packets (groups of columns_per_packet columns) per tile
     int decode_runtime_plans; // 1: never use the compile-time pixel layouts (testing / comparison)
     int decode_prefetch;      // L2 prefetch of the next tile: 0 off, 1 at tile start (evict_last), 2 before phase B
-    int force_fallback;    // 1: use the generic (non-TMA) kernels
+    int force_generic;     // 1: K1 takes the generic GPU kernel (any width / alignment) instead of the TMA one
     int sm_count;
 };
 const Tunables& tunables(int device);
