@@ -20,32 +20,40 @@ struct OUSTER_API_CLASS FieldDecodeInfo {
     int shift{0};
     int num_elements{1};
 
-    /// NOTE: reads 8 bytes at buffer + offset (host-side use: headers and tests; the per-pixel
-    /// decode of whole frames runs on the GPU through the same (offset, mask, shift) triple).
+    /// Raw 64-bit little-endian window at `offset` <-> field value.  The window is always 8 bytes
+    /// wide, whatever the field width (host-side use: headers and tests; the per-pixel decode of
+    /// whole frames runs on the GPU from the same (offset, mask, shift) triple).
+    uint64_t value_of(uint64_t window) const {
+        const uint64_t bits = window & mask;
+        return shift >= 0 ? bits >> shift : bits << -shift;
+    }
+    uint64_t window_of(uint64_t value) const {
+        return (shift >= 0 ? value << shift : value >> -shift) & mask;
+    }
+
     template <typename T>
     T get(const uint8_t* buffer) const {
-        uint64_t word;
-        std::memcpy(&word, buffer + offset, sizeof(word));
-        word &= mask;
-        if (shift > 0) word >>= shift;
-        else if (shift < 0) word <<= -shift;
+        const uint64_t v = value_of(load64(buffer + offset));
         T out{};
-        std::memcpy(&out, &word, sizeof(out));
+        std::memcpy(&out, &v, sizeof(T));  // truncation to T, as the reference does
         return out;
     }
 
     template <typename T>
     void set(uint8_t* buffer, T value) const {
-        uint64_t word = 0;
-        std::memcpy(&word, &value, sizeof(value));
-        if (shift > 0) word <<= shift;
-        if (shift < 0) word >>= -shift;
-        word &= mask;
-        uint64_t cur;
-        std::memcpy(&cur, buffer + offset, sizeof(cur));
-        cur = (cur & ~mask) | word;
-        std::memcpy(buffer + offset, &cur, sizeof(cur));
+        uint64_t v = 0;
+        std::memcpy(&v, &value, sizeof(T));
+        uint8_t* at = buffer + offset;
+        store64(at, (load64(at) & ~mask) | window_of(v));
     }
+
+   private:
+    static uint64_t load64(const uint8_t* p) {
+        uint64_t w;
+        std::memcpy(&w, p, sizeof(w));
+        return w;
+    }
+    static void store64(uint8_t* p, uint64_t w) { std::memcpy(p, &w, sizeof(w)); }
 };
 
 /// Factory (ouster_core/src/parsing.cpp:57-122): bit_start/bit_size in bits, optional up-shift,
