@@ -39,7 +39,6 @@ struct DecodeParams {
     uint32_t TC, P;             // tile columns (= P * cpp), packets per tile
     uint32_t pkt_stride_s;      // bytes reserved per packet in a stage (multiple of 16)
     uint32_t stage_bytes, stages;
-    uint32_t n_words;           // 32-bit words of a pixel kept in registers (0: per-field smem reads)
     uint32_t word_aligned;      // wire layout is 4-byte aligned everywhere
     uint32_t n_returns;         // returns with a range field tagged
     uint32_t vec_ok;            // XYZ rows are 16-byte aligned (W % 4 == 0, aligned pointers)
@@ -68,25 +67,6 @@ struct TileCtl {  // per-stage bookkeeping written by the producer thread
     unsigned char group_fast[kMaxTileCols];
 };
 
-__device__ __forceinline__ uint32_t lds_u32_any(const uint8_t* p, bool aligned) {
-    if (aligned) return *reinterpret_cast<const uint32_t*>(p);
-    return static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) |
-           (static_cast<uint32_t>(p[2]) << 16) | (static_cast<uint32_t>(p[3]) << 24);
-}
-
-__device__ __forceinline__ uint32_t pick(const uint32_t (&w)[8], uint32_t i) {
-    switch (i) {  // i is warp-uniform: a uniform branch, no divergence
-        case 0: return w[0];
-        case 1: return w[1];
-        case 2: return w[2];
-        case 3: return w[3];
-        case 4: return w[4];
-        case 5: return w[5];
-        case 6: return w[6];
-        default: return w[7];
-    }
-}
-
 // FieldDecodeInfo::get: 8-byte little-endian load at `offset`, mask, shift (caller truncates)
 __device__ __forceinline__ uint64_t apply_mask_shift(uint32_t lo, uint32_t hi, const DecodeField& f) {
     uint64_t word = (static_cast<uint64_t>(hi) << 32) | lo;
@@ -94,18 +74,6 @@ __device__ __forceinline__ uint64_t apply_mask_shift(uint32_t lo, uint32_t hi, c
     if (f.shift > 0) word >>= f.shift;
     else if (f.shift < 0) word <<= -f.shift;
     return word;
-}
-
-__device__ __forceinline__ uint64_t extract_regs(const uint32_t (&w)[8], const DecodeField& f) {
-    const uint32_t wo = f.offset >> 2, bo = (f.offset & 3u) * 8u;
-    const uint32_t w0 = pick(w, wo), w1 = pick(w, wo + 1);
-    uint32_t lo = w0, hi = w1;
-    if (bo) {
-        const uint32_t w2 = pick(w, wo + 2);
-        lo = __funnelshift_r(w0, w1, bo);
-        hi = __funnelshift_r(w1, w2, bo);
-    }
-    return apply_mask_shift(lo, hi, f);
 }
 
 __device__ __forceinline__ uint64_t extract_smem(const uint8_t* px, const DecodeField& f, bool aligned) {
@@ -240,17 +208,6 @@ __device__ __forceinline__ void decode_rows_dispatch(bool has_out, bool has_rd, 
         if (shifted) decode_rows_mode<ES, false, true, FULL>(has_out, has_rd, px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
         else decode_rows_mode<ES, false, false, FULL>(has_out, has_rd, px0, cds, pl, col_valid, zv, lane_on, out, pix0, W, H, warp, nwarps, rdp, p);
     }
-}
-
-// range of pixel (row, column offset `co`) straight from the staged packet bytes
-__device__ __forceinline__ uint32_t range_from_stage(const uint8_t* st, int co, unsigned row, unsigned cds,
-                                                     const DecodeParams::Plan& pl) {
-    if (co < 0) return 0u;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(st + co + row * cds) + pl.wa;
-    const uint32_t a = w[0] & pl.ma;
-    const uint32_t b = pl.mb ? (w[1] & pl.mb) : 0u;
-    uint32_t v = __funnelshift_r(a, b, pl.rs);
-    return pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
 }
 
 // Phase B row walk of one thread: chunk position fixed, rows strided.  SIMPLE: both range fields
@@ -818,16 +775,11 @@ cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st) {
     const bool word_aligned = (L.packet_header_size % 4 == 0) && (L.col_header_size % 4 == 0) &&
                               (L.channel_data_size % 4 == 0) && (L.col_size % 4 == 0);
     p.word_aligned = word_aligned ? 1 : 0;
-    // pixel words kept in registers: a field read touches bytes [offset, offset+8)
-    uint32_t max_end = 0;
     p.n_returns = 0;
     for (uint32_t i = 0; i < L.n_fields; ++i) {
-        max_end = std::max(max_end, L.fields[i].offset + 8);
         if (L.fields[i].range_return >= 0)
             p.n_returns = std::max<uint32_t>(p.n_returns, L.fields[i].range_return + 1);
     }
-    const uint32_t need_words = (max_end + 3) / 4;
-    p.n_words = (word_aligned && need_words <= 8) ? need_words : 0;
     // per-field 32-bit extraction plans: core = ((window & mask) >> tz), value = core << (tz - shift)
     for (uint32_t i = 0; i < OB_MAX_FIELDS; ++i) {
         DecodeParams::Plan pl{};
