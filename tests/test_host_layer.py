@@ -308,3 +308,44 @@ def test_python_frame_poses_and_valid_columns(ob):
     fr.status[40] = 3
     fr.status[50] = 2
     assert fr.get_first_valid_column() == 3 and fr.get_last_valid_column() == 40
+
+
+@pytest.mark.parametrize("burst", [1, 5, 16, 37])
+def test_batch_burst_consumption_matches_per_packet_semantics(ob, burst):
+    """FrameBatcher.batch_burst (host logic, header-only, no GPU): a burst stops after the packet
+    that completes a frame and reports how many packets it took; fed burst by burst, the frames,
+    their headers and the drop counter equal the oracle batcher fed packet by packet."""
+    profile, h, w = "RNG19_RFL8_SIG16_NIR16_DUAL", 16, 256
+    opf = oracle_pf(profile, h, w)
+    si = ob.SensorInfo(profile, h, w, fw_rev="v3.2.1")
+    pk, ts = _stream(opf, 5, seed=31)
+    pk, ts = [p.copy() for p in pk], list(ts)
+    pk[3], pk[4] = pk[4], pk[3]
+    ts[3], ts[4] = ts[4], ts[3]
+    del pk[20], ts[20]
+    pk.insert(40, pk[39].copy()); ts.insert(40, ts[39])
+    arr, tsa = np.stack(pk), np.asarray(ts, np.uint64)
+    # oracle, packet by packet: snapshot the headers of every completed frame
+    oframe, obat, want = orc.Frame(opf, with_window=True), orc.Batcher(opf), []
+    for p, t in zip(pk, ts):
+        if obat.batch(p, int(t), oframe):
+            want.append((oframe.frame_id, oframe.timestamp.copy(), oframe.status.copy(),
+                         oframe.packet_timestamp.copy()))
+    b = ob.FrameBatcher(si)
+    b.set_headers_only(True)
+    fr, got, pos = ob.LidarFrame(si), [], 0
+    while pos < len(pk):
+        end = min(pos + burst, len(pk))
+        while pos < end:
+            used, done = b.batch_burst(arr[pos:end], tsa[pos:end], fr)
+            assert 1 <= used <= end - pos
+            assert done or used == end - pos      # an unfinished burst is consumed completely
+            pos += used
+            if done:
+                got.append((fr.frame_id, fr.timestamp.copy(), fr.status.copy(), fr.packet_timestamp.copy()))
+    assert len(got) == len(want) >= 4
+    for g, wv in zip(got, want):
+        assert g[0] == wv[0]
+        for a, c in zip(g[1:], wv[1:]):
+            assert np.array_equal(a, c)
+    assert b.dropped_packets == obat.dropped_packets
