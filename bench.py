@@ -1,31 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native scan->pointcloud path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload k1|k2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--only k1|k2|sweep]
 
-Metric (BASELINE.json): Mpoints/s of 128x2048 dual-return range->XYZ (+ destaggered range), and
-achieved HBM GB/s of the dominant kernel against the measured copy bandwidth.
+ONE JSON line (the last line of stdout).  Top level = BASELINE.json's metric on configs[1]:
+Mpoints/s of 128x2048 dual-return range->XYZ (+ destaggered range) through the fused K1 kernel, with
+`roofline`, `cpu_baseline`, `e2e`, `clocks`.  The same line carries
 
-A "step" is one pass of the hot path over one batch of `frames_per_step` synthetic frames
-(default 64 frames = 33.5 Mpoints, 1.07 GB of algorithmic traffic for K1 -- larger than the
-126 MB L2, so consecutive steps cannot be served from cache).
+  "k2"          configs[2]: synthetic RNG19 dual-return packet stream -> ScanBatcher decode -> LidarScan
+                -> fused destagger + cartesian (the path north_star's >= 70 % target is written on),
+  "k2_streams8" configs[3] semantics: 8 independent sensor streams per GPU (64 at N=8), own LUT each,
+  "sweep"       configs[4]: 32x512 .. 128x2048, single + dual return, K1 and K2, next to the CPU figure,
+  "pcie"        pinned-memory H2D / D2H copy rates measured in this run (the e2e figures sit on them).
+
+A "step" is one pass of the hot path over one batch of `frames_per_step` synthetic frames (64 frames
+= 33.5 Mpoints, > 126 MB L2 of DRAM traffic per step, so consecutive steps cannot be served from cache).
 
   value : device-resident inputs/outputs, one fused launch per step, CUDA-event timed.
-  e2e   : the same batch through the C ABI with HOST (pinned) buffers: H2D of the range
-          images and D2H of XYZ + destaggered range are inside the timed region.
-  --impl reference : the reference's CPU algorithm (oracle port; the reference itself cannot be
-          compiled here -- needs Eigen3) on all host cores, bounded sample per step.
+  e2e   : the same batch through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of
+          the outputs are inside the timed region.
+  --impl reference : the reference's CPU algorithm for the same config, driven from C
+          (oracle/orc_bench.c; the reference itself cannot be compiled here -- needs Eigen3): as shipped
+          (one thread), its opt-in OpenMP mode, one thread per stream; value = the best of them.
 
 Multi-GPU (torchrun, one rank per GPU): independent sensor streams shard across ranks with no
-data-path collective (weak scaling); the LUT is broadcast once from rank 0 over NCCL before
-the timed region.
+data-path collective (weak scaling); the LUT is broadcast once from rank 0 over NCCL before the timed
+region.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -33,128 +38,101 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import bench_common as bc  # noqa: E402
+
 H, W, R = 128, 2048, 2                 # OS1-128 2048x128 dual return (BASELINE configs[1])
 POINTS_PER_FRAME = H * W * R
-K1_BYTES_PER_FRAME_F32 = 16_777_216     # 64 B/px = 8 (range) + 24 (LUT) + 24 (xyz) + 8 (rd)
-K2_BYTES_PER_FRAME_F32 = 23_917_696
 SHIFTS = np.tile(np.array([48, 32, 16, 0], np.int32), H // 4)  # OS1-128 1024-mode shifts x2
+K1_WORKLOAD = "OS1-128 2048x128 dual-return fused destagger+cartesian (K1), LUT tiles staged in smem via TMA"
+METRIC = "Mpoints/s 128x2048 dual-return range->XYZ"
+
+# kept for tools/ that import them
+K1_BYTES_PER_FRAME_F32 = 16_777_216     # SURVEY 8(d) algorithmic: 64 B/px = 8 (range) + 24 (LUT) + 24 (xyz) + 8 (rd)
+measured_peaks = bc.measured_peaks
+ClockSampler = bc.ClockSampler
 
 
-def measured_peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
-
-
-class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names)
-                   if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
-
-
-def synth_pool(n_frames, seed=42):
+def synth_pool(n_frames, seed=42, h=H, w=W, returns=R):
     """Range images as the reference's benchmark generator draws them
     (tests/benchmarks/benchmark_utils.h:93-110): ~50 % zeros (RANGE2 80 %), valid returns uniform
     in [1, 2^19-1] (19-bit RNG19 field)."""
     rs = np.random.default_rng(seed)
-    rng = rs.integers(1, 1 << 19, size=(n_frames, R, H, W), dtype=np.uint32)
-    rng[:, 0][rs.random((n_frames, H, W)) < 0.5] = 0
-    rng[:, 1][rs.random((n_frames, H, W)) < 0.8] = 0
+    rng = rs.integers(1, 1 << 19, size=(n_frames, returns, h, w), dtype=np.uint32)
+    rng[:, 0][rs.random((n_frames, h, w)) < 0.5] = 0
+    if returns > 1:
+        rng[:, 1][rs.random((n_frames, h, w)) < 0.8] = 0
     return rng
 
 
-def synth_lut(seed=43):
+def synth_lut(seed=43, h=H, w=W):
     """Random LUT as tests/benchmarks/benchmark_utils.h:112-126 (dir U(0.5,1.5), off U(0,0.01))."""
     rs = np.random.default_rng(seed)
-    d = (rs.random((H * W, 3)) + 0.5).astype(np.float32)
-    o = (rs.random((H * W, 3)) * 0.01).astype(np.float32)
+    d = (rs.random((h * w, 3)) + 0.5).astype(np.float32)
+    o = (rs.random((h * w, 3)) * 0.01).astype(np.float32)
     return d, o
 
 
-def cpu_reference_pass(orc, rng_frames, d, o, threads):
-    """destagger<uint32_t>() + cartesianT<float>() per frame and return, frames spread over a
-    thread pool (streams are independent; ctypes releases the GIL)."""
-    from concurrent.futures import ThreadPoolExecutor
+def cpu_modes_k1(orc, rng, d, o, shifts, budget_s=8.0):
+    """The reference's CPU path for K1 (destagger<u32>() + cartesian() per return, per-call result
+    allocation) driven from C in its three modes, float and (reference default) double LUT.
+    Returns ({mode_dtype: Mpoints/s}, description)."""
+    F, returns, h, w = rng.shape
+    ppf = h * w * returns
+    cores = os.cpu_count() or 1
+    d64, o64 = d.astype(np.float64), o.astype(np.float64)
+    res = {}
+    orc.bench_k1("thread_per_stream", rng[:min(F, cores)], shifts, d, o, reps=1)   # OpenMP team warm-up
 
-    def one(f):
-        for r in range(R):
-            orc.destagger(rng_frames[f, r], SHIFTS)
-            orc.cartesian(rng_frames[f, r], d, o)
+    def best(mode, sample, dd, oo, reps, tries=3):
+        return min(orc.bench_k1(mode, sample, shifts, dd, oo, reps=reps) / reps for _ in range(tries))
 
-    t0 = time.perf_counter()
-    if threads <= 1:
-        for f in range(rng_frames.shape[0]):
-            one(f)
-    else:
-        with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(one, range(rng_frames.shape[0])))
-    return time.perf_counter() - t0
+    n1, nomp = min(F, 4), min(F, 16)
+    for nm, dd, oo in (("f32", d, o), ("f64", d64, o64)):
+        res[f"as_shipped_1thread_{nm}"] = n1 * ppf / best("as_shipped", rng[:n1], dd, oo, 1) / 1e6
+        res[f"ouster_omp_{nm}"] = nomp * ppf / best("ouster_omp", rng[:nomp], dd, oo, 1) / 1e6
+        t1 = orc.bench_k1("thread_per_stream", rng, shifts, dd, oo, reps=1)
+        reps = int(max(1, min(20, budget_s / 6 / max(t1, 1e-4))))
+        res[f"thread_per_stream_{nm}"] = F * ppf / best("thread_per_stream", rng, dd, oo, reps) / 1e6
+    what = (f"{F} frames {h}x{w}x{returns}: destagger<u32>() + cartesian() per return with the reference's per-call "
+            f"result allocation, driven from C (oracle/orc_bench.c), {cores} host threads; modes: as shipped "
+            "(1 thread), -DOUSTER_OMP (impl/cartesian.h:15-23,50-52), one thread per stream")
+    return res, what
 
 
 def run_reference(args, rank, world):
-    """--impl reference: CPU arm (oracle port of the reference loops) on all host cores."""
+    """--impl reference: the reference's CPU algorithm for configs[1] on the host cores of this box.
+    Same workload string and frames/step as the b200 arm; value = best of the three modes (float LUT,
+    the arm's dtype); the as-shipped double-LUT figures are reported beside it."""
     if rank != 0:
         return
     from oracle import oracle as orc
     orc.build()
     cores = os.cpu_count() or 1
-    sample_frames = max(cores, 16)
-    rng = synth_pool(sample_frames)
+    F = args.frames
+    rng = synth_pool(F)
     d, o = synth_lut()
-    for _ in range(args.warmup):
-        cpu_reference_pass(orc, rng, d, o, cores)
-    ts = [cpu_reference_pass(orc, rng, d, o, cores) for _ in range(args.steps)]
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.bench_k1("thread_per_stream", rng, SHIFTS, d, o, reps=1)
+    modes, what = cpu_modes_k1(orc, rng, d, o, SHIFTS, budget_s=6.0)
+    f32 = {k: v for k, v in modes.items() if k.endswith("f32")}
+    best = max(f32, key=f32.get)
+    mode = "_".join(best.split("_")[:-1])
+    mode = {"as_shipped_1thread": "as_shipped"}.get(mode, mode)
+    ts = [orc.bench_k1(mode, rng, SHIFTS, d, o, reps=1) for _ in range(args.steps)]
     t = float(np.sum(ts))
-    val = sample_frames * POINTS_PER_FRAME * args.steps / t / 1e6
+    val = F * POINTS_PER_FRAME * args.steps / t / 1e6
     line = {
-        "impl": "reference", "metric": "Mpoints/s 128x2048 dual-return range->XYZ", "value": val,
+        "impl": "reference", "metric": METRIC, "value": val,
         "unit": "Mpoints/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "OS1-128 2048x128 dual-return: destagger<u32>+cartesianT<float> on CPU",
-                   "frames_per_step": sample_frames},
-        "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_frames} frames/step x {args.steps} steps, one thread per frame"},
+        "config": {"workload": K1_WORKLOAD, "frames_per_step_per_gpu": F, "points_per_frame": POINTS_PER_FRAME},
+        "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": cores, "kind": "port", "mode": mode,
+                         "modes": modes, "sample": what},
         "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def bind_to_gpu_numa(local_rank):
@@ -177,54 +155,9 @@ def bind_to_gpu_numa(local_rank):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="k1", choices=["k1", "k2"])
-    ap.add_argument("--frames", type=int, default=64, help="frames per step (per GPU)")
-    ap.add_argument("--streams-per-gpu", type=int, default=1,
-                    help="k2: independent sensor streams (own LUT each) batched per launch per GPU; "
-                         "1 = BASELINE configs[2], 8 (x8 GPUs = 64 streams) = configs[3]")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel-only", action="store_true", help="tuning aid: device-resident timing only")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
-    numa_cores = bind_to_gpu_numa(local_rank) if world > 1 else 0
-    args.numa_cores = numa_cores
-    import torch
-    import __graft_entry__ as graft
-    graft.build()
-    ob = graft.load_package()
-    if ob.device_count() <= 0:
-        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
+def measure_k1(args, ob, torch, dist, rank, local_rank, world, pcie):
+    """configs[1]: the top-level record."""
     dev = torch.device("cuda", local_rank)
-
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if not os.environ.get("OB_KEEP_NCCL_DEBUG"):
-            os.environ.pop("NCCL_DEBUG", None)   # keep stdout to the single JSON line
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-
-    if args.workload == "k2":
-        from bench_k2 import run_k2
-        run_k2(args, ob, torch, dist, rank, local_rank, world, ClockSampler, measured_peaks, ROOT)
-        return
-
     F = args.frames
     # ---- inputs: each rank owns F independent frames (one "sensor stream shard") ----
     rng_host = synth_pool(F, seed=42 + rank)
@@ -249,7 +182,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = bc.ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
     l0 = ob.kernel_launch_count()
@@ -264,27 +197,24 @@ def main():
     clocks = sampler.stop()
     ms_total = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t_ms.item())
+    ms_total_max = bc.max_over_ranks(torch, dist, dev, ms_total)
     value = world * F * POINTS_PER_FRAME * args.steps / (ms_total_max * 1e-3) / 1e6
+    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+    alg, comp = bc.k1_bytes(H, W, R, F)
 
     if args.kernel_only:
-        if rank == 0:
-            peak, _ = measured_peaks()
-            avg = float(np.mean(per_launch_ms)) * 1e-3
-            print(json.dumps({"value": value, "ms_per_step": ms_total_max / args.steps,
-                              "gbps": K1_BYTES_PER_FRAME_F32 * F / avg / 1e9,
-                              "frac": K1_BYTES_PER_FRAME_F32 * F / avg / 1e9 / peak,
-                              "env": {k: v for k, v in os.environ.items() if k.startswith("OB_")},
-                              "clocks": clocks}))
-        return
+        return {"value": value, "ms_per_step": ms_total_max / args.steps,
+                "frac": comp / avg_launch_s / 1e9 / bc.measured_peaks()[0],
+                "frac_algorithmic": alg / avg_launch_s / 1e9 / bc.measured_peaks()[0], "clocks": clocks}
 
-    # device results of frame 0, kept for the e2e self-check and the cpu_baseline leg's parity check
-    xyz0 = t_xyz[0].cpu().numpy() if rank == 0 else None
-    rd0 = t_rd[0].cpu().numpy().view(np.uint32) if rank == 0 else None
-    parity = None
+    # ---- parity over ALL frames of the timed launch against the CPU oracle (every rank its own pool) ----
+    from oracle import oracle as orc   # test infrastructure: the checker, never the thing measured
+    ref_xyz, ref_rd = orc.pool_k1(rng_host, SHIFTS, d, o)
+    dev_xyz = t_xyz.cpu().numpy()
+    dev_rd = t_rd.cpu().numpy().view(np.uint32)
+    ok = bool(np.array_equal(dev_xyz, ref_xyz)) and bool(np.array_equal(dev_rd, ref_rd))
+    parity = bc.all_ok(torch, dist, dev, ok)
+    del dev_xyz, dev_rd
 
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region ----
     CH = 8                                   # frames per call
@@ -317,99 +247,158 @@ def main():
         stream.wait_stream(s)
     e1.record(stream)
     barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_val = world * F * POINTS_PER_FRAME * e2e_steps / (float(e2e_ms.item()) * 1e-3) / 1e6
-    e2e_ok = bool(np.array_equal(h_xyz[0, 0], xyz0[0])) if rank == 0 else None
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    e2e_ms = bc.max_over_ranks(torch, dist, dev, e0.elapsed_time(e1))
+    e2e_val = world * F * POINTS_PER_FRAME * e2e_steps / (e2e_ms * 1e-3) / 1e6
+    e2e_ok = bc.all_ok(torch, dist, dev, bool(np.array_equal(h_xyz, ref_xyz)) and bool(np.array_equal(h_rd, ref_rd)))
+    h2d_b, d2h_b = int(F * R * H * W * 4), int(F * R * H * W * (12 + 4))
+    del ref_xyz, ref_rd
 
     # ---- the reference's default XYZLut is double: same launch with a float64 LUT, for the record ----
     f64 = None
-    try:
-        lut64 = ob.XYZLutT.from_arrays(t_dir.double(), t_off.double(), H, W, device=local_rank)
-        t_xyz64 = torch.empty((F, R, H * W, 3), dtype=torch.float64, device=dev)
-        for _ in range(3):
-            ob.scan_to_cloud(lut64, SHIFTS, t_rng, xyz=t_xyz64, range_destaggered=t_rd, stream=obs)
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a0.record(stream)
-        for _ in range(5):
-            ob.scan_to_cloud(lut64, SHIFTS, t_rng, xyz=t_xyz64, range_destaggered=t_rd, stream=obs)
-        a1.record(stream)
-        torch.cuda.synchronize()
-        s64 = a0.elapsed_time(a1) / 5 * 1e-3
-        f64 = {"value_mpoints_s": F * POINTS_PER_FRAME / s64 / 1e6, "bytes_per_frame": 29_360_128,
-               "achieved_gbps": F * 29_360_128 / s64 / 1e9}
-        del t_xyz64, lut64
-    except Exception as ex:  # supplementary figure only
-        f64 = {"error": str(ex)}
+    if rank == 0:
+        try:
+            lut64 = ob.XYZLutT.from_arrays(t_dir.double(), t_off.double(), H, W, device=local_rank)
+            t_xyz64 = torch.empty((F, R, H * W, 3), dtype=torch.float64, device=dev)
+            for _ in range(3):
+                ob.scan_to_cloud(lut64, SHIFTS, t_rng, xyz=t_xyz64, range_destaggered=t_rd, stream=obs)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a0.record(stream)
+            for _ in range(5):
+                ob.scan_to_cloud(lut64, SHIFTS, t_rng, xyz=t_xyz64, range_destaggered=t_rd, stream=obs)
+            a1.record(stream)
+            torch.cuda.synchronize()
+            s64 = a0.elapsed_time(a1) / 5 * 1e-3
+            a64, c64 = bc.k1_bytes(H, W, R, F, esz=8)
+            peak = bc.measured_peaks()[0]
+            f64 = {"value_mpoints_s": F * POINTS_PER_FRAME / s64 / 1e6, "frac": c64 / s64 / 1e9 / peak,
+                   "frac_algorithmic": a64 / s64 / 1e9 / peak}
+            del t_xyz64, lut64
+        except Exception as ex:  # supplementary figure only
+            f64 = {"error": str(ex)}
 
-    # ---- roofline of the dominant kernel (the fused launch IS the step) ----
-    peak, peak_kind = measured_peaks()
-    avg_launch_s = float(np.mean(per_launch_ms)) * 1e-3
-    achieved = K1_BYTES_PER_FRAME_F32 * F / avg_launch_s / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-
-    # ---- CPU baseline in the same run: oracle port on the host cores, bounded sample ----
+    # ---- CPU baseline in the same run: the reference's loops driven from C, bounded sample ----
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        from oracle import oracle as orc   # test infrastructure: used only in this CPU-baseline leg
-        parity = all(np.array_equal(xyz0[r], orc.cartesian(rng_host[0, r], d, o)) and
-                     np.array_equal(rd0[r], orc.destagger(rng_host[0, r], SHIFTS)) for r in range(R))
-        cores = os.cpu_count() or 1
-        nf = max(16, cores)
-        sample = rng_host[:nf] if nf <= F else synth_pool(nf)
-        cpu_reference_pass(orc, sample[:2], d, o, 1)
-        t1 = cpu_reference_pass(orc, sample[:8], d, o, 1)
-        reps = 3
-        tN = min(cpu_reference_pass(orc, sample, d, o, cores) for _ in range(reps))
-        cpu = {"value": sample.shape[0] * POINTS_PER_FRAME / tN / 1e6, "unit": "Mpoints/s",
-               "cores": cores, "kind": "port",
-               "sample": f"{sample.shape[0]} frames, destagger<u32>+cartesianT<float> per return, "
-                         f"one thread per frame, best of {reps}",
-               "single_thread_value": 8 * POINTS_PER_FRAME / t1 / 1e6}
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        modes, what = cpu_modes_k1(orc, rng_host, d, o, SHIFTS)
+        f32 = {k: v for k, v in modes.items() if k.endswith("f32")}
+        best = max(f32, key=f32.get)
+        cpu = {"value": f32[best], "unit": "Mpoints/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "mode": best, "modes": modes, "sample": what,
+               "as_shipped_double_1thread": modes["as_shipped_1thread_f64"]}
 
-    line = {
-        "metric": "Mpoints/s 128x2048 dual-return range->XYZ", "value": value, "unit": "Mpoints/s",
+    return {
+        "metric": METRIC, "value": value, "unit": "Mpoints/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "OS1-128 2048x128 dual-return fused destagger+cartesian (K1), "
-                               "LUT tiles staged in smem via TMA",
+        "config": {"workload": K1_WORKLOAD,
                    "frames_per_step_per_gpu": F, "points_per_frame": POINTS_PER_FRAME,
-                   "l2_policy": f"inputs+outputs per step {F * K1_BYTES_PER_FRAME_F32 / 1e6:.0f} MB > 126 MB L2",
+                   "l2_policy": f"compulsory DRAM traffic per step {comp / 1e6:.0f} MB > 126 MB L2",
                    "parallelism": f"{world} independent stream shards, LUT broadcast only",
-                   "numa_bound_cores_per_rank": numa_cores},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                     "kernel": "cloud_tma_kernel<float,2>",
-                     "algorithmic_bytes_per_launch": K1_BYTES_PER_FRAME_F32 * F,
-                     "avg_launch_ms": avg_launch_s * 1e3,
-                     "frac_of_ncu_dram_traffic": (traffic / avg_launch_s / 1e9 / peak) if traffic else None,
-                     "note": "algorithmic bytes count the 6.3 MB LUT once per frame (SURVEY 8d); it is "
-                             "L2-resident across the frames of a launch, so DRAM traffic (ncu) is lower "
-                             "and frac can exceed 1"},
+                   "numa_bound_cores_per_rank": args.numa_cores},
+        "roofline": bc.roofline(alg, comp, avg_launch_s, "cloud_tma_kernel<float,2>", "k1_traffic.json", bc.K1_SOURCES),
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_val, "unit": "Mpoints/s",
-                "h2d_bytes_per_step": int(F * R * H * W * 4),
-                "d2h_bytes_per_step": int(F * R * H * W * (12 + 4)),
-                "frames_per_call": CH, "streams": NS, "matches_device_path": e2e_ok},
+        "e2e": {"value": e2e_val, "unit": "Mpoints/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                "frames_per_call": CH, "streams": NS, "matches_oracle_all_frames": e2e_ok,
+                "pcie_frac": bc.pcie_fraction(pcie, h2d_b, d2h_b, e2e_ms * 1e-3 / e2e_steps) if pcie else None},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "parity_vs_oracle": parity,
+        "parity_vs_oracle": {"ok": parity, "frames_checked": F * world,
+                             "what": "XYZ + destaggered range of every frame and return of the timed launch vs "
+                                     "oracle cartesianT<float> / destagger<u32>, bit-exact"},
         "f64_lut": f64,
     }
-    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--only", default="all", choices=["all", "k1", "k2", "sweep"],
+                    help="restrict the run to one part (tuning / profiling aid); default: everything")
+    ap.add_argument("--workload", default=None, choices=["k1", "k2"], help="alias of --only (kept for tools)")
+    ap.add_argument("--frames", type=int, default=64, help="K1 frames per step (per GPU)")
+    ap.add_argument("--streams-per-gpu", type=int, default=1,
+                    help="with --only k2: independent sensor streams (own LUT each) per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="tuning aid: device-resident timing only")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload:
+        args.only = args.workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    args.numa_cores = bind_to_gpu_numa(local_rank) if world > 1 else 0
+    import torch
+    import __graft_entry__ as graft
+    graft.build()
+    ob = graft.load_package()
+    if ob.device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG is left as the caller set it (its lines go to stdout); the JSON is the LAST line
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    line = None
+    if args.kernel_only:
+        import bench_k2
+        out = {}
+        if args.only in ("all", "k1"):
+            out["k1"] = measure_k1(args, ob, torch, dist, rank, local_rank, world, None)
+        if args.only in ("all", "k2"):
+            st = bench_k2.K2State(args, ob, torch, dist, rank, local_rank, world)
+            rec = bench_k2.measure_k2(st, args, args.streams_per_gpu, None, with_e2e=False, with_cpu=False)
+            out["k2"] = {"value": rec["value"], "ms_per_step": rec["ms_per_step"], "frac": rec["roofline"]["frac"],
+                         "frac_algorithmic": rec["roofline"]["frac_algorithmic"], "parity": rec["parity_vs_oracle"]["ok"],
+                         "pipe_launches": rec["pipelined_kernel_launches"], "clocks": rec["clocks"]}
+        out["env"] = {k: v for k, v in os.environ.items() if k.startswith("OB_")}
+        line = out
+    else:
+        pcie_all = None
+        pcie = bc.measure_pcie(torch, ob, dev, dist)
+        g = bc.gather_floats(torch, dist, dev, [pcie[k] for k in ("h2d_gbs", "d2h_gbs", "bidir_h2d_gbs", "bidir_d2h_gbs")])
+        pcie_all = {"per_rank_concurrent": [dict(zip(("h2d_gbs", "d2h_gbs", "bidir_h2d_gbs", "bidir_d2h_gbs"), r)) for r in g],
+                    "rank0": pcie,
+                    "note": "pinned 256 MB copies; with N ranks all ranks copy at the same time, so the figures "
+                            "include the contention for each socket's host memory / PCIe root"}
+        if args.only in ("all", "k1"):
+            line = measure_k1(args, ob, torch, dist, rank, local_rank, world, pcie)
+        else:
+            line = {"metric": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "partial": args.only}
+        line["pcie"] = pcie_all
+        if args.only in ("all", "k2"):
+            import bench_k2
+            st = bench_k2.K2State(args, ob, torch, dist, rank, local_rank, world)
+            line["k2"] = bench_k2.measure_k2(st, args, 1, pcie)
+            line["k2_streams8"] = bench_k2.measure_k2(st, args, 8, pcie, with_e2e=False, with_cpu=False)
+            del st
+        if args.only in ("all", "sweep") and not args.no_sweep:
+            import bench_sweep
+            line["sweep"] = bench_sweep.run_sweep(args, ob, torch, dist, rank, local_rank, world)
+
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

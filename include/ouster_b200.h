@@ -57,6 +57,9 @@ const char* ob_last_error(void);
 int ob_device_count(void);
 /* kernels launched by this library since load (all threads); the bench's gpu_launches claim */
 uint64_t ob_kernel_launch_count(void);
+/* launches of one named kernel family since load: "decode_pipe" (pipelined K2), "decode" (K2, any
+ * kernel), "cloud" (K1); 0 for unknown names.  Lets tests assert which code path ran. */
+uint64_t ob_kernel_launch_count_of(const char* name);
 /* tuning hook (launch geometry and code-path selection only, never results): cloud_tw, cloud_stages,
  * cloud_threads (compute threads; a copy warp is added), cloud_ctas_per_sm, cloud_store_lag,
  * cloud_pose_tw, cloud_pose_stages, cloud_pose_ctas_per_sm, decode_stages, decode_threads,

@@ -74,9 +74,9 @@ class CFrame(C.Structure):
 
 def build(force=False):
     """Compile the oracle with its Makefile (gcc); no-op when the .so is up to date."""
-    src = os.path.join(_HERE, "ouster_oracle.c")
+    srcs = [os.path.join(_HERE, f) for f in ("ouster_oracle.c", "orc_bench.c", "ouster_oracle.h")]
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+            and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
@@ -145,6 +145,14 @@ def lib():
         getattr(L, n).restype = sz
     L.orc_snapshot_hash.argtypes = [vp, sz, sz]
     L.orc_snapshot_hash.restype = u64
+    # orc_bench.c: CPU-baseline harness (bench.py only)
+    L.orc_bench_max_threads.restype = i32
+    L.orc_bench_k1.argtypes = [i32, i32, vp, sz, sz, sz, sz, vp, vp, vp, i32, i32, C.POINTER(C.c_double)]
+    L.orc_bench_k1.restype = C.c_double
+    L.orc_bench_k2.argtypes = [i32, i32, PF, vp, sz, sz, vp, vp, vp, i32, i32, C.POINTER(C.c_double)]
+    L.orc_bench_k2.restype = C.c_double
+    L.orc_pool_k1.argtypes = [i32, vp, sz, sz, sz, sz, vp, vp, vp, vp, vp]
+    L.orc_pool_k1.restype = None
     _lib = L
     return L
 
@@ -426,3 +434,57 @@ def snapshot_hash(a):
 def crc64(buf):
     b = np.frombuffer(bytes(buf), np.uint8)
     return lib().orc_crc64(_ptr(b), b.size)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU-baseline harness (orc_bench.c) -- bench.py's cpu_baseline / --impl reference legs only
+# ------------------------------------------------------------------------------------------------
+BENCH_MODES = {"as_shipped": 0, "ouster_omp": 1, "thread_per_stream": 2}
+
+
+def bench_max_threads():
+    return int(lib().orc_bench_max_threads())
+
+
+def bench_k1(mode, rng, shifts, direction, offset, threads=0, reps=1):
+    """Seconds for `reps` passes of destagger<u32>() + cartesian() over rng [F, R, H, W] (uint32), run
+    from C in one of BENCH_MODES; the LUT dtype (float32 / float64) selects cartesianT<float|double>."""
+    rng = np.ascontiguousarray(rng, np.uint32)
+    F, R, h, w = rng.shape
+    f64 = int(direction.dtype == np.float64)
+    d = np.ascontiguousarray(direction)
+    o = np.ascontiguousarray(offset, d.dtype)
+    sh = np.ascontiguousarray(shifts, np.int32)
+    sink = C.c_double(0)
+    return float(lib().orc_bench_k1(BENCH_MODES[mode], f64, _ptr(rng), F, R, h, w, _ptr(sh), _ptr(d), _ptr(o),
+                                    int(threads), int(reps), C.byref(sink)))
+
+
+def bench_k2(mode, pf, packets, shifts, direction, offset, threads=0, reps=1):
+    """Seconds for `reps` passes of FrameBatcher decode + destagger + cartesian over packets
+    [F, n_packets, packet_size] (uint8 wire bytes of complete frames)."""
+    pk = np.ascontiguousarray(packets, np.uint8)
+    F, n_pk, psz = pk.shape
+    assert psz == pf.lidar_packet_size
+    f64 = int(direction.dtype == np.float64)
+    d = np.ascontiguousarray(direction)
+    o = np.ascontiguousarray(offset, d.dtype)
+    sh = np.ascontiguousarray(shifts, np.int32)
+    sink = C.c_double(0)
+    return float(lib().orc_bench_k2(BENCH_MODES[mode], f64, C.byref(pf.c), _ptr(pk), F, n_pk, _ptr(sh), _ptr(d),
+                                    _ptr(o), int(threads), int(reps), C.byref(sink)))
+
+
+def pool_k1(rng, shifts, direction, offset):
+    """cartesianT + destagger<u32> of a whole pool rng [F, R, H, W] -> (xyz [F, R, H*W, 3], rd [F, R, H, W]);
+    every frame computed by the single-thread oracle functions, frames spread over the host cores."""
+    rng = np.ascontiguousarray(rng, np.uint32)
+    F, R, h, w = rng.shape
+    d = np.ascontiguousarray(direction)
+    o = np.ascontiguousarray(offset, d.dtype)
+    sh = np.ascontiguousarray(shifts, np.int32)
+    xyz = np.empty((F, R, h * w, 3), d.dtype)
+    rd = np.empty((F, R, h, w), np.uint32)
+    lib().orc_pool_k1(int(d.dtype == np.float64), _ptr(rng), F, R, h, w, _ptr(sh), _ptr(d), _ptr(o),
+                      _ptr(xyz), _ptr(rd))
+    return xyz, rd

@@ -83,6 +83,7 @@ _sig("ob_abi_sizeof", sz, C.c_char_p)
 _sig("ob_last_error", C.c_char_p)
 _sig("ob_device_count", i32)
 _sig("ob_kernel_launch_count", u64)
+_sig("ob_kernel_launch_count_of", u64, C.c_char_p)
 _sig("ob_set_tunable", i32, i32, C.c_char_p, i32)
 _sig("ob_stream_create", i32, i32, C.POINTER(vp))
 _sig("ob_stream_wrap", i32, i32, vp, C.POINTER(vp))

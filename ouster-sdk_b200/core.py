@@ -18,7 +18,10 @@ def device_count():
     return lib.ob_device_count()
 
 
-def kernel_launch_count():
+def kernel_launch_count(name=None):
+    """Kernels launched since load; `name` restricts the count to one family ("decode_pipe", ...)."""
+    if name is not None:
+        return lib.ob_kernel_launch_count_of(name.encode())
     return lib.ob_kernel_launch_count()
 
 

@@ -16,7 +16,13 @@ namespace ob {
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches{0};
 
+static std::atomic<uint64_t> g_family[4];
+static const char* const kFamilies[4] = {"decode_pipe", "decode", "cloud", "normals"};
+
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_launch_of(int family, uint64_t n) {
+    if (family >= 0 && family < 4) g_family[family].fetch_add(n, std::memory_order_relaxed);
+}
 
 ob_status fail(ob_status st, const std::string& msg) {
     g_last_error = msg;
@@ -55,6 +61,8 @@ static Tunables& tunables_mut(int device) {
         t.decode_tile_packets = std::max(0, env_int("OB_DECODE_TILE_PACKETS", 0));  // 0 = auto
         t.decode_prefetch = env_int("OB_DECODE_PREFETCH", 0);
         t.decode_runtime_plans = env_int("OB_DECODE_RUNTIME_PLANS", 0);
+        t.decode_pipe = env_int("OB_DECODE_PIPE", 1);
+        t.decode_pipe_warps = std::min(24, std::max(6, env_int("OB_DECODE_PIPE_WARPS", 24)));
         t.force_generic = env_int("OB_FORCE_GENERIC", 0);
         int sm = 148;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
@@ -91,6 +99,8 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "decode_tile_packets") t.decode_tile_packets = std::max(0, value);
     else if (n == "decode_prefetch") t.decode_prefetch = value;
     else if (n == "decode_runtime_plans") t.decode_runtime_plans = value ? 1 : 0;
+    else if (n == "decode_pipe") t.decode_pipe = value ? 1 : 0;
+    else if (n == "decode_pipe_warps") t.decode_pipe_warps = std::min(24, std::max(6, value));
     else if (n == "force_generic") t.force_generic = value;
     else return false;
     return true;
@@ -258,6 +268,13 @@ int ob_device_count(void) {
 }
 
 uint64_t ob_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+uint64_t ob_kernel_launch_count_of(const char* name) {
+    if (!name) return 0;
+    for (int i = 0; i < 4; ++i)
+        if (std::string(name) == kFamilies[i]) return g_family[i].load(std::memory_order_relaxed);
+    return 0;
+}
 
 ob_status ob_set_tunable(int device, const char* name, int value) {
     if (!name || !set_tunable(device, name, value)) return fail(OB_INVALID_ARGUMENT, "unknown tunable");
@@ -446,6 +463,7 @@ ob_status ob_lut_device_ptrs(const ob_lut* lut, void** direction, void** offset)
 ob_status ob_lut_destroy(ob_lut* lut) {
     if (!lut) return OB_OK;
     cudaSetDevice(lut->device);
+    forget_lut_tensor_maps(lut->dir);
     cudaFree(lut->dir);
     cudaFree(lut->off);
     delete lut;

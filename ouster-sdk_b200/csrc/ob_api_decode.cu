@@ -39,6 +39,13 @@ static void group_by_lut(std::vector<DecodeFrame>& frames) {
     });
 }
 
+// TMA descriptors of a LUT for the pipelined K2 (null: that kernel is not applicable / not available)
+static const void* maps_for(const DecodeLayout& L, int device, const void* dir, const void* off, int dtype) {
+    uint32_t bw = 0, bh = 0;
+    if (!dir || !off || !decode_pipe_box(L, device, dtype, &bw, &bh)) return nullptr;
+    return lut_tensor_maps(dir, off, dtype, L.H, L.W, bw, bh, device);
+}
+
 extern "C" {
 
 ob_status ob_decoder_create(const ob_packet_layout* layout, const ob_field_desc* fields,
@@ -127,7 +134,7 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
     cudaStream_t st = stream_handle(s);
     Staging stg(st);
     std::vector<DecodeFrame> hf(n_frames);
-    bool vec_ok = true;
+    bool vec_ok = true, frame_maps_ok = true;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     if (lut && (!al16(ldir) || !al16(loff))) vec_ok = false;
     for (size_t i = 0; i < n_frames; ++i) {
@@ -188,6 +195,8 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
             if (!lut) ldtype = fdt;
             f.lut_dir = fd;
             f.lut_off = fo;
+            f.lut_maps = maps_for(L, device, fd, fo, fdt);
+            if (!f.lut_maps) frame_maps_ok = false;
             if (!al16(fd) || !al16(fo)) vec_ok = false;
         }
         for (int r = 0; r < OB_MAX_RETURNS; ++r) {
@@ -221,6 +230,8 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
     a.lut_dtype = ldtype;
     a.shift_host = shifts ? sh.data() : nullptr;
     a.vec_ok = vec_ok;
+    a.lut_maps = maps_for(L, device, ldir, loff, ldtype);
+    a.frame_luts_have_maps = frame_maps_ok;
     e = launch_decode(a, device, st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     e = stg.flush();
@@ -315,6 +326,7 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
         }
     }
     std::vector<DecodeFrame> hf(F);
+    bool frame_maps_ok = true;
     const bool bulk_ok = al16(dpk) && b->packet_stride % 16 == 0 && L.packet_size % 16 == 0 &&
                          b->packets_frame_stride % 16 == 0;
     for (size_t f = 0; f < F; ++f) {
@@ -332,6 +344,8 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
         if (!fl_dir.empty()) {
             d.lut_dir = fl_dir[f];
             d.lut_off = fl_off[f];
+            d.lut_maps = maps_for(L, device, fl_dir[f], fl_off[f], ldtype);
+            if (!d.lut_maps) frame_maps_ok = false;
         }
         for (int r = 0; r < OB_MAX_RETURNS; ++r) {
             if (dxyz[r]) d.xyz[r] = static_cast<uint8_t*>(dxyz[r]) + f * b->xyz_frame_stride;
@@ -353,6 +367,8 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
     a.lut_dtype = ldtype;
     a.shift_host = shifts ? sh.data() : nullptr;
     a.vec_ok = vec_ok;
+    a.lut_maps = maps_for(L, device, ldir, loff, ldtype);
+    a.frame_luts_have_maps = frame_maps_ok;
     e = launch_decode(a, device, st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     e = stg.flush();
@@ -628,6 +644,7 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
     a.lut_dtype = ldtype;
     a.shift_host = shifts ? sh.data() : nullptr;
     a.vec_ok = vec_ok;
+    a.lut_maps = maps_for(L, j->device, ldir, loff, ldtype);
     e = launch_decode(a, j->device, j->st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     for (size_t k = 0; k < n_host;) {  // one D2H per run of outputs contiguous on both sides

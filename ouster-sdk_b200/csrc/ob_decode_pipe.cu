@@ -1,0 +1,586 @@
+// ob_decode_pipe.cu -- K2, pipelined: fused lidar-packet field decode -> LidarFrame fields + destaggered
+// range + XYZ, as one persistent warp-specialised CTA per SM.
+//
+// Same work and same results as decode_kernel (ob_decode.cu; it stays as the path for shapes this
+// kernel does not take), restructured so that no compute warp ever waits on a global load:
+//
+//   * warp NCW   (packet producer): one TMA bulk copy per packet into a 2-deep ring of packet stages;
+//     a stage is refilled the moment the last compute warp has arrived on its `pk_done` mbarrier.
+//     Irregular tiles (dropped / reordered / zero-filled columns) are gathered by this warp's lanes.
+//   * warp NCW+1 (LUT producer): the XYZ LUT slices of a tile stream through a 3-deep ring of
+//     24 KB slots, one 2-D TMA tensor copy per table per sub-tile (box = tile columns x RB rows of
+//     direction resp. offset; descriptors built on the host, lut_tensor_maps()).
+//   * warps 0..NCW-1 (compute): phase A decodes every field of a pixel from registers and stores the
+//     row-major images (lane = frame column); phase B projects the ranges with the LUT slice that is
+//     already in shared memory (thread = one 16-byte chunk of a row segment: two conflict-free LDS.128,
+//     two STG.128) -- only shared-memory loads, ALU and global stores.
+//
+// Reference behaviour replaced: see ob_decode.cu (parsing.cpp:628-675, lidar_frame.cpp:1422-1528,
+// impl/cartesian.h:36-66, impl/lidar_frame_impl.h:733-760).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "ob_decode_tile.cuh"
+
+namespace ob {
+
+constexpr int kPipeMaxComputeWarps = 24;
+constexpr int kPipeStages = 2;    // packet stages
+constexpr int kPipeLutSlots = 3;  // LUT ring depth
+
+struct PipeParams {
+    DecodeParams d;
+    const void* lut_maps;  // launch-level LUT descriptors (2 x CUtensorMap) or null
+    uint32_t ncw;          // compute warps
+    uint32_t cpr;          // 16-byte chunks per row segment of a tile (3 * TC * sizeof(T) / 16)
+    uint32_t RB;           // rows per LUT sub-tile (= ncw * 32 / cpr)
+    uint32_t n_sub;        // sub-tiles per tile (ceil(H / RB))
+    uint32_t slot_bytes;   // bytes of one LUT ring slot (direction + offset box)
+    uint32_t box_bytes;    // bytes of one box
+    uint32_t lut_off;      // byte offsets inside the dynamic shared memory
+    uint32_t stage_off;
+};
+
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
+    decode_pipe_kernel(const __grid_constant__ PipeParams pp) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const DecodeParams& p = pp.d;
+    const DecodeLayout& L = p.L;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int NCW = static_cast<int>(pp.ncw);
+    constexpr int NS = kPipeStages, NL = kPipeLutSlots;
+
+    // ---- shared memory carve-up ----
+    uint64_t* pk_full = reinterpret_cast<uint64_t*>(smem);  // NS
+    uint64_t* pk_done = pk_full + NS;                       // NS
+    uint64_t* lut_full = pk_done + NS;                      // NL
+    uint64_t* lut_done = lut_full + NL;                     // NL
+    TileCtl* ctl = reinterpret_cast<TileCtl*>(smem + 128);  // NS entries
+    uint8_t* lut0 = smem + pp.lut_off;
+    uint8_t* stage0 = smem + pp.stage_off;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&pk_full[s], 1);
+            mbar_init(&pk_done[s], pp.ncw);
+        }
+        for (int s = 0; s < NL; ++s) {
+            mbar_init(&lut_full[s], 1);
+            mbar_init(&lut_done[s], pp.ncw);
+        }
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    __syncthreads();  // the only CTA-wide barrier
+
+    const unsigned first = blockIdx.x;
+    const unsigned n_my = first < p.n_tiles ? (p.n_tiles - first + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned n_ret = p.n_returns;
+    const unsigned cds = L.channel_data_size;
+
+    auto tile_of = [&](unsigned k, unsigned& f, unsigned& j0) {
+        const unsigned t = first + k * gridDim.x;
+        f = t / p.tiles_per_frame;
+        j0 = (t - f * p.tiles_per_frame) * p.TC;
+    };
+    const unsigned tc = p.TC;  // every tile is full (eligibility: W % TC == 0)
+    // byte offset (inside a stage) of pixel 0 of tile column t
+    auto col_offset = [&](unsigned t) -> int {
+        const unsigned g = t >> p.cpp_shift;
+        return static_cast<int>(g * p.pkt_stride_s + L.packet_header_size + (t - (g << p.cpp_shift)) * L.col_size +
+                                L.col_header_size);
+    };
+    // does tile (frame) take the XYZ path?  evaluated identically by the LUT producer and the compute warps
+    auto wants_xyz = [&](const DecodeFrame& fr) -> const void* {
+        const void* maps = fr.lut_dir != nullptr ? fr.lut_maps : pp.lut_maps;
+        if (n_ret == 0 || (fr.xyz[0] == nullptr && fr.xyz[1] == nullptr)) return nullptr;
+        return maps;
+    };
+
+    if (warp == NCW) {
+        // =============================== packet producer ===============================
+        uint64_t pol_stream = policy_evict_first();
+        for (unsigned k = 0; k < n_my; ++k) {
+            const int s = k % NS;
+            if (k >= static_cast<unsigned>(NS)) mbar_wait(&pk_done[s], ((k / NS) - 1) & 1);
+            unsigned f, j0;
+            tile_of(k, f, j0);
+            const DecodeFrame& fr = p.frames[f];
+            TileCtl& c = ctl[s];
+            uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+            const bool identity = (fr.flags & 1u) != 0;
+            const bool bulk_ok = (fr.flags & 2u) != 0;
+            const unsigned n_groups = tc >> p.cpp_shift;
+            if (identity && bulk_ok && (j0 + tc) / L.cpp <= fr.n_slots) {
+                if (lane == 0) {
+                    c.regular = 1;
+                    mbar_expect_tx(&pk_full[s], n_groups * L.packet_size);
+                    const unsigned slot0 = j0 / L.cpp;
+                    for (unsigned g = 0; g < n_groups; ++g)
+                        bulk_g2s_hint(st + static_cast<size_t>(g) * p.pkt_stride_s,
+                                      fr.packets + static_cast<size_t>(slot0 + g) * fr.packet_stride, L.packet_size,
+                                      &pk_full[s], pol_stream);
+                }
+                continue;
+            }
+            // ---- irregular tile: per-column bookkeeping, slow groups gathered by the lanes ----
+            if (lane == 0) {
+                c.regular = 0;
+                for (unsigned g = 0; g < n_groups; ++g) {
+                    const unsigned jg = j0 + g * L.cpp;
+                    bool fast = bulk_ok;
+                    int slot = -1;
+                    for (unsigned i = 0; i < L.cpp; ++i) {
+                        int src;
+                        if (identity) {
+                            const unsigned sl = (jg + i) / L.cpp;
+                            src = sl < fr.n_slots ? static_cast<int>(jg + i) : -1;
+                        } else {
+                            src = fr.col_src[jg + i];
+                        }
+                        c.col_src[g * L.cpp + i] = src;
+                        c.col_off[g * L.cpp + i] = src < 0 ? -1 : col_offset(g * L.cpp + i);
+                        if (src < 0) {
+                            fast = false;
+                        } else {
+                            const int sl = src / static_cast<int>(L.cpp), ci = src - sl * static_cast<int>(L.cpp);
+                            if (ci != static_cast<int>(i) || (i > 0 && sl != slot)) fast = false;
+                            slot = sl;
+                        }
+                    }
+                    c.group_fast[g] = fast ? 1 : 0;
+                }
+            }
+            __syncwarp();
+            uint32_t tx = 0;
+            for (unsigned t = 0; t < tc; ++t) {
+                const unsigned g = t >> p.cpp_shift;
+                if (c.group_fast[g]) {
+                    if ((t & (L.cpp - 1)) == 0) tx += L.packet_size;
+                    continue;
+                }
+                const int src = c.col_src[t];
+                if (src < 0) continue;
+                const int sl = src / static_cast<int>(L.cpp), ci = src - sl * static_cast<int>(L.cpp);
+                const uint8_t* gsrc = fr.packets + static_cast<size_t>(sl) * fr.packet_stride + L.packet_header_size +
+                                      static_cast<size_t>(ci) * L.col_size;
+                uint8_t* dst = st + static_cast<size_t>(g) * p.pkt_stride_s + L.packet_header_size +
+                               static_cast<size_t>(t - (g << p.cpp_shift)) * L.col_size;
+                // the column plus the 8 bytes a trailing field read may touch (clamped to the packet)
+                const size_t col_end = L.packet_header_size + static_cast<size_t>(ci + 1) * L.col_size;
+                const size_t extra = min(static_cast<size_t>(8), L.packet_size - col_end);
+                const unsigned nbytes = L.col_size + static_cast<unsigned>(extra);
+                if ((reinterpret_cast<uintptr_t>(gsrc) & 3u) == 0) {  // layout is word aligned (eligibility)
+                    for (unsigned b = lane * 4; b + 4 <= nbytes; b += 128)
+                        *reinterpret_cast<uint32_t*>(dst + b) = *reinterpret_cast<const uint32_t*>(gsrc + b);
+                    for (unsigned b = (nbytes & ~3u) + lane; b < nbytes; b += 32) dst[b] = gsrc[b];
+                } else {
+                    for (unsigned b = lane; b < nbytes; b += 32) dst[b] = gsrc[b];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(&pk_full[s], tx);  // the one arrival of this phase; completes when tx bytes landed
+                for (unsigned g = 0; g < n_groups; ++g) {
+                    if (!c.group_fast[g]) continue;
+                    const int slot = c.col_src[g * L.cpp] / static_cast<int>(L.cpp);
+                    bulk_g2s_hint(st + static_cast<size_t>(g) * p.pkt_stride_s,
+                                  fr.packets + static_cast<size_t>(slot) * fr.packet_stride, L.packet_size,
+                                  &pk_full[s], pol_stream);
+                }
+            }
+        }
+        return;
+    }
+
+    if (warp == NCW + 1) {
+        // =============================== LUT producer ===============================
+        if (lane != 0) return;
+        const uint64_t pol_keep = policy_evict_last();
+        unsigned g = 0;
+        for (unsigned k = 0; k < n_my; ++k) {
+            unsigned f, j0;
+            tile_of(k, f, j0);
+            const DecodeFrame& fr = p.frames[f];
+            const void* maps = wants_xyz(fr);
+            if (maps == nullptr) continue;
+            const uint8_t* m = static_cast<const uint8_t*>(maps);
+            for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g) {
+                const int slot = g % NL;
+                if (g >= static_cast<unsigned>(NL)) mbar_wait(&lut_done[slot], ((g / NL) - 1) & 1);
+                uint8_t* dst = lut0 + static_cast<size_t>(slot) * pp.slot_bytes;
+                mbar_expect_tx(&lut_full[slot], 2u * pp.box_bytes);
+                tma_load_2d_hint(dst, m, static_cast<int>(j0 * 3u), static_cast<int>(sub * pp.RB), &lut_full[slot],
+                                 pol_keep);
+                tma_load_2d_hint(dst + pp.box_bytes, m + 128, static_cast<int>(j0 * 3u),
+                                 static_cast<int>(sub * pp.RB), &lut_full[slot], pol_keep);
+            }
+        }
+        return;
+    }
+
+    // =================================== compute warps ===================================
+    const bool aligned = p.word_aligned != 0;
+    constexpr int VN = 16 / sizeof(T);  // scalars per 16-byte chunk
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    // phase-B invariants of this thread: chunk q of row (sub-tile row rsub)
+    const unsigned rsub = static_cast<unsigned>(tid) / pp.cpr;
+    const unsigned q = static_cast<unsigned>(tid) - rsub * pp.cpr;
+    const unsigned e0 = q * VN;
+    const unsigned p0 = e0 / 3u;       // first pixel touched by this chunk
+    const unsigned k0 = e0 - 3u * p0;  // component of element 0 inside pixel p0
+    const unsigned p1 = (p0 + 1 < tc) ? p0 + 1 : p0;
+    bool first_px[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) first_px[e] = (k0 + e) < 3u;
+    const DecodeParams::Plan& pl0 = p.plan[p.range_field[0]];
+    const DecodeParams::Plan& pl1 = p.plan[p.range_field[n_ret > 1 ? 1 : 0]];
+    const bool simple = (pl0.mb | pl1.mb | pl0.rs | pl1.rs) == 0 && pl0.d == 0 && pl1.d == 0;
+    auto rng = [](const uint32_t* w, const DecodeParams::Plan& pl, bool valid, bool simple_) -> uint32_t {
+        const uint32_t a = w[pl.wa] & pl.ma;
+        if (simple_) return valid ? a : 0u;
+        const uint32_t b = pl.mb ? (w[pl.wa + 1] & pl.mb) : 0u;
+        uint32_t v = __funnelshift_r(a, b, pl.rs);
+        v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
+        return valid ? v : 0u;
+    };
+
+    unsigned g = 0;  // running LUT sub-tile index (same sequence as the LUT producer)
+    for (unsigned k = 0; k < n_my; ++k) {
+        const int s = k % NS;
+        unsigned f, j0;
+        tile_of(k, f, j0);
+        const DecodeFrame& fr = p.frames[f];
+        TileCtl& c = ctl[s];
+        uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+        // rows rotate over the warps from tile to tile so that H % NCW leftovers even out
+        const int wrot = (warp + static_cast<int>((k * 7u) % static_cast<unsigned>(NCW))) % NCW;
+
+        mbar_wait(&pk_full[s], (k / NS) & 1);
+        const bool regular = c.regular != 0;
+
+        // ---- column headers (timestamp / measurement_id / status) ----
+        if (fr.timestamp != nullptr || fr.measurement_id != nullptr || fr.status != nullptr) {
+            for (unsigned t = tid; t < tc; t += static_cast<unsigned>(NCW) * 32u) {
+                const int co = regular ? col_offset(t) : c.col_off[t];
+                uint64_t ts = 0, mid = 0, stt = 0;
+                if (co >= 0) {
+                    const uint8_t* colp = st + co - L.col_header_size;
+                    ts = extract_smem(colp, L.ts, aligned);
+                    mid = extract_smem(colp, L.mid, aligned);
+                    stt = extract_smem(colp, L.status, aligned);
+                }
+                if (fr.timestamp) fr.timestamp[j0 + t] = ts;
+                if (fr.measurement_id) fr.measurement_id[j0 + t] = static_cast<uint16_t>(mid);
+                if (fr.status) fr.status[j0 + t] = static_cast<uint32_t>(stt);
+            }
+        }
+
+        // ---- phase A: decode; lane = frame column, warp = row (strided) ----
+        for (unsigned cg = 0; cg * 32 < tc; ++cg) {
+            const unsigned t = cg * 32 + lane;
+            const int co = regular ? col_offset(t) : c.col_off[t];
+            const bool col_valid = co >= 0;
+            const uint8_t* px0 = st + (col_valid ? co : col_offset(t));
+            const size_t pix0 = static_cast<size_t>(j0) + t;
+            if (p.layout_id != 0) {
+                uint8_t* outp[kMaxSlots];
+#pragma unroll
+                for (int i = 0; i < kMaxSlots; ++i)
+                    outp[i] = p.slot_field[i] >= 0 ? static_cast<uint8_t*>(fr.fields[p.slot_field[i]]) : nullptr;
+                uint32_t* rdp2[2] = {fr.rd[0], fr.rd[1]};
+                const unsigned col = static_cast<unsigned>(pix0);
+                const unsigned row0 = static_cast<unsigned>(wrot), rstep = static_cast<unsigned>(NCW);
+                const bool all = p.layout_all != 0 && (p.n_returns < 1 || rdp2[0] != nullptr) &&
+                                 (p.n_returns < 2 || rdp2[1] != nullptr) && fr.fields[0] != nullptr &&
+                                 p.n_returns > 0;
+                switch (p.layout_id) {
+                    case 1: decode_static_tile<1>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    case 2: decode_static_tile<2>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    case 3: decode_static_tile<3>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    case 4: decode_static_tile<4>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    default: decode_static_tile<5>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                }
+                continue;
+            }
+            for (unsigned fi = 0; fi < L.n_fields; ++fi) {
+                const DecodeField& fd = L.fields[fi];
+                uint8_t* out = static_cast<uint8_t*>(fr.fields[fi]);
+                const int rr = fd.range_return;
+                uint32_t* rdp = rr >= 0 ? fr.rd[rr] : nullptr;
+                if (out == nullptr && rdp == nullptr) continue;
+                const DecodeParams::Plan& pl = p.plan[fi];
+                const uint32_t es = fd.elem_size;
+                if (pl.fast && es <= 4) {
+                    const uint32_t zv = (fd.zero_pattern & 0xffffu) | ((fd.zero_pattern & 0xffffu) << 16);
+                    const bool ho = out != nullptr, hr = rdp != nullptr;
+                    if (regular) {
+                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                    } else {
+                        if (es == 4) decode_rows_dispatch<4, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                        else decode_rows_dispatch<1, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                    }
+                } else {  // wide or unaligned fields: generic 64-bit extraction
+                    for (unsigned row = wrot; row < L.H; row += NCW) {
+                        const uint8_t* px = px0 + row * cds;
+                        const uint64_t v = !col_valid ? zero_value(fd) : extract_smem(px, fd, aligned);
+                        const size_t pix = static_cast<size_t>(row) * L.W + pix0;
+                        if (out != nullptr) store_elem(out, pix, es, v);
+                        if (rdp != nullptr) {
+                            int dcol = static_cast<int>(pix0) + (p.has_shift ? p.shift[row] : 0);
+                            dcol = dcol >= static_cast<int>(L.W) ? dcol - static_cast<int>(L.W) : dcol;
+                            rdp[static_cast<size_t>(row) * L.W + dcol] = static_cast<uint32_t>(v);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- phase B: XYZ from the LUT slices in shared memory ----
+        if (wants_xyz(fr) != nullptr) {
+            const int co0 = regular ? col_offset(p0) : c.col_off[p0];
+            const int co1 = regular ? col_offset(p1) : c.col_off[p1];
+            const bool v0 = co0 >= 0, v1 = co1 >= 0;
+            const uint8_t* pa = st + (v0 ? co0 : 0);
+            const uint8_t* pb = st + (v1 ? co1 : 0);
+            T* xo0 = static_cast<T*>(fr.xyz[0]);
+            T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
+            if (xo0 != nullptr) __builtin_assume(__isGlobal(xo0));
+            if (xo1 != nullptr) __builtin_assume(__isGlobal(xo1));
+            const size_t ecol = static_cast<size_t>(j0) * 3 + static_cast<size_t>(q) * VN;
+            for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g) {
+                const int slot = g % NL;
+                mbar_wait(&lut_full[slot], (g / NL) & 1);
+                const unsigned row = sub * pp.RB + rsub;
+                if (row < L.H) {
+                    const uint8_t* sl = lut0 + static_cast<size_t>(slot) * pp.slot_bytes + static_cast<size_t>(tid) * 16;
+                    const V dv = *reinterpret_cast<const V*>(sl);
+                    const V ov = *reinterpret_cast<const V*>(sl + pp.box_bytes);
+                    const T* de = reinterpret_cast<const T*>(&dv);
+                    const T* oe = reinterpret_cast<const T*>(&ov);
+                    const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa + static_cast<size_t>(row) * cds);
+                    const uint32_t* wb = reinterpret_cast<const uint32_t*>(pb + static_cast<size_t>(row) * cds);
+                    const size_t eidx = static_cast<size_t>(row) * L.W * 3 + ecol;
+                    if (xo0 != nullptr) {
+                        const uint32_t ra = rng(wa, pl0, v0, simple), rb = rng(wb, pl0, v1, simple);
+                        V outv;
+                        T* o2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) o2[e] = project1(first_px[e] ? ra : rb, de[e], oe[e]);
+                        *reinterpret_cast<V*>(xo0 + eidx) = outv;
+                    }
+                    if (xo1 != nullptr) {
+                        const uint32_t ra = rng(wa, pl1, v0, simple), rb = rng(wb, pl1, v1, simple);
+                        V outv;
+                        T* o2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) o2[e] = project1(first_px[e] ? ra : rb, de[e], oe[e]);
+                        *reinterpret_cast<V*>(xo1 + eidx) = outv;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&lut_done[slot]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pk_done[s]);  // this warp is done with the stage
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: TMA descriptors of a LUT, eligibility, launch
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+struct MapKey {
+    const void* dir;
+    uint32_t box_w, box_h;
+    bool operator==(const MapKey& o) const { return dir == o.dir && box_w == o.box_w && box_h == o.box_h; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        return std::hash<const void*>()(k.dir) ^ (static_cast<size_t>(k.box_w) * 0x9e3779b97f4a7c15ull) ^
+               (static_cast<size_t>(k.box_h) << 17);
+    }
+};
+std::mutex g_map_mx;
+std::unordered_map<MapKey, void*, MapKeyHash> g_maps;  // value: device memory holding 2 CUtensorMap (null: failed)
+
+}  // namespace
+
+const void* lut_tensor_maps(const void* dir, const void* off, int dtype, size_t h, size_t w, uint32_t box_w,
+                            uint32_t box_h, int device) {
+    if (dir == nullptr || off == nullptr || box_w == 0 || box_h == 0) return nullptr;
+    std::lock_guard<std::mutex> lk(g_map_mx);
+    const MapKey key{dir, box_w, box_h};
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) return it->second;
+    void* dev = nullptr;
+    EncodeTiledFn enc = encode_tiled_fn();
+    const size_t es = dtype == OB_F64 ? 8 : 4;
+    const bool ok_shape = enc != nullptr && ((reinterpret_cast<uintptr_t>(dir) | reinterpret_cast<uintptr_t>(off)) & 15u) == 0 &&
+                          (w * 3 * es) % 16 == 0 && box_w <= 256 && box_h <= 256 && (box_w * es) % 16 == 0;
+    if (ok_shape) {
+        alignas(64) CUtensorMap maps[2];
+        const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(w) * 3, static_cast<cuuint64_t>(h)};
+        const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(w) * 3 * es};
+        const cuuint32_t box[2] = {box_w, box_h};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUtensorMapDataType dt = dtype == OB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        bool ok = true;
+        const void* base[2] = {dir, off};
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = enc(&maps[i], dt, 2, const_cast<void*>(base[i]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        if (ok) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(device);
+            if (cudaMalloc(&dev, sizeof(maps)) == cudaSuccess) {
+                if (cudaMemcpy(dev, maps, sizeof(maps), cudaMemcpyHostToDevice) != cudaSuccess) {
+                    cudaFree(dev);
+                    dev = nullptr;
+                }
+            } else {
+                dev = nullptr;
+            }
+            cudaGetLastError();
+            cudaSetDevice(cur);
+        }
+    }
+    g_maps.emplace(key, dev);
+    return dev;
+}
+
+void forget_lut_tensor_maps(const void* dir) {
+    std::lock_guard<std::mutex> lk(g_map_mx);
+    for (auto it = g_maps.begin(); it != g_maps.end();) {
+        if (it->first.dir == dir) {
+            if (it->second) cudaFree(it->second);
+            it = g_maps.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
+static bool pipe_geometry(const DecodeLayout& L, uint32_t TC, int lut_dtype, uint32_t ncw, uint32_t* cpr, uint32_t* RB) {
+    const uint32_t es = lut_dtype == OB_F64 ? 8 : 4;
+    if (TC == 0 || TC % 32 != 0 || TC > 64 || L.W % TC != 0) return false;
+    const uint32_t c = 3 * TC * es / 16;
+    const uint32_t threads = ncw * 32;
+    if (c == 0 || threads % c != 0) return false;
+    *cpr = c;
+    *RB = threads / c;
+    return *RB <= 256;
+}
+
+static uint32_t pipe_tile_cols(const DecodeLayout& L, const Tunables& tn) {
+    const uint32_t stride = (L.packet_size + 16 + 15) & ~15u;
+    uint32_t P = 1;
+    if (tn.decode_tile_packets > 0) P = static_cast<uint32_t>(tn.decode_tile_packets);
+    else
+        while (P * 2 * stride <= 68u * 1024u && P * 2 * L.cpp <= 64u) P *= 2;
+    P = std::max<uint32_t>(1, std::min<uint32_t>(P, static_cast<uint32_t>(kMaxTileCols) / std::max<uint32_t>(L.cpp, 1)));
+    return P * L.cpp;
+}
+
+bool decode_pipe_box(const DecodeLayout& L, int device, int lut_dtype, uint32_t* box_w, uint32_t* box_h) {
+    const Tunables& tn = tunables(device);
+    if (!tn.decode_pipe || L.cpp == 0) return false;
+    uint32_t cpr, RB;
+    const uint32_t TC = pipe_tile_cols(L, tn);
+    if (!pipe_geometry(L, TC, lut_dtype, static_cast<uint32_t>(tn.decode_pipe_warps), &cpr, &RB)) return false;
+    *box_w = TC * 3;
+    *box_h = RB;
+    return true;
+}
+
+static size_t pipe_smem_bytes(const DecodeParams& p, uint32_t ncw, uint32_t* lut_off, uint32_t* stage_off) {
+    size_t off = 128 + static_cast<size_t>(kPipeStages) * sizeof(TileCtl);
+    off = (off + 1023) & ~static_cast<size_t>(1023);
+    *lut_off = static_cast<uint32_t>(off);
+    off += static_cast<size_t>(kPipeLutSlots) * 2u * (ncw * 32u * 16u);
+    *stage_off = static_cast<uint32_t>(off);
+    return off + static_cast<size_t>(kPipeStages) * p.stage_bytes;
+}
+
+bool decode_pipe_eligible(const DecodeParams& p, const DecodeLaunch& a, int device) {
+    const DecodeLayout& L = p.L;
+    const Tunables& tn = tunables(device);
+    if (!p.word_aligned || p.cpp_shift < 0 || L.W % 4 != 0 || (p.TC % L.cpp) != 0) return false;
+    if (static_cast<uint64_t>(L.H) * L.W >= (1ull << 30)) return false;
+    uint32_t cpr, RB, lo, so;
+    if (!pipe_geometry(L, p.TC, a.lut_dtype, static_cast<uint32_t>(tn.decode_pipe_warps), &cpr, &RB)) return false;
+    if (pipe_smem_bytes(p, static_cast<uint32_t>(tn.decode_pipe_warps), &lo, &so) > 227 * 1024) return false;
+    // XYZ path: 16-byte aligned rows, 32-bit range plans and TMA descriptors for every LUT in use
+    if (p.n_returns > 0) {
+        if (!p.vec_ok || !p.plan_ranges_fast) return false;
+        if (a.lut_dir != nullptr && a.lut_maps == nullptr) return false;
+        if (!a.frame_luts_have_maps) return false;
+    }
+    return true;
+}
+
+cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int device, cudaStream_t st) {
+    const Tunables& tn = tunables(device);
+    PipeParams pp;
+    pp.d = p;
+    pp.d.stages = kPipeStages;
+    pp.lut_maps = a.lut_maps;
+    pp.ncw = static_cast<uint32_t>(tn.decode_pipe_warps);
+    if (!pipe_geometry(p.L, p.TC, a.lut_dtype, pp.ncw, &pp.cpr, &pp.RB)) return cudaErrorInvalidValue;
+    pp.n_sub = (p.L.H + pp.RB - 1) / pp.RB;
+    pp.box_bytes = pp.ncw * 32u * 16u;
+    pp.slot_bytes = 2u * pp.box_bytes;
+    const size_t smem = pipe_smem_bytes(p, pp.ncw, &pp.lut_off, &pp.stage_off);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    const int threads = static_cast<int>(pp.ncw + 2) * 32;
+    const int grid = static_cast<int>(std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count)));
+    auto kern = a.lut_dtype == OB_F64 ? decode_pipe_kernel<double> : decode_pipe_kernel<float>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<std::max(grid, 1), threads, smem, st>>>(pp);
+    count_launch();
+    count_launch_of(OB_FAM_DECODE_PIPE);
+    count_launch_of(OB_FAM_DECODE);
+    return cudaGetLastError();
+}
+
+}  // namespace ob

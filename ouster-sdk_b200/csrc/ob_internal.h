@@ -26,6 +26,8 @@ struct Tunables {
     int decode_tile_packets;  // packets (groups of columns_per_packet columns) per tile
     int decode_runtime_plans; // 1: never use the compile-time pixel layouts (testing / comparison)
     int decode_prefetch;      // L2 prefetch of the next tile: 0 off, 1 at tile start (evict_last), 2 before phase B
+    int decode_pipe;          // 1 (default): pipelined K2 (ob_decode_pipe.cu) whenever the launch is eligible
+    int decode_pipe_warps;    // compute warps of the pipelined K2 (24)
     int force_generic;     // 1: K1 takes the generic GPU kernel (any width / alignment) instead of the TMA one
     int sm_count;
 };
@@ -118,6 +120,7 @@ struct DecodeFrame {  // one per frame of a batched launch, lives in device memo
     uint32_t* rd[OB_MAX_RETURNS];
     const void* lut_dir;  // per-frame LUT (independent sensor streams in one launch); null: launch-level
     const void* lut_off;
+    const void* lut_maps;  // device copy of the LUT's two TMA descriptors (direction, offset) or null
 };
 
 struct DecodeLaunch {
@@ -129,9 +132,27 @@ struct DecodeLaunch {
     int lut_dtype;
     const uint16_t* shift_host;  // nullable (H entries reduced to [0,W))
     bool vec_ok;                 // LUT / XYZ pointers are 16-byte aligned
+    const void* lut_maps{nullptr};  // TMA descriptors of the launch-level LUT (lut_tensor_maps) or null
+    bool all_regular{false};     // every frame: identity column map, bulk-copyable packets, all slots present
+    bool frame_luts_have_maps{true};  // every per-frame LUT of the table carries lut_maps
 };
 cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st);
 
+// ---- pipelined K2 (ob_decode_pipe.cu) ----
+struct DecodeParams;
+// TMA box (in LUT scalars x rows) the pipelined kernel would use for this decoder, false if it cannot run
+bool decode_pipe_box(const DecodeLayout& L, int device, int lut_dtype, uint32_t* box_w, uint32_t* box_h);
+// device pointer to two CUtensorMap (direction, offset) describing `box_w x box_h` tiles of a LUT, created
+// on first use and cached; null when the driver entry point is unavailable or the LUT is not 16-byte aligned
+const void* lut_tensor_maps(const void* dir, const void* off, int dtype, size_t h, size_t w, uint32_t box_w,
+                            uint32_t box_h, int device);
+void forget_lut_tensor_maps(const void* dir);
+bool decode_pipe_eligible(const DecodeParams& p, const DecodeLaunch& a, int device);
+cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int device, cudaStream_t st);
+cudaError_t make_decode_params(const DecodeLaunch& a, int device, bool pipe, DecodeParams& p);
+
 void count_launch(uint64_t n = 1);
+enum { OB_FAM_DECODE_PIPE = 0, OB_FAM_DECODE = 1, OB_FAM_CLOUD = 2, OB_FAM_NORMALS = 3 };
+void count_launch_of(int family, uint64_t n = 1);
 
 }  // namespace ob

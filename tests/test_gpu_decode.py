@@ -103,16 +103,21 @@ PROFILE_CASES = [
 ]
 
 
-@pytest.fixture(params=["static_layouts", "runtime_plans", "narrow_tiles"])
+@pytest.fixture(params=["pipe_static", "pipe_runtime", "static_layouts", "runtime_plans", "narrow_tiles"])
 def plans(ob, request):
-    """K2 has two phase-A code paths: compile-time pixel layouts for the standard profiles and
-    runtime extraction plans for everything else; run the parity cases through both, and through
-    one-packet tiles (16 columns: a warp covers two rows per instruction) with a 2-stage ring."""
-    ob.set_tunable("decode_runtime_plans", int(request.param == "runtime_plans"))
+    """K2 has two kernels (the pipelined one, ob_decode_pipe.cu, and decode_kernel for the shapes it
+    does not take) and two phase-A code paths in each: compile-time pixel layouts for the standard
+    profiles and runtime extraction plans for everything else.  The parity cases run through all of
+    them, and through one-packet tiles (16 columns: a warp covers two rows per instruction, 2-stage
+    ring) of decode_kernel."""
+    pipe = request.param.startswith("pipe_")
+    ob.set_tunable("decode_pipe", int(pipe))
+    ob.set_tunable("decode_runtime_plans", int(request.param in ("runtime_plans", "pipe_runtime")))
     if request.param == "narrow_tiles":
         ob.set_tunable("decode_tile_packets", 1)
         ob.set_tunable("decode_stages", 2)
     yield request.param
+    ob.set_tunable("decode_pipe", 1)
     ob.set_tunable("decode_runtime_plans", 0)
     ob.set_tunable("decode_tile_packets", 0)
     ob.set_tunable("decode_stages", 1)
@@ -280,3 +285,22 @@ def test_multi_stream_batch_with_per_frame_luts(ob):
         for r, nm in enumerate(["RANGE", "RANGE2"]):
             assert np.array_equal(xyz[r][i].cpu().numpy(), orc.cartesian(srcs[i].field(nm), d, o)), (i, nm)
             assert np.array_equal(rd[r][i].cpu().numpy().view(np.uint32), orc.destagger(srcs[i].field(nm), shifts))
+
+
+def test_pipelined_kernel_takes_the_standard_shapes(ob):
+    """The default configuration must run the pipelined K2 (not silently fall back to decode_kernel)
+    for a standard profile with a fused cloud, f32 and f64 LUTs."""
+    pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", 128, 1024, 16, "STANDARD")
+    src = random_frame(pf, seed=11)
+    packets, ts = orc.frame_to_packets(src, pf, init_id=5, prod_sn=1234)
+    shifts = np.random.default_rng(2).integers(-40, 41, 128).astype(np.int32)
+    for dt in (np.float32, np.float64):
+        d, o = random_lut(128 * 1024, 5, dt)
+        lut = ob.XYZLutT.from_arrays(d, o, 128, 1024)
+        n0 = ob.kernel_launch_count("decode_pipe")
+        io = gpu_decode(ob, pf, src, packets, None, lut=lut, shifts=shifts)
+        assert ob.kernel_launch_count("decode_pipe") == n0 + 1
+        check_frame(io, src)
+        for r, nm in enumerate(("RANGE", "RANGE2")):
+            assert np.array_equal(io["xyz"][r], orc.cartesian(src.field(nm), d, o))
+            assert np.array_equal(io["range_destaggered"][r], orc.destagger(src.field(nm), shifts))
