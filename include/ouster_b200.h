@@ -50,7 +50,7 @@ typedef struct ob_decoder ob_decoder; /* device-resident PacketFormat decode tab
 /* ---- library ---- */
 int ob_abi_version(void);
 /* sizeof() of a public struct by name ("ob_cloud_io", "ob_field_desc", "ob_packet_layout",
- * "ob_decode_io", "ob_decode_batch", "ob_dewarp_frame_io"); 0 for unknown names.  Lets FFI bindings verify their layout. */
+ * "ob_decode_io", "ob_decode_batch", "ob_dewarp_frame_io", "ob_normals_io"); 0 for unknown names.  Lets FFI bindings verify their layout. */
 size_t ob_abi_sizeof(const char* struct_name);
 const char* ob_last_error(void);
 /* number of visible CUDA devices (0 without a driver/GPU); never fails */
@@ -100,6 +100,15 @@ ob_status ob_lut_download(const ob_lut* lut, void* direction, void* offset);
 ob_status ob_lut_info(const ob_lut* lut, size_t* h, size_t* w, int* dtype, int* device);
 /* device pointers of the tables (for zero-copy consumers such as torch tensors) */
 ob_status ob_lut_device_ptrs(const ob_lut* lut, void** direction, void** offset);
+/* LUT-free projection (opt-in): a lut made by ob_lut_from_intrinsics from per-beam angles
+ * (n_azimuth == n_altitude == h) can have its direction/offset recomputed inside the kernels from
+ * per-row (cos az cos alt, sin az cos alt, sin alt) and per-column (cos enc, sin enc) tables and the
+ * 3x4 extrinsic -- the factorisation of ouster_core/src/xyzlut.cpp:35-86 -- instead of streaming
+ * 24 B/pixel of LUT.  Results agree with the LUT path to <= 1e-5 norm-wise relative (float
+ * rounding), NOT bit for bit, which is why it is off by default.  Set it before the handle is shared
+ * between threads.  error: "LUT-free projection needs a lut built from per-beam intrinsics". */
+ob_status ob_lut_set_analytic(ob_lut* lut, int enable);
+int ob_lut_is_analytic(const ob_lut* lut);
 ob_status ob_lut_destroy(ob_lut* lut);
 
 /* ---- range -> XYZ ----
@@ -156,6 +165,41 @@ typedef struct ob_dewarp_frame_io {
     size_t capacity;             /* in points; h*w always suffices */
 } ob_dewarp_frame_io;
 ob_status ob_dewarp_frame(const ob_lut* lut, const ob_dewarp_frame_io* io, size_t* n_points, ob_stream* s);
+
+/* ---- surface normals on destaggered XYZ ----
+ * replaces algorithm::normals(xyz, range, sensor_origins_xyz, pixel_search_range, min_angle_of_incidence_rad,
+ *          target_distance_m) and the dual-return overload
+ *                                ouster_algorithm/include/ouster/algorithm/normals.h:58-108
+ *          compute_unit_normals / compute_vertical_subtent   ouster_algorithm/src/normals.cpp:32-407
+ * Inputs are DESTAGGERED images (e.g. ob_cloud_io.xyz_destaggered / range_destaggered, in place on the
+ * device); xyz2/range2/normals2 all set = the dual-return overload (both returns share the vertical
+ * pixel subtent of the first and see each other's points as neighbours).  dtype = scalar type of
+ * xyz* and normals* (the reference is double; float inputs are widened, results rounded once).
+ * n_frames > 1 batches independent frames (strides in ELEMENTS, 0 = dense).
+ * errors (OB_RUNTIME_ERROR, the reference's std::runtime_error texts): "normals: target_distance_m
+ * must be positive", "normals: min_angle_of_incidence_rad must be positive", "normals: sensor_origins
+ * size must match image width", "normals: xyz dimensions mismatch", "normals: range2 dimensions mismatch".
+ */
+typedef struct ob_normals_io {
+    size_t n_frames; /* 0 or 1: a single frame */
+    size_t h, w;
+    const void* xyz;              /* h*w x 3 */
+    const uint32_t* range;        /* h x w */
+    const void* xyz2;             /* optional second return */
+    const uint32_t* range2;
+    void* normals;                /* h*w x 3 */
+    void* normals2;
+    size_t xyz_frame_stride, range_frame_stride, normals_frame_stride;
+    const double* sensor_origins_xyz; /* n_origins x 3 per-column sensor origins, NULL = zeros */
+    size_t n_origins;                 /* must equal w when sensor_origins_xyz is set */
+    size_t origins_frame_stride;      /* in doubles; 0 = the same origins for every frame */
+    size_t pixel_search_range;        /* reference default 1 */
+    double min_angle_of_incidence_rad; /* reference default 1 deg (normals.h:25) */
+    double target_distance_m;          /* reference default 0.025 (normals.h:23) */
+    double vertical_subtent_rad;       /* > 0: use this instead of deriving it from the first return */
+    double* vertical_subtent_out;      /* optional, n_frames doubles: the per-pixel vertical subtent used */
+} ob_normals_io;
+ob_status ob_normals(ob_dtype dtype, const ob_normals_io* io, ob_stream* s);
 
 /* ---- fused range -> (XYZ, destaggered range, destaggered XYZ), batched over frames ----
  * One launch performs, for every frame f and return r of the batch, what the reference does as

@@ -74,7 +74,7 @@ class CFrame(C.Structure):
 
 def build(force=False):
     """Compile the oracle with its Makefile (gcc); no-op when the .so is up to date."""
-    srcs = [os.path.join(_HERE, f) for f in ("ouster_oracle.c", "orc_bench.c", "ouster_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("ouster_oracle.c", "orc_bench.c", "orc_normals.c", "ouster_oracle.h")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
@@ -145,6 +145,10 @@ def lib():
         getattr(L, n).restype = sz
     L.orc_snapshot_hash.argtypes = [vp, sz, sz]
     L.orc_snapshot_hash.restype = u64
+    L.orc_normals_vertical_subtent.argtypes = [vp, vp, vp, sz, sz]
+    L.orc_normals_vertical_subtent.restype = C.c_double
+    L.orc_normals.argtypes = [vp, vp, vp, vp, sz, sz, vp, sz, C.c_double, C.c_double, C.c_double, vp, vp]
+    L.orc_normals.restype = i32
     # orc_bench.c: CPU-baseline harness (bench.py only)
     L.orc_bench_max_threads.restype = i32
     L.orc_bench_k1.argtypes = [i32, i32, vp, sz, sz, sz, sz, vp, vp, vp, i32, i32, C.POINTER(C.c_double)]
@@ -488,3 +492,55 @@ def pool_k1(rng, shifts, direction, offset):
     lib().orc_pool_k1(int(d.dtype == np.float64), _ptr(rng), F, R, h, w, _ptr(sh), _ptr(d), _ptr(o),
                       _ptr(xyz), _ptr(rd))
     return xyz, rd
+
+
+# ------------------------------------------------------------------------------------------------
+# surface normals (orc_normals.c) -- ouster_algorithm/src/normals.cpp
+# ------------------------------------------------------------------------------------------------
+DEFAULT_MIN_ANGLE_INCIDENCE_RAD = 1 * np.pi / 180.0   # normals.h:25
+DEFAULT_TARGET_DISTANCE_METER = 0.025                  # normals.h:23
+
+
+def normals_vertical_subtent(xyz, rng, sensor_origins_xyz):
+    h, w = rng.shape
+    x = np.ascontiguousarray(xyz, np.float64).reshape(h * w, 3)
+    r = np.ascontiguousarray(rng, np.uint32)
+    o = np.ascontiguousarray(sensor_origins_xyz, np.float64)
+    return float(lib().orc_normals_vertical_subtent(_ptr(x), _ptr(r), _ptr(o), h, w))
+
+
+def normals(xyz, rng, xyz2=None, range2=None, sensor_origins_xyz=None, pixel_search_range=1,
+            min_angle_of_incidence_rad=DEFAULT_MIN_ANGLE_INCIDENCE_RAD,
+            target_distance_m=DEFAULT_TARGET_DISTANCE_METER, vertical_subtent=0.0):
+    """normals(xyz, range[, xyz2, range2], sensor_origins_xyz, ...) with the reference's error texts
+    (RuntimeError).  Returns (H, W, 3) or a pair of them."""
+    r = np.ascontiguousarray(rng, np.uint32)
+    if r.ndim != 2:
+        raise RuntimeError("normals: xyz dimensions mismatch")
+    h, w = r.shape
+    x = np.ascontiguousarray(xyz, np.float64)
+    if x.size != h * w * 3:
+        raise RuntimeError("normals: xyz dimensions mismatch")
+    dual = xyz2 is not None
+    x2 = r2 = None
+    if dual:
+        x2 = np.ascontiguousarray(xyz2, np.float64)
+        r2 = np.ascontiguousarray(range2, np.uint32)
+        if x2.size != h * w * 3:
+            raise RuntimeError("normals: xyz dimensions mismatch")
+        if r2.shape != (h, w):
+            raise RuntimeError("normals: range2 dimensions mismatch")
+    o = np.ascontiguousarray(sensor_origins_xyz, np.float64)
+    if o.ndim != 2 or o.shape[0] != w or o.shape[1] != 3:
+        raise RuntimeError("normals: sensor_origins size must match image width")
+    n1 = np.zeros((h, w, 3), np.float64)
+    n2 = np.zeros((h, w, 3), np.float64) if dual else None
+    rc = lib().orc_normals(_ptr(x), _ptr(r), _ptr(x2) if dual else None, _ptr(r2) if dual else None, h, w,
+                           _ptr(o), int(pixel_search_range), float(min_angle_of_incidence_rad),
+                           float(target_distance_m), float(vertical_subtent), _ptr(n1),
+                           _ptr(n2) if dual else None)
+    if rc == -1:
+        raise RuntimeError("normals: target_distance_m must be positive")
+    if rc == -2:
+        raise RuntimeError("normals: min_angle_of_incidence_rad must be positive")
+    return (n1, n2) if dual else n1

@@ -206,6 +206,22 @@ size_t orc_dewarp_frame_f32(float* out, uint32_t* col_idx, uint64_t* ts_out, con
                             const uint32_t* status, const uint64_t* timestamps, size_t h, size_t w,
                             double min_range, double max_range);
 
+/* ---- surface normals on destaggered XYZ -- ouster_algorithm/src/normals.cpp:32-483 (orc_normals.c) ----
+ * xyz: h*w x 3 doubles (destaggered), range: h x w, origins: w x 3 (per-column sensor origin) or NULL.
+ * orc_normals: single return when xyz2/range2 are NULL (normals.cpp:411-430), else both returns with
+ * one shared vertical subtent (:432-483).  subtent_override <= 0: derive it from the first return.
+ * returns 0, -1 "normals: target_distance_m must be positive", -2 "normals: min_angle_of_incidence_rad
+ * must be positive". */
+double orc_normals_vertical_subtent(const double* xyz, const uint32_t* range, const double* origins,
+                                    size_t h, size_t w);
+int orc_normals_compute(const double* xyz, const uint32_t* range, const double* xyz2,
+                        const uint32_t* range2, size_t h, size_t w, const double* origins,
+                        double* normals, size_t search, double min_aoi_rad, double target_m,
+                        double subtent_override);
+int orc_normals(const double* xyz, const uint32_t* range, const double* xyz2, const uint32_t* range2,
+                size_t h, size_t w, const double* origins, size_t search, double min_aoi_rad,
+                double target_m, double subtent_override, double* n1, double* n2);
+
 /* std::hash-combine snapshot of a field, tests/frame_batcher_test.cpp:595-606 */
 uint64_t orc_snapshot_hash(const void* data, size_t n, size_t elem_size);
 

@@ -37,6 +37,15 @@ class DewarpFrameIO(C.Structure):
                 ("points", vp), ("col_idx", vp), ("timestamps_out", vp), ("capacity", sz)]
 
 
+class NormalsIO(C.Structure):
+    _fields_ = [("n_frames", sz), ("h", sz), ("w", sz), ("xyz", vp), ("range", vp), ("xyz2", vp), ("range2", vp),
+                ("normals", vp), ("normals2", vp), ("xyz_frame_stride", sz), ("range_frame_stride", sz),
+                ("normals_frame_stride", sz), ("sensor_origins_xyz", vp), ("n_origins", sz),
+                ("origins_frame_stride", sz), ("pixel_search_range", sz),
+                ("min_angle_of_incidence_rad", C.c_double), ("target_distance_m", C.c_double),
+                ("vertical_subtent_rad", C.c_double), ("vertical_subtent_out", vp)]
+
+
 class FieldDesc(C.Structure):
     _fields_ = [("offset", u32), ("elem_size", u32), ("mask", u64), ("shift", C.c_int32),
                 ("range_return", C.c_int32), ("zero_pattern", u32), ("reserved", u32)]
@@ -99,11 +108,14 @@ _sig("ob_lut_download", i32, vp, vp, vp)
 _sig("ob_lut_info", i32, vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32))
 _sig("ob_lut_device_ptrs", i32, vp, C.POINTER(vp), C.POINTER(vp))
 _sig("ob_lut_destroy", i32, vp)
+_sig("ob_lut_set_analytic", i32, vp, i32)
+_sig("ob_lut_is_analytic", i32, vp)
 _sig("ob_cartesian", i32, vp, vp, sz, vp, vp)
 _sig("ob_destagger", i32, sz, sz, vp, vp, sz, sz, sz, i32, vp, vp)
 _sig("ob_dewarp", i32, i32, vp, vp, sz, sz, vp, vp)
 _sig("ob_scan_to_cloud", i32, vp, vp, sz, C.POINTER(CloudIO), vp)
 _sig("ob_dewarp_frame", i32, vp, C.POINTER(DewarpFrameIO), C.POINTER(sz), vp)
+_sig("ob_normals", i32, i32, C.POINTER(NormalsIO), vp)
 if hasattr(lib, "ob_decoder_create"):
     _sig("ob_decoder_create", i32, C.POINTER(PacketLayout), C.POINTER(FieldDesc), sz, i32,
          C.POINTER(vp))

@@ -208,6 +208,17 @@ class XYZLutT:
     def offset(self):
         return self._download()[1]
 
+    def set_analytic(self, enable=True):
+        """Opt into the LUT-free projection (ob_lut_set_analytic): direction/offset recomputed in the
+        kernels from per-row / per-column tables; <= 1e-5 norm-wise vs the LUT path, not bit-exact.
+        Only LUTs built from per-beam intrinsics have the tables (ValueError otherwise)."""
+        check(lib.ob_lut_set_analytic(self._h, int(bool(enable))))
+        return self
+
+    @property
+    def analytic(self):
+        return bool(lib.ob_lut_is_analytic(self._h))
+
     def __call__(self, rng, out=None, stream=None):
         """lut(range) -> (h*w, 3) points, staggered order (xyzlut.h:139-150)."""
         return cartesian(self, rng, out=out, stream=stream)
@@ -350,6 +361,103 @@ def dewarp_frame(lut, rng, poses, status, timestamps=None, min_range=0.0, max_ra
     if provenance:
         return pts[:n.value], ci[:n.value], ts_out[:n.value]
     return pts[:n.value]
+
+
+DEFAULT_TARGET_DISTANCE_METER = 0.025                    # ouster/algorithm/normals.h:23
+DEFAULT_MIN_ANGLE_INCIDENCE_RAD = 1 * np.pi / 180.0     # ouster/algorithm/normals.h:25
+
+
+def normals(xyz, rng, *args, sensor_origins_xyz=None, pixel_search_range=1,
+            min_angle_of_incidence_rad=DEFAULT_MIN_ANGLE_INCIDENCE_RAD,
+            target_distance_m=DEFAULT_TARGET_DISTANCE_METER, vertical_subtent=0.0, return_subtent=False,
+            stream=None, device=0):
+    """algorithm.normals(xyz, range, sensor_origins_xyz, ...) and the dual-return form
+    normals(xyz, range, xyz2, range2, sensor_origins_xyz, ...) (python binding of
+    ouster_algorithm/include/ouster/algorithm/normals.h:58-108): destaggered (H, W, 3) points and
+    (H, W) ranges in, (H, W, 3) unit normals out (a pair for dual returns).  numpy arrays or torch
+    tensors (CUDA tensors stay on the device); float32 / float64.  RuntimeError texts as the reference."""
+    from ._capi import NormalsIO
+    pos = list(args)
+    xyz2 = range2 = None
+    # dual-return form: the two leading extra positionals are arrays (xyz2, range2); in the single-return
+    # form the second one is the scalar pixel_search_range
+    if len(pos) >= 2 and hasattr(pos[0], "shape") and hasattr(pos[1], "shape") and len(pos[1].shape) == 2:
+        xyz2, range2 = pos[0], pos[1]
+        pos = pos[2:]
+    names = ["sensor_origins_xyz", "pixel_search_range", "min_angle_of_incidence_rad", "target_distance_m"]
+    kw = {"sensor_origins_xyz": sensor_origins_xyz, "pixel_search_range": pixel_search_range,
+          "min_angle_of_incidence_rad": min_angle_of_incidence_rad, "target_distance_m": target_distance_m}
+    for nm, v in zip(names, pos):
+        kw[nm] = v
+    st = _stream(stream, device)
+    if len(rng.shape) != 2:
+        raise RuntimeError("normals: xyz dimensions mismatch")
+    h, w = int(rng.shape[0]), int(rng.shape[1])
+    dt = _np_dtype(xyz)
+    if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+        xyz = np.ascontiguousarray(xyz, np.float64)
+        dt = np.dtype(np.float64)
+    if _numel(xyz) != h * w * 3:
+        raise RuntimeError("normals: xyz dimensions mismatch")
+    dual = xyz2 is not None
+    if dual:
+        if _np_dtype(xyz2) != dt:
+            xyz2 = np.ascontiguousarray(xyz2, dt)
+        if _numel(xyz2) != h * w * 3:
+            raise RuntimeError("normals: xyz dimensions mismatch")
+        if tuple(range2.shape) != (h, w):
+            raise RuntimeError("normals: range2 dimensions mismatch")
+    org = kw["sensor_origins_xyz"]
+    if org is None:
+        raise TypeError("normals(): incompatible function arguments (sensor_origins_xyz is required)")
+    if not _is_torch(org):
+        org = np.ascontiguousarray(org, np.float64)
+    if len(org.shape) != 2 or org.shape[1] != 3:
+        raise TypeError("normals(): incompatible function arguments (sensor_origins_xyz must be (W, 3))")
+    if org.shape[0] != w:
+        raise RuntimeError("normals: sensor_origins size must match image width")
+
+    def prep_rng(a):
+        if _is_torch(a):
+            return a
+        return np.ascontiguousarray(a, np.uint32)
+
+    def prep_xyz(a):
+        return a if _is_torch(a) else np.ascontiguousarray(a)
+
+    xyz, rng = prep_xyz(xyz), prep_rng(rng)
+    on_dev = _is_torch(xyz) and xyz.is_cuda
+
+    def new_out():
+        if _is_torch(xyz):
+            import torch
+            return torch.empty((h, w, 3), dtype=xyz.dtype, device=xyz.device)
+        return np.empty((h, w, 3), dt)
+
+    n1 = new_out()
+    io = NormalsIO()
+    io.n_frames, io.h, io.w = 1, h, w
+    io.xyz, io.range, io.normals = _ptr(xyz), _ptr(rng), _ptr(n1)
+    n2 = None
+    if dual:
+        xyz2, range2 = prep_xyz(xyz2), prep_rng(range2)
+        n2 = new_out()
+        io.xyz2, io.range2, io.normals2 = _ptr(xyz2), _ptr(range2), _ptr(n2)
+    io.sensor_origins_xyz, io.n_origins = _ptr(org), w
+    io.pixel_search_range = int(kw["pixel_search_range"])
+    io.min_angle_of_incidence_rad = float(kw["min_angle_of_incidence_rad"])
+    io.target_distance_m = float(kw["target_distance_m"])
+    io.vertical_subtent_rad = float(vertical_subtent)
+    sub = np.zeros(1, np.float64)
+    io.vertical_subtent_out = sub.ctypes.data
+    status = lib.ob_normals(_capi.OB_F64 if dt == np.float64 else _capi.OB_F32, C.byref(io), st.h)
+    if status == _capi.OB_RUNTIME_ERROR:
+        raise RuntimeError(lib.ob_last_error().decode())
+    check(status)
+    if not on_dev or return_subtent:
+        st.sync()
+    res = (n1, n2) if dual else n1
+    return (res, float(sub[0])) if return_subtent else res
 
 
 def transform(points, pose, out=None, stream=None, device=0):

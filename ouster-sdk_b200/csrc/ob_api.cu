@@ -223,6 +223,11 @@ struct ob_lut {
     size_t h, w;
     void* dir;
     void* off;
+    // LUT-free mode (LUTs built from per-beam intrinsics only): device LutAnalyticT<T> + its tables
+    void* an{nullptr};
+    void* an_row{nullptr};
+    void* an_col{nullptr};
+    bool analytic_on{false};
 };
 
 // used by ob_decode.cu
@@ -236,6 +241,7 @@ void lut_view(const ob_lut* lut, const void** dir, const void** off, int* dtype,
     *w = lut->w;
     *device = lut->device;
 }
+const void* lut_analytic(const ob_lut* lut) { return lut->analytic_on ? lut->an : nullptr; }
 cudaStream_t stream_handle(ob_stream* s) { return s->st; }
 int stream_device(ob_stream* s) { return s->device; }
 }  // namespace ob
@@ -253,6 +259,7 @@ size_t ob_abi_sizeof(const char* name) {
     if (n == "ob_decode_io") return sizeof(ob_decode_io);
     if (n == "ob_decode_batch") return sizeof(ob_decode_batch);
     if (n == "ob_dewarp_frame_io") return sizeof(ob_dewarp_frame_io);
+    if (n == "ob_normals_io") return sizeof(ob_normals_io);
     return 0;
 }
 
@@ -350,6 +357,56 @@ ob_status ob_host_free(void* p) {
 // ---------------------------------------------------------------------------------------------
 static size_t dtype_size(int dtype) { return dtype == OB_F64 ? 8 : 4; }
 
+}  // extern "C"
+
+// Per-row / per-column tables of the LUT-free projection, from the same intrinsics and in the same
+// double arithmetic as make_xyz_lut (ouster_core/src/xyzlut.cpp:24-86), then cast to the LUT's scalar.
+template <typename T>
+static cudaError_t build_analytic(ob_lut* l, double range_unit, const double* b2l, const double* tr,
+                                  const double* az_deg, const double* alt_deg) {
+    const size_t h = l->h, w = l->w;
+    std::vector<T> row(h * 4), col(w * 2);
+    const double b03 = b2l[3], b23 = b2l[11];
+    double dist = b03;
+    if (b23 != 0) dist = std::sqrt(b03 * b03 + b23 * b23);
+    for (size_t r = 0; r < h; ++r) {
+        const double az = -az_deg[r] * M_PI / 180.0, alt = alt_deg[r] * M_PI / 180.0;
+        row[4 * r + 0] = static_cast<T>(std::cos(az) * std::cos(alt));
+        row[4 * r + 1] = static_cast<T>(std::sin(az) * std::cos(alt));
+        row[4 * r + 2] = static_cast<T>(std::sin(alt));
+        row[4 * r + 3] = 0;
+    }
+    const double azimuth_radians = M_PI * 2.0 / static_cast<double>(w);
+    for (size_t c = 0; c < w; ++c) {
+        const double enc = 2.0 * M_PI - static_cast<double>(c) * azimuth_radians;
+        col[2 * c + 0] = static_cast<T>(std::cos(enc));
+        col[2 * c + 1] = static_cast<T>(std::sin(enc));
+    }
+    LutAnalyticT<T> a;
+    a.dist = static_cast<T>(dist);
+    a.b03 = static_cast<T>(b03);
+    a.b23 = static_cast<T>(b23);
+    for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 4; ++k) a.m[4 * j + k] = static_cast<T>(tr[4 * j + k] * range_unit);
+    cudaError_t e = cudaMalloc(&l->an_row, row.size() * sizeof(T));
+    if (e == cudaSuccess) e = cudaMalloc(&l->an_col, col.size() * sizeof(T));
+    if (e == cudaSuccess) e = cudaMalloc(&l->an, sizeof(a));
+    if (e == cudaSuccess) e = cudaMemcpy(l->an_row, row.data(), row.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(l->an_col, col.data(), col.size() * sizeof(T), cudaMemcpyHostToDevice);
+    a.row = static_cast<const T*>(l->an_row);
+    a.col = static_cast<const T*>(l->an_col);
+    if (e == cudaSuccess) e = cudaMemcpy(l->an, &a, sizeof(a), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(l->an);
+        cudaFree(l->an_row);
+        cudaFree(l->an_col);
+        l->an = l->an_row = l->an_col = nullptr;
+    }
+    return e;
+}
+
+extern "C" {
+
 ob_status ob_lut_create(ob_dtype dtype, const void* direction, const void* offset, size_t h,
                         size_t w, int device, ob_lut** out) {
     if (!out || !direction || !offset) return fail(OB_INVALID_ARGUMENT, "null pointer");
@@ -430,9 +487,25 @@ ob_status ob_lut_from_intrinsics(ob_dtype dtype, size_t w, size_t h, double rang
         cudaFree(doff);
         return fail_cuda(e, "ob_lut_from_intrinsics");
     }
-    *out = new ob_lut{device, static_cast<int>(dtype), h, w, rd, ro};
+    ob_lut* l = new ob_lut{device, static_cast<int>(dtype), h, w, rd, ro};
+    if (n_az == h && n_alt == h) {  // per-beam angles: the LUT-free tables exist (off until ob_lut_set_analytic)
+        cudaError_t ea = dtype == OB_F64 ? build_analytic<double>(l, range_unit, b2l, transform, az, alt)
+                                         : build_analytic<float>(l, range_unit, b2l, transform, az, alt);
+        if (ea != cudaSuccess) cudaGetLastError();  // optional feature: the LUT itself is complete
+    }
+    *out = l;
     return OB_OK;
 }
+
+ob_status ob_lut_set_analytic(ob_lut* lut, int enable) {
+    if (!lut) return fail(OB_INVALID_ARGUMENT, "null lut");
+    if (enable && !lut->an)
+        return fail(OB_INVALID_ARGUMENT, "LUT-free projection needs a lut built from per-beam intrinsics");
+    lut->analytic_on = enable != 0;
+    return OB_OK;
+}
+
+int ob_lut_is_analytic(const ob_lut* lut) { return lut && lut->analytic_on ? 1 : 0; }
 
 ob_status ob_lut_download(const ob_lut* lut, void* direction, void* offset) {
     if (!lut || !direction || !offset) return fail(OB_INVALID_ARGUMENT, "null pointer");
@@ -466,6 +539,9 @@ ob_status ob_lut_destroy(ob_lut* lut) {
     forget_lut_tensor_maps(lut->dir);
     cudaFree(lut->dir);
     cudaFree(lut->off);
+    cudaFree(lut->an);
+    cudaFree(lut->an_row);
+    cudaFree(lut->an_col);
     delete lut;
     return OB_OK;
 }
@@ -489,6 +565,7 @@ static ob_status scan_to_cloud_t(const ob_lut* lut, const uint16_t* shift, const
     CloudArgs<T> a;
     a.dir = static_cast<const T*>(lut->dir);
     a.off = static_cast<const T*>(lut->off);
+    a.analytic = lut->analytic_on ? static_cast<const LutAnalyticT<T>*>(lut->an) : nullptr;
     a.range_fs = io->range_frame_stride;
     a.range_rs = io->range_return_stride;
     a.xyz_fs = io->xyz_frame_stride;

@@ -39,6 +39,7 @@ class Staging {
 // accessors for the opaque handles (defined in ob_api.cu)
 void lut_view(const ob_lut* lut, const void** dir, const void** off, int* dtype, size_t* h,
               size_t* w, int* device);
+const void* lut_analytic(const ob_lut* lut);  // device LutAnalyticT<T> when the LUT-free mode is on, else null
 cudaStream_t stream_handle(ob_stream* s);
 int stream_device(ob_stream* s);
 

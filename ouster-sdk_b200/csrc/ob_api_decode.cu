@@ -196,7 +196,8 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
             f.lut_dir = fd;
             f.lut_off = fo;
             f.lut_maps = maps_for(L, device, fd, fo, fdt);
-            if (!f.lut_maps) frame_maps_ok = false;
+            f.lut_an = lut_analytic(io.lut);
+            if (!f.lut_maps && !f.lut_an) frame_maps_ok = false;
             if (!al16(fd) || !al16(fo)) vec_ok = false;
         }
         for (int r = 0; r < OB_MAX_RETURNS; ++r) {
@@ -231,6 +232,7 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
     a.shift_host = shifts ? sh.data() : nullptr;
     a.vec_ok = vec_ok;
     a.lut_maps = maps_for(L, device, ldir, loff, ldtype);
+    a.lut_an = lut ? lut_analytic(lut) : nullptr;
     a.frame_luts_have_maps = frame_maps_ok;
     e = launch_decode(a, device, st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
@@ -345,7 +347,8 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
             d.lut_dir = fl_dir[f];
             d.lut_off = fl_off[f];
             d.lut_maps = maps_for(L, device, fl_dir[f], fl_off[f], ldtype);
-            if (!d.lut_maps) frame_maps_ok = false;
+            d.lut_an = lut_analytic(b->frame_luts[f]);
+            if (!d.lut_maps && !d.lut_an) frame_maps_ok = false;
         }
         for (int r = 0; r < OB_MAX_RETURNS; ++r) {
             if (dxyz[r]) d.xyz[r] = static_cast<uint8_t*>(dxyz[r]) + f * b->xyz_frame_stride;
@@ -368,6 +371,7 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
     a.shift_host = shifts ? sh.data() : nullptr;
     a.vec_ok = vec_ok;
     a.lut_maps = maps_for(L, device, ldir, loff, ldtype);
+    a.lut_an = lut ? lut_analytic(lut) : nullptr;
     a.frame_luts_have_maps = frame_maps_ok;
     e = launch_decode(a, device, st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
@@ -645,6 +649,7 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
     a.shift_host = shifts ? sh.data() : nullptr;
     a.vec_ok = vec_ok;
     a.lut_maps = maps_for(L, j->device, ldir, loff, ldtype);
+    a.lut_an = use_lut ? lut_analytic(use_lut) : nullptr;
     e = launch_decode(a, j->device, j->st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     for (size_t k = 0; k < n_host;) {  // one D2H per run of outputs contiguous on both sides

@@ -43,6 +43,7 @@ struct CloudParams {
     unsigned long long range_fs, range_rs, xyz_fs, xyz_rs, rd_fs, rd_rs, xd_fs, xd_rs;
     const T* poses;            // optional: n_frames x W x 16 (row-major 4x4 per column), dewarp fused
     unsigned long long poses_fs;
+    const LutAnalyticT<T>* an; // LUT-free mode: per-row / per-column tables instead of dir/off (else null)
     int H, W, TW, tiles_per_row, stages;
     int RT, row_blocks;        // rows per work item (1, or kPoseRows with poses) and ceil(H / RT)
     int store_lag;             // tiles between a stage's bulk stores and its refill (0 or 1)
@@ -153,7 +154,12 @@ __device__ __forceinline__ double pose_row(const double* m, double x, double y, 
 // in items of RPI consecutive rows of one column range; a CTA streams the rows of an item through
 // the ring while the item's pose slice (16 scalars per column, one bulk copy) is re-laid out once
 // into 12 planes [element][column], so poses cost one L2 read per RPI rows.
-template <typename T, int R, bool POSE>
+//
+// ANALYTIC: the LUT-free variant: nothing of the LUT is loaded; every thread rebuilds the
+// beam direction of its 4 pixels from the row's (cos az cos alt, sin az cos alt, sin alt) and the
+// columns' (cos enc, sin enc) -- L1-resident tables of a few KB -- and applies the 3x4 extrinsic.
+// Results agree with the LUT path to float rounding (<= 1e-5 norm-wise), not bit for bit.
+template <typename T, int R, bool POSE, bool ANALYTIC = false>
 __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ CloudParams<T> p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // [kMaxStagesK1] loads landed
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
     const int ctid = tid - 32;                          // index among them (< 0: copy warp)
     const int S = p.stages;
     const bool need_lut = (p.xyz != nullptr) || (p.xd != nullptr);
+    const bool load_lut = need_lut && !ANALYTIC;
     const unsigned lut_bytes_full = 3u * p.TW * sizeof(T);
     const unsigned RPI = POSE ? static_cast<unsigned>(p.RT) : 1u;
 
@@ -219,8 +226,8 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
             const size_t px = static_cast<size_t>(tc.row) * p.W + tc.c0;
             const unsigned lut_b = 3u * tc.tw * sizeof(T);
             const unsigned rng_b = 4u * tc.tw;
-            mbar_expect_tx(&full[s], (need_lut ? 2u * lut_b : 0u) + R * rng_b);
-            if (need_lut) {
+            mbar_expect_tx(&full[s], (load_lut ? 2u * lut_b : 0u) + R * rng_b);
+            if (load_lut) {
                 bulk_g2s_hint(st, p.dir + px * 3, lut_b, &full[s], pol_keep);
                 bulk_g2s_hint(st + lut_bytes_full, p.off + px * 3, lut_b, &full[s], pol_keep);
             }
@@ -372,8 +379,59 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
             }
         }
 
+        // ---- LUT-free projection into the (otherwise unused) direction / offset slices ----
+        if (ANALYTIC && need_lut && !POSE) {
+            using V = typename Vec<T>::type;
+            const LutAnalyticT<T>& an = *p.an;
+            const T* rowt = an.row + 4 * static_cast<size_t>(tc.row);
+            const T A = __ldg(rowt), B = __ldg(rowt + 1), sa = __ldg(rowt + 2);
+            const T dist = an.dist, b03 = an.b03, b23 = an.b23;
+            T m[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) m[i] = an.m[i];
+            for (int g = ctid; g < n_groups; g += nct) {
+                T cs[8];  // (cos enc, sin enc) of the 4 columns
+                const V* cp = reinterpret_cast<const V*>(an.col + 2 * static_cast<size_t>(tc.c0 + 4 * g));
+#pragma unroll
+                for (int i = 0; i < 8 / Vec<T>::N; ++i) {
+                    const V x = __ldg(cp + i);
+                    const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+                    for (int j = 0; j < Vec<T>::N; ++j) cs[i * Vec<T>::N + j] = e[j];
+                }
+                uint4 rv4[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) rv4[r] = reinterpret_cast<const uint4*>(rng_s + r * p.TW)[g];
+                T d0[4], d1[4], q0[4], q1[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const T ce = cs[2 * i], se = cs[2 * i + 1];
+                    d0[i] = fma(ce, A, -se * B);
+                    d1[i] = fma(se, A, ce * B);
+                    q0[i] = ce * b03;
+                    q1[i] = se * b03;
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t rv[4] = {rv4[r].x, rv4[r].y, rv4[r].z, rv4[r].w};
+                    T out[12];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const T t = static_cast<T>(rv[i]) - dist;
+                        const T p0 = fma(d0[i], t, q0[i]), p1 = fma(d1[i], t, q1[i]), p2 = fma(sa, t, b23);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const T v = fma(m[4 * j], p0, fma(m[4 * j + 1], p1, fma(m[4 * j + 2], p2, m[4 * j + 3])));
+                            out[3 * i + j] = rv[i] == 0 ? static_cast<T>(0) : v;
+                        }
+                    }
+                    sts12((r == 0 ? dir_s : off_s) + 12 * g, out);
+                }
+            }
+        }
+
         // ---- projection (and pose), in place ----
-        if (need_lut && !POSE) {
+        if (!ANALYTIC && need_lut && !POSE) {
             for (int g = ctid; g < n_groups; g += nct) {
                 T d[12], o[12];
                 lds12(dir_s + 12 * g, d);
@@ -523,7 +581,8 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     const size_t t4 = 16 / sizeof(T);  // T elements per 16 bytes
     bool fast = !tn.force_generic && (a.W % 4 == 0) && a.H <= kMaxRows && aligned16(a.range) &&
                 a.range_fs % 4 == 0 && a.range_rs % 4 == 0;
-    if (need_lut) fast = fast && aligned16(a.dir) && aligned16(a.off);
+    const bool analytic = a.analytic != nullptr && need_lut && a.poses == nullptr;
+    if (need_lut && !analytic) fast = fast && aligned16(a.dir) && aligned16(a.off);
     if (a.xyz) fast = fast && aligned16(a.xyz) && a.xyz_fs % t4 == 0 && a.xyz_rs % t4 == 0;
     if (a.rd) fast = fast && aligned16(a.rd) && a.rd_fs % 4 == 0 && a.rd_rs % 4 == 0;
     if (a.xd) fast = fast && aligned16(a.xd) && a.xd_fs % t4 == 0 && a.xd_rs % t4 == 0;
@@ -533,6 +592,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     if (a.poses) fast = fast && aligned16(a.poses) && a.poses_fs % t4 == 0;
     p.poses = a.poses;
     p.poses_fs = a.poses_fs;
+    p.an = a.analytic;
     p.store_lag = 0;
     p.RT = 1;
     p.row_blocks = a.H;
@@ -583,6 +643,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
         static_cast<int>(std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * ctas));
     void (*kern)(CloudParams<T>);
     if (pose) kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2, true> : cloud_tma_kernel<T, 1, true>;
+    else if (analytic) kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2, false, true> : cloud_tma_kernel<T, 1, false, true>;
     else kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2, false> : cloud_tma_kernel<T, 1, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;

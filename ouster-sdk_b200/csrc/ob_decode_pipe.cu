@@ -34,6 +34,7 @@ constexpr int kPipeLutSlots = 3;  // LUT ring depth
 struct PipeParams {
     DecodeParams d;
     const void* lut_maps;  // launch-level LUT descriptors (2 x CUtensorMap) or null
+    const void* lut_an;    // launch-level LUT in LUT-free mode: device LutAnalyticT<T> (else null)
     uint32_t ncw;          // compute warps
     uint32_t cpr;          // 16-byte chunks per row segment of a tile (3 * TC * sizeof(T) / 16)
     uint32_t RB;           // rows per LUT sub-tile (= ncw * 32 / cpr)
@@ -104,11 +105,18 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
         return static_cast<int>(g * p.pkt_stride_s + L.packet_header_size + (t - (g << p.cpp_shift)) * L.col_size +
                                 L.col_header_size);
     };
-    // does tile (frame) take the XYZ path?  evaluated identically by the LUT producer and the compute warps
+    // does tile (frame) take the XYZ path through the LUT ring?  evaluated identically by the LUT producer
+    // and the compute warps (frames whose LUT is in LUT-free mode do not use the ring)
     auto wants_xyz = [&](const DecodeFrame& fr) -> const void* {
         const void* maps = fr.lut_dir != nullptr ? fr.lut_maps : pp.lut_maps;
-        if (n_ret == 0 || (fr.xyz[0] == nullptr && fr.xyz[1] == nullptr)) return nullptr;
+        const void* an = fr.lut_dir != nullptr ? fr.lut_an : pp.lut_an;
+        if (n_ret == 0 || an != nullptr || (fr.xyz[0] == nullptr && fr.xyz[1] == nullptr)) return nullptr;
         return maps;
+    };
+    auto wants_analytic = [&](const DecodeFrame& fr) -> const LutAnalyticT<T>* {
+        const void* an = fr.lut_dir != nullptr ? fr.lut_an : pp.lut_an;
+        if (n_ret == 0 || (fr.xyz[0] == nullptr && fr.xyz[1] == nullptr)) return nullptr;
+        return static_cast<const LutAnalyticT<T>*>(an);
     };
 
     if (warp == NCW) {
@@ -399,6 +407,62 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
                 if (lane == 0) mbar_arrive(&lut_done[slot]);
             }
         }
+        // ---- phase B, LUT-free: direction/offset rebuilt from the per-row / per-column tables ----
+        if (const LutAnalyticT<T>* anp = wants_analytic(fr)) {
+            const LutAnalyticT<T>& an = *anp;
+            const int co0 = regular ? col_offset(p0) : c.col_off[p0];
+            const int co1 = regular ? col_offset(p1) : c.col_off[p1];
+            const bool v0 = co0 >= 0, v1 = co1 >= 0;
+            const uint8_t* pa = st + (v0 ? co0 : 0);
+            const uint8_t* pb = st + (v1 ? co1 : 0);
+            T* xo0 = static_cast<T*>(fr.xyz[0]);
+            T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
+            if (xo0 != nullptr) __builtin_assume(__isGlobal(xo0));
+            if (xo1 != nullptr) __builtin_assume(__isGlobal(xo1));
+            const size_t ecol = static_cast<size_t>(j0) * 3 + static_cast<size_t>(q) * VN;
+            const T cea = __ldg(an.col + 2 * (j0 + p0)), sea = __ldg(an.col + 2 * (j0 + p0) + 1);
+            const T ceb = __ldg(an.col + 2 * (j0 + p1)), seb = __ldg(an.col + 2 * (j0 + p1) + 1);
+            const T dist = an.dist, b23 = an.b23;
+            const T qa0 = cea * an.b03, qa1 = sea * an.b03, qb0 = ceb * an.b03, qb1 = seb * an.b03;
+            // extrinsic row of every element of the chunk (component (k0 + e) % 3)
+            T mr[VN][4];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const unsigned comp = (k0 + e) % 3u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    mr[e][i] = comp == 0 ? an.m[i] : (comp == 1 ? an.m[4 + i] : an.m[8 + i]);
+            }
+            for (unsigned row = rsub; row < L.H; row += pp.RB) {
+                const T* rowt = an.row + 4 * static_cast<size_t>(row);
+                const T A = __ldg(rowt), B = __ldg(rowt + 1), sa = __ldg(rowt + 2);
+                const T da0 = fma(cea, A, -sea * B), da1 = fma(sea, A, cea * B);
+                const T db0 = fma(ceb, A, -seb * B), db1 = fma(seb, A, ceb * B);
+                const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa + static_cast<size_t>(row) * cds);
+                const uint32_t* wb = reinterpret_cast<const uint32_t*>(pb + static_cast<size_t>(row) * cds);
+                const size_t eidx = static_cast<size_t>(row) * L.W * 3 + ecol;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    T* xo = r == 0 ? xo0 : xo1;
+                    if (xo == nullptr) continue;
+                    const DecodeParams::Plan& pl = r == 0 ? pl0 : pl1;
+                    const uint32_t ra = rng(wa, pl, v0, simple), rb = rng(wb, pl, v1, simple);
+                    const T ta = static_cast<T>(ra) - dist, tb = static_cast<T>(rb) - dist;
+                    const T pa0 = fma(da0, ta, qa0), pa1 = fma(da1, ta, qa1), pa2 = fma(sa, ta, b23);
+                    const T pb0 = fma(db0, tb, qb0), pb1 = fma(db1, tb, qb1), pb2 = fma(sa, tb, b23);
+                    V outv;
+                    T* o2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) {
+                        const bool fa = first_px[e];
+                        const T x0 = fa ? pa0 : pb0, x1 = fa ? pa1 : pb1, x2 = fa ? pa2 : pb2;
+                        const T v = fma(mr[e][0], x0, fma(mr[e][1], x1, fma(mr[e][2], x2, mr[e][3])));
+                        o2[e] = (fa ? ra : rb) == 0 ? static_cast<T>(0) : v;
+                    }
+                    *reinterpret_cast<V*>(xo + eidx) = outv;
+                }
+            }
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&pk_done[s]);  // this warp is done with the stage
     }
@@ -552,7 +616,7 @@ bool decode_pipe_eligible(const DecodeParams& p, const DecodeLaunch& a, int devi
     // XYZ path: 16-byte aligned rows, 32-bit range plans and TMA descriptors for every LUT in use
     if (p.n_returns > 0) {
         if (!p.vec_ok || !p.plan_ranges_fast) return false;
-        if (a.lut_dir != nullptr && a.lut_maps == nullptr) return false;
+        if (a.lut_dir != nullptr && a.lut_maps == nullptr && a.lut_an == nullptr) return false;
         if (!a.frame_luts_have_maps) return false;
     }
     return true;
@@ -564,6 +628,7 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
     pp.d = p;
     pp.d.stages = kPipeStages;
     pp.lut_maps = a.lut_maps;
+    pp.lut_an = a.lut_an;
     pp.ncw = static_cast<uint32_t>(tn.decode_pipe_warps);
     if (!pipe_geometry(p.L, p.TC, a.lut_dtype, pp.ncw, &pp.cpr, &pp.RB)) return cudaErrorInvalidValue;
     pp.n_sub = (p.L.H + pp.RB - 1) / pp.RB;

@@ -34,6 +34,18 @@ struct Tunables {
 const Tunables& tunables(int device);
 bool set_tunable(int device, const char* name, int value);
 
+// LUT-free ("analytic") projection of a LUT built from per-beam intrinsics (ouster_core/src/xyzlut.cpp:35-86
+// refactored): direction = R * (cos(enc+az)cos(alt), sin(enc+az)cos(alt), sin(alt)), offset from the same
+// angles, so XYZ = M * ((r - dist) * d_beam + (cos(enc) b03, sin(enc) b03, b23)) with M = [R|t] * range_unit.
+// Per-row and per-column tables replace the 24 B/pixel LUT stream.  Lives in device memory.
+template <typename T>
+struct LutAnalyticT {
+    const T* row;  // H x 4: cos(az)cos(alt), sin(az)cos(alt), sin(alt), 0
+    const T* col;  // W x 2: cos(enc), sin(enc)
+    T dist, b03, b23;
+    T m[12];       // row-major 3x4, already scaled by range_unit
+};
+
 // ---- launchers implemented in the .cu files; all return cudaError_t ----
 template <typename T>
 struct CloudArgs {
@@ -49,6 +61,7 @@ struct CloudArgs {
     const uint16_t* shift;  // H entries, already reduced to [0, W) (host memory); may be null if no rd/xd
     const T* poses{nullptr};  // optional per-column poses: n_frames x W x 16 (device), fused dewarp
     size_t poses_fs{0};
+    const LutAnalyticT<T>* analytic{nullptr};  // device; non-null: recompute direction/offset, dir/off unused
 };
 
 template <typename T>
@@ -121,6 +134,7 @@ struct DecodeFrame {  // one per frame of a batched launch, lives in device memo
     const void* lut_dir;  // per-frame LUT (independent sensor streams in one launch); null: launch-level
     const void* lut_off;
     const void* lut_maps;  // device copy of the LUT's two TMA descriptors (direction, offset) or null
+    const void* lut_an;    // device LutAnalyticT<T> of the frame's LUT when its LUT-free mode is on, else null
 };
 
 struct DecodeLaunch {
@@ -133,6 +147,7 @@ struct DecodeLaunch {
     const uint16_t* shift_host;  // nullable (H entries reduced to [0,W))
     bool vec_ok;                 // LUT / XYZ pointers are 16-byte aligned
     const void* lut_maps{nullptr};  // TMA descriptors of the launch-level LUT (lut_tensor_maps) or null
+    const void* lut_an{nullptr};    // launch-level LUT in LUT-free mode: device LutAnalyticT<T>
     bool all_regular{false};     // every frame: identity column map, bulk-copyable packets, all slots present
     bool frame_luts_have_maps{true};  // every per-frame LUT of the table carries lut_maps
 };

@@ -175,3 +175,53 @@ def test_lut_from_intrinsics_matches_oracle_and_reference_py(ob):
         xyzf = lutf(rng).reshape(h, w, 3)
         err = np.linalg.norm(xyzf - ref_xyz, axis=-1)
         assert np.all(err <= 1e-5 * np.linalg.norm(ref_xyz, axis=-1) + 1e-7)  # north_star tolerance
+
+
+def _normwise_ok(got, ref, tol=1e-5):
+    err = np.linalg.norm(got.astype(np.float64) - ref.astype(np.float64), axis=-1)
+    return bool(np.all(err <= tol * np.linalg.norm(ref.astype(np.float64), axis=-1) + 1e-7))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lut_free_projection_within_tolerance_of_lut_path(ob, dtype):
+    """SURVEY 8d's LUT-free variant (opt-in): direction/offset rebuilt in the kernel from per-row and
+    per-column tables (factorisation of xyzlut.cpp:35-86).  north_star tolerance: 1e-5 norm-wise
+    relative vs the oracle's LUT path of the same dtype; empty returns stay exactly +0.0; the
+    destaggered range is untouched (bit-exact)."""
+    meta, _ = load_fixture("OS-1-128_767798045_1024x10_20230712_120049")
+    h, w = meta["h"], meta["w"]
+    args = (w, h, 0.001, meta["beam_to_lidar_transform"], meta["lidar_to_sensor_transform"],
+            meta["beam_azimuth_angles"], meta["beam_altitude_angles"])
+    d, o = orc.make_xyz_lut(*args)
+    d, o = d.astype(dtype), o.astype(dtype)
+    lut = ob.XYZLutT.from_intrinsics(*args, dtype=dtype)
+    assert not lut.analytic
+    lut.set_analytic(True)
+    assert lut.analytic
+    F = 3
+    rng = np.stack([np.stack([random_range(h, w, 5 + 2 * f), random_range(h, w, 6 + 2 * f, 0.8)]) for f in range(F)])
+    rng[0, 0, :, :8] = (1 << 19) - 1          # longest 19-bit range
+    shifts = np.asarray(meta["pixel_shift_by_row"], np.int32)
+    xyz = np.empty((F, 2, h * w, 3), dtype)
+    rd = np.empty((F, 2, h, w), np.uint32)
+    st = ob.Stream(0)
+    ob.scan_to_cloud(lut, shifts, rng, xyz=xyz, range_destaggered=rd, stream=st)
+    st.sync()
+    for f in range(F):
+        for r in range(2):
+            ref = orc.cartesian(rng[f, r], d, o)
+            assert _normwise_ok(xyz[f, r], ref)
+            assert np.all(xyz[f, r][rng[f, r].reshape(-1) == 0] == 0.0)
+            assert np.array_equal(rd[f, r], orc.destagger(rng[f, r], shifts))
+    # single-frame entry point takes the same path
+    assert _normwise_ok(lut(rng[1, 0]), orc.cartesian(rng[1, 0], d, o))
+    # back to the bit-exact LUT path
+    lut.set_analytic(False)
+    assert np.array_equal(lut(rng[1, 0]), orc.cartesian(rng[1, 0], lut.direction, lut.offset))
+
+
+def test_lut_free_projection_needs_intrinsics(ob):
+    d, o = random_lut(32 * 512, 3)
+    lut = ob.XYZLutT.from_arrays(d, o, 32, 512)
+    with pytest.raises(ValueError, match="LUT-free projection needs a lut built from per-beam intrinsics"):
+        lut.set_analytic(True)

@@ -304,3 +304,29 @@ def test_pipelined_kernel_takes_the_standard_shapes(ob):
         for r, nm in enumerate(("RANGE", "RANGE2")):
             assert np.array_equal(io["xyz"][r], orc.cartesian(src.field(nm), d, o))
             assert np.array_equal(io["range_destaggered"][r], orc.destagger(src.field(nm), shifts))
+
+
+def test_lut_free_projection_in_fused_decode(ob):
+    """K2 with a LUT in LUT-free mode: fields and destaggered ranges bit-exact, XYZ within the
+    north_star tolerance (1e-5 norm-wise) of the oracle's float LUT path."""
+    from tests.helpers import default_os1_64
+    si = default_os1_64(1024)
+    h, w = si["h"], si["w"]
+    args = (w, h, 0.001, si["beam_to_lidar_transform"], si["lidar_to_sensor_transform"],
+            si["beam_azimuth_angles"], si["beam_altitude_angles"])
+    d, o = orc.make_xyz_lut(*args)
+    d, o = d.astype(np.float32), o.astype(np.float32)
+    lut = ob.XYZLutT.from_intrinsics(*args, dtype=np.float32).set_analytic(True)
+    pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", h, w, 16, "STANDARD")
+    src = random_frame(pf, seed=21)
+    packets, ts = orc.frame_to_packets(src, pf, init_id=5, prod_sn=1234)
+    n0 = ob.kernel_launch_count("decode_pipe")
+    io = gpu_decode(ob, pf, src, packets, None, lut=lut, shifts=si["pixel_shift_by_row"])
+    assert ob.kernel_launch_count("decode_pipe") == n0 + 1
+    check_frame(io, src)
+    for r, nm in enumerate(("RANGE", "RANGE2")):
+        ref = orc.cartesian(src.field(nm), d, o)
+        err = np.linalg.norm(io["xyz"][r].astype(np.float64) - ref, axis=-1)
+        assert np.all(err <= 1e-5 * np.linalg.norm(ref.astype(np.float64), axis=-1) + 1e-7)
+        assert np.all(io["xyz"][r][src.field(nm).reshape(-1) == 0] == 0.0)
+        assert np.array_equal(io["range_destaggered"][r], orc.destagger(src.field(nm), si["pixel_shift_by_row"]))
