@@ -71,7 +71,8 @@ def run_sweep(args, ob, torch, dist, rank, local_rank, world):
                 sample = np.concatenate([pool] * ((cores + len(pool) - 1) // len(pool)))[:max(cores, nf)]
                 orc.bench_k1("thread_per_stream", sample, shifts, d, o, reps=1)
                 reps = 2
-                t = min(orc.bench_k1("thread_per_stream", sample, shifts, d, o, reps=reps) / reps for _ in range(2))
+                t = min(orc.bench_k1("thread_per_stream", sample, shifts, d, o, threads=tn, reps=reps) / reps
+                        for tn in (cores, max(1, cores // 2)))
                 e["cpu_mpoints_s"] = sample.shape[0] * ppf / t / 1e6
             out.append(e)
             del t_rng, t_xyz, t_rd
@@ -93,10 +94,10 @@ def run_sweep(args, ob, torch, dist, rank, local_rank, world):
             if dist is not None:
                 dist.barrier()
             lp0 = ob.kernel_launch_count("decode_pipe")
-            s = _time(torch, stream,
-                      lambda: dec.decode_batch(F2, t_pk, n_slots, psz, n_slots * psz, fields, lut=lut,
-                                               pixel_shift_by_row=shifts, xyz=xyz, range_destaggered=rd, timestamp=t_ts,
-                                               measurement_id=t_mid, status=t_st, stream=obs), steps, warmup)
+            plan = dec.prepare_batch(F2, t_pk, n_slots, psz, n_slots * psz, fields, lut=lut,
+                                     pixel_shift_by_row=shifts, xyz=xyz, range_destaggered=rd, timestamp=t_ts,
+                                     measurement_id=t_mid, status=t_st, stream=obs)
+            s = _time(torch, stream, plan, steps, warmup)
             piped = ob.kernel_launch_count("decode_pipe") > lp0
             s = bc.max_over_ranks(torch, dist, dev, s)
             # round trip of frame 0 and the last frame (encode -> decode == source)
@@ -116,7 +117,8 @@ def run_sweep(args, ob, torch, dist, rank, local_rank, world):
                 nfr = max(8, min(cores, 128))
                 sample = np.stack([pk[i % 2] for i in range(nfr)])
                 orc.bench_k2("thread_per_stream", opf, sample, shifts, d, o, reps=1)
-                t = min(orc.bench_k2("thread_per_stream", opf, sample, shifts, d, o, reps=1) for _ in range(2))
+                t = min(orc.bench_k2("thread_per_stream", opf, sample, shifts, d, o, threads=tn, reps=1)
+                        for tn in (cores, max(1, cores // 2)))
                 e["cpu_mpoints_s"] = nfr * ppf / t / 1e6
             out.append(e)
             del t_pk, fields, xyz, rd, dec

@@ -34,6 +34,12 @@ OUSTER_API_FUNCTION std::vector<Packet> frame_to_packets(const LidarFrame& frame
 template <typename OutputItT>
 void frame_to_packets(const LidarFrame& frame, std::shared_ptr<PacketFormat> pf, OutputItT iter,
                       uint32_t init_id, uint64_t prod_sn);
+/// The same packets produced on the GPU (K4, ob_encode_frames): the host only writes the packet-level
+/// headers with the PacketFormat setters; column headers, set_block of every field and the CRC64 run
+/// in one launch.  Byte-identical to frame_to_packets().
+OUSTER_API_FUNCTION std::vector<Packet> frame_to_packets_device(const LidarFrame& frame,
+                                                                const PacketFormat& pf, uint32_t init_id,
+                                                                uint64_t prod_sn);
 }  // namespace impl
 
 /// destagger_into(img, shifts, inverse, destaggered) -- :733-760.

@@ -317,6 +317,18 @@ class OUSTER_API_CLASS FrameBatcher {
     /// Header-only batching: keep the state machine and the per-column / per-packet headers but
     /// skip the pixel decode (no GPU work; pixel fields are left untouched).
     OUSTER_API_FUNCTION void set_headers_only(bool on);
+    /// Device-resident pixel outputs (the f-4 row of SURVEY 8f: results that stay in HBM for the next
+    /// GPU consumer): fields named here are decoded straight into the given DEVICE buffers
+    /// (h*w elements of the field's type each) instead of the LidarFrame's host storage, and, with a
+    /// fused cloud attached, XYZ / destaggered range go to `xyz` / `range_destaggered` (device, per
+    /// return; null = the FusedCloud's host buffers).  Headers still land in the LidarFrame.  The
+    /// buffers must stay valid until batch() has returned true (or wait() with a pipeline).
+    struct DeviceOutputs {
+        std::vector<std::pair<std::string, void*>> fields;
+        void* xyz[2]{nullptr, nullptr};
+        uint32_t* range_destaggered[2]{nullptr, nullptr};
+    };
+    OUSTER_API_FUNCTION void set_device_outputs(const DeviceOutputs* outputs);  ///< nullptr detaches (copied)
     /// Kernel launches issued by this batcher.
     OUSTER_API_FUNCTION size_t gpu_launches() const;
     /// Cumulative host-side time of the calling thread, by phase (nanoseconds).  ns_burst is the
@@ -330,8 +342,10 @@ class OUSTER_API_CLASS FrameBatcher {
     OUSTER_API_FUNCTION const Stats& stats() const;
     /// Feed `n` packets laid out `stride` bytes apart (host_timestamps[i] belongs to packet i) until
     /// a frame completes; returns the number of packets consumed.  When the burst lies in
-    /// page-locked (cudaHostAlloc / cudaHostRegister) or device memory the copy engine reads the
+    /// page-locked (cudaHostAlloc / cudaHostRegister) or managed memory the copy engine reads the
     /// packets where they are (no staging memcpy); the memory may be reused as soon as the call returns.
+    /// The host state machine parses the headers with the CPU: plain device memory is rejected
+    /// (std::invalid_argument "batch_burst needs host-readable packets ...").
     OUSTER_API_FUNCTION size_t batch_burst(const uint8_t* packets, size_t n, size_t stride, size_t size,
                                            const uint64_t* host_timestamps, LidarFrame& lidar_frame,
                                            bool& complete);
@@ -339,7 +353,11 @@ class OUSTER_API_CLASS FrameBatcher {
     /// reference.  n >= 2: batch() returns true as soon as the frame's GPU pass is *submitted*; the
     /// caller batches the next frame into another LidarFrame (and FusedCloud) meanwhile and calls
     /// wait(frame) before reading pixel fields / fused outputs.  Column and packet headers are
-    /// host-written and valid immediately.  A frame must outlive its wait().  See FramePipeline
+    /// host-written and valid immediately.  A frame must outlive its wait(): the in-flight job holds
+    /// raw pointers into the frame's page-locked storage, so a LidarFrame (or FusedCloud) that is
+    /// destroyed, moved or resized before wait(frame) leaves a device->host copy aimed at memory that
+    /// may already belong to another frame.  FramePipeline owns its frames and does this correctly;
+    /// direct users of depth >= 2 must keep every submitted frame alive and unmoved until waited.  See FramePipeline
     /// (frame_pipeline.h) for a ready-made ring of frames.
     OUSTER_API_FUNCTION void set_pipeline_depth(size_t n);
     OUSTER_API_FUNCTION size_t pipeline_depth() const;
@@ -371,6 +389,8 @@ class OUSTER_API_CLASS FrameBatcher {
     std::unique_ptr<Staging> stg_;
     FusedCloud* fused_{nullptr};
     bool headers_only_{false};
+    bool dev_out_on_{false};
+    DeviceOutputs dev_out_;
     size_t launches_{0};
     int n_returns_{0};
     Stats stats_;

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "ouster/core/b200_runtime.h"
+#include "ouster/core/frame_set.h"
 #include "ouster/core/lidar_frame.h"
 #include "ouster/core/typedefs.h"
 #include "ouster/core/xyzlut.h"
@@ -96,6 +97,51 @@ PointCloudXYZ<T> dewarp(const LidarFrame& lidar_frame, const XYZLutT<T>& xyzlut,
     if (col_idxs) col_idxs->insert(col_idxs->end(), ci.begin(), ci.begin() + static_cast<std::ptrdiff_t>(count));
     if (timestamps_ns)
         timestamps_ns->insert(timestamps_ns->end(), ts.begin(), ts.begin() + static_cast<std::ptrdiff_t>(count));
+    return out;
+}
+
+/// dewarp(frame_set, xyzluts, min_range, max_range) (pose_util.h:475, impl/dewarp_impl.h:84-117): the
+/// dewarped points of every frame of the set, frame after frame, each frame with its own LUT.  One batched
+/// GPU pass for the whole set (ob_dewarp_frames: three launches, one host round trip).  Optional per-point
+/// provenance like impl::dewarp_impl: frame index, column index, column timestamp (appended).
+template <typename T>
+PointCloudXYZ<T> dewarp(const FrameSet& frame_set, const std::vector<XYZLutT<T>>& xyzluts, double min_range,
+                        double max_range, std::vector<uint32_t>* frame_idxs = nullptr,
+                        std::vector<uint32_t>* col_idxs = nullptr, std::vector<uint64_t>* timestamps_ns = nullptr) {
+    if (frame_set.size() != xyzluts.size())
+        throw std::invalid_argument("Number of frames and number of XYZLuts must be the same");
+    std::vector<ob_dewarp_frames_io> ios(frame_set.size());
+    size_t cap = 0;
+    for (size_t idx : frame_set.valid_indices()) {
+        const LidarFrame& f = *frame_set[idx];
+        const XYZLutT<T>& lut = xyzluts[idx];
+        auto range = f.field<uint32_t>(ChanField::RANGE);
+        const size_t n = static_cast<size_t>(lut.h) * lut.w;
+        if (static_cast<size_t>(range.rows()) * range.cols() != n || f.w != lut.w)
+            throw std::invalid_argument("unexpected image dimensions");
+        ios[idx].lut = lut.device_lut().get();
+        ios[idx].range = range.data();
+        ios[idx].poses = f.body_to_world().template get<double>();
+        ios[idx].status = f.status().data();
+        ios[idx].timestamps = f.timestamp().data();
+        cap += n;
+    }
+    PointCloudXYZ<T> all(cap, 3);
+    const bool prov = frame_idxs || col_idxs || timestamps_ns;
+    std::vector<uint32_t> fi(frame_idxs ? cap : 0), ci(col_idxs ? cap : 0);
+    std::vector<uint64_t> ts(timestamps_ns ? cap : 0);
+    (void)prov;
+    size_t count = 0;
+    if (cap)
+        b200::check(ob_dewarp_frames(ios.data(), ios.size(), min_range, max_range, all.data(), cap,
+                                     frame_idxs ? fi.data() : nullptr, col_idxs ? ci.data() : nullptr,
+                                     timestamps_ns ? ts.data() : nullptr, nullptr, &count, b200::thread_stream()));
+    PointCloudXYZ<T> out(count, 3);
+    if (count) std::memcpy(out.data(), all.data(), count * 3 * sizeof(T));
+    const auto n = static_cast<std::ptrdiff_t>(count);
+    if (frame_idxs) frame_idxs->insert(frame_idxs->end(), fi.begin(), fi.begin() + n);
+    if (col_idxs) col_idxs->insert(col_idxs->end(), ci.begin(), ci.begin() + n);
+    if (timestamps_ns) timestamps_ns->insert(timestamps_ns->end(), ts.begin(), ts.begin() + n);
     return out;
 }
 

@@ -50,7 +50,7 @@ typedef struct ob_decoder ob_decoder; /* device-resident PacketFormat decode tab
 /* ---- library ---- */
 int ob_abi_version(void);
 /* sizeof() of a public struct by name ("ob_cloud_io", "ob_field_desc", "ob_packet_layout",
- * "ob_decode_io", "ob_decode_batch", "ob_dewarp_frame_io", "ob_normals_io"); 0 for unknown names.  Lets FFI bindings verify their layout. */
+ * "ob_decode_io", "ob_decode_batch", "ob_dewarp_frame_io", "ob_normals_io", "ob_encode_io", "ob_dewarp_frames_io"); 0 for unknown names.  Lets FFI bindings verify their layout. */
 size_t ob_abi_sizeof(const char* struct_name);
 const char* ob_last_error(void);
 /* number of visible CUDA devices (0 without a driver/GPU); never fails */
@@ -165,6 +165,28 @@ typedef struct ob_dewarp_frame_io {
     size_t capacity;             /* in points; h*w always suffices */
 } ob_dewarp_frame_io;
 ob_status ob_dewarp_frame(const ob_lut* lut, const ob_dewarp_frame_io* io, size_t* n_points, ob_stream* s);
+
+/* ---- the frames of a set in one go ----
+ * replaces dewarp<T>(const FrameSet&, const std::vector<XYZLutT<T>>&, min_range, max_range)
+ *                                                ouster_core/include/ouster/core/pose_util.h:475
+ *          impl::dewarp_impl (FrameSet)          ouster_core/include/ouster/core/impl/dewarp_impl.h:84-117
+ * Every frame has its own LUT (lut == NULL marks an empty slot of the set, skipped like
+ * FrameSet::valid_indices()), range image, poses, status and timestamps; the points of frame i follow those
+ * of the frames before it, each frame in the single-frame order above.  THREE launches and ONE host round
+ * trip for the whole set (the single-frame entry costs three launches and a round trip per frame).
+ * Optional per-point provenance: frame index, column index, column timestamp (dewarp_impl.h:88-90).
+ * counts[i] (optional, n_frames entries) = points of frame i.  Buffers may be host or device memory.
+ * errors: "output capacity too small", "the luts of a set must share one dtype". */
+typedef struct ob_dewarp_frames_io {
+    const ob_lut* lut;           /* NULL: no frame in this slot */
+    const uint32_t* range;       /* h x w, staggered */
+    const double* poses;         /* w x 16 */
+    const uint32_t* status;      /* w */
+    const uint64_t* timestamps;  /* w; only read when timestamps_out != NULL */
+} ob_dewarp_frames_io;
+ob_status ob_dewarp_frames(const ob_dewarp_frames_io* frames, size_t n_frames, double min_range, double max_range,
+                           void* points, size_t capacity, uint32_t* frame_idx, uint32_t* col_idx,
+                           uint64_t* timestamps_out, size_t* counts, size_t* n_points, ob_stream* s);
 
 /* ---- surface normals on destaggered XYZ ----
  * replaces algorithm::normals(xyz, range, sensor_origins_xyz, pixel_search_range, min_angle_of_incidence_rad,
@@ -353,8 +375,38 @@ ob_status ob_decode_job_wait(ob_decode_job* job);
 int ob_decode_job_busy(const ob_decode_job* job); /* 1 while a submission has not been waited for */
 ob_status ob_decode_job_destroy(ob_decode_job* job);
 
+/* ---- K4: LidarFrame fields -> lidar packets (+ CRC64) on the device, the inverse of ob_decode_frames ----
+ * replaces impl::frame_to_packets (lidar packets)   ouster_core/include/ouster/core/impl/lidar_frame_impl.h:435-531
+ *          PacketFormat::set_block<T>               ouster_core/src/parsing.cpp:1056-1090
+ *          FieldDecodeInfo::set<T>                  ouster_core/include/ouster/core/field_decode_info.h:64-78
+ *          PacketFormat::calculate_crc (ECMA-182)   ouster_core/src/parsing.cpp:1183-1234
+ * `dec` supplies the packet layout and the field table (the same FieldDecodeInfo serves get and set).
+ * Per frame: fields[k] = h x w image of decoder field k (NULL: left zero), per-column timestamp / status
+ * (measurement_id = column index, as frame_to_packets writes it; columns without status bit 0 get headers
+ * but no pixel data, like set_block), and `packet_headers` = the first packet_header_bytes bytes of every
+ * packet as the caller's PacketFormat setters wrote them (frame id, init id, serial number, packet type,
+ * alert flags, countdowns; >= packet_header_size, may be the whole packet for LEGACY column headers).
+ * with_crc != 0 writes the CRC64 of bytes [0, packet_size - 8) into the last 8 bytes (standard headers,
+ * non-LEGACY profiles -- the caller decides, as frame_to_packets does at :512-518).  Every one of the
+ * w / columns_per_packet packets is produced; dropping packets "with ts == 0 and no valid column"
+ * (:497-500) is the caller's (host-side) choice.  Buffers may be host or device memory.
+ * errors: "Mismatch between expected number of packets and PacketFormat.columns_per_packet". */
+typedef struct ob_encode_io {
+    const void* fields[OB_MAX_FIELDS];
+    const uint64_t* timestamp;
+    const uint32_t* status;
+    const uint8_t* packet_headers;
+    size_t packet_header_bytes;
+    uint8_t* packets; /* out: n_packets x packet_stride */
+    size_t packet_stride;
+} ob_encode_io;
+ob_status ob_encode_frames(const ob_decoder* dec, const ob_encode_io* frames, size_t n_frames, int with_crc,
+                           ob_stream* s);
+
 /* 0: pageable host memory (or unknown), 1: page-locked host memory, 2: device / managed memory */
 int ob_pointer_kind(const void* p);
+/* 1 when the CPU may dereference p: anything but plain (non-managed) device memory */
+int ob_pointer_host_readable(const void* p);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,9 @@ ob_status obh_frame_destroy(obh_frame* f);
  * packet_size bytes; returns the number emitted through n_out */
 ob_status obh_frame_to_packets(const obh_frame* f, const obh_sensor* s, uint32_t init_id,
                                uint64_t prod_sn, uint8_t* out, uint64_t* host_ts, size_t* n_out);
+/* the same packets, produced by the GPU encoder (K4, ob_encode_frames); byte-identical */
+ob_status obh_frame_to_packets_device(const obh_frame* f, const obh_sensor* s, uint32_t init_id,
+                               uint64_t prod_sn, uint8_t* out, uint64_t* host_ts, size_t* n_out);
 
 /* ---- FrameBatcher ---- */
 ob_status obh_batcher_create(const obh_sensor* s, obh_batcher** out);
@@ -106,6 +109,13 @@ ob_status obh_batcher_set_fused(obh_batcher* b, ob_lut* lut /* borrowed; NULL de
                                 const int32_t* pixel_shift_by_row, size_t n_shifts);
 ob_status obh_batcher_fused_outputs(obh_batcher* b, int ret, void** xyz, size_t* xyz_bytes,
                                     uint32_t** range_destaggered);
+/* FrameBatcher::set_device_outputs: decode the named fields (and, with a fused cloud, XYZ / destaggered
+ * range per return; arrays of 2 pointers or NULL) straight into DEVICE buffers, so that the results stay
+ * in HBM for the next GPU consumer.  n_fields == 0 and NULL arrays detach.  Headers still go to the frame.
+ * error: "device outputs must be device memory" */
+ob_status obh_batcher_set_device_outputs(obh_batcher* b, size_t n_fields, const char* const* names,
+                                         void* const* field_ptrs, void* const* xyz,
+                                         uint32_t* const* range_destaggered);
 /* FrameBatcher::set_pipeline_depth / wait (frame == NULL: wait_all) -- see lidar_frame.h */
 ob_status obh_batcher_set_pipeline_depth(obh_batcher* b, size_t n);
 ob_status obh_batcher_wait(obh_batcher* b, obh_frame* frame);

@@ -46,6 +46,10 @@ class NormalsIO(C.Structure):
                 ("vertical_subtent_rad", C.c_double), ("vertical_subtent_out", vp)]
 
 
+class DewarpFramesIO(C.Structure):
+    _fields_ = [("lut", vp), ("range", vp), ("poses", vp), ("status", vp), ("timestamps", vp)]
+
+
 class FieldDesc(C.Structure):
     _fields_ = [("offset", u32), ("elem_size", u32), ("mask", u64), ("shift", C.c_int32),
                 ("range_return", C.c_int32), ("zero_pattern", u32), ("reserved", u32)]
@@ -78,6 +82,11 @@ class DecodeBatch(C.Structure):
                 ("xyz", vp * OB_MAX_RETURNS), ("xyz_frame_stride", sz),
                 ("range_destaggered", vp * OB_MAX_RETURNS), ("rd_frame_stride", sz),
                 ("frame_luts", C.POINTER(vp))]
+
+
+class EncodeIO(C.Structure):
+    _fields_ = [("fields", vp * OB_MAX_FIELDS), ("timestamp", vp), ("status", vp), ("packet_headers", vp),
+                ("packet_header_bytes", sz), ("packets", vp), ("packet_stride", sz)]
 
 
 def _sig(name, restype, *argtypes):
@@ -116,12 +125,15 @@ _sig("ob_dewarp", i32, i32, vp, vp, sz, sz, vp, vp)
 _sig("ob_scan_to_cloud", i32, vp, vp, sz, C.POINTER(CloudIO), vp)
 _sig("ob_dewarp_frame", i32, vp, C.POINTER(DewarpFrameIO), C.POINTER(sz), vp)
 _sig("ob_normals", i32, i32, C.POINTER(NormalsIO), vp)
+_sig("ob_dewarp_frames", i32, C.POINTER(DewarpFramesIO), sz, C.c_double, C.c_double, vp, sz, vp, vp, vp,
+     C.POINTER(sz), C.POINTER(sz), vp)
 if hasattr(lib, "ob_decoder_create"):
     _sig("ob_decoder_create", i32, C.POINTER(PacketLayout), C.POINTER(FieldDesc), sz, i32,
          C.POINTER(vp))
     _sig("ob_decoder_destroy", i32, vp)
     _sig("ob_decode_frames", i32, vp, C.POINTER(DecodeIO), sz, vp, vp, sz, vp)
     _sig("ob_decode_batch_run", i32, vp, C.POINTER(DecodeBatch), vp, vp, sz, vp)
+    _sig("ob_encode_frames", i32, vp, C.POINTER(EncodeIO), sz, i32, vp)
 
 
 class OusterB200Error(RuntimeError):

@@ -460,6 +460,58 @@ def normals(xyz, rng, *args, sensor_origins_xyz=None, pixel_search_range=1,
     return (res, float(sub[0])) if return_subtent else res
 
 
+def dewarp_frames(frames, min_range=0.0, max_range=float("inf"), provenance=False, stream=None):
+    """dewarp(frame_set, xyzluts, min_range, max_range) (pose_util.h:475, impl/dewarp_impl.h:84-117):
+    `frames` is a list with one entry per slot of the set -- None for an empty slot, else a dict
+    {lut, range, poses, status[, timestamps]} -- and the result is the concatenation of the frames'
+    dewarped points in slot order.  provenance=True also returns (frame_idx, col_idx, timestamps).
+    Three launches and one host round trip for the whole set."""
+    from ._capi import DewarpFramesIO
+    n = len(frames)
+    ios = (DewarpFramesIO * max(n, 1))()
+    keep, cap, lut0 = [], 0, None
+    for i, fr in enumerate(frames):
+        if fr is None:
+            continue
+        lut = fr["lut"]
+        lut0 = lut0 or lut
+        rng = fr["range"] if _is_torch(fr["range"]) else np.ascontiguousarray(fr["range"], np.uint32)
+        poses = fr["poses"] if _is_torch(fr["poses"]) else np.ascontiguousarray(fr["poses"], np.float64)
+        status = fr["status"] if _is_torch(fr["status"]) else np.ascontiguousarray(fr["status"], np.uint32)
+        if _numel(rng) != lut.h * lut.w:
+            raise ValueError("unexpected image dimensions")
+        if _numel(poses) != lut.w * 16 or _numel(status) != lut.w:
+            raise ValueError("poses must be [W, 4, 4] and status [W]")
+        ts = fr.get("timestamps")
+        if provenance:
+            if ts is None:
+                raise ValueError("provenance needs the column timestamps")
+            ts = ts if _is_torch(ts) else np.ascontiguousarray(ts, np.uint64)
+        keep += [rng, poses, status, ts]
+        ios[i].lut, ios[i].range, ios[i].poses, ios[i].status = lut._h, _ptr(rng), _ptr(poses), _ptr(status)
+        ios[i].timestamps = _ptr(ts) if provenance else None
+        cap += lut.h * lut.w
+    if lut0 is None:
+        empty = np.empty((0, 3), np.float64)
+        return (empty, np.empty(0, np.uint32), np.empty(0, np.uint32), np.empty(0, np.uint64)) if provenance else empty
+    st = _stream(stream, lut0.device)
+    if max_range == float("inf"):
+        max_range = 4294967.295
+    pts = np.empty((cap, 3), lut0.dtype)
+    fi = ci = ts_out = None
+    if provenance:
+        fi, ci, ts_out = np.empty(cap, np.uint32), np.empty(cap, np.uint32), np.empty(cap, np.uint64)
+    counts = (C.c_size_t * max(n, 1))()
+    total = C.c_size_t(0)
+    check(lib.ob_dewarp_frames(ios, n, float(min_range), float(max_range), pts.ctypes.data, cap,
+                               fi.ctypes.data if provenance else None, ci.ctypes.data if provenance else None,
+                               ts_out.ctypes.data if provenance else None, counts, C.byref(total), st.h))
+    k = total.value
+    if provenance:
+        return pts[:k], fi[:k], ci[:k], ts_out[:k]
+    return pts[:k]
+
+
 def transform(points, pose, out=None, stream=None, device=0):
     """transform(points (..., 3), pose (4, 4)): one pose for every point (pose_util.h:118-131)."""
     pose = pose if _is_torch(pose) else np.ascontiguousarray(pose, _np_dtype(points)).reshape(1, 16)
@@ -469,12 +521,10 @@ def transform(points, pose, out=None, stream=None, device=0):
     return res.reshape(shape)
 
 
-def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None,
-                  xyz_destaggered=None, stream=None, poses=None):
-    """Fused batch: rng is [F, R, H, W] uint32; outputs [F, R, H*W, 3] (xyz), [F, R, H, W]
-    (range_destaggered), [F, R, H, W, 3] (xyz_destaggered).  `poses` ([W, 4, 4] shared by all
-    frames or [F, W, 4, 4], LUT dtype, e.g. LidarScan.body_to_world) fuses dewarp(xyz, poses) into
-    the same pass.  Asynchronous on `stream`."""
+def plan_scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None,
+                       xyz_destaggered=None, stream=None, poses=None):
+    """Marshal an ob_scan_to_cloud call once and return a callable that launches it (`plan()`): for
+    steady-state callers that process into the same buffers every step.  Arguments as scan_to_cloud."""
     st = _stream(stream, lut.device)
     F, R, H, W = tuple(rng.shape)
     io = CloudIO()
@@ -501,8 +551,22 @@ def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None
     if pixel_shift_by_row is not None:
         sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
         nsh = sh.size
-    check(lib.ob_scan_to_cloud(lut._h, sh.ctypes.data if sh is not None else None, nsh,
-                               C.byref(io), st.h))
+    lut_h, sh_p, io_ref, st_h, run = lut._h, (sh.ctypes.data if sh is not None else None), C.byref(io), st.h, \
+        lib.ob_scan_to_cloud
+
+    def plan():
+        check(run(lut_h, sh_p, nsh, io_ref, st_h))
+    plan._keep = (lut, sh, io, st, rng, xyz, range_destaggered, xyz_destaggered, poses)
+    return plan
+
+
+def scan_to_cloud(lut, pixel_shift_by_row, rng, xyz=None, range_destaggered=None,
+                  xyz_destaggered=None, stream=None, poses=None):
+    """Fused batch: rng is [F, R, H, W] uint32; outputs [F, R, H*W, 3] (xyz), [F, R, H, W]
+    (range_destaggered), [F, R, H, W, 3] (xyz_destaggered).  `poses` ([W, 4, 4] shared by all
+    frames or [F, W, 4, 4], LUT dtype, e.g. LidarScan.body_to_world) fuses dewarp(xyz, poses) into
+    the same pass.  Asynchronous on `stream`."""
+    plan_scan_to_cloud(lut, pixel_shift_by_row, rng, xyz, range_destaggered, xyz_destaggered, stream, poses)()
 
 
 class Decoder:
@@ -597,12 +661,13 @@ class Decoder:
                            "zero_pattern": 0x7e00 if name == "RGB" else 0})
         return cls(layout, fields, device)
 
-    def decode_batch(self, n_frames, packets, n_slots, packet_stride, packets_frame_stride, fields,
-                     lut=None, pixel_shift_by_row=None, xyz=None, range_destaggered=None,
-                     timestamp=None, measurement_id=None, status=None, stream=None, frame_luts=None):
-        """Uniformly strided batch of complete frames (ob_decode_batch_run).  `fields` maps a field
-        name to an array/tensor shaped [n_frames, H, W(, k)]; xyz / range_destaggered are lists (one
-        entry per return) of [n_frames, H*W, 3] / [n_frames, H, W] arrays."""
+    def prepare_batch(self, n_frames, packets, n_slots, packet_stride, packets_frame_stride, fields,
+                      lut=None, pixel_shift_by_row=None, xyz=None, range_destaggered=None,
+                      timestamp=None, measurement_id=None, status=None, stream=None, frame_luts=None):
+        """Build the ob_decode_batch descriptor of a uniformly strided batch ONCE and return a callable
+        that launches it (`plan()`): a steady-state caller decodes into the same buffers every step, and
+        re-marshalling ~100 pointers through ctypes costs more host time than the launch takes on the GPU.
+        Arguments as decode_batch."""
         from ._capi import DecodeBatch
         st = _stream(stream, self.device)
         b = DecodeBatch()
@@ -623,8 +688,10 @@ class Decoder:
             b.status, b.status_frame_stride = _ptr(status), self.w_px * 4
         any_lut = lut if lut is not None else (frame_luts[0] if frame_luts else None)
         esz = 8 if (any_lut is not None and any_lut.dtype == np.float64) else 4
+        keep = [packets, fields, xyz, range_destaggered, timestamp, measurement_id, status, lut, frame_luts]
         if frame_luts:
             arr = (C.c_void_p * n_frames)(*[l._h.value for l in frame_luts])
+            keep.append(arr)
             b.frame_luts = C.cast(arr, C.POINTER(C.c_void_p))
         for r, a in enumerate(xyz or []):
             if a is not None:
@@ -638,8 +705,24 @@ class Decoder:
         if pixel_shift_by_row is not None:
             sh = np.ascontiguousarray(pixel_shift_by_row, np.int32)
             nsh = sh.size
-        check(lib.ob_decode_batch_run(self._h, C.byref(b), lut._h if lut is not None else None,
-                                      sh.ctypes.data if sh is not None else None, nsh, st.h))
+        keep.append(sh)
+        dec_h, b_ref, lut_h = self._h, C.byref(b), (lut._h if lut is not None else None)
+        sh_p, st_h, run = (sh.ctypes.data if sh is not None else None), st.h, lib.ob_decode_batch_run
+
+        def plan():
+            check(run(dec_h, b_ref, lut_h, sh_p, nsh, st_h))
+        plan._keep = (keep, b, st)
+        return plan
+
+    def decode_batch(self, n_frames, packets, n_slots, packet_stride, packets_frame_stride, fields,
+                     lut=None, pixel_shift_by_row=None, xyz=None, range_destaggered=None,
+                     timestamp=None, measurement_id=None, status=None, stream=None, frame_luts=None):
+        """Uniformly strided batch of complete frames (ob_decode_batch_run).  `fields` maps a field
+        name to an array/tensor shaped [n_frames, H, W(, k)]; xyz / range_destaggered are lists (one
+        entry per return) of [n_frames, H*W, 3] / [n_frames, H, W] arrays."""
+        self.prepare_batch(n_frames, packets, n_slots, packet_stride, packets_frame_stride, fields, lut,
+                           pixel_shift_by_row, xyz, range_destaggered, timestamp, measurement_id, status,
+                           stream, frame_luts)()
 
     def __del__(self):
         if getattr(self, "_h", None) and lib is not None:

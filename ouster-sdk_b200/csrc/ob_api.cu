@@ -63,6 +63,8 @@ static Tunables& tunables_mut(int device) {
         t.decode_runtime_plans = env_int("OB_DECODE_RUNTIME_PLANS", 0);
         t.decode_pipe = env_int("OB_DECODE_PIPE", 1);
         t.decode_pipe_warps = std::min(24, std::max(6, env_int("OB_DECODE_PIPE_WARPS", 24)));
+        t.decode_pipe_dyn_rows = env_int("OB_DECODE_PIPE_DYN_ROWS", 1);
+        t.decode_pipe_prefetch = env_int("OB_DECODE_PIPE_PREFETCH", 0);  // measured: the extra L2 fills are evicted again (+19 % DRAM reads)
         t.force_generic = env_int("OB_FORCE_GENERIC", 0);
         int sm = 148;
         if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
@@ -101,6 +103,8 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "decode_runtime_plans") t.decode_runtime_plans = value ? 1 : 0;
     else if (n == "decode_pipe") t.decode_pipe = value ? 1 : 0;
     else if (n == "decode_pipe_warps") t.decode_pipe_warps = std::min(24, std::max(6, value));
+    else if (n == "decode_pipe_prefetch") t.decode_pipe_prefetch = value;
+    else if (n == "decode_pipe_dyn_rows") t.decode_pipe_dyn_rows = value ? 1 : 0;
     else if (n == "force_generic") t.force_generic = value;
     else return false;
     return true;
@@ -215,6 +219,14 @@ struct ob_stream {
     int device;
     cudaStream_t st;
     bool owned;
+    // small device-resident tables (frame tables of the decode / encode launches) kept across calls:
+    // a steady-state caller passes the same pointers again and again, and re-uploading an identical
+    // table costs a host-staged H2D copy per launch during which the GPU idles
+    struct Table {
+        void* dev{nullptr};
+        size_t cap{0};
+        std::vector<uint8_t> host;
+    } tables[2];
 };
 
 struct ob_lut {
@@ -243,6 +255,36 @@ void lut_view(const ob_lut* lut, const void** dir, const void** off, int* dtype,
 }
 const void* lut_analytic(const ob_lut* lut) { return lut->analytic_on ? lut->an : nullptr; }
 cudaStream_t stream_handle(ob_stream* s) { return s->st; }
+
+cudaError_t stream_table(ob_stream* s, int which, const void* host, size_t bytes, const void** dev) {
+    ob_stream::Table& t = s->tables[which & 1];
+    if (t.dev != nullptr && t.host.size() == bytes && std::memcmp(t.host.data(), host, bytes) == 0) {
+        *dev = t.dev;  // identical to what the device already holds
+        return cudaSuccess;
+    }
+    if (bytes > t.cap) {
+        if (t.dev) {
+            cudaError_t e = cudaStreamSynchronize(s->st);  // a running launch may still read the old table
+            if (e != cudaSuccess) return e;
+            cudaFree(t.dev);
+            t.dev = nullptr;
+            t.cap = 0;
+        }
+        const size_t cap = std::max<size_t>(bytes * 2, 4096);
+        cudaError_t e = cudaMalloc(&t.dev, cap);
+        if (e != cudaSuccess) return e;
+        t.cap = cap;
+    }
+    t.host.assign(static_cast<const uint8_t*>(host), static_cast<const uint8_t*>(host) + bytes);
+    // stream-ordered: lands after every earlier launch of this stream that reads the previous contents
+    cudaError_t e = cudaMemcpyAsync(t.dev, t.host.data(), bytes, cudaMemcpyHostToDevice, s->st);
+    if (e != cudaSuccess) {
+        t.host.clear();
+        return e;
+    }
+    *dev = t.dev;
+    return cudaSuccess;
+}
 int stream_device(ob_stream* s) { return s->device; }
 }  // namespace ob
 
@@ -260,6 +302,8 @@ size_t ob_abi_sizeof(const char* name) {
     if (n == "ob_decode_batch") return sizeof(ob_decode_batch);
     if (n == "ob_dewarp_frame_io") return sizeof(ob_dewarp_frame_io);
     if (n == "ob_normals_io") return sizeof(ob_normals_io);
+    if (n == "ob_encode_io") return sizeof(ob_encode_io);
+    if (n == "ob_dewarp_frames_io") return sizeof(ob_dewarp_frames_io);
     return 0;
 }
 
@@ -301,7 +345,11 @@ ob_status ob_stream_create(int device, ob_stream** out) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    *out = new ob_stream{device, st, true};
+    ob_stream* ns = new ob_stream;
+    ns->device = device;
+    ns->st = st;
+    ns->owned = true;
+    *out = ns;
     return OB_OK;
 }
 
@@ -314,7 +362,11 @@ ob_status ob_stream_wrap(int device, void* cuda_stream, ob_stream** out) {
         uint64_t thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    *out = new ob_stream{device, static_cast<cudaStream_t>(cuda_stream), false};
+    ob_stream* ns = new ob_stream;
+    ns->device = device;
+    ns->st = static_cast<cudaStream_t>(cuda_stream);
+    ns->owned = false;
+    *out = ns;
     return OB_OK;
 }
 
@@ -329,10 +381,12 @@ void* ob_stream_cuda_handle(ob_stream* s) { return s ? static_cast<void*>(s->st)
 
 ob_status ob_stream_destroy(ob_stream* s) {
     if (!s) return OB_OK;
-    if (s->owned) {
-        cudaStreamSynchronize(s->st);
-        cudaStreamDestroy(s->st);
-    }
+    bool have_tables = false;
+    for (auto& t : s->tables) have_tables |= t.dev != nullptr;
+    if (s->owned || have_tables) cudaStreamSynchronize(s->st);
+    for (auto& t : s->tables)
+        if (t.dev) cudaFree(t.dev);
+    if (s->owned) cudaStreamDestroy(s->st);
     delete s;
     return OB_OK;
 }
@@ -763,6 +817,118 @@ ob_status ob_dewarp_frame(const ob_lut* lut, const ob_dewarp_frame_io* io, size_
     if (!is_device_ptr(io->points)) {
         e = cudaStreamSynchronize(s->st);
         if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame");
+    }
+    *n_points = static_cast<size_t>(total);
+    return OB_OK;
+}
+
+ob_status ob_dewarp_frames(const ob_dewarp_frames_io* frames, size_t n_frames, double min_range, double max_range,
+                           void* points, size_t capacity, uint32_t* frame_idx, uint32_t* col_idx,
+                           uint64_t* timestamps_out, size_t* counts, size_t* n_points, ob_stream* s) {
+    if (!s || !n_points || (n_frames && !frames)) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    *n_points = 0;
+    if (counts) std::fill(counts, counts + n_frames, static_cast<size_t>(0));
+    if (n_frames == 0) return OB_OK;
+    if (!points) return fail(OB_INVALID_ARGUMENT, "null points buffer");
+    ob_status rs = require_device(s->device);
+    if (rs != OB_OK) return rs;
+    const double lo = std::ceil(min_range * 1e3), hi = std::floor(max_range * 1e3);  // dewarp_impl.h:34-35
+    if (!(lo <= 4294967295.0) || !(hi >= 0.0) || !(lo <= hi)) return OB_OK;
+    const uint32_t min_r = lo <= 0.0 ? 0u : static_cast<uint32_t>(lo);
+    const uint32_t max_r = hi >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(hi);
+    int dtype = -1;
+    Staging stg(s->st);
+    std::vector<K3Frame> hf;
+    hf.reserve(n_frames);
+    unsigned max_warps = 0;
+    for (size_t i = 0; i < n_frames; ++i) {
+        const ob_dewarp_frames_io& io = frames[i];
+        if (!io.lut) continue;  // FrameSet::valid_indices(): empty slots of the set are skipped
+        if (!io.range || !io.poses || !io.status) return fail(OB_INVALID_ARGUMENT, "null range / poses / status");
+        if (timestamps_out && !io.timestamps)
+            return fail(OB_INVALID_ARGUMENT, "timestamps_out requested without column timestamps");
+        const ob_lut* lut = io.lut;
+        if (lut->device != s->device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
+        if (dtype < 0) dtype = lut->dtype;
+        if (lut->dtype != dtype) return fail(OB_INVALID_ARGUMENT, "the luts of a set must share one dtype");
+        K3Frame f{};
+        f.H = static_cast<unsigned>(lut->h);
+        f.W = static_cast<unsigned>(lut->w);
+        f.n_cg = (f.W + 31) / 32;
+        f.n_slabs = (f.H + 15) / 16;
+        f.index = static_cast<unsigned>(i);
+        f.dir = lut->dir;
+        f.off = lut->off;
+        const size_t n_px = lut->h * lut->w;
+        const void* d = nullptr;
+        cudaError_t e = stg.in(io.range, n_px * 4, &d);
+        f.range = static_cast<const uint32_t*>(d);
+        if (e == cudaSuccess) e = stg.in(io.poses, lut->w * 16 * sizeof(double), &d);
+        f.poses = static_cast<const double*>(d);
+        if (e == cudaSuccess) e = stg.in(io.status, lut->w * 4, &d);
+        f.status = static_cast<const uint32_t*>(d);
+        if (e == cudaSuccess && timestamps_out) {
+            e = stg.in(io.timestamps, lut->w * 8, &d);
+            f.timestamps = static_cast<const uint64_t*>(d);
+        }
+        void* sc = nullptr;
+        if (e == cudaSuccess) e = stg.scratch(dewarp_frames_scratch_bytes(f.H, f.W), &sc);
+        if (e != cudaSuccess) return fail_cuda(e, "stage dewarp inputs");
+        f.cnt = static_cast<uint32_t*>(sc);
+        f.base = f.cnt + static_cast<size_t>(f.n_slabs) * f.W;
+        max_warps = std::max(max_warps, f.n_cg * f.n_slabs);
+        hf.push_back(f);
+    }
+    if (hf.empty()) return OB_OK;
+    const size_t esz = dtype_size(dtype);
+    void *fdev = nullptr, *tdev = nullptr, *o = nullptr;
+    cudaError_t e = stg.scratch(hf.size() * sizeof(K3Frame), &fdev);
+    if (e == cudaSuccess) e = stg.scratch(hf.size() * 8, &tdev);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fdev, hf.data(), hf.size() * sizeof(K3Frame), cudaMemcpyHostToDevice, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
+    // outputs: device pointers in place, host pointers through device scratch of `capacity` points
+    const bool host_out = !is_device_ptr(points);
+    void* dpts = points;
+    uint32_t *dfi = frame_idx, *dci = col_idx;
+    uint64_t* dts = timestamps_out;
+    if (host_out) {
+        e = stg.scratch(capacity * 3 * esz, &o);
+        dpts = o;
+        if (e == cudaSuccess && frame_idx) {
+            e = stg.scratch(capacity * 4, &o);
+            dfi = static_cast<uint32_t*>(o);
+        }
+        if (e == cudaSuccess && col_idx) {
+            e = stg.scratch(capacity * 4, &o);
+            dci = static_cast<uint32_t*>(o);
+        }
+        if (e == cudaSuccess && timestamps_out) {
+            e = stg.scratch(capacity * 8, &o);
+            dts = static_cast<uint64_t*>(o);
+        }
+        if (e != cudaSuccess) return fail_cuda(e, "stage dewarp outputs");
+    }
+    e = launch_dewarp_frames(static_cast<const K3Frame*>(fdev), static_cast<unsigned>(hf.size()), max_warps, min_r, max_r,
+                             dtype, static_cast<unsigned long long*>(tdev), dpts, dfi, dci, dts, capacity, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frames launch");
+    std::vector<unsigned long long> totals(hf.size());
+    e = cudaMemcpyAsync(totals.data(), tdev, hf.size() * 8, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);  // the one host round trip of the whole set
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frames count");
+    unsigned long long total = 0;
+    for (size_t k = 0; k < hf.size(); ++k) {
+        if (counts) counts[hf[k].index] = static_cast<size_t>(totals[k]);
+        total += totals[k];
+    }
+    if (total > capacity) return fail(OB_INVALID_ARGUMENT, "output capacity too small");
+    if (host_out && total) {
+        e = cudaMemcpyAsync(points, dpts, total * 3 * esz, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess && frame_idx) e = cudaMemcpyAsync(frame_idx, dfi, total * 4, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess && col_idx) e = cudaMemcpyAsync(col_idx, dci, total * 4, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess && timestamps_out)
+            e = cudaMemcpyAsync(timestamps_out, dts, total * 8, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        if (e != cudaSuccess) return fail_cuda(e, "dewarp_frames D2H");
     }
     *n_points = static_cast<size_t>(total);
     return OB_OK;

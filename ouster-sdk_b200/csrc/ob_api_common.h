@@ -41,6 +41,9 @@ void lut_view(const ob_lut* lut, const void** dir, const void** off, int* dtype,
               size_t* w, int* device);
 const void* lut_analytic(const ob_lut* lut);  // device LutAnalyticT<T> when the LUT-free mode is on, else null
 cudaStream_t stream_handle(ob_stream* s);
+// device copy of a small per-launch table (which: 0 decode frames, 1 encode frames), re-uploaded only when
+// its contents changed since the stream's previous launch of that kind
+cudaError_t stream_table(ob_stream* s, int which, const void* host, size_t bytes, const void** dev);
 int stream_device(ob_stream* s);
 
 }  // namespace ob

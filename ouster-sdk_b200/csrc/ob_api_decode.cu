@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "ob_api_common.h"
+#include "ob_encode.h"
 
 using namespace ob;
 
@@ -217,10 +218,8 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
         }
     }
     group_by_lut(hf);
-    void* fdev = nullptr;
-    cudaError_t e = stg.scratch(n_frames * sizeof(DecodeFrame), &fdev);
-    if (e != cudaSuccess) return fail_cuda(e, "frame table alloc");
-    e = cudaMemcpyAsync(fdev, hf.data(), n_frames * sizeof(DecodeFrame), cudaMemcpyHostToDevice, st);
+    const void* fdev = nullptr;
+    cudaError_t e = stream_table(s, 0, hf.data(), n_frames * sizeof(DecodeFrame), &fdev);
     if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
     DecodeLaunch a;
     a.layout_host = &L;
@@ -356,10 +355,8 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
         }
     }
     group_by_lut(hf);
-    void* fdev = nullptr;
-    e = stg.scratch(F * sizeof(DecodeFrame), &fdev);
-    if (e != cudaSuccess) return fail_cuda(e, "frame table alloc");
-    e = cudaMemcpyAsync(fdev, hf.data(), F * sizeof(DecodeFrame), cudaMemcpyHostToDevice, st);
+    const void* fdev = nullptr;
+    e = stream_table(s, 0, hf.data(), F * sizeof(DecodeFrame), &fdev);
     if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
     DecodeLaunch a;
     a.layout_host = &L;
@@ -670,6 +667,68 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
     return OB_OK;
 }
 
+ob_status ob_encode_frames(const ob_decoder* dec, const ob_encode_io* frames, size_t n_frames, int with_crc,
+                           ob_stream* s) {
+    if (!dec || !s || (n_frames && !frames)) return fail(OB_INVALID_ARGUMENT, "null pointer");
+    if (n_frames == 0) return OB_OK;
+    const DecodeLayout& L = dec->L;
+    const int device = stream_device(s);
+    if (device != dec->device) return fail(OB_INVALID_ARGUMENT, "decoder and stream are on different devices");
+    if (L.W % L.cpp != 0)
+        return fail(OB_INVALID_ARGUMENT, "Mismatch between expected number of packets and PacketFormat.columns_per_packet");
+    if (with_crc && (L.packet_size % 4 != 0 || L.packet_size < 8))
+        return fail(OB_INVALID_ARGUMENT, "packet size must be a multiple of 4 for the CRC64 footer");
+    ob_status rs = require_device(device);
+    if (rs != OB_OK) return rs;
+    cudaStream_t st = stream_handle(s);
+    Staging stg(st);
+    const size_t n_px = static_cast<size_t>(L.H) * L.W, n_pk = L.W / L.cpp;
+    std::vector<EncodeFrame> hf(n_frames);
+    for (size_t i = 0; i < n_frames; ++i) {
+        const ob_encode_io& io = frames[i];
+        EncodeFrame& f = hf[i];
+        std::memset(&f, 0, sizeof(f));
+        if (!io.packets) return fail(OB_INVALID_ARGUMENT, "null packet buffer");
+        if (io.packet_stride < L.packet_size)
+            return fail(OB_INVALID_ARGUMENT, "packet_stride smaller than the lidar packet size");
+        if (io.packet_headers && io.packet_header_bytes < L.packet_header_size)
+            return fail(OB_INVALID_ARGUMENT, "packet_header_bytes smaller than the packet header");
+        const void* d = nullptr;
+        cudaError_t e = cudaSuccess;
+        for (uint32_t k = 0; k < L.n_fields && e == cudaSuccess; ++k) {
+            if (!io.fields[k]) continue;
+            e = stg.in(io.fields[k], n_px * L.fields[k].elem_size, &d);
+            f.fields[k] = d;
+        }
+        if (e == cudaSuccess && io.timestamp) {
+            e = stg.in(io.timestamp, static_cast<size_t>(L.W) * 8, &d);
+            f.timestamp = static_cast<const uint64_t*>(d);
+        }
+        if (e == cudaSuccess && io.status) {
+            e = stg.in(io.status, static_cast<size_t>(L.W) * 4, &d);
+            f.status = static_cast<const uint32_t*>(d);
+        }
+        if (e == cudaSuccess && io.packet_headers) {
+            e = stg.in(io.packet_headers, n_pk * io.packet_header_bytes, &d);
+            f.packet_headers = static_cast<const uint8_t*>(d);
+            f.header_bytes = static_cast<uint32_t>(io.packet_header_bytes);
+        }
+        void* o = nullptr;
+        if (e == cudaSuccess) e = stg.out(io.packets, (n_pk - 1) * io.packet_stride + L.packet_size, &o);
+        if (e != cudaSuccess) return fail_cuda(e, "stage encode buffers");
+        f.packets = static_cast<uint8_t*>(o);
+        f.packet_stride = io.packet_stride;
+    }
+    const void* fdev = nullptr;
+    cudaError_t e = stream_table(s, 1, hf.data(), n_frames * sizeof(EncodeFrame), &fdev);
+    if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
+    e = launch_encode(L, static_cast<const EncodeFrame*>(fdev), static_cast<uint32_t>(n_frames), with_crc != 0, device, st);
+    if (e != cudaSuccess) return fail_cuda(e, "encode launch");
+    e = stg.flush();
+    if (e != cudaSuccess) return fail_cuda(e, "encode D2H");
+    return OB_OK;
+}
+
 int ob_pointer_kind(const void* p) {
     if (!p) return 0;
     cudaPointerAttributes at;
@@ -680,6 +739,16 @@ int ob_pointer_kind(const void* p) {
     if (at.type == cudaMemoryTypeHost) return 1;
     if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return 2;
     return 0;
+}
+
+int ob_pointer_host_readable(const void* p) {
+    if (!p) return 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    return at.type == cudaMemoryTypeDevice ? 0 : 1;
 }
 
 }  // extern "C"

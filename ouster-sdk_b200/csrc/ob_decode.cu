@@ -360,7 +360,10 @@ cudaError_t make_decode_params(const DecodeLaunch& a, int device, bool pipe, Dec
     p.lut_dir = a.lut_dir;
     p.lut_off = a.lut_off;
     p.n_frames = a.n_frames;
-    p.pkt_stride_s = (L.packet_size + 16 + 15) & ~15u;  // +16: slack for trailing 8-byte field reads
+    // bytes reserved per packet in a stage.  decode_kernel: + 16 slack for trailing 8-byte field reads; the
+    // pipelined kernel packs the packets back to back (an over-read lands in the next packet's header, masked
+    // off anyway) and keeps one 16-byte slack after the last stage -- that is what lets a 4-slot LUT ring fit
+    p.pkt_stride_s = pipe ? ((L.packet_size + 15) & ~15u) : ((L.packet_size + 16 + 15) & ~15u);
     if (tn.decode_tile_packets > 0) {
         p.P = static_cast<uint32_t>(tn.decode_tile_packets);
     } else {

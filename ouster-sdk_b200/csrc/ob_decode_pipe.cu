@@ -7,9 +7,13 @@
 //   * warp NCW   (packet producer): one TMA bulk copy per packet into a 2-deep ring of packet stages;
 //     a stage is refilled the moment the last compute warp has arrived on its `pk_done` mbarrier.
 //     Irregular tiles (dropped / reordered / zero-filled columns) are gathered by this warp's lanes.
-//   * warp NCW+1 (LUT producer): the XYZ LUT slices of a tile stream through a 3-deep ring of
-//     24 KB slots, one 2-D TMA tensor copy per table per sub-tile (box = tile columns x RB rows of
-//     direction resp. offset; descriptors built on the host, lut_tensor_maps()).
+//   * warp NCW+1 (LUT producer): the XYZ LUT slices of a tile stream through a 4-deep ring of
+//     24 KB slots (a whole 128-row tile), one 2-D TMA tensor copy per table per sub-tile (box = tile
+//     columns x RB rows of direction resp. offset; descriptors built on the host, lut_tensor_maps()).
+//   * warp NCW+2 (L2 prefetcher): warms L2 with the packets of the tile after next, so that the packet
+//     producer's TMA loads are L2 hits even when DRAM is saturated by the output streams.
+//   Both producers read the frame-table entry of tile k+1 while tile k is in flight (the table lives
+//   in global memory and a dependent chain of L2 round trips under load costs microseconds).
 //   * warps 0..NCW-1 (compute): phase A decodes every field of a pixel from registers and stores the
 //     row-major images (lane = frame column); phase B projects the ranges with the LUT slice that is
 //     already in shared memory (thread = one 16-byte chunk of a row segment: two conflict-free LDS.128,
@@ -29,7 +33,8 @@ namespace ob {
 
 constexpr int kPipeMaxComputeWarps = 24;
 constexpr int kPipeStages = 2;    // packet stages
-constexpr int kPipeLutSlots = 3;  // LUT ring depth
+constexpr int kPipeLutSlotsMax = 4;  // LUT ring depth: 4 when it fits the 227 KB, else 3
+constexpr int kPipeTileCols = 64;    // widest tile of this kernel
 
 struct PipeParams {
     DecodeParams d;
@@ -43,6 +48,9 @@ struct PipeParams {
     uint32_t box_bytes;    // bytes of one box
     uint32_t lut_off;      // byte offsets inside the dynamic shared memory
     uint32_t stage_off;
+    uint32_t nl;           // LUT ring slots (3 or 4)
+    uint32_t prefetch;     // L2 prefetch distance of the packet tiles (0 = off)
+    uint32_t dyn_rows;     // phase A rows handed out through a shared-memory counter (static layouts)
 };
 
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar,
@@ -54,8 +62,45 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
         : "memory");
 }
 
+
+// explicit shared-memory accesses by 32-bit shared address: the compiler cannot always prove that a
+// pointer derived from the stage base is shared memory and then emits generic loads (measured: they were
+// the kernel's main long-scoreboard stall)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_vec(uint32_t a, float4*) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_vec(uint32_t a, double2*) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+
+// per-stage bookkeeping of the pipelined kernel: the column tables of TileCtl plus a copy of the frame's
+// table entry (pointers, flags), staged by the packet producer one tile ahead so that the compute warps
+// read them from shared memory instead of chasing the global frame table at the start of every tile
+struct PipeTileCtl {  // TileCtl for at most kPipeTileCols columns
+    int regular;
+    int col_src[kPipeTileCols];
+    int col_off[kPipeTileCols];
+    unsigned char group_fast[16];  // per packet of the tile (eligibility: at most 16 packets per tile)
+};
+struct PipeCtl {
+    PipeTileCtl t;
+    DecodeFrame fr;
+    uint32_t j0;    // first frame column of the tile
+    uint32_t mode;  // XYZ path of the tile: 0 none, 1 LUT ring, 2 LUT-free
+    uint32_t row_ctr[2];  // next undecoded row per 32-column group (dynamic row hand-out of phase A)
+};
+
 template <typename T>
-__global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
+__global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
     decode_pipe_kernel(const __grid_constant__ PipeParams pp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const DecodeParams& p = pp.d;
@@ -63,14 +108,15 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int NCW = static_cast<int>(pp.ncw);
-    constexpr int NS = kPipeStages, NL = kPipeLutSlots;
+    constexpr int NS = kPipeStages;
+    const unsigned NL = pp.nl;
 
     // ---- shared memory carve-up ----
     uint64_t* pk_full = reinterpret_cast<uint64_t*>(smem);  // NS
     uint64_t* pk_done = pk_full + NS;                       // NS
-    uint64_t* lut_full = pk_done + NS;                      // NL
-    uint64_t* lut_done = lut_full + NL;                     // NL
-    TileCtl* ctl = reinterpret_cast<TileCtl*>(smem + 128);  // NS entries
+    uint64_t* lut_full = pk_done + NS;                      // kPipeLutSlotsMax
+    uint64_t* lut_done = lut_full + kPipeLutSlotsMax;       // kPipeLutSlotsMax
+    PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem + 96);   // NS entries
     uint8_t* lut0 = smem + pp.lut_off;
     uint8_t* stage0 = smem + pp.stage_off;
 
@@ -79,7 +125,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
             mbar_init(&pk_full[s], 1);
             mbar_init(&pk_done[s], pp.ncw);
         }
-        for (int s = 0; s < NL; ++s) {
+        for (unsigned s = 0; s < NL; ++s) {
             mbar_init(&lut_full[s], 1);
             mbar_init(&lut_done[s], pp.ncw);
         }
@@ -105,35 +151,57 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
         return static_cast<int>(g * p.pkt_stride_s + L.packet_header_size + (t - (g << p.cpp_shift)) * L.col_size +
                                 L.col_header_size);
     };
-    // does tile (frame) take the XYZ path through the LUT ring?  evaluated identically by the LUT producer
-    // and the compute warps (frames whose LUT is in LUT-free mode do not use the ring)
-    auto wants_xyz = [&](const DecodeFrame& fr) -> const void* {
+    // XYZ path of a frame: evaluated identically by both producers (from the global frame table)
+    auto xyz_mode = [&](const DecodeFrame& fr) -> unsigned {
+        if (n_ret == 0 || (fr.xyz[0] == nullptr && fr.xyz[1] == nullptr)) return 0u;
+        const void* an = fr.lut_dir != nullptr ? fr.lut_an : pp.lut_an;
+        if (an != nullptr) return 2u;
         const void* maps = fr.lut_dir != nullptr ? fr.lut_maps : pp.lut_maps;
-        const void* an = fr.lut_dir != nullptr ? fr.lut_an : pp.lut_an;
-        if (n_ret == 0 || an != nullptr || (fr.xyz[0] == nullptr && fr.xyz[1] == nullptr)) return nullptr;
-        return maps;
-    };
-    auto wants_analytic = [&](const DecodeFrame& fr) -> const LutAnalyticT<T>* {
-        const void* an = fr.lut_dir != nullptr ? fr.lut_an : pp.lut_an;
-        if (n_ret == 0 || (fr.xyz[0] == nullptr && fr.xyz[1] == nullptr)) return nullptr;
-        return static_cast<const LutAnalyticT<T>*>(an);
+        return maps != nullptr ? 1u : 0u;
     };
 
     if (warp == NCW) {
         // =============================== packet producer ===============================
         uint64_t pol_stream = policy_evict_first();
+        constexpr unsigned NWORDS = sizeof(DecodeFrame) / 8;
+        static_assert(NWORDS <= 64, "frame table entry larger than two words per lane");
+        // entry of the NEXT tile, two 8-byte words per lane, loaded one tile ahead
+        uint64_t w0 = 0, w1 = 0;
+        auto fetch_entry = [&](unsigned k) {
+            unsigned f, j0;
+            tile_of(k, f, j0);
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(&p.frames[f]);
+            if (static_cast<unsigned>(lane) < NWORDS) w0 = src[lane];
+            if (static_cast<unsigned>(lane) + 32u < NWORDS) w1 = src[lane + 32];
+        };
+        if (n_my > 0) fetch_entry(0);
         for (unsigned k = 0; k < n_my; ++k) {
             const int s = k % NS;
             if (k >= static_cast<unsigned>(NS)) mbar_wait(&pk_done[s], ((k / NS) - 1) & 1);
             unsigned f, j0;
             tile_of(k, f, j0);
-            const DecodeFrame& fr = p.frames[f];
-            TileCtl& c = ctl[s];
+            PipeCtl& pc = ctl[s];
+            PipeTileCtl& c = pc.t;
             uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
+            // stage the frame's table entry for the compute warps (and for this warp: `fr` below is the copy)
+            {
+                uint64_t* dst = reinterpret_cast<uint64_t*>(&pc.fr);
+                if (static_cast<unsigned>(lane) < NWORDS) dst[lane] = w0;
+                if (static_cast<unsigned>(lane) + 32u < NWORDS) dst[lane + 32] = w1;
+            }
+            __syncwarp();
+            if (k + 1 < n_my) fetch_entry(k + 1);  // in flight while this tile is issued and the next wait runs
+            const DecodeFrame& fr = pc.fr;
+            if (lane == 0) {
+                pc.j0 = j0;
+                pc.mode = xyz_mode(fr);
+                pc.row_ctr[0] = pc.row_ctr[1] = 0u;
+            }
             const bool identity = (fr.flags & 1u) != 0;
             const bool bulk_ok = (fr.flags & 2u) != 0;
             const unsigned n_groups = tc >> p.cpp_shift;
             if (identity && bulk_ok && (j0 + tc) / L.cpp <= fr.n_slots) {
+                __syncwarp();  // every lane's part of the table entry is written before the arrival below
                 if (lane == 0) {
                     c.regular = 1;
                     mbar_expect_tx(&pk_full[s], n_groups * L.packet_size);
@@ -219,17 +287,36 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
         // =============================== LUT producer ===============================
         if (lane != 0) return;
         const uint64_t pol_keep = policy_evict_last();
+        // the few words of the frame entry this warp needs, fetched one tile ahead
+        struct Need {
+            const void *xyz0, *xyz1, *lut_dir, *lut_maps, *lut_an;
+        };
+        auto fetch = [&](unsigned k) -> Need {
+            unsigned f, j0;
+            tile_of(k, f, j0);
+            const DecodeFrame& fr = p.frames[f];
+            return Need{fr.xyz[0], fr.xyz[1], fr.lut_dir, fr.lut_maps, fr.lut_an};
+        };
+        Need nx{};
+        if (n_my > 0) nx = fetch(0);
         unsigned g = 0;
         for (unsigned k = 0; k < n_my; ++k) {
             unsigned f, j0;
             tile_of(k, f, j0);
-            const DecodeFrame& fr = p.frames[f];
-            const void* maps = wants_xyz(fr);
-            if (maps == nullptr) continue;
-            const uint8_t* m = static_cast<const uint8_t*>(maps);
+            const Need cur = nx;
+            if (k + 1 < n_my) nx = fetch(k + 1);
+            unsigned mode = 0;
+            if (n_ret != 0 && (cur.xyz0 != nullptr || cur.xyz1 != nullptr)) {
+                const void* an = cur.lut_dir != nullptr ? cur.lut_an : pp.lut_an;
+                const void* maps = cur.lut_dir != nullptr ? cur.lut_maps : pp.lut_maps;
+                mode = an != nullptr ? 2u : (maps != nullptr ? 1u : 0u);
+            }
+            if (mode != 1u) continue;
+            const uint8_t* m = static_cast<const uint8_t*>(cur.lut_dir != nullptr ? cur.lut_maps : pp.lut_maps);
             for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g) {
-                const int slot = g % NL;
-                if (g >= static_cast<unsigned>(NL)) mbar_wait(&lut_done[slot], ((g / NL) - 1) & 1);
+                const unsigned slot = NL == 4u ? (g & 3u) : g % 3u;
+                const unsigned round = NL == 4u ? (g >> 2) : g / 3u;
+                if (g >= NL) mbar_wait(&lut_done[slot], (round - 1u) & 1u);
                 uint8_t* dst = lut0 + static_cast<size_t>(slot) * pp.slot_bytes;
                 mbar_expect_tx(&lut_full[slot], 2u * pp.box_bytes);
                 tma_load_2d_hint(dst, m, static_cast<int>(j0 * 3u), static_cast<int>(sub * pp.RB), &lut_full[slot],
@@ -237,6 +324,30 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
                 tma_load_2d_hint(dst + pp.box_bytes, m + 128, static_cast<int>(j0 * 3u),
                                  static_cast<int>(sub * pp.RB), &lut_full[slot], pol_keep);
             }
+        }
+        return;
+    }
+
+    if (warp == NCW + 2) {
+        // =============================== L2 prefetcher ===============================
+        // paced by the packet stages: when the packets of tile k have landed, warm L2 with those of tile
+        // k + pf (pf = 2: its TMA load is issued one tile from now).  Regular tiles only.
+        if (lane != 0 || pp.prefetch == 0) return;
+        const unsigned pf = pp.prefetch;
+        for (unsigned k = 0; k + pf < n_my + pf; ++k) {
+            if (k >= pf) {
+                const unsigned kk = k - pf;  // pace: tile kk has landed
+                mbar_wait(&pk_full[kk % NS], (kk / NS) & 1);
+            }
+            if (k >= n_my) break;
+            if (k < static_cast<unsigned>(NS)) continue;  // the first tiles are loaded directly
+            unsigned f, j0;
+            tile_of(k, f, j0);
+            const DecodeFrame& fr = p.frames[f];
+            if ((fr.flags & 3u) != 3u || (j0 + tc) / L.cpp > fr.n_slots) continue;
+            const unsigned slot0 = j0 / L.cpp, n_groups = tc >> p.cpp_shift;
+            for (unsigned gi = 0; gi < n_groups; ++gi)
+                bulk_prefetch_l2(fr.packets + static_cast<size_t>(slot0 + gi) * fr.packet_stride, L.packet_size);
         }
         return;
     }
@@ -252,12 +363,19 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
     const unsigned p0 = e0 / 3u;       // first pixel touched by this chunk
     const unsigned k0 = e0 - 3u * p0;  // component of element 0 inside pixel p0
     const unsigned p1 = (p0 + 1 < tc) ? p0 + 1 : p0;
-    bool first_px[VN];
+    bool first_px[VN];                 // element e belongs to pixel p0 (else to p1)
 #pragma unroll
     for (int e = 0; e < VN; ++e) first_px[e] = (k0 + e) < 3u;
     const DecodeParams::Plan& pl0 = p.plan[p.range_field[0]];
     const DecodeParams::Plan& pl1 = p.plan[p.range_field[n_ret > 1 ? 1 : 0]];
     const bool simple = (pl0.mb | pl1.mb | pl0.rs | pl1.rs) == 0 && pl0.d == 0 && pl1.d == 0;
+    const uint32_t ma0 = pl0.ma, ma1 = pl1.ma;
+    // shared addresses of the two pixels' range words inside stage 0, row 0 (regular tiles)
+    const uint32_t stage_sa = smem_u32(stage0);
+    const uint32_t lut_sa = smem_u32(lut0) + static_cast<uint32_t>(tid) * 16u;
+    const uint32_t coa = static_cast<uint32_t>(col_offset(p0)) + rsub * cds;
+    const uint32_t cob = static_cast<uint32_t>(col_offset(p1)) + rsub * cds;
+    const uint32_t sub_step = pp.RB * cds;
     auto rng = [](const uint32_t* w, const DecodeParams::Plan& pl, bool valid, bool simple_) -> uint32_t {
         const uint32_t a = w[pl.wa] & pl.ma;
         if (simple_) return valid ? a : 0u;
@@ -266,19 +384,34 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
         v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
         return valid ? v : 0u;
     };
+    // one output chunk: element e = (e-th pixel's range) * dir + off, +0.0 for an empty return
+    auto chunk = [&](uint32_t ra, uint32_t rb, const V& dv, const V& ov) -> V {
+        const T fa = static_cast<T>(ra), fb = static_cast<T>(rb);
+        const T* de = reinterpret_cast<const T*>(&dv);
+        const T* oe = reinterpret_cast<const T*>(&ov);
+        V outv;
+        T* o2 = reinterpret_cast<T*>(&outv);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            const bool fa_e = first_px[e];
+            const T v = project_nz(fa_e ? fa : fb, de[e], oe[e]);
+            o2[e] = (fa_e ? ra : rb) == 0 ? static_cast<T>(0) : v;
+        }
+        return outv;
+    };
 
     unsigned g = 0;  // running LUT sub-tile index (same sequence as the LUT producer)
     for (unsigned k = 0; k < n_my; ++k) {
         const int s = k % NS;
-        unsigned f, j0;
-        tile_of(k, f, j0);
-        const DecodeFrame& fr = p.frames[f];
-        TileCtl& c = ctl[s];
+        PipeCtl& pc = ctl[s];
+        PipeTileCtl& c = pc.t;
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
         // rows rotate over the warps from tile to tile so that H % NCW leftovers even out
         const int wrot = (warp + static_cast<int>((k * 7u) % static_cast<unsigned>(NCW))) % NCW;
 
         mbar_wait(&pk_full[s], (k / NS) & 1);
+        const DecodeFrame& fr = pc.fr;  // shared-memory copy
+        const unsigned j0 = pc.j0, mode = pc.mode;
         const bool regular = c.regular != 0;
 
         // ---- column headers (timestamp / measurement_id / status) ----
@@ -298,8 +431,11 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
             }
         }
 
-        // ---- phase A: decode; lane = frame column, warp = row (strided) ----
-        for (unsigned cg = 0; cg * 32 < tc; ++cg) {
+        // ---- phase A: decode the whole tile; lane = frame column, warp = row (strided) ----
+        {
+        const unsigned rb = 0u, re = L.H;
+        const unsigned wfirst = rb + static_cast<unsigned>(wrot);  // first row of this warp's residue class
+        for (unsigned cg = 0; (pp.dyn_rows || wfirst < re) && cg * 32 < tc; ++cg) {
             const unsigned t = cg * 32 + lane;
             const int co = regular ? col_offset(t) : c.col_off[t];
             const bool col_valid = co >= 0;
@@ -312,16 +448,27 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
                     outp[i] = p.slot_field[i] >= 0 ? static_cast<uint8_t*>(fr.fields[p.slot_field[i]]) : nullptr;
                 uint32_t* rdp2[2] = {fr.rd[0], fr.rd[1]};
                 const unsigned col = static_cast<unsigned>(pix0);
-                const unsigned row0 = static_cast<unsigned>(wrot), rstep = static_cast<unsigned>(NCW);
+                const unsigned rstep = static_cast<unsigned>(NCW);
                 const bool all = p.layout_all != 0 && (p.n_returns < 1 || rdp2[0] != nullptr) &&
                                  (p.n_returns < 2 || rdp2[1] != nullptr) && fr.fields[0] != nullptr &&
                                  p.n_returns > 0;
+                if (pp.dyn_rows) {
+                    unsigned* ctr = &pc.row_ctr[cg];
+                    switch (p.layout_id) {
+                        case 1: decode_static_tile_dyn<1>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
+                        case 2: decode_static_tile_dyn<2>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
+                        case 3: decode_static_tile_dyn<3>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
+                        case 4: decode_static_tile_dyn<4>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
+                        default: decode_static_tile_dyn<5>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
+                    }
+                    continue;
+                }
                 switch (p.layout_id) {
-                    case 1: decode_static_tile<1>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
-                    case 2: decode_static_tile<2>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
-                    case 3: decode_static_tile<3>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
-                    case 4: decode_static_tile<4>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
-                    default: decode_static_tile<5>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
+                    case 1: decode_static_tile<1>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, wfirst, rstep, p); break;
+                    case 2: decode_static_tile<2>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, wfirst, rstep, p); break;
+                    case 3: decode_static_tile<3>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, wfirst, rstep, p); break;
+                    case 4: decode_static_tile<4>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, wfirst, rstep, p); break;
+                    default: decode_static_tile<5>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, wfirst, rstep, p); break;
                 }
                 continue;
             }
@@ -333,20 +480,21 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
                 if (out == nullptr && rdp == nullptr) continue;
                 const DecodeParams::Plan& pl = p.plan[fi];
                 const uint32_t es = fd.elem_size;
+                const int wf = static_cast<int>(wfirst);
                 if (pl.fast && es <= 4) {
                     const uint32_t zv = (fd.zero_pattern & 0xffffu) | ((fd.zero_pattern & 0xffffu) << 16);
                     const bool ho = out != nullptr, hr = rdp != nullptr;
                     if (regular) {
-                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
-                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
-                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
+                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
                     } else {
-                        if (es == 4) decode_rows_dispatch<4, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
-                        else if (es == 2) decode_rows_dispatch<2, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
-                        else decode_rows_dispatch<1, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, L.H, wrot, NCW, rdp, p);
+                        if (es == 4) decode_rows_dispatch<4, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
+                        else decode_rows_dispatch<1, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
                     }
                 } else {  // wide or unaligned fields: generic 64-bit extraction
-                    for (unsigned row = wrot; row < L.H; row += NCW) {
+                    for (unsigned row = wfirst; row < re; row += NCW) {
                         const uint8_t* px = px0 + row * cds;
                         const uint64_t v = !col_valid ? zero_value(fd) : extract_smem(px, fd, aligned);
                         const size_t pix = static_cast<size_t>(row) * L.W + pix0;
@@ -360,56 +508,85 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 2) * 32, 1)
                 }
             }
         }
+        }
 
-        // ---- phase B: XYZ from the LUT slices in shared memory ----
-        if (wants_xyz(fr) != nullptr) {
-            const int co0 = regular ? col_offset(p0) : c.col_off[p0];
-            const int co1 = regular ? col_offset(p1) : c.col_off[p1];
-            const bool v0 = co0 >= 0, v1 = co1 >= 0;
-            const uint8_t* pa = st + (v0 ? co0 : 0);
-            const uint8_t* pb = st + (v1 ? co1 : 0);
+        // ---- phase B: XYZ of the tile's sub-tiles from the LUT slices in shared memory.  All of them were
+        //      prefetched into the ring while phase A ran (4 slots = a whole 128-row tile), so the waits
+        //      below normally fall through ----
+        if (mode == 1u) {
             T* xo0 = static_cast<T*>(fr.xyz[0]);
             T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
-            if (xo0 != nullptr) __builtin_assume(__isGlobal(xo0));
-            if (xo1 != nullptr) __builtin_assume(__isGlobal(xo1));
             const size_t ecol = static_cast<size_t>(j0) * 3 + static_cast<size_t>(q) * VN;
-            for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g) {
-                const int slot = g % NL;
-                mbar_wait(&lut_full[slot], (g / NL) & 1);
-                const unsigned row = sub * pp.RB + rsub;
-                if (row < L.H) {
-                    const uint8_t* sl = lut0 + static_cast<size_t>(slot) * pp.slot_bytes + static_cast<size_t>(tid) * 16;
-                    const V dv = *reinterpret_cast<const V*>(sl);
-                    const V ov = *reinterpret_cast<const V*>(sl + pp.box_bytes);
-                    const T* de = reinterpret_cast<const T*>(&dv);
-                    const T* oe = reinterpret_cast<const T*>(&ov);
-                    const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa + static_cast<size_t>(row) * cds);
-                    const uint32_t* wb = reinterpret_cast<const uint32_t*>(pb + static_cast<size_t>(row) * cds);
-                    const size_t eidx = static_cast<size_t>(row) * L.W * 3 + ecol;
-                    if (xo0 != nullptr) {
-                        const uint32_t ra = rng(wa, pl0, v0, simple), rb = rng(wb, pl0, v1, simple);
-                        V outv;
-                        T* o2 = reinterpret_cast<T*>(&outv);
-#pragma unroll
-                        for (int e = 0; e < VN; ++e) o2[e] = project1(first_px[e] ? ra : rb, de[e], oe[e]);
-                        *reinterpret_cast<V*>(xo0 + eidx) = outv;
+            const bool fast_b = regular && simple && xo0 != nullptr && (n_ret < 2 || xo1 != nullptr);
+            const size_t row_step = static_cast<size_t>(pp.RB) * L.W * 3;
+            T* x0 = xo0 != nullptr ? xo0 + static_cast<size_t>(rsub) * L.W * 3 + ecol : nullptr;
+            T* x1 = xo1 != nullptr ? xo1 + static_cast<size_t>(rsub) * L.W * 3 + ecol : nullptr;
+            if (x0 != nullptr) __builtin_assume(__isGlobal(x0));
+            if (x1 != nullptr) __builtin_assume(__isGlobal(x1));
+            if (fast_b) {
+                // lean path (the normal case): running 32-bit shared addresses and running global pointers
+                const uint32_t sst = stage_sa + static_cast<uint32_t>(s) * p.stage_bytes;
+                uint32_t aa0 = sst + coa + pl0.wa * 4u, ab0 = sst + cob + pl0.wa * 4u;
+                uint32_t aa1 = sst + coa + pl1.wa * 4u, ab1 = sst + cob + pl1.wa * 4u;
+                unsigned row = rsub;
+                for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g, row += pp.RB) {
+                    const unsigned slot = NL == 4u ? (g & 3u) : g % 3u;
+                    const unsigned round = NL == 4u ? (g >> 2) : g / 3u;
+                    mbar_wait(&lut_full[slot], round & 1u);
+                    if (row < L.H) {
+                        const uint32_t la = lut_sa + slot * pp.slot_bytes;
+                        const V dv = lds_vec(la, static_cast<V*>(nullptr));
+                        const V ov = lds_vec(la + pp.box_bytes, static_cast<V*>(nullptr));
+                        const uint32_t ra0 = lds_u32(aa0) & ma0, rb0 = lds_u32(ab0) & ma0;
+                        *reinterpret_cast<V*>(x0) = chunk(ra0, rb0, dv, ov);
+                        if (x1 != nullptr) {
+                            const uint32_t ra1 = lds_u32(aa1) & ma1, rb1 = lds_u32(ab1) & ma1;
+                            *reinterpret_cast<V*>(x1) = chunk(ra1, rb1, dv, ov);
+                        }
                     }
-                    if (xo1 != nullptr) {
-                        const uint32_t ra = rng(wa, pl1, v0, simple), rb = rng(wb, pl1, v1, simple);
-                        V outv;
-                        T* o2 = reinterpret_cast<T*>(&outv);
-#pragma unroll
-                        for (int e = 0; e < VN; ++e) o2[e] = project1(first_px[e] ? ra : rb, de[e], oe[e]);
-                        *reinterpret_cast<V*>(xo1 + eidx) = outv;
-                    }
+                    aa0 += sub_step;
+                    ab0 += sub_step;
+                    aa1 += sub_step;
+                    ab1 += sub_step;
+                    x0 += row_step;
+                    if (x1 != nullptr) x1 += row_step;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&lut_done[slot]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&lut_done[slot]);
+            } else {
+                // general path: irregular tiles (zero-filled / gathered columns), straddling or shifted
+                // range fields, a single requested return
+                const int co0 = regular ? col_offset(p0) : c.col_off[p0];
+                const int co1 = regular ? col_offset(p1) : c.col_off[p1];
+                const bool v0 = co0 >= 0, v1 = co1 >= 0;
+                const uint8_t* pa = st + (v0 ? co0 : 0);
+                const uint8_t* pb = st + (v1 ? co1 : 0);
+                for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g) {
+                    const unsigned slot = NL == 4u ? (g & 3u) : g % 3u;
+                    const unsigned round = NL == 4u ? (g >> 2) : g / 3u;
+                    mbar_wait(&lut_full[slot], round & 1u);
+                    const unsigned row = sub * pp.RB + rsub;
+                    if (row < L.H) {
+                        const uint32_t la = lut_sa + slot * pp.slot_bytes;
+                        const V dv = lds_vec(la, static_cast<V*>(nullptr));
+                        const V ov = lds_vec(la + pp.box_bytes, static_cast<V*>(nullptr));
+                        const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa + static_cast<size_t>(row) * cds);
+                        const uint32_t* wb = reinterpret_cast<const uint32_t*>(pb + static_cast<size_t>(row) * cds);
+                        if (x0 != nullptr) *reinterpret_cast<V*>(x0) = chunk(rng(wa, pl0, v0, simple), rng(wb, pl0, v1, simple), dv, ov);
+                        if (x1 != nullptr) *reinterpret_cast<V*>(x1) = chunk(rng(wa, pl1, v0, simple), rng(wb, pl1, v1, simple), dv, ov);
+                    }
+                    if (x0 != nullptr) x0 += row_step;
+                    if (x1 != nullptr) x1 += row_step;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&lut_done[slot]);
+                }
             }
         }
+
         // ---- phase B, LUT-free: direction/offset rebuilt from the per-row / per-column tables ----
-        if (const LutAnalyticT<T>* anp = wants_analytic(fr)) {
-            const LutAnalyticT<T>& an = *anp;
+        if (mode == 2u) {
+            const LutAnalyticT<T>& an =
+                *static_cast<const LutAnalyticT<T>*>(fr.lut_dir != nullptr ? fr.lut_an : pp.lut_an);
             const int co0 = regular ? col_offset(p0) : c.col_off[p0];
             const int co1 = regular ? col_offset(p1) : c.col_off[p1];
             const bool v0 = co0 >= 0, v1 = co1 >= 0;
@@ -576,7 +753,7 @@ static bool pipe_geometry(const DecodeLayout& L, uint32_t TC, int lut_dtype, uin
 }
 
 static uint32_t pipe_tile_cols(const DecodeLayout& L, const Tunables& tn) {
-    const uint32_t stride = (L.packet_size + 16 + 15) & ~15u;
+    const uint32_t stride = (L.packet_size + 15) & ~15u;
     uint32_t P = 1;
     if (tn.decode_tile_packets > 0) P = static_cast<uint32_t>(tn.decode_tile_packets);
     else
@@ -596,13 +773,21 @@ bool decode_pipe_box(const DecodeLayout& L, int device, int lut_dtype, uint32_t*
     return true;
 }
 
-static size_t pipe_smem_bytes(const DecodeParams& p, uint32_t ncw, uint32_t* lut_off, uint32_t* stage_off) {
-    size_t off = 128 + static_cast<size_t>(kPipeStages) * sizeof(TileCtl);
-    off = (off + 1023) & ~static_cast<size_t>(1023);
+// dynamic shared memory layout: [mbarriers 96 B][PipeCtl x stages][LUT ring][packet stages][16 B slack]
+static size_t pipe_smem_bytes(const DecodeParams& p, uint32_t ncw, uint32_t nl, uint32_t* lut_off, uint32_t* stage_off) {
+    size_t off = 96 + static_cast<size_t>(kPipeStages) * sizeof(PipeCtl);
+    off = (off + 127) & ~static_cast<size_t>(127);
     *lut_off = static_cast<uint32_t>(off);
-    off += static_cast<size_t>(kPipeLutSlots) * 2u * (ncw * 32u * 16u);
+    off += static_cast<size_t>(nl) * 2u * (ncw * 32u * 16u);
     *stage_off = static_cast<uint32_t>(off);
-    return off + static_cast<size_t>(kPipeStages) * p.stage_bytes;
+    return off + static_cast<size_t>(kPipeStages) * p.stage_bytes + 16;  // + slack for trailing 8-byte field reads
+}
+// deepest LUT ring that fits: 4 slots hold the LUT of a whole 128-row tile (no refill is ever waited for)
+static uint32_t pipe_ring_slots(const DecodeParams& p, uint32_t ncw) {
+    uint32_t lo, so;
+    for (uint32_t nl = kPipeLutSlotsMax; nl >= 3; --nl)
+        if (pipe_smem_bytes(p, ncw, nl, &lo, &so) <= 227 * 1024) return nl;
+    return 0;
 }
 
 bool decode_pipe_eligible(const DecodeParams& p, const DecodeLaunch& a, int device) {
@@ -612,7 +797,10 @@ bool decode_pipe_eligible(const DecodeParams& p, const DecodeLaunch& a, int devi
     if (static_cast<uint64_t>(L.H) * L.W >= (1ull << 30)) return false;
     uint32_t cpr, RB, lo, so;
     if (!pipe_geometry(L, p.TC, a.lut_dtype, static_cast<uint32_t>(tn.decode_pipe_warps), &cpr, &RB)) return false;
-    if (pipe_smem_bytes(p, static_cast<uint32_t>(tn.decode_pipe_warps), &lo, &so) > 227 * 1024) return false;
+    (void)lo;
+    (void)so;
+    if (p.TC > static_cast<uint32_t>(kPipeTileCols) || p.TC / L.cpp > 16u) return false;
+    if (pipe_ring_slots(p, static_cast<uint32_t>(tn.decode_pipe_warps)) == 0) return false;
     // XYZ path: 16-byte aligned rows, 32-bit range plans and TMA descriptors for every LUT in use
     if (p.n_returns > 0) {
         if (!p.vec_ok || !p.plan_ranges_fast) return false;
@@ -634,9 +822,12 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
     pp.n_sub = (p.L.H + pp.RB - 1) / pp.RB;
     pp.box_bytes = pp.ncw * 32u * 16u;
     pp.slot_bytes = 2u * pp.box_bytes;
-    const size_t smem = pipe_smem_bytes(p, pp.ncw, &pp.lut_off, &pp.stage_off);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    const int threads = static_cast<int>(pp.ncw + 2) * 32;
+    pp.nl = pipe_ring_slots(p, pp.ncw);
+    if (pp.nl == 0) return cudaErrorInvalidValue;
+    const size_t smem = pipe_smem_bytes(p, pp.ncw, pp.nl, &pp.lut_off, &pp.stage_off);
+    pp.dyn_rows = tn.decode_pipe_dyn_rows ? 1u : 0u;
+    pp.prefetch = static_cast<uint32_t>(std::max(0, std::min(8, tn.decode_pipe_prefetch)));
+    const int threads = static_cast<int>(pp.ncw + 3) * 32;
     const int grid = static_cast<int>(std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count)));
     auto kern = a.lut_dtype == OB_F64 ? decode_pipe_kernel<double> : decode_pipe_kernel<float>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

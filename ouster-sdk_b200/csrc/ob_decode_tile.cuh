@@ -100,6 +100,9 @@ __device__ __forceinline__ float project1(uint32_t r, float d, float o) {
 __device__ __forceinline__ double project1(uint32_t r, double d, double o) {
     return r == 0 ? 0.0 : __dadd_rn(__dmul_rn(static_cast<double>(r), d), o);
 }
+// range already converted: r * dir + ofs with the reference's two roundings (the caller handles r == 0)
+__device__ __forceinline__ float project_nz(float r, float d, float o) { return __fadd_rn(__fmul_rn(r, d), o); }
+__device__ __forceinline__ double project_nz(double r, double d, double o) { return __dadd_rn(__dmul_rn(r, d), o); }
 
 // Row loop of phase A for one field.  Compile-time specialisations remove every per-pixel branch:
 //   ES      destination element size (1, 2, 4)
@@ -394,6 +397,50 @@ __device__ __forceinline__ void decode_static(const uint8_t* px0, bool col_valid
         wp += wstep;
         pix += pstep;
     }
+}
+
+// The same row body with the rows handed out dynamically: every warp takes the next undecoded row of the
+// tile from a shared-memory counter (one atomic per row and warp), so the warps of a CTA finish a tile
+// together whatever H modulo the warp count is (128 rows over 24 warps is 5.33 rows each: with a fixed
+// stride the 6-row warps set the pace and the 5-row warps wait for the next tile's packets).
+template <int L, bool FULL, bool ALL>
+__device__ __forceinline__ void decode_static_dyn(const uint8_t* px0, bool col_valid, bool lane_on,
+                                                  uint8_t* const (&outp)[kMaxSlots], uint32_t* const (&rdp)[2],
+                                                  unsigned col, unsigned W, unsigned H, unsigned* row_ctr,
+                                                  const DecodeParams& p) {
+    constexpr int NW = PxLayout<L>::cds / 4;
+    const bool has_rd = ALL || rdp[0] != nullptr || rdp[1] != nullptr;
+    const bool has_shift = p.has_shift != 0;
+    const unsigned lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned row = 0;
+        if (lane == 0) row = atomicAdd(row_ctr, 1u);
+        row = __shfl_sync(0xffffffffu, row, 0);
+        if (row >= H) break;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(px0) + row * NW;
+        uint32_t w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = wp[i];
+        const unsigned pix = row * W + col;
+        unsigned rdpix = pix;
+        if (has_rd) {
+            unsigned dcol = col + (has_shift ? p.shift[row] : 0u);
+            dcol = dcol >= W ? dcol - W : dcol;
+            rdpix = pix - col + dcol;
+        }
+        store_all<L, FULL, ALL>(w, outp, rdp, pix, rdpix, col_valid, lane_on,
+                                std::make_integer_sequence<int, PxLayout<L>::n>{});
+    }
+}
+
+template <int L>
+__device__ __forceinline__ void decode_static_tile_dyn(bool full, bool all, const uint8_t* px0, bool col_valid,
+                                                       bool lane_on, uint8_t* const (&outp)[kMaxSlots],
+                                                       uint32_t* const (&rdp)[2], unsigned col, unsigned W,
+                                                       unsigned H, unsigned* row_ctr, const DecodeParams& p) {
+    if (full && all) decode_static_dyn<L, true, true>(px0, true, true, outp, rdp, col, W, H, row_ctr, p);
+    else if (full) decode_static_dyn<L, true, false>(px0, true, true, outp, rdp, col, W, H, row_ctr, p);
+    else decode_static_dyn<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, row_ctr, p);
 }
 
 template <int L>

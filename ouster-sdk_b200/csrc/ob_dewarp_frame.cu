@@ -200,4 +200,161 @@ cudaError_t launch_dewarp_frame_emit(const DewarpFrameArgs& a, cudaStream_t st) 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched form: dewarp(FrameSet, xyzluts, min_range, max_range) (pose_util.h:475, impl/dewarp_impl.h:84-102)
+// -- the frames of a set, each with its own LUT / poses / status, in THREE launches for the whole set
+// (the single-frame path above needs three per frame plus a host round trip for its count): the points of
+// frame f follow those of frame f-1 in the output, exactly like the reference's concatenation.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k3_count_batch_kernel(const K3Frame* __restrict__ frames, uint32_t min_r,
+                                                             uint32_t max_r) {
+    const K3Frame& fr = frames[blockIdx.y];
+    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= fr.n_cg * fr.n_slabs) return;
+    const unsigned cg = gw % fr.n_cg, slab = gw / fr.n_cg;
+    const unsigned col = cg * 32u + (threadIdx.x & 31u);
+    if (col >= fr.W) return;
+    const unsigned r0 = slab * kSlabRows, r1 = min(fr.H, r0 + kSlabRows);
+    uint32_t c = 0;
+    for (unsigned row = r0; row < r1; ++row) {
+        const uint32_t r = fr.range[static_cast<size_t>(row) * fr.W + col];
+        c += (r >= min_r && r <= max_r) ? 1u : 0u;
+    }
+    fr.cnt[static_cast<size_t>(slab) * fr.W + col] = c;
+}
+
+__global__ void __launch_bounds__(1024) k3_scan_batch_kernel(const K3Frame* __restrict__ frames,
+                                                             unsigned long long* __restrict__ totals) {
+    const K3Frame& fr = frames[blockIdx.x];
+    __shared__ int s_first, s_last;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const unsigned tid = threadIdx.x, nt = blockDim.x, W = fr.W, n_slabs = fr.n_slabs;
+    if (tid == 0) {
+        s_first = 0x7fffffff;
+        s_last = -1;
+        s_carry = 0;
+    }
+    __syncthreads();
+    int lf = 0x7fffffff, ll = -1;
+    for (unsigned c = tid; c < W; c += nt)
+        if ((fr.status[c] & 1u) != 0) {
+            lf = min(lf, static_cast<int>(c));
+            ll = max(ll, static_cast<int>(c));
+        }
+    atomicMin(&s_first, lf);
+    atomicMax(&s_last, ll);
+    __syncthreads();
+    const int first = s_first, last = s_last;
+    for (unsigned c0 = 0; c0 < W; c0 += nt) {
+        const unsigned c = c0 + tid;
+        const bool on = c < W && last >= first && static_cast<int>(c) >= first && static_cast<int>(c) <= last &&
+                        fr.status[c] != 0;
+        uint32_t mine = 0;
+        if (on)
+            for (unsigned sl = 0; sl < n_slabs; ++sl) mine += fr.cnt[static_cast<size_t>(sl) * W + c];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31u) >= static_cast<unsigned>(d)) incl += v;
+        }
+        if ((tid & 31u) == 31u) s_warp[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t w = tid < (nt >> 5) ? s_warp[tid] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
+                if (tid >= static_cast<unsigned>(d)) wi += v;
+            }
+            s_warp[tid] = wi - w;
+        }
+        __syncthreads();
+        uint32_t off = s_carry + s_warp[tid >> 5] + (incl - mine);
+        if (c < W) {
+            for (unsigned sl = 0; sl < n_slabs; ++sl) {
+                fr.base[static_cast<size_t>(sl) * W + c] = on ? off : 0xffffffffu;
+                if (on) off += fr.cnt[static_cast<size_t>(sl) * W + c];
+            }
+        }
+        __syncthreads();
+        if (tid == nt - 1) s_carry = s_carry + s_warp[tid >> 5] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) totals[blockIdx.x] = s_carry;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k3_emit_batch_kernel(const K3Frame* __restrict__ frames,
+                                                            const unsigned long long* __restrict__ totals,
+                                                            uint32_t min_r, uint32_t max_r, T* __restrict__ points,
+                                                            uint32_t* __restrict__ frame_idx,
+                                                            uint32_t* __restrict__ col_idx, uint64_t* __restrict__ ts_out,
+                                                            unsigned long long capacity) {
+    const unsigned f = blockIdx.y;
+    const K3Frame& fr = frames[f];
+    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= fr.n_cg * fr.n_slabs) return;
+    const unsigned cg = gw % fr.n_cg, slab = gw / fr.n_cg;
+    const unsigned col = cg * 32u + (threadIdx.x & 31u);
+    if (col >= fr.W) return;
+    const uint32_t b = fr.base[static_cast<size_t>(slab) * fr.W + col];
+    if (b == 0xffffffffu) return;
+    unsigned long long fbase = 0;  // points of the frames before this one (a set holds a handful of frames)
+    for (unsigned i = 0; i < f; ++i) fbase += totals[i];
+    unsigned long long w = fbase + b;
+    const T* dir = static_cast<const T*>(fr.dir);
+    const T* off = static_cast<const T*>(fr.off);
+    T m[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) m[k] = static_cast<T>(fr.poses[static_cast<size_t>(col) * 16 + k]);
+    const uint64_t ts = (ts_out != nullptr && fr.timestamps != nullptr) ? fr.timestamps[col] : 0ull;
+    const unsigned r0 = slab * kSlabRows, r1 = min(fr.H, r0 + kSlabRows);
+    for (unsigned row = r0; row < r1; ++row) {
+        const size_t px = static_cast<size_t>(row) * fr.W + col;
+        const uint32_t r = fr.range[px];
+        if (r >= min_r && r <= max_r) {
+            if (w < capacity) {
+                const T x = k3_project(r, dir[px * 3], off[px * 3]);
+                const T y = k3_project(r, dir[px * 3 + 1], off[px * 3 + 1]);
+                const T z = k3_project(r, dir[px * 3 + 2], off[px * 3 + 2]);
+                T* o = points + w * 3;
+                o[0] = k3_pose_row(m, x, y, z);
+                o[1] = k3_pose_row(m + 4, x, y, z);
+                o[2] = k3_pose_row(m + 8, x, y, z);
+                if (frame_idx != nullptr) frame_idx[w] = fr.index;
+                if (col_idx != nullptr) col_idx[w] = col;
+                if (ts_out != nullptr) ts_out[w] = ts;
+            }
+            ++w;
+        }
+    }
+}
+
+size_t dewarp_frames_scratch_bytes(unsigned H, unsigned W) {
+    const size_t n_slabs = (H + kSlabRows - 1) / kSlabRows;
+    return 2 * n_slabs * W * sizeof(uint32_t);
+}
+
+cudaError_t launch_dewarp_frames(const K3Frame* frames_dev, unsigned n_frames, unsigned max_warps, uint32_t min_r,
+                                 uint32_t max_r, int dtype, unsigned long long* totals_dev, void* points,
+                                 uint32_t* frame_idx, uint32_t* col_idx, uint64_t* ts_out, unsigned long long capacity,
+                                 cudaStream_t st) {
+    if (n_frames == 0) return cudaSuccess;
+    if (n_frames > 65535) return cudaErrorInvalidValue;
+    const dim3 grid((max_warps + 7) / 8, n_frames);
+    k3_count_batch_kernel<<<grid, 256, 0, st>>>(frames_dev, min_r, max_r);
+    k3_scan_batch_kernel<<<n_frames, 1024, 0, st>>>(frames_dev, totals_dev);
+    if (dtype == OB_F64)
+        k3_emit_batch_kernel<double><<<grid, 256, 0, st>>>(frames_dev, totals_dev, min_r, max_r,
+                                                            static_cast<double*>(points), frame_idx, col_idx, ts_out, capacity);
+    else
+        k3_emit_batch_kernel<float><<<grid, 256, 0, st>>>(frames_dev, totals_dev, min_r, max_r,
+                                                           static_cast<float*>(points), frame_idx, col_idx, ts_out, capacity);
+    count_launch(3);
+    return cudaGetLastError();
+}
+
 }  // namespace ob

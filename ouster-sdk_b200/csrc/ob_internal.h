@@ -28,6 +28,8 @@ struct Tunables {
     int decode_prefetch;      // L2 prefetch of the next tile: 0 off, 1 at tile start (evict_last), 2 before phase B
     int decode_pipe;          // 1 (default): pipelined K2 (ob_decode_pipe.cu) whenever the launch is eligible
     int decode_pipe_warps;    // compute warps of the pipelined K2 (24)
+    int decode_pipe_dyn_rows; // 1 (default): phase A rows of the pipelined K2 are handed out dynamically
+    int decode_pipe_prefetch; // L2 prefetch distance (tiles) of the pipelined K2's packet loads, 0 = off
     int force_generic;     // 1: K1 takes the generic GPU kernel (any width / alignment) instead of the TMA one
     int sm_count;
 };
@@ -99,6 +101,26 @@ size_t dewarp_frame_scratch_bytes(unsigned H, unsigned W);
 cudaError_t launch_dewarp_frame_count(const DewarpFrameArgs& a, cudaStream_t st);  // counts + offsets
 const unsigned long long* dewarp_frame_total_ptr(const DewarpFrameArgs& a);         // device pointer
 cudaError_t launch_dewarp_frame_emit(const DewarpFrameArgs& a, cudaStream_t st);
+
+// batched K3 (dewarp of a FrameSet): one entry per frame, device memory
+struct K3Frame {
+    const uint32_t* range;
+    const void* dir;
+    const void* off;
+    const double* poses;
+    const uint32_t* status;
+    const uint64_t* timestamps;  // nullable
+    uint32_t* cnt;               // n_slabs x W scratch
+    uint32_t* base;              // n_slabs x W scratch
+    unsigned H, W, n_cg, n_slabs;
+    unsigned index;              // the frame's index in the set (reported as frame_idx)
+    unsigned pad;
+};
+size_t dewarp_frames_scratch_bytes(unsigned H, unsigned W);
+cudaError_t launch_dewarp_frames(const K3Frame* frames_dev, unsigned n_frames, unsigned max_warps, uint32_t min_r,
+                                 uint32_t max_r, int dtype, unsigned long long* totals_dev, void* points,
+                                 uint32_t* frame_idx, uint32_t* col_idx, uint64_t* ts_out, unsigned long long capacity,
+                                 cudaStream_t st);
 
 // ---- decode ----
 struct DecodeField {  // device-side copy of ob_field_desc, pre-digested

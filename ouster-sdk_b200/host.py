@@ -46,6 +46,7 @@ _sig("obh_frame_get_status", u64, vp, PP(C.c_uint8), PP(C.c_uint8))
 _sig("obh_frame_set_status", None, vp, u64, C.c_uint8, C.c_uint8)
 _sig("obh_frame_destroy", i32, vp)
 _sig("obh_frame_to_packets", i32, vp, vp, u32, u64, vp, vp, PP(sz))
+_sig("obh_frame_to_packets_device", i32, vp, vp, u32, u64, vp, vp, PP(sz))
 _sig("obh_batcher_create", i32, vp, PP(vp))
 _sig("obh_batcher_batch", i32, vp, vp, sz, u64, vp, PP(i32))
 _sig("obh_batcher_flush", i32, vp, vp)
@@ -58,6 +59,7 @@ _sig("obh_batcher_set_max_cache_size", i32, vp, sz)
 _sig("obh_batcher_set_fused", i32, vp, vp, vp, sz)
 _sig("obh_batcher_set_headers_only", i32, vp, i32)
 _sig("obh_batcher_fused_outputs", i32, vp, i32, PP(vp), PP(sz), PP(vp))
+_sig("obh_batcher_set_device_outputs", i32, vp, sz, PP(C.c_char_p), PP(vp), PP(vp), PP(vp))
 _sig("obh_batcher_set_pipeline_depth", i32, vp, sz)
 _sig("obh_batcher_wait", i32, vp, vp)
 _sig("obh_batcher_destroy", i32, vp)
@@ -305,14 +307,15 @@ class LidarFrame:
         self._h = None
 
 
-def frame_to_packets(frame, info, init_id=0, prod_sn=0):
-    """impl::frame_to_packets -> (packets uint8 [n, size], host_ts uint64 [n])."""
+def frame_to_packets(frame, info, init_id=0, prod_sn=0, device=False):
+    """impl::frame_to_packets -> (packets uint8 [n, size], host_ts uint64 [n]).  device=True: the
+    GPU encoder (K4: set_block of every field + CRC64 in one launch), byte-identical output."""
     psz = info.lidar_packet_size
     out = np.zeros((frame.n_packets, psz), np.uint8)
     ts = np.zeros(frame.n_packets, np.uint64)
     n = sz()
-    check(lib.obh_frame_to_packets(frame._h, info._h, init_id, prod_sn, out.ctypes.data, ts.ctypes.data,
-                                   C.byref(n)))
+    fn = lib.obh_frame_to_packets_device if device else lib.obh_frame_to_packets
+    check(fn(frame._h, info._h, init_id, prod_sn, out.ctypes.data, ts.ctypes.data, C.byref(n)))
     return out[:n.value].copy(), ts[:n.value].copy()
 
 
@@ -375,6 +378,30 @@ class FrameBatcher:
             n = sh.size
         check(lib.obh_batcher_set_fused(self._h, lut._h if lut is not None else None,
                                         sh.ctypes.data if sh is not None else None, n))
+
+    def set_device_outputs(self, fields=None, xyz=None, range_destaggered=None):
+        """FrameBatcher::set_device_outputs: `fields` maps a field name to a CUDA tensor / device
+        pointer holder (h x w of the field's dtype); xyz / range_destaggered are per-return lists of
+        CUDA tensors (need set_fused_cloud).  The decode then writes there instead of the host frame,
+        so the results stay in HBM.  Call with no arguments to detach.  Tensors are kept alive here."""
+        from .core import _ptr
+        self._dev_keep = (fields, xyz, range_destaggered)
+        if not fields and not xyz and not range_destaggered:
+            check(lib.obh_batcher_set_device_outputs(self._h, 0, None, None, None, None))
+            return
+        names = list((fields or {}).keys())
+        c_names = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+        c_ptrs = (vp * max(len(names), 1))(*[_ptr(fields[n]) for n in names])
+
+        def two(lst):
+            if not lst:
+                return None
+            a = (vp * 2)()
+            for r, t in enumerate(lst[:2]):
+                a[r] = _ptr(t) if t is not None else None
+            return a
+        check(lib.obh_batcher_set_device_outputs(self._h, len(names), c_names, c_ptrs, two(xyz),
+                                                 two(range_destaggered)))
 
     def set_pipeline_depth(self, n):
         """n >= 2: batch() returns True once the frame's GPU pass is submitted; wait(frame) before

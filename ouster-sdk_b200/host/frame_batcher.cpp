@@ -377,6 +377,12 @@ void FrameBatcher::flush(LidarFrame& f) {
 
 void FrameBatcher::set_headers_only(bool on) { headers_only_ = on; }
 
+void FrameBatcher::set_device_outputs(const DeviceOutputs* outputs) {
+    wait_all();  // nothing in flight may still target the previous buffers
+    dev_out_on_ = outputs != nullptr;
+    dev_out_ = outputs ? *outputs : DeviceOutputs{};
+}
+
 // (Re)build the device decode table for the fields this frame shares with the profile
 // (foreach_channel_field: profile order, only fields the frame has; impl/lidar_frame_impl.h:367-375)
 // and make sure the current job exists.  Returns the names of the decoded fields, in table order.
@@ -407,7 +413,8 @@ std::vector<std::string> FrameBatcher::ensure_decoder(LidarFrame& f) {
         descs.push_back(d);
         names.push_back(name);
         sig += name + ":" + std::to_string(elem) + ":" + std::to_string(info.offset) + ":" +
-               std::to_string(info.mask) + ":" + std::to_string(info.shift) + ";";
+               std::to_string(info.mask) + ":" + std::to_string(info.shift) + ":" +
+               std::to_string(d.zero_pattern) + ":" + std::to_string(d.range_return) + ";";
     }
     if (descs.size() > OB_MAX_FIELDS) throw std::invalid_argument("too many fields to decode");
     n_returns_ = 0;
@@ -480,7 +487,12 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
     bool identity = s.n_slots * static_cast<size_t>(pf.columns_per_packet) >= f.w;
     for (size_t c = 0; c < f.w && identity; ++c) identity = s.col_src[c] == static_cast<int32_t>(c);
     io.col_src = identity ? nullptr : s.col_src.data();
-    for (size_t i = 0; i < names.size(); ++i) io.fields[i] = f.field(names[i]).get();
+    for (size_t i = 0; i < names.size(); ++i) {
+        io.fields[i] = f.field(names[i]).get();
+        if (dev_out_on_)
+            for (const auto& df : dev_out_.fields)
+                if (df.first == names[i] && df.second) io.fields[i] = df.second;
+    }
 
     const ob_lut* lut = nullptr;
     const int32_t* shifts = nullptr;
@@ -490,8 +502,11 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
         fused_->reserve(f.h, f.w, n_returns_);
         for (int r = 0; r < n_returns_; ++r) {
             io.xyz[r] = fused_->xyz[r].data();
-            if (!fused_->pixel_shift_by_row.empty())
+            if (dev_out_on_ && dev_out_.xyz[r]) io.xyz[r] = dev_out_.xyz[r];
+            if (!fused_->pixel_shift_by_row.empty()) {
                 io.range_destaggered[r] = reinterpret_cast<uint32_t*>(fused_->range_destaggered[r].data());
+                if (dev_out_on_ && dev_out_.range_destaggered[r]) io.range_destaggered[r] = dev_out_.range_destaggered[r];
+            }
         }
         if (!fused_->pixel_shift_by_row.empty()) {
             shifts = fused_->pixel_shift_by_row.data();
@@ -519,9 +534,13 @@ size_t FrameBatcher::batch_burst(const uint8_t* packets, size_t n, size_t stride
     if (!packets || !host_timestamps) throw std::invalid_argument("null pointer");
     if (n > 1 && stride < size) throw std::invalid_argument("packet stride smaller than the packet size");
     Staging& s = *stg_;
-    // page-locked or device memory can be read by the copy engine where it lies
-    const bool dma = !headers_only_ && ob_pointer_kind(packets) != 0 &&
-                     ob_pointer_kind(packets + (n - 1) * stride + size - 1) != 0;
+    // The host state machine reads the packet headers with the CPU, so the burst must be host-readable.
+    // Page-locked host memory (and managed memory, which reports as device-kind) can additionally be read
+    // by the copy engine where it lies; plain device memory is rejected instead of segfaulting below.
+    const int kind0 = ob_pointer_kind(packets), kind1 = ob_pointer_kind(packets + (n - 1) * stride + size - 1);
+    if ((kind0 == 2 || kind1 == 2) && !ob_pointer_host_readable(packets))
+        throw std::invalid_argument("batch_burst needs host-readable packets (pageable, page-locked or managed memory)");
+    const bool dma = !headers_only_ && kind0 != 0 && kind1 != 0;
     if (dma) {
         s.burst_begin = packets;
         s.burst_end = packets + (n - 1) * stride + size;
@@ -540,6 +559,12 @@ size_t FrameBatcher::batch_burst(const uint8_t* packets, size_t n, size_t stride
                              s.runs.end());
                 try {
                     b.settle_user_uploads();
+                } catch (...) {
+                }
+                // the slots of the dropped runs were never uploaded: forget every column that points into
+                // the current frame's staging so that a later finalize cannot decode stale device bytes
+                try {
+                    b.reset();
                 } catch (...) {
                 }
             }
@@ -671,8 +696,12 @@ bool FrameBatcher::batch(const uint8_t* buf, size_t size, uint64_t host_timestam
 }
 
 bool FrameBatcher::batch(const Packet& packet, LidarFrame& f) {
-    if (packet.type() == PacketType::Imu || packet.type() == PacketType::Zone)
-        return false;  // IMU / zone-monitor packets are outside the accelerated path
+    // lidar_frame.cpp batch_packet: only Lidar packets are batched (a LEGACY stream has no packet type
+    // word, so its untyped buffers are taken as lidar); IMU / zone-monitor packets are outside the
+    // accelerated path
+    if (packet.type() != PacketType::Lidar &&
+        !(packet.type() == PacketType::Unknown && pf.udp_profile_lidar == UDPProfileLidar::LEGACY))
+        return false;
     return batch_impl(packet.buf.data(), packet.buf.size(), packet.host_timestamp, f);
 }
 

@@ -313,6 +313,20 @@ ob_status obh_frame_to_packets(const obh_frame* f, const obh_sensor* s, uint32_t
     });
 }
 
+ob_status obh_frame_to_packets_device(const obh_frame* f, const obh_sensor* s, uint32_t init_id,
+                                      uint64_t prod_sn, uint8_t* out, uint64_t* host_ts, size_t* n_out) {
+    return guard([&] {
+        if (!f || !s || !out || !n_out) throw std::invalid_argument("null pointer");
+        auto packets = impl::frame_to_packets_device(f->ref(), *s->pf, init_id, prod_sn);
+        const size_t psz = s->pf->lidar_packet_size;
+        for (size_t i = 0; i < packets.size(); ++i) {
+            std::memcpy(out + i * psz, packets[i].buf.data(), psz);
+            if (host_ts) host_ts[i] = packets[i].host_timestamp;
+        }
+        *n_out = packets.size();
+    });
+}
+
 // ---- FrameBatcher ----
 ob_status obh_batcher_create(const obh_sensor* s, obh_batcher** out) {
     return guard([&] {
@@ -391,6 +405,31 @@ ob_status obh_batcher_fused_outputs(obh_batcher* b, int ret, void** xyz, size_t*
             *rd = b->fused.range_destaggered[ret].size()
                       ? reinterpret_cast<uint32_t*>(b->fused.range_destaggered[ret].data())
                       : nullptr;
+    });
+}
+
+ob_status obh_batcher_set_device_outputs(obh_batcher* b, size_t n_fields, const char* const* names,
+                                         void* const* field_ptrs, void* const* xyz,
+                                         uint32_t* const* range_destaggered) {
+    return guard([&] {
+        if (!b) throw std::invalid_argument("null pointer");
+        if (n_fields == 0 && !xyz && !range_destaggered) {
+            b->b->set_device_outputs(nullptr);
+            return;
+        }
+        if (n_fields && (!names || !field_ptrs)) throw std::invalid_argument("null pointer");
+        FrameBatcher::DeviceOutputs o;
+        for (size_t i = 0; i < n_fields; ++i) {
+            if (!names[i]) throw std::invalid_argument("null field name");
+            if (field_ptrs[i] && ob_pointer_kind(field_ptrs[i]) != 2)
+                throw std::invalid_argument("device outputs must be device memory");
+            o.fields.emplace_back(names[i], field_ptrs[i]);
+        }
+        for (int r = 0; r < 2; ++r) {
+            if (xyz) o.xyz[r] = xyz[r];
+            if (range_destaggered) o.range_destaggered[r] = range_destaggered[r];
+        }
+        b->b->set_device_outputs(&o);
     });
 }
 

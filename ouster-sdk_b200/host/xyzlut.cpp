@@ -145,6 +145,116 @@ std::vector<Packet> frame_to_packets(const LidarFrame& frame, const PacketFormat
     return out;
 }
 
+// ---- frame_to_packets on the device (K4) ----
+std::vector<Packet> frame_to_packets_device(const LidarFrame& frame, const PacketFormat& pf, uint32_t init_id,
+                                            uint64_t prod_sn) {
+    const size_t cpp = static_cast<size_t>(pf.columns_per_packet);
+    const size_t n_packets = frame.packet_timestamp().size();
+    if (frame.w / cpp != n_packets)
+        throw std::invalid_argument(
+            "Mismatch between expected number of packets and PacketFormat.columns_per_packet");
+    const bool legacy = pf.udp_profile_lidar == UDPProfileLidar::LEGACY;
+    const bool with_crc = !legacy && pf.header_type == HeaderType::STANDARD;
+    const size_t psz = pf.lidar_packet_size;
+    // packet-level headers by the reference's setters; LEGACY keeps frame-level words inside its column
+    // headers, so its template is the whole packet
+    const size_t hb = legacy ? psz : pf.packet_header_size;
+    std::vector<uint8_t> headers(n_packets * hb + 16, 0);
+    std::vector<uint8_t> tmp(psz + 16);
+    std::vector<bool> emit(n_packets, false);
+    for (size_t pid = 0; pid < n_packets; ++pid) {
+        std::fill(tmp.begin(), tmp.end(), 0);
+        uint8_t* b = tmp.data();
+        pf.set_shutdown(b, static_cast<uint8_t>(frame.thermal_shutdown()));
+        pf.set_shot_limiting(b, static_cast<uint8_t>(frame.shot_limiting()));
+        pf.set_shutdown_countdown(b, frame.shutdown_countdown);
+        pf.set_shot_limiting_countdown(b, frame.shot_limiting_countdown);
+        pf.set_frame_id(b, static_cast<uint32_t>(frame.frame_id));
+        pf.set_init_id(b, init_id);
+        pf.set_prod_sn(b, prod_sn);
+        pf.set_packet_type(b, 0x1);
+        pf.set_alert_flags(b, frame.alert_flags()[pid]);
+        bool any_valid = false;
+        for (size_t c = 0; c < cpp; ++c) {
+            const size_t id = pid * cpp + c;
+            if (legacy) {
+                uint8_t* col = pf.nth_col(static_cast<int>(c), b);
+                pf.set_col_status(col, frame.status()[id]);
+                pf.set_col_measurement_id(col, static_cast<uint16_t>(id));
+                pf.set_col_timestamp(col, frame.timestamp()[id]);
+            }
+            any_valid = any_valid || (frame.status()[id] & 0x01);
+        }
+        emit[pid] = any_valid || frame.packet_timestamp()[pid] != 0;
+        std::memcpy(headers.data() + pid * hb, b, hb);
+    }
+    // decoder table: the fields the frame shares with the profile, profile order (foreach_channel_field)
+    std::vector<ob_field_desc> descs;
+    std::vector<const void*> srcs;
+    for (auto it = pf.begin(); it != pf.end(); ++it) {
+        const std::string& name = it->first;
+        if (!frame.has_field(name) || name == ChanField::RAW_HEADERS) continue;
+        const Field& fld = frame.field(name);
+        const FieldDecodeInfo& info = pf.field_decode_info(name);
+        size_t elem = fld.element_size();
+        for (size_t d = 2; d < fld.shape().size(); ++d) elem *= fld.shape()[d];
+        ob_field_desc d{};
+        d.offset = static_cast<uint32_t>(info.offset);
+        d.elem_size = static_cast<uint32_t>(elem);
+        d.mask = info.mask;
+        d.shift = info.shift;
+        d.range_return = -1;
+        descs.push_back(d);
+        srcs.push_back(fld.get());
+    }
+    if (descs.size() > OB_MAX_FIELDS) throw std::invalid_argument("too many fields to encode");
+    auto conv = [](const FieldDecodeInfo& fi) {
+        ob_field_desc d{};
+        d.offset = static_cast<uint32_t>(fi.offset);
+        d.elem_size = 8;
+        d.mask = fi.mask;
+        d.shift = fi.shift;
+        d.range_return = -1;
+        return d;
+    };
+    ob_packet_layout L{};
+    L.packet_header_size = static_cast<uint32_t>(pf.packet_header_size);
+    L.col_header_size = static_cast<uint32_t>(pf.col_header_size);
+    L.channel_data_size = static_cast<uint32_t>(pf.channel_data_size);
+    L.col_size = static_cast<uint32_t>(pf.col_size);
+    L.packet_size = static_cast<uint32_t>(psz);
+    L.columns_per_packet = static_cast<uint32_t>(pf.columns_per_packet);
+    L.pixels_per_column = static_cast<uint32_t>(pf.pixels_per_column);
+    L.columns_per_frame = static_cast<uint32_t>(frame.w);
+    L.col_timestamp = conv(pf.col_timestamp_info());
+    L.col_measurement_id = conv(pf.col_measurement_id_info());
+    L.col_status = conv(pf.col_status_info());
+    ob_decoder* dec = nullptr;
+    b200::check(ob_decoder_create(&L, descs.data(), descs.size(), b200::device(), &dec));
+    std::shared_ptr<ob_decoder> guard_dec(dec, [](ob_decoder* d) { ob_decoder_destroy(d); });
+    std::vector<uint8_t> wire(n_packets * psz);
+    ob_encode_io io{};
+    for (size_t k = 0; k < srcs.size(); ++k) io.fields[k] = srcs[k];
+    io.timestamp = frame.timestamp().data();
+    io.status = frame.status().data();
+    io.packet_headers = headers.data();
+    io.packet_header_bytes = hb;
+    io.packets = wire.data();
+    io.packet_stride = psz;
+    b200::check(ob_encode_frames(dec, &io, 1, with_crc ? 1 : 0, b200::thread_stream()));
+    b200::synchronize();
+    std::vector<Packet> out;
+    out.reserve(n_packets);
+    for (size_t pid = 0; pid < n_packets; ++pid) {
+        if (!emit[pid]) continue;  // nothing to send (lidar_frame_impl.h:497-500)
+        LidarPacket pkt(psz);
+        std::memcpy(pkt.buf.data(), wire.data() + pid * psz, psz);
+        pkt.host_timestamp = frame.packet_timestamp()[pid];
+        out.push_back(std::move(pkt));
+    }
+    return out;
+}
+
 }  // namespace impl
 
 Field destagger(const SensorInfo& info, const Field& field, bool inverse) {

@@ -14,6 +14,7 @@
 
 #include "ouster/core/frame_pipeline.h"
 #include "ouster/core/lidar_scan.h"  // deprecated forwarding header
+#include "ouster/algorithm/normals.h"
 #include "ouster/core/pose_util.h"
 #include "ouster/core/xyzlut.h"
 
@@ -184,12 +185,55 @@ int main() {
         CHECK(k == static_cast<size_t>(world.rows()) && k > 0);
         expect_throw<std::out_of_range>([&] { posed.set_column_pose(-1, mat4d::Identity()); },
                                         "Column index out of range");
+        // dewarp(frame_set, xyzluts, ...): the frames of a set, an empty slot skipped, concatenated
+        auto f0 = std::make_shared<LidarScan>(posed);
+        auto f2 = std::make_shared<LidarScan>(posed);
+        f2->status()[1] = 0;
+        FrameSet set{f0, nullptr, f2};
+        std::vector<XYZLut> luts{lut, lut, lut};
+        std::vector<uint32_t> fidx;
+        PointCloudXYZd set_pts = dewarp<double>(set, luts, 0.3, 50.0, &fidx);
+        PointCloudXYZd second = dewarp<double>(*f2, lut, 0.3, 50.0);
+        CHECK(set_pts.rows() == world.rows() + second.rows() && fidx.size() == static_cast<size_t>(set_pts.rows()));
+        CHECK(std::memcmp(set_pts.data(), world.data(), sizeof(double) * 3 * world.rows()) == 0);
+        CHECK(std::memcmp(set_pts.data() + 3 * world.rows(), second.data(), sizeof(double) * 3 * second.rows()) == 0);
+        CHECK(fidx.front() == 0 && fidx.back() == 2);
+    }
+
+    // ---- surface normals on the destaggered cloud (ouster/algorithm/normals.h) ----
+    {
+        auto range = scan.field<uint32_t>(ChanField::RANGE);
+        PointCloudXYZd cloud = lut(range);
+        img_t<uint32_t> rd = destagger<uint32_t>(*info, range);
+        PointCloudXYZd xd(h * w, 3);
+        destagger_into<double>(cloud.data(), h, w, 3, info->format.pixel_shift_by_row, false, xd.data());
+        DenseArray<double> origins(w, 3);
+        auto n = ouster::sdk::algorithm::normals(ArrayRef<const double>(xd), ArrayRef<const uint32_t>(rd),
+                                                 ArrayRef<const double>(origins));
+        CHECK(n.rows() == h * w && n.cols() == 3);
+        size_t unit = 0;
+        for (size_t i = 0; i < h * w; ++i) {
+            const double l2 = n(i, 0) * n(i, 0) + n(i, 1) * n(i, 1) + n(i, 2) * n(i, 2);
+            CHECK(l2 == 0.0 || std::abs(l2 - 1.0) < 1e-9);
+            unit += l2 > 0.5;
+            if (rd.data()[i] == 0) CHECK(l2 == 0.0);
+        }
+        CHECK(unit > 0);
+        expect_throw<std::runtime_error>(
+            [&] { ouster::sdk::algorithm::normals(ArrayRef<const double>(xd), ArrayRef<const uint32_t>(rd),
+                                                  ArrayRef<const double>(origins), 1, 0.0174, -1.0); },
+            "normals: target_distance_m must be positive");
     }
 
     // ---- frame_to_packets -> ScanBatcher -> LidarScan round trip ----
     PacketFormat pf(*info);
     std::vector<Packet> packets = impl::frame_to_packets(scan, pf, 0, 0);
     CHECK(packets.size() == w / 16);
+    {   // the same packets from the GPU encoder (set_block of every field + CRC64 in one launch)
+        std::vector<Packet> dev_packets = impl::frame_to_packets_device(scan, pf, 0, 0);
+        CHECK(dev_packets.size() == packets.size());
+        for (size_t i = 0; i < packets.size(); ++i) CHECK(dev_packets[i].buf == packets[i].buf);
+    }
     LidarScan out(info);
     ScanBatcher batcher(*info);  // deprecated alias of FrameBatcher
     for (size_t i = 0; i < packets.size(); ++i) {

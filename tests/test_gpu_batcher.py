@@ -171,3 +171,39 @@ def test_custom_profile_through_batcher(ob):
     assert [b2.batch(p, 5, fr2) for p in packets][-1]
     for n in ("RANGE", "FLAGS", "REFLECTIVITY", "SIGNAL", "NEAR_IR"):
         assert np.array_equal(fr.field(n), fr2.field(n)), n
+
+
+@pytest.mark.parametrize("profile,header,h,w", [
+    ("RNG19_RFL8_SIG16_NIR16_DUAL", "STANDARD", 128, 1024), ("RNG19_RFL8_SIG16_NIR16", "STANDARD", 64, 512),
+    ("RNG15_RFL8_NIR8", "STANDARD", 32, 512), ("LEGACY", "STANDARD", 32, 512),
+    ("FUSA_RNG15_RFL8_NIR8_DUAL", "FUSA", 32, 512), ("RNG19_RFL8_SIG16_NIR16_RGB16", "STANDARD", 32, 512),
+])
+def test_gpu_frame_to_packets_is_byte_identical(ob, profile, header, h, w):
+    """K4 (ob_encode_frames): set_block of every field + column headers + CRC64 on the device ==
+    the host encoder == the oracle's frame_to_packets (impl/lidar_frame_impl.h:435-531), byte for
+    byte, including invalid columns (no pixel data) and packets that are not emitted at all."""
+    from tests.helpers import oracle_pf, random_frame
+    si = ob.SensorInfo(profile, h, w, 16, header_type=header, fw_rev="v3.2.1")
+    masks = {f[0]: f[6] for f in si.fields()}
+    rs = np.random.default_rng(99)
+    src = ob.LidarFrame(si)
+    for name in src.fields:
+        a = src.field(name)
+        a[...] = (rs.integers(0, 1 << 32, size=a.shape, dtype=np.uint64) & np.uint64(masks.get(name, 0xffff))).astype(a.dtype)
+    src.measurement_id[:] = np.arange(w)
+    src.timestamp[:] = 1000 + np.arange(w)
+    src.status[:] = 1
+    src.status[5::7] = 0                      # invalid columns: headers only
+    src.status[32:48] = 0                     # a whole packet without valid columns ...
+    src.packet_timestamp[:] = 10 + np.arange(w // 16)
+    src.packet_timestamp[2] = 0               # ... and no host timestamp: not emitted
+    src.alert_flags[:] = rs.integers(0, 256, w // 16)
+    src.frame_id = 1234
+    host_pk, host_ts = ob.frame_to_packets(src, si, init_id=77, prod_sn=991)
+    dev_pk, dev_ts = ob.frame_to_packets(src, si, init_id=77, prod_sn=991, device=True)
+    assert host_pk.shape == dev_pk.shape == (w // 16 - 1, si.lidar_packet_size)
+    assert np.array_equal(host_ts, dev_ts)
+    assert np.array_equal(host_pk, dev_pk)
+    if profile != "LEGACY" and header == "STANDARD":   # the CRC the sensor would have computed
+        for p in dev_pk[:3]:
+            assert int(p[-8:].view(np.uint64)[0]) == si.calculate_crc(p)

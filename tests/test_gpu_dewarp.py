@@ -160,3 +160,42 @@ def test_dewarp_frame_matches_reference_loop(ob, h, w, dtype):
     none[3] = 2
     assert ob.dewarp_frame(lut, rng, poses, none, ts, 0.5, 30.0).shape == (0, 3)
     assert orc.dewarp_frame(rng, d, o, poses, none, ts, 0.5, 30.0)[0].shape == (0, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_dewarp_frame_set_is_the_concatenation_of_its_frames(ob, dtype):
+    """dewarp(FrameSet, xyzluts, min_range, max_range) (pose_util.h:475, impl/dewarp_impl.h:84-117): the
+    frames of a set -- different sensors, different shapes, one empty slot -- dewarped in one batched
+    pass == the oracle's single-frame loop applied frame by frame and concatenated, with the
+    frame / column / timestamp provenance of dewarp_impl."""
+    from tests.helpers import random_lut, random_range
+    shapes = [(64, 1024), None, (128, 512), (20, 516)]
+    frames, want_p, want_f, want_c, want_t = [], [], [], [], []
+    for i, hw in enumerate(shapes):
+        if hw is None:
+            frames.append(None)
+            continue
+        h, w = hw
+        rng = random_range(h, w, 11 + i, p_zero=0.3, max_range=60000)
+        d, o = random_lut(h * w, 5 + i, dtype)
+        poses = _random_poses(w, np.float64, 3 + i)
+        status = np.ones(w, np.uint32)
+        status[: w // 9] = 0
+        status[np.random.default_rng(i).integers(w // 9, w, w // 7)] = 0
+        ts = (500 * i + 3 * np.arange(w)).astype(np.uint64)
+        frames.append({"lut": ob.XYZLutT.from_arrays(d, o, h, w), "range": rng, "poses": poses, "status": status,
+                       "timestamps": ts})
+        p, c, t = orc.dewarp_frame(rng, d, o, poses, status, ts, 0.5, 45.0)
+        want_p.append(p)
+        want_c.append(c)
+        want_t.append(t)
+        want_f.append(np.full(len(c), i, np.uint32))
+    got_p, got_f, got_c, got_t = ob.dewarp_frames(frames, 0.5, 45.0, provenance=True)
+    assert np.array_equal(got_p, np.concatenate(want_p))
+    assert np.array_equal(got_f, np.concatenate(want_f))
+    assert np.array_equal(got_c, np.concatenate(want_c))
+    assert np.array_equal(got_t, np.concatenate(want_t))
+    assert np.array_equal(ob.dewarp_frames(frames, 0.5, 45.0), np.concatenate(want_p))
+    assert ob.dewarp_frames([None, None]).shape == (0, 3)
+    assert ob.dewarp_frames(frames, 50.0, 40.0).shape == (0, 3)     # empty range window

@@ -115,3 +115,66 @@ def test_pyapi_dewarp_transform_dispatch(core):
         core.dewarp(pts.astype(np.int32), poses)
     with pytest.raises(RuntimeError, match="Number of points per set must match number of poses"):
         core.dewarp(np.zeros((2, 5, 3)), poses)
+
+
+def test_device_chain_scanbatcher_xyzlut_destagger_normals(core):
+    """ScanBatcher -> XYZLut -> destagger -> normals on CUDA tensors / DLPack, nothing
+    copied to the host in between; every stage equal to the CPU oracle on the same packets."""
+    import torch
+    from oracle import oracle as orc
+    from tests.helpers import oracle_pf
+    meta, packets = load_fixture("OS-1-128_767798045_1024x10_20230712_120049")
+    info = core.SensorInfo.from_meta(meta)
+    h, w = info.h, info.w
+    lut = core.XYZLut(info)
+    batcher = core.DeviceScanBatcher(info, lut=lut)
+    scan = batcher.new_scan()
+    done = [batcher(p, 77, scan) for p in packets]
+    if not done[-1]:                  # the fixture ends inside the frame: materialise what arrived
+        batcher.flush(scan)
+    # oracle decode of the same packets
+    pf = oracle_pf(meta)
+    oframe = orc.Frame(pf)
+    ob_ = orc.Batcher(pf, init_id=meta["init_id"], column_window=meta["column_window"])
+    for p in packets:
+        ob_.batch(p, 77, oframe)
+    for name in scan.fields:
+        t = scan.field(name)
+        assert t.is_cuda
+        ref = oframe.field(name)
+        assert np.array_equal(t.cpu().numpy().view(ref.dtype), ref), name
+    assert np.array_equal(scan.timestamp, oframe.timestamp)
+    shifts = np.asarray(meta["pixel_shift_by_row"], np.int32)
+    d, o = lut.direction, lut.offset
+    ref_xyz = orc.cartesian(oframe.field("RANGE"), d, o)
+    # fused products of the same launch, on the device
+    assert scan.xyz[0].is_cuda and np.array_equal(scan.xyz[0].cpu().numpy(), ref_xyz)
+    assert np.array_equal(scan.range_destaggered[0].cpu().numpy().view(np.uint32),
+                          orc.destagger(oframe.field("RANGE"), shifts))
+    # XYZLut on a device range image (through DLPack) -> device points
+    class Capsule:   # a foreign DLPack exporter
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+    pts = lut(Capsule(scan.field("RANGE")))
+    assert pts.is_cuda and pts.shape == (h, w, 3)
+    assert np.array_equal(pts.cpu().numpy().reshape(-1, 3), ref_xyz)
+    # destagger on the device, any dtype / trailing dims
+    xd = core.destagger(info, pts)
+    rd = core.destagger(info, scan.field("RANGE"))
+    assert xd.is_cuda and rd.is_cuda
+    assert np.array_equal(xd.cpu().numpy(), orc.destagger(ref_xyz.reshape(h, w, 3), shifts))
+    # normals on the device
+    org = np.zeros((w, 3))
+    n, sub = core.normals(xd, rd, org, return_subtent=True)
+    assert n.is_cuda and n.shape == (h, w, 3)
+    ref_n = orc.normals(xd.cpu().numpy(), rd.cpu().numpy().view(np.uint32), sensor_origins_xyz=org,
+                        vertical_subtent=sub)
+    assert np.array_equal(n.cpu().numpy(), ref_n)
+    back = torch.from_dlpack(n)          # results are DLPack exporters themselves
+    assert back.data_ptr() == n.data_ptr()
