@@ -13,8 +13,9 @@ Mpoints/s of 128x2048 dual-return range->XYZ (+ destaggered range) through the f
   "sweep"       configs[4]: 32x512 .. 128x2048, single + dual return, K1 and K2, next to the CPU figure,
   "pcie"        pinned-memory H2D / D2H copy rates measured in this run (the e2e figures sit on them).
 
-A "step" is one pass of the hot path over one batch of `frames_per_step` synthetic frames (64 frames
-= 33.5 Mpoints, > 126 MB L2 of DRAM traffic per step, so consecutive steps cannot be served from cache).
+A "step" is one pass of the hot path over one batch of `frames_per_step` synthetic frames (K1: 128 frames
+= 67 Mpoints and 1.35 GB of DRAM traffic per step; K2: 64 frames, 1.13 GB -- far beyond the 126 MB L2, so
+consecutive steps cannot be served from cache).
 
   value : device-resident inputs/outputs, one fused launch per step, CUDA-event timed.
   e2e   : the same batch through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of
@@ -326,6 +327,90 @@ def measure_k1(args, ob, torch, dist, rank, local_rank, world, pcie):
     }
 
 
+def measure_lut_free(args, ob, torch, dist, rank, local_rank, world):
+    """SURVEY 8d's LUT-free variant, reported beside the LUT path: the same K1 / K2 launches with a LUT
+    built from the OS1-128 intrinsics and switched to the analytic projection (ob_lut_set_analytic).
+    Opt-in mode: XYZ agrees with the oracle's float LUT path to 1e-5 norm-wise (checked here on every
+    frame), it is not bit-exact."""
+    import bench_k2
+    dev = torch.device("cuda", local_rank)
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "OS-1-128_767798045_1024x10_20230712_120049.json")))
+    args_i = (W, H, 0.001, meta["beam_to_lidar_transform"], meta["lidar_to_sensor_transform"],
+              meta["beam_azimuth_angles"], meta["beam_altitude_angles"])
+    lut = ob.XYZLutT.from_intrinsics(*args_i, dtype=np.float32, device=local_rank)
+    d, o = lut.direction.copy(), lut.offset.copy()          # the float LUT the analytic mode replaces
+    lut.set_analytic(True)
+    stream = torch.cuda.current_stream()
+    obs = ob.Stream(local_rank, cuda_stream=stream.cuda_stream)
+    peak, _ = bc.measured_peaks()
+    out = {}
+
+    def timed(step, steps=10, warmup=3):
+        for _ in range(warmup):
+            step()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return bc.max_over_ranks(torch, dist, dev, e0.elapsed_time(e1) / steps * 1e-3)
+
+    def normwise_ok(got, ref):
+        err = np.linalg.norm(got.astype(np.float64) - ref.astype(np.float64), axis=-1)
+        return bool(np.all(err <= 1e-5 * np.linalg.norm(ref.astype(np.float64), axis=-1) + 1e-7))
+
+    from oracle import oracle as orc   # checker only
+    # ---- K1 ----
+    for returns in (2, 1):
+        F = 64
+        rng_host = synth_pool(F, seed=142 + rank, returns=returns)
+        t_rng = torch.from_numpy(rng_host.view(np.int32)).to(dev)
+        t_xyz = torch.empty((F, returns, H * W, 3), dtype=torch.float32, device=dev)
+        t_rd = torch.empty((F, returns, H, W), dtype=torch.int32, device=dev)
+        s = timed(ob.plan_scan_to_cloud(lut, SHIFTS, t_rng, xyz=t_xyz, range_destaggered=t_rd, stream=obs))
+        ref_xyz, ref_rd = orc.pool_k1(rng_host, SHIFTS, d, o)
+        got = t_xyz.cpu().numpy()
+        ok = normwise_ok(got, ref_xyz) and bool(np.array_equal(t_rd.cpu().numpy().view(np.uint32), ref_rd))
+        ok = ok and bool(np.all(got[rng_host.reshape(F, returns, -1) == 0] == 0.0))
+        n = H * W
+        dram = F * n * returns * (4 + 12 + 4)          # range in + XYZ + destaggered range out; no LUT stream
+        out[f"k1_{'dual' if returns == 2 else 'single'}"] = {
+            "value": world * F * n * returns / s / 1e6, "unit": "Mpoints/s", "ms_per_step": s * 1e3,
+            "frac": dram / s / 1e9 / peak, "within_1e-5_of_oracle_lut_path": bc.all_ok(torch, dist, dev, ok)}
+        del t_rng, t_xyz, t_rd
+    # ---- K2 ----
+    st = bench_k2.K2State(args, ob, torch, dist, rank, local_rank, world)
+    F = st.F
+    plan = st.dec.prepare_batch(F, st.t_pk, st.n_slots, st.psz, st.n_slots * st.psz, st.fields, lut=lut,
+                                pixel_shift_by_row=SHIFTS, xyz=st.xyz, range_destaggered=st.rd, timestamp=st.t_ts,
+                                measurement_id=st.t_mid, status=st.t_st, stream=st.obs)
+    lp0 = ob.kernel_launch_count("decode_pipe")
+    s = timed(plan)
+    piped = ob.kernel_launch_count("decode_pipe") > lp0
+    opf, oframes = st.oracle_frames(orc)
+    ok = True
+    dev_xyz = [t.cpu().numpy() for t in st.xyz]
+    for i in range(F):
+        of = oframes[i % st.ND]
+        ok &= bool(np.array_equal(st.fields["RANGE"][i].cpu().numpy().view(np.uint32), of.field("RANGE")))
+        for r, nm in enumerate(("RANGE", "RANGE2")):
+            if i < st.ND:
+                ok &= normwise_ok(dev_xyz[r][i], orc.cartesian(of.field(nm), d, o))
+            else:
+                ok &= bool(np.array_equal(dev_xyz[r][i], dev_xyz[r][i % st.ND]))
+    _, comp = bc.k2_bytes(H, W, R, F, st.psz, bench_k2.CPP, st.field_bytes_px, n_luts=0)
+    out["k2_dual"] = {"value": world * F * POINTS_PER_FRAME / s / 1e6, "unit": "Mpoints/s", "ms_per_step": s * 1e3,
+                      "frac": comp / s / 1e9 / peak, "pipelined_kernel": bool(piped),
+                      "within_1e-5_of_oracle_lut_path": bc.all_ok(torch, dist, dev, ok)}
+    out["note"] = ("opt-in LUT-free projection (ob_lut_set_analytic): direction/offset rebuilt in-kernel from per-row / "
+                   "per-column tables of a LUT made from intrinsics; frac = compulsory DRAM bytes without any LUT stream")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,7 +420,7 @@ def main():
     ap.add_argument("--only", default="all", choices=["all", "k1", "k2", "sweep"],
                     help="restrict the run to one part (tuning / profiling aid); default: everything")
     ap.add_argument("--workload", default=None, choices=["k1", "k2"], help="alias of --only (kept for tools)")
-    ap.add_argument("--frames", type=int, default=64, help="K1 frames per step (per GPU)")
+    ap.add_argument("--frames", type=int, default=128, help="K1 frames per step (per GPU)")
     ap.add_argument("--streams-per-gpu", type=int, default=1,
                     help="with --only k2: independent sensor streams (own LUT each) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -404,6 +489,8 @@ def main():
             line["k2"] = bench_k2.measure_k2(st, args, 1, pcie)
             line["k2_streams8"] = bench_k2.measure_k2(st, args, 8, pcie, with_e2e=False, with_cpu=False)
             del st
+        if args.only == "all":
+            line["lut_free"] = measure_lut_free(args, ob, torch, dist, rank, local_rank, world)
         if args.only in ("all", "sweep") and not args.no_sweep:
             import bench_sweep
             line["sweep"] = bench_sweep.run_sweep(args, ob, torch, dist, rank, local_rank, world)
@@ -411,9 +498,19 @@ def main():
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+        # NCCL_DEBUG output (left as the caller set it) also arrives from library finalisers at process
+        # exit.  The JSON must be the LAST stdout line: the other ranks leave first and without running
+        # finalisers, rank 0 prints after they are gone and leaves the same way.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if rank != 0:
+            os._exit(0)
+        time.sleep(1.0)
     if rank == 0:
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
+        if dist is not None:
+            os._exit(0)
 
 
 if __name__ == "__main__":

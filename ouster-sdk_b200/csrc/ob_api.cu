@@ -47,6 +47,8 @@ static Tunables& tunables_mut(int device) {
     if (device < 0 || device >= 64) device = 0;
     if (!g_tun_have[device]) {
         Tunables t;
+        t.cloud_auto = (std::getenv("OB_CLOUD_TW") || std::getenv("OB_CLOUD_STAGES") || std::getenv("OB_CLOUD_CTAS_PER_SM") ||
+                        std::getenv("OB_CLOUD_THREADS")) ? 0 : 1;
         t.cloud_tw = env_int("OB_CLOUD_TW", 512);
         t.cloud_stages = std::max(2, env_int("OB_CLOUD_STAGES", 3));
         t.cloud_threads = std::min(256, std::max(32, env_int("OB_CLOUD_THREADS", 128) / 32 * 32));  // compute threads
@@ -87,6 +89,7 @@ bool set_tunable(int device, const char* name, int value) {
     std::lock_guard<std::mutex> lk(g_tun_mx);
     Tunables& t = tunables_mut(device);
     const std::string n(name);
+    if (n.rfind("cloud_", 0) == 0 && n != "cloud_store_lag" && n.find("pose") == std::string::npos) t.cloud_auto = 0;
     if (n == "cloud_tw") t.cloud_tw = std::max(4, value / 4 * 4);
     else if (n == "cloud_stages") t.cloud_stages = std::max(2, value);
     else if (n == "cloud_threads") t.cloud_threads = std::min(256, std::max(32, value / 32 * 32));

@@ -613,7 +613,11 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     }
 
     const bool pose = a.poses != nullptr && need_lut;
-    int TW = pose ? tn.cloud_pose_tw : tn.cloud_tw;
+    // Single-return frames move half the bytes per tile, so the per-tile fixed cost (mbarrier hand-offs,
+    // TMA issue) weighs twice as much: 1024-pixel tiles, 4 stages, 2 CTAs per SM measured 0.91 of the copy
+    // peak vs 0.73 with the dual-return geometry (profiles/r02_sweep_k1_single.md).
+    const bool wide = tn.cloud_auto && !pose && a.n_returns == 1 && sizeof(T) == 4;
+    int TW = pose ? tn.cloud_pose_tw : (wide ? 1024 : tn.cloud_tw);
     if (sizeof(T) == 8) TW = std::max(4, TW / 2 / 4 * 4);
     TW = std::min(TW, a.W);
     TW = std::max(4, TW / 4 * 4);
@@ -627,7 +631,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     p.RT = RT;
     p.row_blocks = row_blocks;
     p.tiles_per_row = (a.W + TW - 1) / TW;
-    p.stages = pose ? tn.cloud_pose_stages : tn.cloud_stages;
+    p.stages = pose ? tn.cloud_pose_stages : (wide ? 4 : tn.cloud_stages);
     p.store_lag = tn.cloud_store_lag ? 1 : 0;
     if (pose) p.stages = std::max(2, std::min(p.stages, RT - 1));  // the pose double buffer relies on RPI > stages
     p.n_tiles = static_cast<unsigned>(row_blocks) * p.tiles_per_row * a.n_frames;  // work items
@@ -638,7 +642,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     const size_t smem = 256 + pose_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
     if (smem > 227u * 1024u) return cudaErrorInvalidValue;
     const int ctas = std::max<int>(
-        1, std::min<size_t>(pose ? tn.cloud_pose_ctas_per_sm : tn.cloud_ctas_per_sm, (227u * 1024u) / smem));
+        1, std::min<size_t>(pose ? tn.cloud_pose_ctas_per_sm : (wide ? 2 : tn.cloud_ctas_per_sm), (227u * 1024u) / smem));
     const int grid =
         static_cast<int>(std::min<unsigned>(p.n_tiles, static_cast<unsigned>(tn.sm_count) * ctas));
     void (*kern)(CloudParams<T>);

@@ -20,6 +20,7 @@ struct Tunables {
     int cloud_pose_tw;     // pixels per row of a tile of the pose-fused variant
     int cloud_pose_stages, cloud_pose_ctas_per_sm;
     int cloud_store_lag;   // 1: refill the stage of tile k-2 instead of k-1 (hides the store drain)
+    int cloud_auto;        // 1: nobody touched the cloud_* geometry -> launch_cloud picks it per return count
     int decode_stages;
     int decode_threads;
     int decode_ctas_per_sm;
