@@ -14,7 +14,7 @@ Mpoints/s of 128x2048 dual-return range->XYZ (+ destaggered range) through the f
   "pcie"        pinned-memory H2D / D2H copy rates measured in this run (the e2e figures sit on them).
 
 A "step" is one pass of the hot path over one batch of `frames_per_step` synthetic frames (K1: 128 frames
-= 67 Mpoints and 1.35 GB of DRAM traffic per step; K2: 64 frames, 1.13 GB -- far beyond the 126 MB L2, so
+= 67 Mpoints and 1.35 GB of DRAM traffic per step; K2: 32 frames, 0.57 GB -- far beyond the 126 MB L2, so
 consecutive steps cannot be served from cache).
 
   value : device-resident inputs/outputs, one fused launch per step, CUDA-event timed.

@@ -67,7 +67,7 @@ class K2State:
     def __init__(self, args, ob, torch, dist, rank, local_rank, world):
         self.ob, self.torch, self.dist, self.rank, self.local_rank, self.world = ob, torch, dist, rank, local_rank, world
         self.dev = dev = torch.device("cuda", local_rank)
-        self.F = F = 64
+        self.F = F = 32
         self.ND = ND = 4
         self.si, pk, self.src_frames = synth_packets(ob, ND, seed=0xdeadbeef ^ rank)
         self.n_slots, self.psz = pk.shape[1], pk.shape[2]
@@ -208,9 +208,10 @@ def measure_k2(st, args, streams_per_gpu, pcie, with_e2e=True, with_cpu=True):
     #      3 frames in flight) -> host LidarFrame fields + fused cloud, every frame H2D + D2H ----
     ob.set_device(st.local_rank)
     pipe = ob.FramePipeline(st.si, depth=3, lut=frame_luts[0], pixel_shift_by_row=SHIFTS)
-    e2e_frames = F
+    e2e_frames = 2 * F
     pin_pool = ob.pinned_empty((e2e_frames,) + st.pool.shape[1:], np.uint8)
     pin_pool[:F] = st.pool
+    pin_pool[F:] = st.pool
     host_ts = 10 + np.arange(st.n_slots, dtype=np.uint64)
 
     def stamp_ids(base):   # distinct, increasing frame ids so that no packet is dropped as "old frame"

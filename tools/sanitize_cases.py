@@ -151,4 +151,76 @@ for f, (r, x, rd2) in zip(want, got):
     assert np.array_equal(x, orc.cartesian(f.field("RANGE"), d, o))
     assert np.array_equal(rd2, orc.destagger(f.field("RANGE2"), shifts))
 print("pipeline ok")
+# ---- round 2 kernels: pipelined K2 with both LUT dtypes and the LUT-free mode, K4 encode, normals, batched K3 ----
+from tests.helpers import default_os1_64
+from tests.test_oracle_normals import room_scene
+pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", 64, 128)
+src = random_frame(pf, seed=8)
+pk, ts = orc.frame_to_packets(src, pf)
+layout, fields = decoder_desc_from_oracle(pf, src)
+dec = ob.Decoder(layout, fields)
+shifts = (np.arange(64, dtype=np.int32) * 3) % 17
+n0 = ob.kernel_launch_count("decode_pipe")
+for dt in (np.float32, np.float64):
+    d, o = random_lut(64 * 128, 7, dt)
+    lut = ob.XYZLutT.from_arrays(d, o, 64, 128)
+    io = {"packets": np.ascontiguousarray(pk), "n_slots": len(pk), "packet_stride": pk.shape[1], "col_src": None,
+          "fields": {f["name"]: np.zeros(src.field(f["name"]).shape, src.field(f["name"]).dtype) for f in fields},
+          "xyz": [np.zeros((64 * 128, 3), dt) for _ in range(2)],
+          "range_destaggered": [np.zeros((64, 128), np.uint32) for _ in range(2)]}
+    dec.decode([io], lut=lut, pixel_shift_by_row=shifts, stream=st)
+    st.sync()
+    for n, a in io["fields"].items():
+        assert np.array_equal(a, src.field(n)), n
+    for r, nm in enumerate(("RANGE", "RANGE2")):
+        assert np.array_equal(io["xyz"][r], orc.cartesian(src.field(nm), d, o))
+        assert np.array_equal(io["range_destaggered"][r], orc.destagger(src.field(nm), shifts))
+assert ob.kernel_launch_count("decode_pipe") == n0 + 2, "the pipelined K2 did not run"
+si64 = default_os1_64(1024)
+al = ob.XYZLutT.from_intrinsics(128, 64, 0.001, si64["beam_to_lidar_transform"], si64["lidar_to_sensor_transform"],
+                                si64["beam_azimuth_angles"], si64["beam_altitude_angles"], dtype=np.float32).set_analytic(True)
+io = {"packets": np.ascontiguousarray(pk), "n_slots": len(pk), "packet_stride": pk.shape[1], "col_src": None,
+      "fields": {}, "xyz": [np.zeros((64 * 128, 3), np.float32) for _ in range(2)]}
+dec.decode([io], lut=al, pixel_shift_by_row=shifts, stream=st)
+rngs = np.stack([np.stack([src.field("RANGE"), src.field("RANGE2")])])
+xa = np.zeros((1, 2, 64 * 128, 3), np.float32)
+ob.scan_to_cloud(al, shifts, rngs, xyz=xa, stream=st)
+st.sync()
+assert np.allclose(xa[0, 0], io["xyz"][0], rtol=1e-5, atol=1e-4)
+print("K2 pipelined (f32, f64, LUT-free) ok")
+sih = ob.SensorInfo("RNG19_RFL8_SIG16_NIR16_DUAL", 16, 128, fw_rev="v3.2.1")
+fr = ob.LidarFrame(sih)
+rs = np.random.default_rng(12)
+for name in fr.fields:
+    a = fr.field(name)
+    a[...] = rs.integers(0, 200, size=a.shape).astype(a.dtype)
+fr.status[:] = 1
+fr.status[3] = 0
+fr.timestamp[:] = 5 + np.arange(128)
+fr.packet_timestamp[:] = 1 + np.arange(8)
+fr.frame_id = 77
+hp, _ = ob.frame_to_packets(fr, sih, 3, 9)
+dp, _ = ob.frame_to_packets(fr, sih, 3, 9, device=True)
+assert np.array_equal(hp, dp)
+print("K4 encode ok")
+xyz, rngd, dirs = room_scene(24, 96)
+org = np.zeros((96, 3))
+nn, sub = ob.normals(xyz, rngd, org, 2, return_subtent=True)
+assert np.array_equal(nn, orc.normals(xyz, rngd, sensor_origins_xyz=org, pixel_search_range=2, vertical_subtent=sub))
+n1, n2 = ob.normals(xyz, rngd, xyz * 1.1, rngd, org)
+print("normals ok")
+frames = []
+want = []
+for i, (hh, ww) in enumerate(((16, 64), (24, 96))):
+    rg = random_range(hh, ww, 80 + i, p_zero=0.3, max_range=50000)
+    d, o = random_lut(hh * ww, 9 + i)
+    poses = np.tile(np.eye(4), (ww, 1, 1))
+    poses[:, :3, 3] = np.random.default_rng(i).random((ww, 3))
+    stt = np.ones(ww, np.uint32)
+    stt[:3] = 0
+    tsn = np.arange(ww, dtype=np.uint64)
+    frames.append({"lut": ob.XYZLutT.from_arrays(d, o, hh, ww), "range": rg, "poses": poses, "status": stt, "timestamps": tsn})
+    want.append(orc.dewarp_frame(rg, d, o, poses, stt, tsn, 0.5, 40.0)[0])
+assert np.array_equal(ob.dewarp_frames(frames, 0.5, 40.0), np.concatenate(want))
+print("batched K3 ok")
 print("SANITIZE CASES OK")
