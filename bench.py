@@ -421,6 +421,7 @@ def main():
                     help="restrict the run to one part (tuning / profiling aid); default: everything")
     ap.add_argument("--workload", default=None, choices=["k1", "k2"], help="alias of --only (kept for tools)")
     ap.add_argument("--frames", type=int, default=128, help="K1 frames per step (per GPU)")
+    ap.add_argument("--k2-frames", type=int, default=32, help="K2 frames per step (per GPU)")
     ap.add_argument("--streams-per-gpu", type=int, default=1,
                     help="with --only k2: independent sensor streams (own LUT each) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -67,7 +67,7 @@ class K2State:
     def __init__(self, args, ob, torch, dist, rank, local_rank, world):
         self.ob, self.torch, self.dist, self.rank, self.local_rank, self.world = ob, torch, dist, rank, local_rank, world
         self.dev = dev = torch.device("cuda", local_rank)
-        self.F = F = 32
+        self.F = F = max(4, int(getattr(args, 'k2_frames', 32)))
         self.ND = ND = 4
         self.si, pk, self.src_frames = synth_packets(ob, ND, seed=0xdeadbeef ^ rank)
         self.n_slots, self.psz = pk.shape[1], pk.shape[2]

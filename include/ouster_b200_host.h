@@ -121,6 +121,19 @@ ob_status obh_batcher_set_pipeline_depth(obh_batcher* b, size_t n);
 ob_status obh_batcher_wait(obh_batcher* b, obh_frame* frame);
 ob_status obh_batcher_destroy(obh_batcher* b);
 
+/* ---- PcapLidarSource (include/ouster/core/pcap_source.h): capture file -> page-locked ring of lidar packets ----
+ * replaces, for this path, the read loop of ouster_pcap/src/pcap_packet_source.cpp (classic pcap, Ethernet/IPv4/UDP,
+ * unfragmented).  A burst (pointer, stride, capture timestamps in ns) feeds obh_batcher_batch_burst /
+ * obh_pipeline_push_burst in place.  errors: "Failed to open pcap file", "Unsupported pcap format". */
+typedef struct obh_pcap obh_pcap;
+ob_status obh_pcap_open(const char* path, size_t lidar_packet_size, uint16_t dst_port, size_t ring_packets,
+                        obh_pcap** out);
+ob_status obh_pcap_next_burst(obh_pcap* p, size_t max_packets, const uint8_t** packets, size_t* stride,
+                              const uint64_t** timestamps_ns, size_t* n);
+size_t obh_pcap_packets_read(const obh_pcap* p);
+size_t obh_pcap_skipped(const obh_pcap* p);
+ob_status obh_pcap_close(obh_pcap* p);
+
 /* ---- FramePipeline (include/ouster/core/frame_pipeline.h): ring of frames, `depth` in flight ---- */
 typedef struct obh_pipeline obh_pipeline;
 typedef struct obh_slot {

@@ -8,6 +8,6 @@ from . import _capi  # noqa: F401  (fails loudly when the CUDA library is not bu
 from .core import (Decoder, Stream, XYZLut, XYZLutFloat, XYZLutT, cartesian, destagger, dewarp, dewarp_frame, dewarp_frames, normals, transform, scan_to_cloud, plan_scan_to_cloud,  # noqa: F401
                    device_count, kernel_launch_count, pinned_empty, set_tunable)
 from .host import get_device, set_device  # noqa: F401,E402
-from .host import FrameBatcher, FramePipeline, LidarFrame, LidarScan, ScanBatcher, SensorInfo, frame_to_packets  # noqa: F401,E402
+from .host import FrameBatcher, FramePipeline, PcapLidarSource, LidarFrame, LidarScan, ScanBatcher, SensorInfo, frame_to_packets  # noqa: F401,E402
 from . import sharding  # noqa: F401,E402
 from . import pyapi  # noqa: F401,E402

@@ -12,8 +12,14 @@
 // scatter; here a tile of TC frame columns (the columns of P whole packets) is brought into shared
 // memory once by TMA bulk copies (one cp.async.bulk per packet, mbarrier-tracked, S-deep ring),
 // every pixel is decoded once for all fields from registers, and the outputs leave as row-major
-// coalesced stores (lane = frame column).  Decoded ranges are kept in a shared-memory tile so that
-// the XYZ projection can run on 16-byte LUT loads / XYZ stores (lane = 16-byte chunk of a row).
+// coalesced stores (lane = frame column).  The XYZ projection re-reads the range words from the staged
+// packet bytes and runs on 16-byte LUT loads / XYZ stores (lane = 16-byte chunk of a row).
+//
+// This file holds decode_kernel, the round-1 kernel (3 CTAs per SM, LUT rows loaded with LDG inside the
+// compute loop).  Since round 2 the default is the pipelined, warp-specialised decode_pipe_kernel
+// (ob_decode_pipe.cu); decode_kernel stays as the path for the launches that one does not take (frame
+// width not a multiple of the tile, columns per packet not a power of two, unaligned LUT / XYZ pointers,
+// range fields wider than a 32-bit plan) and as the A/B reference of the parity tests.
 //
 // Column map: frame column j takes its pixels from packet column col_src[j] (slot*cpp + c), or is
 // zero-filled when col_src[j] < 0.  With the identity map (complete in-order frame) whole packets

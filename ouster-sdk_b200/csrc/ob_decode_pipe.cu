@@ -122,8 +122,10 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(&pk_full[s], 1);
-            mbar_init(&pk_done[s], pp.ncw);
+            // every lane arrives for itself (its own generic-proxy writes / reads of the stage control block):
+            // no ordering is borrowed from a __syncwarp in front of a single elected arrival
+            mbar_init(&pk_full[s], 32);
+            mbar_init(&pk_done[s], pp.ncw * 32);
         }
         for (unsigned s = 0; s < NL; ++s) {
             mbar_init(&lut_full[s], 1);
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
             const bool bulk_ok = (fr.flags & 2u) != 0;
             const unsigned n_groups = tc >> p.cpp_shift;
             if (identity && bulk_ok && (j0 + tc) / L.cpp <= fr.n_slots) {
-                __syncwarp();  // every lane's part of the table entry is written before the arrival below
+                if (lane != 0) mbar_arrive(&pk_full[s]);  // this lane's part of the table entry is written
                 if (lane == 0) {
                     c.regular = 1;
                     mbar_expect_tx(&pk_full[s], n_groups * L.packet_size);
@@ -269,8 +271,9 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                 }
             }
             __syncwarp();
+            if (lane != 0) mbar_arrive(&pk_full[s]);  // this lane's gathered bytes and table words are written
             if (lane == 0) {
-                mbar_expect_tx(&pk_full[s], tx);  // the one arrival of this phase; completes when tx bytes landed
+                mbar_expect_tx(&pk_full[s], tx);  // lane 0's arrival carries the bulk-copy byte count
                 for (unsigned g = 0; g < n_groups; ++g) {
                     if (!c.group_fast[g]) continue;
                     const int slot = c.col_src[g * L.cpp] / static_cast<int>(L.cpp);
@@ -640,8 +643,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&pk_done[s]);  // this warp is done with the stage
+        mbar_arrive(&pk_done[s]);  // this lane is done with the stage and its control block
     }
 }
 

@@ -63,6 +63,11 @@ _sig("obh_batcher_set_device_outputs", i32, vp, sz, PP(C.c_char_p), PP(vp), PP(v
 _sig("obh_batcher_set_pipeline_depth", i32, vp, sz)
 _sig("obh_batcher_wait", i32, vp, vp)
 _sig("obh_batcher_destroy", i32, vp)
+_sig("obh_pcap_open", i32, C.c_char_p, sz, C.c_uint16, sz, PP(vp))
+_sig("obh_pcap_next_burst", i32, vp, sz, PP(vp), PP(sz), PP(vp), PP(sz))
+_sig("obh_pcap_packets_read", sz, vp)
+_sig("obh_pcap_skipped", sz, vp)
+_sig("obh_pcap_close", i32, vp)
 
 
 class Slot(C.Structure):
@@ -317,6 +322,57 @@ def frame_to_packets(frame, info, init_id=0, prod_sn=0, device=False):
     fn = lib.obh_frame_to_packets_device if device else lib.obh_frame_to_packets
     check(fn(frame._h, info._h, init_id, prod_sn, out.ctypes.data, ts.ctypes.data, C.byref(n)))
     return out[:n.value].copy(), ts[:n.value].copy()
+
+
+class PcapLidarSource:
+    """Capture file -> page-locked ring of lidar packets (include/ouster/core/pcap_source.h; replaces the
+    read loop of ouster_pcap/src/pcap_packet_source.cpp for this path).  `next_burst` returns numpy VIEWS of
+    the ring ([n, packet_size] uint8 with the ring's stride, [n] uint64 capture timestamps in ns), valid
+    until the next call -- feed them to FrameBatcher.batch_burst / FramePipeline.push_burst as they are."""
+
+    def __init__(self, path, lidar_packet_size, dst_port=0, ring_packets=256):
+        hd = vp()
+        check(lib.obh_pcap_open(str(path).encode(), int(lidar_packet_size), int(dst_port), int(ring_packets),
+                                C.byref(hd)))
+        self._h, self.packet_size = hd, int(lidar_packet_size)
+
+    def next_burst(self, max_packets):
+        pk, ts, stride, n = vp(), vp(), sz(), sz()
+        check(lib.obh_pcap_next_burst(self._h, int(max_packets), C.byref(pk), C.byref(stride), C.byref(ts),
+                                      C.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, self.packet_size), np.uint8), np.zeros(0, np.uint64)
+        raw = np.ctypeslib.as_array(C.cast(pk, C.POINTER(C.c_uint8)), shape=(n.value * stride.value,))
+        packets = np.lib.stride_tricks.as_strided(raw, shape=(n.value, self.packet_size),
+                                                  strides=(stride.value, 1), writeable=False)
+        tsv = np.ctypeslib.as_array(C.cast(ts, C.POINTER(C.c_uint64)), shape=(n.value,))
+        return packets, tsv
+
+    def __iter__(self):
+        while True:
+            p, t = self.next_burst(64)
+            if len(t) == 0:
+                return
+            yield p, t
+
+    @property
+    def packets_read(self):
+        return lib.obh_pcap_packets_read(self._h)
+
+    @property
+    def skipped(self):
+        return lib.obh_pcap_skipped(self._h)
+
+    def close(self):
+        if self._h:
+            lib.obh_pcap_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class FrameBatcher:

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "ouster/core/frame_pipeline.h"
+#include "ouster/core/pcap_source.h"
 #include "ouster/core/lidar_frame.h"
 #include "ouster/core/xyzlut.h"
 #include "ouster_b200_host.h"
@@ -325,6 +326,34 @@ ob_status obh_frame_to_packets_device(const obh_frame* f, const obh_sensor* s, u
         }
         *n_out = packets.size();
     });
+}
+
+// ---- PcapLidarSource ----
+struct obh_pcap {
+    std::unique_ptr<PcapLidarSource> src;
+};
+ob_status obh_pcap_open(const char* path, size_t lidar_packet_size, uint16_t dst_port, size_t ring_packets,
+                        obh_pcap** out) {
+    return guard([&] {
+        if (!path || !out) throw std::invalid_argument("null pointer");
+        auto p = std::make_unique<obh_pcap>();
+        p->src = std::make_unique<PcapLidarSource>(path, lidar_packet_size, dst_port, ring_packets);
+        *out = p.release();
+    });
+}
+ob_status obh_pcap_next_burst(obh_pcap* p, size_t max_packets, const uint8_t** packets, size_t* stride,
+                              const uint64_t** timestamps_ns, size_t* n) {
+    return guard([&] {
+        if (!p || !n) throw std::invalid_argument("null pointer");
+        *n = p->src->next_burst(max_packets, packets, timestamps_ns);
+        if (stride) *stride = p->src->stride();
+    });
+}
+size_t obh_pcap_packets_read(const obh_pcap* p) { return p ? p->src->packets_read() : 0; }
+size_t obh_pcap_skipped(const obh_pcap* p) { return p ? p->src->skipped() : 0; }
+ob_status obh_pcap_close(obh_pcap* p) {
+    delete p;
+    return OB_OK;
 }
 
 // ---- FrameBatcher ----
