@@ -149,9 +149,12 @@ ob_status ob_dewarp(ob_dtype dtype, const void* points, const void* poses, size_
  * ceil(min_range*1e3) <= r <= floor(max_range*1e3) are emitted top to bottom as R_col*lut(r) + t_col
  * (body_to_world cast to the LUT dtype) -- the reference's order and arithmetic, without
  * materialising the full cloud first (the fusion its own note at dewarp_impl.h:27-29 asks for).
- * The call returns after the point count is known (it synchronises the stream once); host
- * outputs are final on return, device outputs after ob_stream_sync.
- * error: "output capacity too small" when more than `capacity` points pass the filter.
+ * ONE kernel launch (count, decoupled look-back scan and emit fused; the count is a device-side word).
+ * n_points in host memory: the call returns after the count is known (one stream synchronisation; host
+ * outputs are final on return, device outputs after ob_stream_sync) and raises
+ * "output capacity too small" when more than `capacity` points pass the filter.
+ * n_points in DEVICE memory (8 bytes; all outputs in device memory): nothing waits for the GPU, the count is
+ * written in stream order next to the points, and a count above `capacity` means the list was cut there.
  */
 typedef struct ob_dewarp_frame_io {
     const uint32_t* range;       /* h x w, staggered (the RANGE field) */
@@ -172,8 +175,9 @@ ob_status ob_dewarp_frame(const ob_lut* lut, const ob_dewarp_frame_io* io, size_
  *          impl::dewarp_impl (FrameSet)          ouster_core/include/ouster/core/impl/dewarp_impl.h:84-117
  * Every frame has its own LUT (lut == NULL marks an empty slot of the set, skipped like
  * FrameSet::valid_indices()), range image, poses, status and timestamps; the points of frame i follow those
- * of the frames before it, each frame in the single-frame order above.  THREE launches and ONE host round
- * trip for the whole set (the single-frame entry costs three launches and a round trip per frame).
+ * of the frames before it, each frame in the single-frame order above.  ONE launch for the whole set (the
+ * look-back chain of the compaction simply continues across the frames); n_points may be device memory as
+ * for ob_dewarp_frame (then counts must be NULL).
  * Optional per-point provenance: frame index, column index, column timestamp (dewarp_impl.h:88-90).
  * counts[i] (optional, n_frames entries) = points of frame i.  Buffers may be host or device memory.
  * errors: "output capacity too small", "the luts of a set must share one dtype". */

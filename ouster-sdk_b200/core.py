@@ -326,12 +326,15 @@ def dewarp(points, poses, out=None, stream=None, device=0):
 
 
 def dewarp_frame(lut, rng, poses, status, timestamps=None, min_range=0.0, max_range=float("inf"),
-                 provenance=False, stream=None):
+                 provenance=False, stream=None, out=None, out_count=None):
     """dewarp(lidar_frame, xyzlut, min_range, max_range) (pose_util.h:456-485): project the range
     image, apply each column's body_to_world pose, keep the points with min_range <= r <= max_range
     (metres) of the columns between the first and last valid one, in column-major order.
     Returns points [n, 3] (LUT dtype); with provenance=True also (col_idx u32 [n], timestamps u64 [n]).
-    One fused GPU pass: nothing but the surviving points is written."""
+    One fused GPU launch: nothing but the surviving points is written.
+    Asynchronous device form: `out` = CUDA tensor [capacity, 3] of the LUT dtype and `out_count` = CUDA int64
+    tensor [1] (inputs in device memory too): nothing waits for the GPU; returns (out, out_count), the count
+    being written in stream order (a count above the capacity means the list was cut there)."""
     from ._capi import DewarpFrameIO
     st = _stream(stream, lut.device)
     n_px = lut.h * lut.w
@@ -347,6 +350,12 @@ def dewarp_frame(lut, rng, poses, status, timestamps=None, min_range=0.0, max_ra
     io = DewarpFrameIO()
     io.range, io.poses, io.status = _ptr(rng), _ptr(poses), _ptr(status)
     io.min_range, io.max_range = float(min_range), float(max_range)
+    if out is not None:
+        if out_count is None or provenance:
+            raise ValueError("the asynchronous form takes out= and out_count= (device tensors) and no provenance")
+        io.points, io.capacity = _ptr(out), _numel(out) // 3
+        check(lib.ob_dewarp_frame(lut._h, C.byref(io), C.cast(_ptr(out_count), C.POINTER(C.c_size_t)), st.h))
+        return out, out_count
     pts = np.empty((n_px, 3), lut.dtype)
     io.points, io.capacity = pts.ctypes.data, n_px
     ci = ts_out = None
@@ -465,7 +474,7 @@ def dewarp_frames(frames, min_range=0.0, max_range=float("inf"), provenance=Fals
     `frames` is a list with one entry per slot of the set -- None for an empty slot, else a dict
     {lut, range, poses, status[, timestamps]} -- and the result is the concatenation of the frames'
     dewarped points in slot order.  provenance=True also returns (frame_idx, col_idx, timestamps).
-    Three launches and one host round trip for the whole set."""
+    One launch for the whole set."""
     from ._capi import DewarpFramesIO
     n = len(frames)
     ios = (DewarpFramesIO * max(n, 1))()

@@ -55,8 +55,10 @@ static Tunables& tunables_mut(int device) {
         t.cloud_ctas_per_sm = std::max(1, env_int("OB_CLOUD_CTAS_PER_SM", 3));
         t.cloud_pose_tw = std::max(16, env_int("OB_CLOUD_POSE_TW", 256));
         t.cloud_store_lag = env_int("OB_CLOUD_STORE_LAG", 1);
-        t.cloud_pose_stages = std::max(2, env_int("OB_CLOUD_POSE_STAGES", 3));
-        t.cloud_pose_ctas_per_sm = std::max(1, env_int("OB_CLOUD_POSE_CTAS_PER_SM", 6));
+        t.cloud_pose_stages = std::max(2, env_int("OB_CLOUD_POSE_STAGES", 4));
+        t.cloud_pose_ctas_per_sm = std::max(1, env_int("OB_CLOUD_POSE_CTAS_PER_SM", 5));
+        t.cloud_pose_threads = std::min(256, std::max(32, env_int("OB_CLOUD_POSE_THREADS", 64) / 32 * 32));
+        t.cloud_pose_rows = std::min(64, std::max(4, env_int("OB_CLOUD_POSE_ROWS", 16)));
         t.decode_stages = std::max(1, env_int("OB_DECODE_STAGES", 1));
         t.decode_threads = std::min(384, std::max(64, env_int("OB_DECODE_THREADS", 384) / 32 * 32));
         t.decode_ctas_per_sm = std::max(1, env_int("OB_DECODE_CTAS_PER_SM", 3));
@@ -98,6 +100,8 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "cloud_store_lag") t.cloud_store_lag = value ? 1 : 0;
     else if (n == "cloud_pose_stages") t.cloud_pose_stages = std::max(2, value);
     else if (n == "cloud_pose_ctas_per_sm") t.cloud_pose_ctas_per_sm = std::max(1, value);
+    else if (n == "cloud_pose_threads") t.cloud_pose_threads = std::min(256, std::max(32, value / 32 * 32));
+    else if (n == "cloud_pose_rows") t.cloud_pose_rows = std::min(64, std::max(4, value));
     else if (n == "decode_stages") t.decode_stages = std::max(1, value);
     else if (n == "decode_threads") t.decode_threads = std::min(384, std::max(64, value / 32 * 32));
     else if (n == "decode_ctas_per_sm") t.decode_ctas_per_sm = std::max(1, value);
@@ -746,104 +750,163 @@ ob_status ob_dewarp(ob_dtype dtype, const void* points, const void* poses, size_
     return OB_OK;
 }
 
+// Shared driver of ob_dewarp_frame / ob_dewarp_frames: frame table upload, ONE kernel launch, then the
+// device-side counts.  Results for device outputs are complete in stream order; the only host wait is the
+// one a host-memory result needs anyway.
+static ob_status run_dewarp(std::vector<K3Frame>& hf, int dtype, uint32_t min_r, uint32_t max_r, void* points,
+                            size_t capacity, uint32_t* frame_idx, uint32_t* col_idx, uint64_t* timestamps_out,
+                            size_t* counts, size_t* n_points, Staging& stg, ob_stream* s) {
+    unsigned n_blocks = 0, max_slabs = 0;
+    for (K3Frame& f : hf) {
+        f.first_block = n_blocks;
+        n_blocks += f.n_cg;
+        max_slabs = std::max(max_slabs, f.n_slabs);
+    }
+    const size_t esz = dtype_size(dtype);
+    void *fdev = nullptr, *scan = nullptr, *o = nullptr;
+    cudaError_t e = stg.scratch(hf.size() * sizeof(K3Frame), &fdev);
+    if (e == cudaSuccess) e = stg.scratch(dewarp_scan_scratch_bytes(n_blocks, static_cast<unsigned>(hf.size())), &scan);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fdev, hf.data(), hf.size() * sizeof(K3Frame), cudaMemcpyHostToDevice, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
+    // outputs: device pointers in place, host pointers through device scratch of `capacity` points
+    const bool host_out = !is_device_ptr(points);
+    void* dpts = points;
+    uint32_t *dfi = frame_idx, *dci = col_idx;
+    uint64_t* dts = timestamps_out;
+    if (host_out) {
+        e = stg.scratch(std::max<size_t>(1, capacity) * 3 * esz, &o);
+        dpts = o;
+        if (e == cudaSuccess && frame_idx) {
+            e = stg.scratch(std::max<size_t>(1, capacity) * 4, &o);
+            dfi = static_cast<uint32_t*>(o);
+        }
+        if (e == cudaSuccess && col_idx) {
+            e = stg.scratch(std::max<size_t>(1, capacity) * 4, &o);
+            dci = static_cast<uint32_t*>(o);
+        }
+        if (e == cudaSuccess && timestamps_out) {
+            e = stg.scratch(std::max<size_t>(1, capacity) * 8, &o);
+            dts = static_cast<uint64_t*>(o);
+        }
+        if (e != cudaSuccess) return fail_cuda(e, "stage dewarp outputs");
+    }
+    const unsigned long long* fend = nullptr;
+    e = launch_dewarp_fused(static_cast<const K3Frame*>(fdev), static_cast<unsigned>(hf.size()), n_blocks, max_slabs,
+                            min_r, max_r, dtype, scan, dpts, dfi, dci, dts, capacity, &fend, s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp launch");
+    if (is_device_ptr(n_points)) {
+        // fully asynchronous form: the count stays on the device next to the points (a count above
+        // `capacity` means the list was cut at `capacity` points; no error can be raised from here)
+        if (host_out || counts) return fail(OB_INVALID_ARGUMENT, "a device-side count needs device outputs and no per-frame counts");
+        e = cudaMemcpyAsync(n_points, fend + (hf.size() - 1), 8, cudaMemcpyDeviceToDevice, s->st);
+        if (e != cudaSuccess) return fail_cuda(e, "dewarp count");
+        return OB_OK;
+    }
+    std::vector<unsigned long long> ends(hf.size());
+    e = cudaMemcpyAsync(ends.data(), fend, hf.size() * 8, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) return fail_cuda(e, "dewarp count");
+    const unsigned long long total = ends.back();
+    if (counts)
+        for (size_t k = 0; k < hf.size(); ++k) counts[hf[k].index] = static_cast<size_t>(ends[k] - (k ? ends[k - 1] : 0ull));
+    if (total > capacity) return fail(OB_INVALID_ARGUMENT, "output capacity too small");
+    if (host_out && total) {
+        e = cudaMemcpyAsync(points, dpts, total * 3 * esz, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess && frame_idx) e = cudaMemcpyAsync(frame_idx, dfi, total * 4, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess && col_idx) e = cudaMemcpyAsync(col_idx, dci, total * 4, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess && timestamps_out)
+            e = cudaMemcpyAsync(timestamps_out, dts, total * 8, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        if (e != cudaSuccess) return fail_cuda(e, "dewarp D2H");
+    }
+    *n_points = static_cast<size_t>(total);
+    return OB_OK;
+}
+
+static ob_status stage_k3_frame(const ob_lut* lut, const uint32_t* range, const double* poses, const uint32_t* status,
+                                const uint64_t* timestamps, bool want_ts, unsigned index, Staging& stg, K3Frame* out) {
+    K3Frame f{};
+    f.H = static_cast<unsigned>(lut->h);
+    f.W = static_cast<unsigned>(lut->w);
+    f.n_cg = (f.W + 31) / 32;
+    f.n_slabs = (f.H + 15) / 16;
+    f.index = index;
+    f.dir = lut->dir;
+    f.off = lut->off;
+    const size_t n_px = lut->h * lut->w;
+    const void* d = nullptr;
+    cudaError_t e = stg.in(range, n_px * 4, &d);
+    f.range = static_cast<const uint32_t*>(d);
+    if (e == cudaSuccess) e = stg.in(poses, lut->w * 16 * sizeof(double), &d);
+    f.poses = static_cast<const double*>(d);
+    if (e == cudaSuccess) e = stg.in(status, lut->w * 4, &d);
+    f.status = static_cast<const uint32_t*>(d);
+    if (e == cudaSuccess && want_ts) {
+        e = stg.in(timestamps, lut->w * 8, &d);
+        f.timestamps = static_cast<const uint64_t*>(d);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "stage dewarp inputs");
+    *out = f;
+    return OB_OK;
+}
+
+// same conversions as the reference (dewarp_impl.h:34-35); NaN / negative limits select nothing
+static bool range_window(double min_range, double max_range, uint32_t* min_r, uint32_t* max_r) {
+    const double lo = std::ceil(min_range * 1e3), hi = std::floor(max_range * 1e3);
+    if (!(lo <= 4294967295.0) || !(hi >= 0.0) || !(lo <= hi)) return false;
+    *min_r = lo <= 0.0 ? 0u : static_cast<uint32_t>(lo);
+    *max_r = hi >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(hi);
+    return true;
+}
+
+static ob_status zero_count(size_t* n_points, ob_stream* s) {
+    if (is_device_ptr(n_points)) {
+        cudaError_t e = cudaMemsetAsync(n_points, 0, 8, s->st);
+        return e == cudaSuccess ? OB_OK : fail_cuda(e, "dewarp count");
+    }
+    *n_points = 0;
+    return OB_OK;
+}
+
 ob_status ob_dewarp_frame(const ob_lut* lut, const ob_dewarp_frame_io* io, size_t* n_points, ob_stream* s) {
     if (!lut || !io || !n_points || !s) return fail(OB_INVALID_ARGUMENT, "null pointer");
-    *n_points = 0;
+    ob_status rs = require_device(s->device);
+    if (rs != OB_OK) return rs;
+    rs = zero_count(n_points, s);
+    if (rs != OB_OK) return rs;
     if (!io->range || !io->poses || !io->status || !io->points)
         return fail(OB_INVALID_ARGUMENT, "null range / poses / status / points");
     if (io->timestamps_out && !io->timestamps)
         return fail(OB_INVALID_ARGUMENT, "timestamps_out requested without column timestamps");
-    ob_status rs = require_device(s->device);
-    if (rs != OB_OK) return rs;
     if (lut->device != s->device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
-    const size_t h = lut->h, w = lut->w, n_px = h * w;
-    const size_t esz = dtype_size(lut->dtype);
-    // same conversions as the reference (dewarp_impl.h:34-35); NaN / negative limits select nothing
-    const double lo = std::ceil(io->min_range * 1e3), hi = std::floor(io->max_range * 1e3);
-    if (!(lo <= 4294967295.0) || !(hi >= 0.0) || !(lo <= hi)) return OB_OK;
-    DewarpFrameArgs a;
-    a.min_r = lo <= 0.0 ? 0u : static_cast<uint32_t>(lo);
-    a.max_r = hi >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(hi);
-    a.H = static_cast<unsigned>(h);
-    a.W = static_cast<unsigned>(w);
-    a.dtype = lut->dtype;
-    a.dir = lut->dir;
-    a.off = lut->off;
+    uint32_t min_r, max_r;
+    if (!range_window(io->min_range, io->max_range, &min_r, &max_r)) return OB_OK;
+    if (lut->h == 0 || lut->w == 0) return OB_OK;
     Staging stg(s->st);
-    const void* d = nullptr;
-    cudaError_t e = stg.in(io->range, n_px * 4, &d);
-    if (e != cudaSuccess) return fail_cuda(e, "stage range");
-    a.range = static_cast<const uint32_t*>(d);
-    e = stg.in(io->poses, w * 16 * sizeof(double), &d);
-    if (e != cudaSuccess) return fail_cuda(e, "stage poses");
-    a.poses = static_cast<const double*>(d);
-    e = stg.in(io->status, w * 4, &d);
-    if (e != cudaSuccess) return fail_cuda(e, "stage status");
-    a.status = static_cast<const uint32_t*>(d);
-    a.timestamps = nullptr;
-    if (io->timestamps_out) {
-        e = stg.in(io->timestamps, w * 8, &d);
-        if (e != cudaSuccess) return fail_cuda(e, "stage timestamps");
-        a.timestamps = static_cast<const uint64_t*>(d);
-    }
-    e = stg.scratch(dewarp_frame_scratch_bytes(a.H, a.W), &a.scratch);
-    if (e != cudaSuccess) return fail_cuda(e, "scratch alloc");
-    e = launch_dewarp_frame_count(a, s->st);
-    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame count launch");
-    unsigned long long total = 0;
-    e = cudaMemcpyAsync(&total, dewarp_frame_total_ptr(a), sizeof(total), cudaMemcpyDeviceToHost, s->st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
-    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame count");
-    if (total > io->capacity) return fail(OB_INVALID_ARGUMENT, "output capacity too small");
-    if (total == 0) return OB_OK;
-    // outputs: device pointers in place, host pointers through scratch sized to the real count
-    void* o = nullptr;
-    e = stg.out(io->points, total * 3 * esz, &o);
-    if (e != cudaSuccess) return fail_cuda(e, "stage points");
-    a.points = o;
-    a.col_idx = nullptr;
-    a.ts_out = nullptr;
-    if (io->col_idx) {
-        e = stg.out(io->col_idx, total * 4, &o);
-        if (e != cudaSuccess) return fail_cuda(e, "stage col_idx");
-        a.col_idx = static_cast<uint32_t*>(o);
-    }
-    if (io->timestamps_out) {
-        e = stg.out(io->timestamps_out, total * 8, &o);
-        if (e != cudaSuccess) return fail_cuda(e, "stage timestamps_out");
-        a.ts_out = static_cast<uint64_t*>(o);
-    }
-    e = launch_dewarp_frame_emit(a, s->st);
-    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame emit launch");
-    e = stg.flush();
-    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame D2H");
-    if (!is_device_ptr(io->points)) {
-        e = cudaStreamSynchronize(s->st);
-        if (e != cudaSuccess) return fail_cuda(e, "dewarp_frame");
-    }
-    *n_points = static_cast<size_t>(total);
-    return OB_OK;
+    std::vector<K3Frame> hf(1);
+    rs = stage_k3_frame(lut, io->range, io->poses, io->status, io->timestamps, io->timestamps_out != nullptr, 0, stg, &hf[0]);
+    if (rs != OB_OK) return rs;
+    return run_dewarp(hf, lut->dtype, min_r, max_r, io->points, io->capacity, nullptr, io->col_idx, io->timestamps_out,
+                      nullptr, n_points, stg, s);
 }
 
 ob_status ob_dewarp_frames(const ob_dewarp_frames_io* frames, size_t n_frames, double min_range, double max_range,
                            void* points, size_t capacity, uint32_t* frame_idx, uint32_t* col_idx,
                            uint64_t* timestamps_out, size_t* counts, size_t* n_points, ob_stream* s) {
     if (!s || !n_points || (n_frames && !frames)) return fail(OB_INVALID_ARGUMENT, "null pointer");
-    *n_points = 0;
+    ob_status rs = require_device(s->device);
+    if (rs != OB_OK) return rs;
+    rs = zero_count(n_points, s);
+    if (rs != OB_OK) return rs;
     if (counts) std::fill(counts, counts + n_frames, static_cast<size_t>(0));
     if (n_frames == 0) return OB_OK;
     if (!points) return fail(OB_INVALID_ARGUMENT, "null points buffer");
-    ob_status rs = require_device(s->device);
-    if (rs != OB_OK) return rs;
-    const double lo = std::ceil(min_range * 1e3), hi = std::floor(max_range * 1e3);  // dewarp_impl.h:34-35
-    if (!(lo <= 4294967295.0) || !(hi >= 0.0) || !(lo <= hi)) return OB_OK;
-    const uint32_t min_r = lo <= 0.0 ? 0u : static_cast<uint32_t>(lo);
-    const uint32_t max_r = hi >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(hi);
+    uint32_t min_r, max_r;
+    if (!range_window(min_range, max_range, &min_r, &max_r)) return OB_OK;
     int dtype = -1;
     Staging stg(s->st);
     std::vector<K3Frame> hf;
     hf.reserve(n_frames);
-    unsigned max_warps = 0;
     for (size_t i = 0; i < n_frames; ++i) {
         const ob_dewarp_frames_io& io = frames[i];
         if (!io.lut) continue;  // FrameSet::valid_indices(): empty slots of the set are skipped
@@ -854,87 +917,16 @@ ob_status ob_dewarp_frames(const ob_dewarp_frames_io* frames, size_t n_frames, d
         if (lut->device != s->device) return fail(OB_INVALID_ARGUMENT, "lut and stream are on different devices");
         if (dtype < 0) dtype = lut->dtype;
         if (lut->dtype != dtype) return fail(OB_INVALID_ARGUMENT, "the luts of a set must share one dtype");
-        K3Frame f{};
-        f.H = static_cast<unsigned>(lut->h);
-        f.W = static_cast<unsigned>(lut->w);
-        f.n_cg = (f.W + 31) / 32;
-        f.n_slabs = (f.H + 15) / 16;
-        f.index = static_cast<unsigned>(i);
-        f.dir = lut->dir;
-        f.off = lut->off;
-        const size_t n_px = lut->h * lut->w;
-        const void* d = nullptr;
-        cudaError_t e = stg.in(io.range, n_px * 4, &d);
-        f.range = static_cast<const uint32_t*>(d);
-        if (e == cudaSuccess) e = stg.in(io.poses, lut->w * 16 * sizeof(double), &d);
-        f.poses = static_cast<const double*>(d);
-        if (e == cudaSuccess) e = stg.in(io.status, lut->w * 4, &d);
-        f.status = static_cast<const uint32_t*>(d);
-        if (e == cudaSuccess && timestamps_out) {
-            e = stg.in(io.timestamps, lut->w * 8, &d);
-            f.timestamps = static_cast<const uint64_t*>(d);
-        }
-        void* sc = nullptr;
-        if (e == cudaSuccess) e = stg.scratch(dewarp_frames_scratch_bytes(f.H, f.W), &sc);
-        if (e != cudaSuccess) return fail_cuda(e, "stage dewarp inputs");
-        f.cnt = static_cast<uint32_t*>(sc);
-        f.base = f.cnt + static_cast<size_t>(f.n_slabs) * f.W;
-        max_warps = std::max(max_warps, f.n_cg * f.n_slabs);
+        if (lut->h == 0 || lut->w == 0) continue;
+        K3Frame f;
+        rs = stage_k3_frame(lut, io.range, io.poses, io.status, io.timestamps, timestamps_out != nullptr,
+                            static_cast<unsigned>(i), stg, &f);
+        if (rs != OB_OK) return rs;
         hf.push_back(f);
     }
     if (hf.empty()) return OB_OK;
-    const size_t esz = dtype_size(dtype);
-    void *fdev = nullptr, *tdev = nullptr, *o = nullptr;
-    cudaError_t e = stg.scratch(hf.size() * sizeof(K3Frame), &fdev);
-    if (e == cudaSuccess) e = stg.scratch(hf.size() * 8, &tdev);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(fdev, hf.data(), hf.size() * sizeof(K3Frame), cudaMemcpyHostToDevice, s->st);
-    if (e != cudaSuccess) return fail_cuda(e, "frame table upload");
-    // outputs: device pointers in place, host pointers through device scratch of `capacity` points
-    const bool host_out = !is_device_ptr(points);
-    void* dpts = points;
-    uint32_t *dfi = frame_idx, *dci = col_idx;
-    uint64_t* dts = timestamps_out;
-    if (host_out) {
-        e = stg.scratch(capacity * 3 * esz, &o);
-        dpts = o;
-        if (e == cudaSuccess && frame_idx) {
-            e = stg.scratch(capacity * 4, &o);
-            dfi = static_cast<uint32_t*>(o);
-        }
-        if (e == cudaSuccess && col_idx) {
-            e = stg.scratch(capacity * 4, &o);
-            dci = static_cast<uint32_t*>(o);
-        }
-        if (e == cudaSuccess && timestamps_out) {
-            e = stg.scratch(capacity * 8, &o);
-            dts = static_cast<uint64_t*>(o);
-        }
-        if (e != cudaSuccess) return fail_cuda(e, "stage dewarp outputs");
-    }
-    e = launch_dewarp_frames(static_cast<const K3Frame*>(fdev), static_cast<unsigned>(hf.size()), max_warps, min_r, max_r,
-                             dtype, static_cast<unsigned long long*>(tdev), dpts, dfi, dci, dts, capacity, s->st);
-    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frames launch");
-    std::vector<unsigned long long> totals(hf.size());
-    e = cudaMemcpyAsync(totals.data(), tdev, hf.size() * 8, cudaMemcpyDeviceToHost, s->st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);  // the one host round trip of the whole set
-    if (e != cudaSuccess) return fail_cuda(e, "dewarp_frames count");
-    unsigned long long total = 0;
-    for (size_t k = 0; k < hf.size(); ++k) {
-        if (counts) counts[hf[k].index] = static_cast<size_t>(totals[k]);
-        total += totals[k];
-    }
-    if (total > capacity) return fail(OB_INVALID_ARGUMENT, "output capacity too small");
-    if (host_out && total) {
-        e = cudaMemcpyAsync(points, dpts, total * 3 * esz, cudaMemcpyDeviceToHost, s->st);
-        if (e == cudaSuccess && frame_idx) e = cudaMemcpyAsync(frame_idx, dfi, total * 4, cudaMemcpyDeviceToHost, s->st);
-        if (e == cudaSuccess && col_idx) e = cudaMemcpyAsync(col_idx, dci, total * 4, cudaMemcpyDeviceToHost, s->st);
-        if (e == cudaSuccess && timestamps_out)
-            e = cudaMemcpyAsync(timestamps_out, dts, total * 8, cudaMemcpyDeviceToHost, s->st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
-        if (e != cudaSuccess) return fail_cuda(e, "dewarp_frames D2H");
-    }
-    *n_points = static_cast<size_t>(total);
-    return OB_OK;
+    return run_dewarp(hf, dtype, min_r, max_r, points, capacity, frame_idx, col_idx, timestamps_out, counts, n_points,
+                      stg, s);
 }
 
 ob_status ob_destagger(size_t elem_size, size_t k, const void* img, const int32_t* shifts,

@@ -30,7 +30,6 @@
 
 namespace ob {
 
-constexpr int kPoseRows = 32;  // rows per work item of the pose-fused variant
 
 template <typename T>
 struct CloudParams {
@@ -43,9 +42,10 @@ struct CloudParams {
     unsigned long long range_fs, range_rs, xyz_fs, xyz_rs, rd_fs, rd_rs, xd_fs, xd_rs;
     const T* poses;            // optional: n_frames x W x 16 (row-major 4x4 per column), dewarp fused
     unsigned long long poses_fs;
+    const T* planes;           // tiled kernel: the same poses as n_frames x 12 planes of W (pose_planes_kernel)
     const LutAnalyticT<T>* an; // LUT-free mode: per-row / per-column tables instead of dir/off (else null)
     int H, W, TW, tiles_per_row, stages;
-    int RT, row_blocks;        // rows per work item (1, or kPoseRows with poses) and ceil(H / RT)
+    int RT, row_blocks;        // rows per work item (1, or Tunables::cloud_pose_rows with poses) and ceil(H / RT)
     int store_lag;             // tiles between a stage's bulk stores and its refill (0 or 1)
     unsigned n_frames, n_tiles, stage_bytes;
     unsigned short shift[kMaxRows];
@@ -152,8 +152,10 @@ __device__ __forceinline__ double pose_row(const double* m, double x, double y, 
 //
 // POSE: the variant with per-column poses (dewarp fused after the projection).  Work is handed out
 // in items of RPI consecutive rows of one column range; a CTA streams the rows of an item through
-// the ring while the item's pose slice (16 scalars per column, one bulk copy) is re-laid out once
-// into 12 planes [element][column], so poses cost one L2 read per RPI rows.
+// the ring while the item's poses sit in shared memory as 12 planes [element][column] (12 bulk copies per
+// item out of the plane form a pre-pass makes of the launch's poses: the 4 columns of a thread are then
+// one conflict-free 16-byte access per element), so poses cost one L2 read per RPI rows and no
+// shared-memory transposition, and the planes are the only pose bytes a CTA holds.
 //
 // ANALYTIC: the LUT-free variant: nothing of the LUT is loaded; every thread rebuilds the
 // beam direction of its 4 pixels from the row's (cos az cos alt, sin az cos alt, sin alt) and the
@@ -165,11 +167,9 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);           // [kMaxStagesK1] loads landed
     uint64_t* done = reinterpret_cast<uint64_t*>(smem + 64);      // [kMaxStagesK1] compute finished
     uint64_t* pose_bar = reinterpret_cast<uint64_t*>(smem + 128);  // pose slice landed
-    const unsigned pose_raw_bytes = POSE ? 16u * p.TW * static_cast<unsigned>(sizeof(T)) : 0u;
     const unsigned pose_soa_bytes = POSE ? 12u * p.TW * static_cast<unsigned>(sizeof(T)) : 0u;
-    uint8_t* pose_raw = smem + 256;
-    T* pose_soa = reinterpret_cast<T*>(pose_raw + pose_raw_bytes);
-    uint8_t* stage0 = pose_raw + pose_raw_bytes + pose_soa_bytes;
+    T* pose_soa = reinterpret_cast<T*>(smem + 256);
+    uint8_t* stage0 = smem + 256 + pose_soa_bytes;
 
     const int tid = threadIdx.x;
     const int nct = static_cast<int>(blockDim.x) - 32;  // compute threads
@@ -210,15 +210,6 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
             const TileCoord tc = coord(k);
             const int s = k % S;
             uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
-            if (POSE && (k % RPI) == 0) {
-                // first row of an item: its pose slice.  The raw buffer is free: the compute warps
-                // re-laid the previous slice out at that item's first row, and this load is only
-                // issued after they have finished a later tile of it (RPI > S).
-                const unsigned pb = 16u * tc.tw * static_cast<unsigned>(sizeof(T));
-                mbar_expect_tx(pose_bar, pb);
-                bulk_g2s_hint(pose_raw, p.poses + tc.f * p.poses_fs + static_cast<size_t>(tc.c0) * 16, pb,
-                              pose_bar, pol_keep);
-            }
             if (tc.row >= p.H) {  // item overhangs the last rows: empty tile
                 mbar_expect_tx(&full[s], 0);
                 return;
@@ -238,6 +229,19 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
                               pol_stream);
             }
         };
+        // pose planes of item i: 12 bulk copies of the tile's columns.  The single plane buffer is free once
+        // every compute thread has arrived on done[] of the previous item's last tile (the loop below waits
+        // for the tiles in order), and the compute warps wait on pose_bar before the item's first row.
+        auto load_planes = [&](unsigned item) {
+            const TileCoord tc = tile_coord(p, first + item * gridDim.x);
+            const unsigned pb = tc.tw * static_cast<unsigned>(sizeof(T));
+            mbar_expect_tx(pose_bar, 12u * pb);
+            const T* src = p.planes + static_cast<size_t>(tc.f) * 12u * p.W + tc.c0;
+#pragma unroll
+            for (int e = 0; e < 12; ++e)
+                bulk_g2s_hint(pose_soa + e * p.TW, src + static_cast<size_t>(e) * p.W, pb, pose_bar, pol_keep);
+        };
+        if (POSE && n_items_my > 0) load_planes(0);
         const unsigned pre = min(n_my, static_cast<unsigned>(S));
         for (unsigned k = 0; k < pre; ++k) issue_load(k);
         const unsigned lag = p.store_lag ? 1u : 0u;
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
             const int s = k % S;
             const TileCoord tc = coord(k);
             mbar_wait(&done[s], (k / S) & 1);  // results of tile k are in place
+            if (POSE && (k % RPI) == RPI - 1 && k + 1 < n_my) load_planes(k / RPI + 1);
             if (tc.row < p.H) {
                 uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
                 const T* dir_s = reinterpret_cast<const T*>(st);
@@ -320,16 +325,7 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
         uint32_t* rng_s = reinterpret_cast<uint32_t*>(st + 2 * lut_bytes_full);
 
         mbar_wait(&full[s], phase);
-        if (POSE && rr == 0) {  // new item: rows 0..2 of every column pose -> planes
-            mbar_wait(pose_bar, item & 1u);
-            const T* raw = reinterpret_cast<const T*>(pose_raw);
-            named_barrier_sync(1, nct);  // nobody still reads the planes of the previous item
-            for (int idx = ctid; idx < tc.tw * 12; idx += nct) {
-                const int col = idx / 12, e = idx - col * 12;
-                pose_soa[e * p.TW + col] = raw[col * 16 + e];
-            }
-            named_barrier_sync(1, nct);
-        }
+        if (POSE && rr == 0) mbar_wait(pose_bar, item & 1u);  // the item's pose planes have landed
         if (POSE && tc.row >= p.H) {
             mbar_arrive(&done[s]);
             continue;
@@ -450,27 +446,42 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
             }
         }
         if (need_lut && POSE) {
-            // one pixel per thread: the pose math is a long dependent chain, so thread-level
-            // parallelism matters more than vector width here (scalar accesses at strides of 1 and
-            // 3 words are bank-conflict free)
-            for (int j = ctid; j < tc.tw; j += nct) {
-                T d[3], o[3], m[12];
+            // 4 pixels per thread, like the plain path: 16-byte accesses of the LUT slices, the range words and
+            // the pose planes (plane e holds element e of the tile's column poses, so the 4 columns of a thread
+            // are one conflict-free vector).  One pose row (4 planes) is live at a time to keep the register
+            // count of the plain path's occupancy.
+            for (int g = ctid; g < n_groups; g += nct) {
+                T pt[R][12];  // projected points, sensor frame
+                {
+                    T d[12], o[12];
+                    lds12(dir_s + 12 * g, d);
+                    lds12(off_s + 12 * g, o);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    d[c] = dir_s[3 * j + c];
-                    o[c] = off_s[3 * j + c];
+                    for (int r = 0; r < R; ++r) {
+                        const uint4 rv4 = reinterpret_cast<const uint4*>(rng_s + r * p.TW)[g];
+                        const uint32_t rv[4] = {rv4.x, rv4.y, rv4.z, rv4.w};
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) pt[r][i] = project(rv[i / 3], d[i], o[i]);
+                    }
+                }
+                T out[R][12];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    T m0[4], m1[4], m2[4], m3[4];
+                    lds4(pose_soa + (4 * j + 0) * p.TW + 4 * g, m0);
+                    lds4(pose_soa + (4 * j + 1) * p.TW + 4 * g, m1);
+                    lds4(pose_soa + (4 * j + 2) * p.TW + 4 * g, m2);
+                    lds4(pose_soa + (4 * j + 3) * p.TW + 4 * g, m3);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const T mm[4] = {m0[i], m1[i], m2[i], m3[i]};
+                            out[r][3 * i + j] = pose_row(mm, pt[r][3 * i], pt[r][3 * i + 1], pt[r][3 * i + 2]);
+                        }
                 }
 #pragma unroll
-                for (int e = 0; e < 12; ++e) m[e] = pose_soa[e * p.TW + j];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t rv = rng_s[r * p.TW + j];
-                    const T x = project(rv, d[0], o[0]), y = project(rv, d[1], o[1]), z = project(rv, d[2], o[2]);
-                    T* dst = (r == 0 ? dir_s : off_s) + 3 * j;
-                    dst[0] = pose_row(m, x, y, z);
-                    dst[1] = pose_row(m + 4, x, y, z);
-                    dst[2] = pose_row(m + 8, x, y, z);
-                }
+                for (int r = 0; r < R; ++r) sts12((r == 0 ? dir_s : off_s) + 12 * g, out[r]);
             }
         }
 
@@ -497,6 +508,28 @@ __global__ void __launch_bounds__(288) cloud_tma_kernel(const __grid_constant__ 
         }
         if (need_lut) fence_proxy_async();  // generic-proxy results -> visible to the TMA stores
         mbar_arrive(&done[s]);
+    }
+}
+
+// Pre-pass of the pose-fused variant: poses [frame][column][16] -> planes [frame][element 0..11][column]
+// (rows 0..2 of every 4x4), so that the tiled kernel bulk-copies an item's planes straight into shared
+// memory.  64 bytes in, 48 bytes out per column: < 1 % of the launch's traffic.
+template <typename T>
+__global__ void __launch_bounds__(256) pose_planes_kernel(const T* __restrict__ poses, unsigned long long poses_fs,
+                                                          T* __restrict__ planes, unsigned W, unsigned n_frames) {
+    const unsigned f = blockIdx.y;
+    const unsigned col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames || col >= W) return;
+    using V = typename Vec<T>::type;
+    const V* src = reinterpret_cast<const V*>(poses + f * poses_fs + static_cast<size_t>(col) * 16);
+    T* dst = planes + static_cast<size_t>(f) * 12u * W + col;
+    constexpr int NV = 12 / Vec<T>::N;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const V x = __ldg(src + i);
+        const T* e = reinterpret_cast<const T*>(&x);
+#pragma unroll
+        for (int j = 0; j < Vec<T>::N; ++j) dst[static_cast<size_t>(i * Vec<T>::N + j) * W] = e[j];
     }
 }
 
@@ -592,6 +625,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     if (a.poses) fast = fast && aligned16(a.poses) && a.poses_fs % t4 == 0;
     p.poses = a.poses;
     p.poses_fs = a.poses_fs;
+    p.planes = nullptr;
     p.an = a.analytic;
     p.store_lag = 0;
     p.RT = 1;
@@ -621,7 +655,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     if (sizeof(T) == 8) TW = std::max(4, TW / 2 / 4 * 4);
     TW = std::min(TW, a.W);
     TW = std::max(4, TW / 4 * 4);
-    const int RT = pose ? std::min(kPoseRows, std::max(8, a.H)) : 1;
+    const int RT = pose ? std::min(tn.cloud_pose_rows, std::max(4, a.H)) : 1;
     const int row_blocks = (a.H + RT - 1) / RT;
     // small launches: shrink tiles until every SM has work for a few CTAs
     const unsigned want_tiles = static_cast<unsigned>(tn.sm_count) * tn.cloud_ctas_per_sm * 2;
@@ -637,7 +671,7 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     p.n_tiles = static_cast<unsigned>(row_blocks) * p.tiles_per_row * a.n_frames;  // work items
     p.stage_bytes = 2u * 3u * TW * sizeof(T) + static_cast<unsigned>(a.n_returns) * 4u * TW;
     p.stage_bytes = (p.stage_bytes + 127u) & ~127u;
-    const size_t pose_bytes = pose ? (16u + 12u) * TW * sizeof(T) : 0u;  // raw slice + 12 planes
+    const size_t pose_bytes = pose ? 12u * TW * sizeof(T) : 0u;  // the item's 12 pose planes
     if (p.stages > 8) p.stages = 8;  // barrier arrays hold 8 entries each
     const size_t smem = 256 + pose_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
     if (smem > 227u * 1024u) return cudaErrorInvalidValue;
@@ -651,9 +685,23 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     else kern = a.n_returns == 2 ? cloud_tma_kernel<T, 2, false> : cloud_tma_kernel<T, 1, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kern<<<std::max(grid, 1), tn.cloud_threads + 32, smem, st>>>(p);  // + the copy warp
+    T* planes = nullptr;
+    if (pose) {  // stream-ordered scratch: the launch's poses as planes
+        if (a.n_frames > 65535) return cudaErrorInvalidValue;
+        e = cudaMallocAsync(reinterpret_cast<void**>(&planes), static_cast<size_t>(a.n_frames) * 12u * a.W * sizeof(T), st);
+        if (e != cudaSuccess) return e;
+        pose_planes_kernel<T><<<dim3((a.W + 255) / 256, a.n_frames), 256, 0, st>>>(a.poses, a.poses_fs, planes, a.W, a.n_frames);
+        count_launch();
+        p.planes = planes;
+    }
+    kern<<<std::max(grid, 1), (pose ? tn.cloud_pose_threads : tn.cloud_threads) + 32, smem, st>>>(p);  // + the copy warp
     count_launch();
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (planes != nullptr) {
+        const cudaError_t e2 = cudaFreeAsync(planes, st);
+        if (e == cudaSuccess) e = e2;
+    }
+    return e;
 }
 
 // ---------------------------------------------------------------------------------------------

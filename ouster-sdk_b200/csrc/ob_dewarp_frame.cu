@@ -1,18 +1,27 @@
-// ob_dewarp_frame.cu -- K3: range image -> world-frame point list in one pass:
+// ob_dewarp_frame.cu -- K3: range image -> world-frame point list in ONE launch:
 // LUT projection + per-column pose + range filter + order-preserving compaction.
 //
 // What it replaces (reference paths relative to /root/reference):
 //   dewarp<T>(LidarFrame, XYZLutT<T>, min_range, max_range)  ouster_core/include/ouster/core/pose_util.h:456-485
 //   impl::dewarp_impl (single frame)                         ouster_core/include/ouster/core/impl/dewarp_impl.h:22-76
+//   dewarp<T>(FrameSet, xyzluts, min_range, max_range)       pose_util.h:475, impl/dewarp_impl.h:84-102
 // The reference projects the whole image (cartesian), then walks the columns between the first and
 // the last valid one and appends the posed points that pass the range filter; its own note
-// (dewarp_impl.h:27-29) asks for the projection to be folded in.  Here nothing is materialised:
-//   count : one warp per (32 columns x 16 rows) block counts the surviving pixels of each column
-//   scan  : one CTA finds the first/last valid column, masks excluded columns and turns the counts
-//           into write offsets (column-major order, rows ascending inside a column -- the order
-//           of the reference's loop)
-//   emit  : the count mapping again; each lane projects its pixel from the LUT, applies the
-//           column pose (cast from double to T like the reference) and writes at offset + rank.
+// (dewarp_impl.h:27-29) asks for the projection to be folded in.  Here nothing is materialised and the
+// three passes of a compaction (count, scan, emit) are one kernel:
+//   * a CTA owns 32 consecutive columns of one frame (all rows); CTAs take their logical index from a
+//     ticket counter, so a CTA's predecessors are always running (or done) when it waits for them;
+//   * count : warp = 16-row slab, lane = column: surviving pixels per (slab, column) in shared memory;
+//   * scan  : the columns' totals are scanned inside the CTA; the CTA's base comes from a decoupled
+//             look-back over its predecessors' published aggregates / inclusive prefixes (one warp looks
+//             at 32 predecessors at a time), frames of a set simply continue the chain, so the points of
+//             frame f follow those of frame f-1 exactly like the reference's concatenation;
+//   * emit  : the count mapping again (the CTA's 16 KB of range are L1 hits): each lane projects its
+//             pixel from the LUT, applies the column pose (cast from double to T like the reference) and
+//             writes at base + rank (column-major order, rows ascending inside a column -- the order of
+//             the reference's loop).
+// The number of points is a device-side word (per frame: the inclusive prefix at the frame's last CTA):
+// no host round trip sits between the passes.
 #include <algorithm>
 
 #include "ob_internal.h"
@@ -34,326 +43,222 @@ __device__ __forceinline__ double k3_pose_row(const double* m, double x, double 
     return __dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dadd_rn(__dmul_rn(m[1], y), __dmul_rn(m[2], z))), m[3]);
 }
 
-// cnt[slab * W + col] = pixels of column col, rows of the slab, with min_r <= r <= max_r
-__global__ void __launch_bounds__(256) k3_count_kernel(const uint32_t* __restrict__ range, unsigned H, unsigned W,
-                                                       uint32_t min_r, uint32_t max_r, unsigned n_cg,
-                                                       unsigned n_slabs, uint32_t* __restrict__ cnt) {
-    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= n_cg * n_slabs) return;
-    const unsigned cg = gw % n_cg, slab = gw / n_cg;
-    const unsigned col = cg * 32u + (threadIdx.x & 31u);
-    if (col >= W) return;
-    const unsigned r0 = slab * kSlabRows, r1 = min(H, r0 + kSlabRows);
-    uint32_t c = 0;
-    for (unsigned row = r0; row < r1; ++row) {
-        const uint32_t r = range[static_cast<size_t>(row) * W + col];
-        c += (r >= min_r && r <= max_r) ? 1u : 0u;
-    }
-    cnt[static_cast<size_t>(slab) * W + col] = c;
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
 }
 
-// One CTA.  base[slab * W + col] = write offset of the first surviving pixel of (col, slab), or
-// 0xffffffff for excluded columns; *total = number of points.
-__global__ void __launch_bounds__(1024) k3_scan_kernel(const uint32_t* __restrict__ cnt,
-                                                       const uint32_t* __restrict__ status, unsigned W,
-                                                       unsigned n_slabs, uint32_t* __restrict__ base,
-                                                       unsigned long long* __restrict__ total) {
-    __shared__ int s_first, s_last;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const unsigned tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) {
-        s_first = 0x7fffffff;
-        s_last = -1;
-        s_carry = 0;
-    }
-    __syncthreads();
-    // LidarFrame::get_first_valid_column / get_last_valid_column (lidar_frame.cpp:907-925)
-    int lf = 0x7fffffff, ll = -1;
-    for (unsigned c = tid; c < W; c += nt)
-        if ((status[c] & 1u) != 0) {
-            lf = min(lf, static_cast<int>(c));
-            ll = max(ll, static_cast<int>(c));
-        }
-    atomicMin(&s_first, lf);
-    atomicMax(&s_last, ll);
-    __syncthreads();
-    const int first = s_first, last = s_last;
-    // columns in chunks of blockDim: block-wide exclusive scan with a running carry
-    for (unsigned c0 = 0; c0 < W; c0 += nt) {
-        const unsigned c = c0 + tid;
-        // dewarp_impl.h:59-62: columns outside [first, last] are never visited, status == 0 is skipped
-        const bool on = c < W && last >= first && static_cast<int>(c) >= first && static_cast<int>(c) <= last &&
-                        status[c] != 0;
-        uint32_t mine = 0;
-        if (on)
-            for (unsigned s = 0; s < n_slabs; ++s) mine += cnt[static_cast<size_t>(s) * W + c];
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((tid & 31u) >= static_cast<unsigned>(d)) incl += v;
-        }
-        if ((tid & 31u) == 31u) s_warp[tid >> 5] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t w = tid < (nt >> 5) ? s_warp[tid] : 0u;
-            uint32_t wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-                if (tid >= static_cast<unsigned>(d)) wi += v;
-            }
-            s_warp[tid] = wi - w;  // exclusive prefix of the warp sums
-        }
-        __syncthreads();
-        uint32_t off = s_carry + s_warp[tid >> 5] + (incl - mine);
-        if (c < W) {
-            for (unsigned s = 0; s < n_slabs; ++s) {
-                base[static_cast<size_t>(s) * W + c] = on ? off : 0xffffffffu;
-                if (on) off += cnt[static_cast<size_t>(s) * W + c];
-            }
-        }
-        __syncthreads();
-        if (tid == nt - 1) s_carry = s_carry + s_warp[tid >> 5] + incl;
-        __syncthreads();
-    }
-    if (tid == 0) *total = s_carry;
-}
+// Scratch of one launch (zeroed by the launcher): ticket, then per logical CTA a state word
+// (0 = nothing yet, 1 = aggregate published, 2 = inclusive prefix published) and the two values.
+struct K3Scan {
+    unsigned* ticket;
+    uint32_t* state;
+    unsigned long long* agg;
+    unsigned long long* incl;
+    unsigned long long* frame_end;  // [n_frames] points up to and including frame f
+};
 
 template <typename T>
-__global__ void __launch_bounds__(256) k3_emit_kernel(const uint32_t* __restrict__ range, const T* __restrict__ dir,
-                                                      const T* __restrict__ off, const double* __restrict__ poses,
-                                                      const uint64_t* __restrict__ timestamps, unsigned H,
-                                                      unsigned W, uint32_t min_r, uint32_t max_r, unsigned n_cg,
-                                                      unsigned n_slabs, const uint32_t* __restrict__ base,
-                                                      T* __restrict__ points, uint32_t* __restrict__ col_idx,
-                                                      uint64_t* __restrict__ ts_out) {
-    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= n_cg * n_slabs) return;
-    const unsigned cg = gw % n_cg, slab = gw / n_cg;
-    const unsigned col = cg * 32u + (threadIdx.x & 31u);
-    if (col >= W) return;
-    uint32_t w = base[static_cast<size_t>(slab) * W + col];
-    if (w == 0xffffffffu) return;
-    T m[12];  // rows 0..2 of body_to_world[col], cast to T (dewarp_impl.h:64-65)
-#pragma unroll
-    for (int k = 0; k < 12; ++k) m[k] = static_cast<T>(poses[static_cast<size_t>(col) * 16 + k]);
-    const uint64_t ts = ts_out != nullptr ? timestamps[col] : 0ull;
-    const unsigned r0 = slab * kSlabRows, r1 = min(H, r0 + kSlabRows);
-    for (unsigned row = r0; row < r1; ++row) {
-        const size_t px = static_cast<size_t>(row) * W + col;
-        const uint32_t r = range[px];
-        if (r >= min_r && r <= max_r) {
-            const T x = k3_project(r, dir[px * 3], off[px * 3]);
-            const T y = k3_project(r, dir[px * 3 + 1], off[px * 3 + 1]);
-            const T z = k3_project(r, dir[px * 3 + 2], off[px * 3 + 2]);
-            T* o = points + static_cast<size_t>(w) * 3;
-            o[0] = k3_pose_row(m, x, y, z);
-            o[1] = k3_pose_row(m + 4, x, y, z);
-            o[2] = k3_pose_row(m + 8, x, y, z);
-            if (col_idx != nullptr) col_idx[w] = col;
-            if (ts_out != nullptr) ts_out[w] = ts;
-            ++w;
-        }
-    }
-}
-
-size_t dewarp_frame_scratch_bytes(unsigned H, unsigned W) {
-    const size_t n_slabs = (H + kSlabRows - 1) / kSlabRows;
-    return 2 * n_slabs * W * sizeof(uint32_t) + 16;
-}
-
-cudaError_t launch_dewarp_frame_count(const DewarpFrameArgs& a, cudaStream_t st) {
-    const unsigned n_cg = (a.W + 31) / 32, n_slabs = (a.H + kSlabRows - 1) / kSlabRows;
-    uint32_t* cnt = static_cast<uint32_t*>(a.scratch);
-    uint32_t* base = cnt + static_cast<size_t>(n_slabs) * a.W;
-    unsigned long long* total = reinterpret_cast<unsigned long long*>(
-        static_cast<uint8_t*>(a.scratch) + ((2 * static_cast<size_t>(n_slabs) * a.W * 4 + 7) & ~static_cast<size_t>(7)));
-    const unsigned warps = n_cg * n_slabs;
-    k3_count_kernel<<<(warps + 7) / 8, 256, 0, st>>>(a.range, a.H, a.W, a.min_r, a.max_r, n_cg, n_slabs, cnt);
-    k3_scan_kernel<<<1, 1024, 0, st>>>(cnt, a.status, a.W, n_slabs, base, total);
-    count_launch(2);
-    return cudaGetLastError();
-}
-
-const unsigned long long* dewarp_frame_total_ptr(const DewarpFrameArgs& a) {
-    const size_t n_slabs = (a.H + kSlabRows - 1) / kSlabRows;
-    return reinterpret_cast<const unsigned long long*>(
-        static_cast<const uint8_t*>(a.scratch) + ((2 * n_slabs * a.W * 4 + 7) & ~static_cast<size_t>(7)));
-}
-
-cudaError_t launch_dewarp_frame_emit(const DewarpFrameArgs& a, cudaStream_t st) {
-    const unsigned n_cg = (a.W + 31) / 32, n_slabs = (a.H + kSlabRows - 1) / kSlabRows;
-    const uint32_t* cnt = static_cast<const uint32_t*>(a.scratch);
-    const uint32_t* base = cnt + static_cast<size_t>(n_slabs) * a.W;
-    const unsigned warps = n_cg * n_slabs;
-    if (a.dtype == OB_F64)
-        k3_emit_kernel<double><<<(warps + 7) / 8, 256, 0, st>>>(
-            a.range, static_cast<const double*>(a.dir), static_cast<const double*>(a.off), a.poses, a.timestamps,
-            a.H, a.W, a.min_r, a.max_r, n_cg, n_slabs, base, static_cast<double*>(a.points), a.col_idx, a.ts_out);
-    else
-        k3_emit_kernel<float><<<(warps + 7) / 8, 256, 0, st>>>(
-            a.range, static_cast<const float*>(a.dir), static_cast<const float*>(a.off), a.poses, a.timestamps,
-            a.H, a.W, a.min_r, a.max_r, n_cg, n_slabs, base, static_cast<float*>(a.points), a.col_idx, a.ts_out);
-    count_launch();
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// Batched form: dewarp(FrameSet, xyzluts, min_range, max_range) (pose_util.h:475, impl/dewarp_impl.h:84-102)
-// -- the frames of a set, each with its own LUT / poses / status, in THREE launches for the whole set
-// (the single-frame path above needs three per frame plus a host round trip for its count): the points of
-// frame f follow those of frame f-1 in the output, exactly like the reference's concatenation.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k3_count_batch_kernel(const K3Frame* __restrict__ frames, uint32_t min_r,
-                                                             uint32_t max_r) {
-    const K3Frame& fr = frames[blockIdx.y];
-    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= fr.n_cg * fr.n_slabs) return;
-    const unsigned cg = gw % fr.n_cg, slab = gw / fr.n_cg;
-    const unsigned col = cg * 32u + (threadIdx.x & 31u);
-    if (col >= fr.W) return;
-    const unsigned r0 = slab * kSlabRows, r1 = min(fr.H, r0 + kSlabRows);
-    uint32_t c = 0;
-    for (unsigned row = r0; row < r1; ++row) {
-        const uint32_t r = fr.range[static_cast<size_t>(row) * fr.W + col];
-        c += (r >= min_r && r <= max_r) ? 1u : 0u;
-    }
-    fr.cnt[static_cast<size_t>(slab) * fr.W + col] = c;
-}
-
-__global__ void __launch_bounds__(1024) k3_scan_batch_kernel(const K3Frame* __restrict__ frames,
-                                                             unsigned long long* __restrict__ totals) {
-    const K3Frame& fr = frames[blockIdx.x];
+__global__ void __launch_bounds__(256) k3_fused_kernel(const K3Frame* __restrict__ frames, unsigned n_frames,
+                                                       uint32_t min_r, uint32_t max_r, K3Scan sc,
+                                                       T* __restrict__ points, uint32_t* __restrict__ frame_idx,
+                                                       uint32_t* __restrict__ col_idx, uint64_t* __restrict__ ts_out,
+                                                       unsigned long long capacity) {
+    extern __shared__ uint32_t s_cnt[];  // [n_slabs][32]
+    __shared__ unsigned s_bid;
     __shared__ int s_first, s_last;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const unsigned tid = threadIdx.x, nt = blockDim.x, W = fr.W, n_slabs = fr.n_slabs;
+    __shared__ unsigned long long s_excl;
+    __shared__ uint32_t s_coloff[32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nw = blockDim.x >> 5;
     if (tid == 0) {
+        s_bid = atomicAdd(sc.ticket, 1u);
         s_first = 0x7fffffff;
         s_last = -1;
-        s_carry = 0;
     }
     __syncthreads();
-    int lf = 0x7fffffff, ll = -1;
-    for (unsigned c = tid; c < W; c += nt)
-        if ((fr.status[c] & 1u) != 0) {
-            lf = min(lf, static_cast<int>(c));
-            ll = max(ll, static_cast<int>(c));
-        }
-    atomicMin(&s_first, lf);
-    atomicMax(&s_last, ll);
-    __syncthreads();
-    const int first = s_first, last = s_last;
-    for (unsigned c0 = 0; c0 < W; c0 += nt) {
-        const unsigned c = c0 + tid;
-        const bool on = c < W && last >= first && static_cast<int>(c) >= first && static_cast<int>(c) <= last &&
-                        fr.status[c] != 0;
-        uint32_t mine = 0;
-        if (on)
-            for (unsigned sl = 0; sl < n_slabs; ++sl) mine += fr.cnt[static_cast<size_t>(sl) * W + c];
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if ((tid & 31u) >= static_cast<unsigned>(d)) incl += v;
-        }
-        if ((tid & 31u) == 31u) s_warp[tid >> 5] = incl;
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t w = tid < (nt >> 5) ? s_warp[tid] : 0u;
-            uint32_t wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, wi, d);
-                if (tid >= static_cast<unsigned>(d)) wi += v;
-            }
-            s_warp[tid] = wi - w;
-        }
-        __syncthreads();
-        uint32_t off = s_carry + s_warp[tid >> 5] + (incl - mine);
-        if (c < W) {
-            for (unsigned sl = 0; sl < n_slabs; ++sl) {
-                fr.base[static_cast<size_t>(sl) * W + c] = on ? off : 0xffffffffu;
-                if (on) off += fr.cnt[static_cast<size_t>(sl) * W + c];
-            }
-        }
-        __syncthreads();
-        if (tid == nt - 1) s_carry = s_carry + s_warp[tid >> 5] + incl;
-        __syncthreads();
-    }
-    if (tid == 0) totals[blockIdx.x] = s_carry;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) k3_emit_batch_kernel(const K3Frame* __restrict__ frames,
-                                                            const unsigned long long* __restrict__ totals,
-                                                            uint32_t min_r, uint32_t max_r, T* __restrict__ points,
-                                                            uint32_t* __restrict__ frame_idx,
-                                                            uint32_t* __restrict__ col_idx, uint64_t* __restrict__ ts_out,
-                                                            unsigned long long capacity) {
-    const unsigned f = blockIdx.y;
+    const unsigned bid = s_bid;
+    unsigned f = 0;
+    while (f + 1 < n_frames && frames[f + 1].first_block <= bid) ++f;
     const K3Frame& fr = frames[f];
-    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (gw >= fr.n_cg * fr.n_slabs) return;
-    const unsigned cg = gw % fr.n_cg, slab = gw / fr.n_cg;
-    const unsigned col = cg * 32u + (threadIdx.x & 31u);
-    if (col >= fr.W) return;
-    const uint32_t b = fr.base[static_cast<size_t>(slab) * fr.W + col];
-    if (b == 0xffffffffu) return;
-    unsigned long long fbase = 0;  // points of the frames before this one (a set holds a handful of frames)
-    for (unsigned i = 0; i < f; ++i) fbase += totals[i];
-    unsigned long long w = fbase + b;
+    const unsigned cg = bid - fr.first_block, W = fr.W, H = fr.H, n_slabs = fr.n_slabs;
+
+    // LidarFrame::get_first_valid_column / get_last_valid_column (lidar_frame.cpp:907-925)
+    {
+        int lf = 0x7fffffff, ll = -1;
+        for (unsigned c = tid; c < W; c += blockDim.x)
+            if ((fr.status[c] & 1u) != 0) {
+                lf = min(lf, static_cast<int>(c));
+                ll = max(ll, static_cast<int>(c));
+            }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            lf = min(lf, __shfl_xor_sync(0xffffffffu, lf, d));
+            ll = max(ll, __shfl_xor_sync(0xffffffffu, ll, d));
+        }
+        if (lane == 0) {
+            atomicMin(&s_first, lf);
+            atomicMax(&s_last, ll);
+        }
+    }
+    // ---- count ----
+    const unsigned col = cg * 32u + lane;
+    const bool col_ok = col < W;
+    for (unsigned slab = warp; slab < n_slabs; slab += nw) {
+        const unsigned r0 = slab * kSlabRows, r1 = min(H, r0 + kSlabRows);
+        uint32_t c = 0;
+        if (col_ok)
+            for (unsigned row = r0; row < r1; ++row) {
+                const uint32_t r = fr.range[static_cast<size_t>(row) * W + col];
+                c += (r >= min_r && r <= max_r) ? 1u : 0u;
+            }
+        s_cnt[slab * 32u + lane] = c;
+    }
+    __syncthreads();
+    // ---- scan: columns of the CTA, then the look-back over the CTAs before it ----
+    if (warp == 0) {
+        const int first = s_first, last = s_last;
+        // dewarp_impl.h:59-62: columns outside [first, last] are never visited, status == 0 is skipped
+        const bool on = col_ok && last >= first && static_cast<int>(col) >= first && static_cast<int>(col) <= last &&
+                        fr.status[col] != 0;
+        uint32_t mine = 0;
+        if (on)
+            for (unsigned sl = 0; sl < n_slabs; ++sl) mine += s_cnt[sl * 32u + lane];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= static_cast<unsigned>(d)) incl += v;
+        }
+        s_coloff[lane] = on ? incl - mine : 0xffffffffu;
+        const unsigned long long aggregate = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {
+            if (bid == 0) {
+                sc.incl[0] = aggregate;
+                st_release_u32(&sc.state[0], 2u);
+            } else {
+                sc.agg[bid] = aggregate;
+                st_release_u32(&sc.state[bid], 1u);
+            }
+        }
+        unsigned long long excl = 0;
+        if (bid > 0) {
+            int p = static_cast<int>(bid) - 1;
+            for (;;) {
+                const int idx = p - static_cast<int>(lane);
+                uint32_t st = 2u;  // positions before CTA 0 behave like a published prefix of zero
+                unsigned long long v = 0;
+                if (idx >= 0) {
+                    do {
+                        st = ld_acquire_u32(&sc.state[idx]);
+                    } while (st == 0u);
+                    v = __ldcg(st == 2u ? &sc.incl[idx] : &sc.agg[idx]);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, st == 2u);
+                if (pm != 0u) {  // nearest predecessor with an inclusive prefix closes the chain
+                    const unsigned fl = __ffs(pm) - 1u;
+                    excl += warp_sum_u64(lane <= fl ? v : 0ull);
+                    break;
+                }
+                excl += warp_sum_u64(v);
+                p -= 32;
+            }
+            if (lane == 0) {
+                sc.incl[bid] = excl + aggregate;
+                st_release_u32(&sc.state[bid], 2u);
+            }
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (cg + 1 == fr.n_cg) sc.frame_end[f] = excl + aggregate;
+        }
+    }
+    __syncthreads();
+    // ---- emit ----
+    const uint32_t coloff = s_coloff[lane];
+    if (coloff == 0xffffffffu) return;
+    const unsigned long long cbase = s_excl + coloff;
     const T* dir = static_cast<const T*>(fr.dir);
     const T* off = static_cast<const T*>(fr.off);
-    T m[12];
+    T m[12];  // rows 0..2 of body_to_world[col], cast to T (dewarp_impl.h:64-65)
 #pragma unroll
     for (int k = 0; k < 12; ++k) m[k] = static_cast<T>(fr.poses[static_cast<size_t>(col) * 16 + k]);
     const uint64_t ts = (ts_out != nullptr && fr.timestamps != nullptr) ? fr.timestamps[col] : 0ull;
-    const unsigned r0 = slab * kSlabRows, r1 = min(fr.H, r0 + kSlabRows);
-    for (unsigned row = r0; row < r1; ++row) {
-        const size_t px = static_cast<size_t>(row) * fr.W + col;
-        const uint32_t r = fr.range[px];
-        if (r >= min_r && r <= max_r) {
-            if (w < capacity) {
-                const T x = k3_project(r, dir[px * 3], off[px * 3]);
-                const T y = k3_project(r, dir[px * 3 + 1], off[px * 3 + 1]);
-                const T z = k3_project(r, dir[px * 3 + 2], off[px * 3 + 2]);
-                T* o = points + w * 3;
-                o[0] = k3_pose_row(m, x, y, z);
-                o[1] = k3_pose_row(m + 4, x, y, z);
-                o[2] = k3_pose_row(m + 8, x, y, z);
-                if (frame_idx != nullptr) frame_idx[w] = fr.index;
-                if (col_idx != nullptr) col_idx[w] = col;
-                if (ts_out != nullptr) ts_out[w] = ts;
+    for (unsigned slab = warp; slab < n_slabs; slab += nw) {
+        unsigned long long w = cbase;
+        for (unsigned sl = 0; sl < slab; ++sl) w += s_cnt[sl * 32u + lane];
+        if (s_cnt[slab * 32u + lane] == 0u) continue;
+        const unsigned r0 = slab * kSlabRows, r1 = min(H, r0 + kSlabRows);
+        for (unsigned row = r0; row < r1; ++row) {
+            const size_t px = static_cast<size_t>(row) * W + col;
+            const uint32_t r = fr.range[px];
+            if (r >= min_r && r <= max_r) {
+                if (w < capacity) {
+                    const T x = k3_project(r, dir[px * 3], off[px * 3]);
+                    const T y = k3_project(r, dir[px * 3 + 1], off[px * 3 + 1]);
+                    const T z = k3_project(r, dir[px * 3 + 2], off[px * 3 + 2]);
+                    T* o = points + w * 3;
+                    o[0] = k3_pose_row(m, x, y, z);
+                    o[1] = k3_pose_row(m + 4, x, y, z);
+                    o[2] = k3_pose_row(m + 8, x, y, z);
+                    if (frame_idx != nullptr) frame_idx[w] = fr.index;
+                    if (col_idx != nullptr) col_idx[w] = col;
+                    if (ts_out != nullptr) ts_out[w] = ts;
+                }
+                ++w;
             }
-            ++w;
         }
     }
 }
 
-size_t dewarp_frames_scratch_bytes(unsigned H, unsigned W) {
-    const size_t n_slabs = (H + kSlabRows - 1) / kSlabRows;
-    return 2 * n_slabs * W * sizeof(uint32_t);
+// scratch layout: [ticket + pad : 16 B][state u32 x nb, padded to 8][agg u64 x nb][incl u64 x nb][frame_end u64 x nf]
+static size_t k3_state_bytes(unsigned n_blocks) { return 16 + ((static_cast<size_t>(n_blocks) * 4 + 7) & ~static_cast<size_t>(7)); }
+size_t dewarp_scan_scratch_bytes(unsigned n_blocks, unsigned n_frames) {
+    return k3_state_bytes(n_blocks) + static_cast<size_t>(n_blocks) * 16 + static_cast<size_t>(n_frames) * 8;
 }
 
-cudaError_t launch_dewarp_frames(const K3Frame* frames_dev, unsigned n_frames, unsigned max_warps, uint32_t min_r,
-                                 uint32_t max_r, int dtype, unsigned long long* totals_dev, void* points,
-                                 uint32_t* frame_idx, uint32_t* col_idx, uint64_t* ts_out, unsigned long long capacity,
-                                 cudaStream_t st) {
-    if (n_frames == 0) return cudaSuccess;
-    if (n_frames > 65535) return cudaErrorInvalidValue;
-    const dim3 grid((max_warps + 7) / 8, n_frames);
-    k3_count_batch_kernel<<<grid, 256, 0, st>>>(frames_dev, min_r, max_r);
-    k3_scan_batch_kernel<<<n_frames, 1024, 0, st>>>(frames_dev, totals_dev);
-    if (dtype == OB_F64)
-        k3_emit_batch_kernel<double><<<grid, 256, 0, st>>>(frames_dev, totals_dev, min_r, max_r,
-                                                            static_cast<double*>(points), frame_idx, col_idx, ts_out, capacity);
-    else
-        k3_emit_batch_kernel<float><<<grid, 256, 0, st>>>(frames_dev, totals_dev, min_r, max_r,
-                                                           static_cast<float*>(points), frame_idx, col_idx, ts_out, capacity);
-    count_launch(3);
+cudaError_t launch_dewarp_fused(const K3Frame* frames_dev, unsigned n_frames, unsigned n_blocks, unsigned max_slabs,
+                                uint32_t min_r, uint32_t max_r, int dtype, void* scratch, void* points,
+                                uint32_t* frame_idx, uint32_t* col_idx, uint64_t* ts_out, unsigned long long capacity,
+                                const unsigned long long** frame_end_dev, cudaStream_t st) {
+    if (frame_end_dev) *frame_end_dev = nullptr;
+    if (n_frames == 0 || n_blocks == 0) return cudaSuccess;
+    uint8_t* b = static_cast<uint8_t*>(scratch);
+    K3Scan sc;
+    sc.ticket = reinterpret_cast<unsigned*>(b);
+    sc.state = reinterpret_cast<uint32_t*>(b + 16);
+    sc.agg = reinterpret_cast<unsigned long long*>(b + k3_state_bytes(n_blocks));
+    sc.incl = sc.agg + n_blocks;
+    sc.frame_end = sc.incl + n_blocks;
+    if (frame_end_dev) *frame_end_dev = sc.frame_end;
+    cudaError_t e = cudaMemsetAsync(b, 0, k3_state_bytes(n_blocks), st);  // ticket + state words
+    if (e != cudaSuccess) return e;
+    const size_t smem = static_cast<size_t>(max_slabs) * 32 * sizeof(uint32_t);
+    if (smem > 200u * 1024u) return cudaErrorInvalidValue;
+    if (dtype == OB_F64) {
+        if (smem > 48u * 1024u) {
+            e = cudaFuncSetAttribute(k3_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return e;
+        }
+        k3_fused_kernel<double><<<n_blocks, 256, smem, st>>>(frames_dev, n_frames, min_r, max_r, sc,
+                                                               static_cast<double*>(points), frame_idx, col_idx, ts_out, capacity);
+    } else {
+        if (smem > 48u * 1024u) {
+            e = cudaFuncSetAttribute(k3_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+            if (e != cudaSuccess) return e;
+        }
+        k3_fused_kernel<float><<<n_blocks, 256, smem, st>>>(frames_dev, n_frames, min_r, max_r, sc,
+                                                              static_cast<float*>(points), frame_idx, col_idx, ts_out, capacity);
+    }
+    count_launch();
     return cudaGetLastError();
 }
 

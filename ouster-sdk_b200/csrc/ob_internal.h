@@ -19,6 +19,8 @@ struct Tunables {
     int cloud_ctas_per_sm; // persistent CTAs per SM
     int cloud_pose_tw;     // pixels per row of a tile of the pose-fused variant
     int cloud_pose_stages, cloud_pose_ctas_per_sm;
+    int cloud_pose_threads;  // compute threads per CTA of the pose-fused variant
+    int cloud_pose_rows;   // rows per work item of the pose-fused variant (one pose slice load per item)
     int cloud_store_lag;   // 1: refill the stage of tile k-2 instead of k-1 (hides the store drain)
     int cloud_auto;        // 1: nobody touched the cloud_* geometry -> launch_cloud picks it per return count
     int decode_stages;
@@ -82,46 +84,25 @@ cudaError_t launch_make_lut(size_t w, size_t h, double range_unit, const double*
                             cudaStream_t st);
 cudaError_t launch_cast_f64_f32(const double* src, float* dst, size_t n, cudaStream_t st);
 
-// ---- K3: range -> posed, filtered, compacted point list (ob_dewarp_frame.cu) ----
-struct DewarpFrameArgs {  // all pointers are device memory
+// ---- K3: range -> posed, filtered, compacted point list, one launch (ob_dewarp_frame.cu) ----
+// one entry per frame of the launch (a single frame or the frames of a FrameSet), device memory
+struct K3Frame {
     const uint32_t* range;       // H x W
-    const void* dir;             // LUT tables of `dtype`
+    const void* dir;             // LUT tables of the launch's dtype
     const void* off;
     const double* poses;         // W x 16
     const uint32_t* status;      // W
-    const uint64_t* timestamps;  // W, may be null when ts_out is null
-    unsigned H, W;
-    uint32_t min_r, max_r;
-    int dtype;
-    void* scratch;               // dewarp_frame_scratch_bytes(H, W)
-    void* points;                // capacity x 3 of dtype
-    uint32_t* col_idx;           // nullable
-    uint64_t* ts_out;            // nullable
-};
-size_t dewarp_frame_scratch_bytes(unsigned H, unsigned W);
-cudaError_t launch_dewarp_frame_count(const DewarpFrameArgs& a, cudaStream_t st);  // counts + offsets
-const unsigned long long* dewarp_frame_total_ptr(const DewarpFrameArgs& a);         // device pointer
-cudaError_t launch_dewarp_frame_emit(const DewarpFrameArgs& a, cudaStream_t st);
-
-// batched K3 (dewarp of a FrameSet): one entry per frame, device memory
-struct K3Frame {
-    const uint32_t* range;
-    const void* dir;
-    const void* off;
-    const double* poses;
-    const uint32_t* status;
-    const uint64_t* timestamps;  // nullable
-    uint32_t* cnt;               // n_slabs x W scratch
-    uint32_t* base;              // n_slabs x W scratch
-    unsigned H, W, n_cg, n_slabs;
+    const uint64_t* timestamps;  // W, nullable
+    unsigned H, W, n_cg, n_slabs;  // n_cg = ceil(W / 32) CTAs, n_slabs = ceil(H / 16)
+    unsigned first_block;        // logical index of the frame's first CTA (sum of n_cg of the frames before)
     unsigned index;              // the frame's index in the set (reported as frame_idx)
-    unsigned pad;
 };
-size_t dewarp_frames_scratch_bytes(unsigned H, unsigned W);
-cudaError_t launch_dewarp_frames(const K3Frame* frames_dev, unsigned n_frames, unsigned max_warps, uint32_t min_r,
-                                 uint32_t max_r, int dtype, unsigned long long* totals_dev, void* points,
-                                 uint32_t* frame_idx, uint32_t* col_idx, uint64_t* ts_out, unsigned long long capacity,
-                                 cudaStream_t st);
+size_t dewarp_scan_scratch_bytes(unsigned n_blocks, unsigned n_frames);
+// *frame_end_dev: device array [n_frames], points up to and including frame f (valid when the launch is done)
+cudaError_t launch_dewarp_fused(const K3Frame* frames_dev, unsigned n_frames, unsigned n_blocks, unsigned max_slabs,
+                                uint32_t min_r, uint32_t max_r, int dtype, void* scratch, void* points,
+                                uint32_t* frame_idx, uint32_t* col_idx, uint64_t* ts_out, unsigned long long capacity,
+                                const unsigned long long** frame_end_dev, cudaStream_t st);
 
 // ---- decode ----
 struct DecodeField {  // device-side copy of ob_field_desc, pre-digested

@@ -199,3 +199,45 @@ def test_dewarp_frame_set_is_the_concatenation_of_its_frames(ob, dtype):
     assert np.array_equal(ob.dewarp_frames(frames, 0.5, 45.0), np.concatenate(want_p))
     assert ob.dewarp_frames([None, None]).shape == (0, 3)
     assert ob.dewarp_frames(frames, 50.0, 40.0).shape == (0, 3)     # empty range window
+
+
+@pytest.mark.gpu
+def test_dewarp_frame_long_lookback_chain_and_device_count(ob):
+    """The single-launch compaction: 128 CTAs in one frame (four look-back windows of 32) and a set of
+    wide frames whose chain continues across the frames; then the asynchronous form (device outputs and a
+    device-side count, no host wait inside the call) against the host-output form."""
+    import torch
+    from tests.helpers import random_lut, random_range
+    h, w = 32, 4096
+    rng = random_range(h, w, 21, p_zero=0.6, max_range=60000)
+    rng[:, 700:2100] = 0                      # long runs of CTAs with nothing to emit
+    d, o = random_lut(h * w, 4, np.float32)
+    lut = ob.XYZLutT.from_arrays(d, o, h, w)
+    poses = _random_poses(w, np.float64, 5)
+    status = np.ones(w, np.uint32)
+    status[np.random.default_rng(8).integers(0, w, w // 5)] = 0
+    ts = np.arange(w, dtype=np.uint64)
+    want_p, want_c, _ = orc.dewarp_frame(rng, d, o, poses, status, ts, 0.2, 55.0)
+    for _ in range(3):                        # scheduling order of the CTAs differs from run to run
+        got_p, got_c, _ = ob.dewarp_frame(lut, rng, poses, status, ts, 0.2, 55.0, provenance=True)
+        assert np.array_equal(got_p, want_p) and np.array_equal(got_c, want_c)
+    frames = [{"lut": lut, "range": np.roll(rng, 37 * i, axis=1), "poses": poses, "status": status, "timestamps": ts}
+              for i in range(5)]
+    want = np.concatenate([orc.dewarp_frame(f["range"], d, o, poses, status, ts, 0.2, 55.0)[0] for f in frames])
+    assert np.array_equal(ob.dewarp_frames(frames, 0.2, 55.0), want)
+    # asynchronous device form
+    dev = torch.device("cuda", 0)
+    out = torch.full((h * w, 3), -1.0, dtype=torch.float32, device=dev)
+    cnt = torch.full((1,), -1, dtype=torch.int64, device=dev)
+    t = {k: torch.from_numpy(v).to(dev) for k, v in
+         (("rng", rng.view(np.int32)), ("poses", poses), ("status", status.view(np.int32)))}
+    ob.dewarp_frame(lut, t["rng"], t["poses"], t["status"], None, 0.2, 55.0, out=out, out_count=cnt)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == len(want_p)
+    assert np.array_equal(out[:len(want_p)].cpu().numpy(), want_p)
+    assert bool((out[len(want_p):] == -1.0).all())
+    # capacity smaller than the result: the list is cut, the count still says how many passed
+    small = torch.full((100, 3), -1.0, dtype=torch.float32, device=dev)
+    ob.dewarp_frame(lut, t["rng"], t["poses"], t["status"], None, 0.2, 55.0, out=small, out_count=cnt)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == len(want_p) and np.array_equal(small.cpu().numpy(), want_p[:100])

@@ -33,6 +33,20 @@ n_host = len(ob.dewarp_frame(lut, rng, poses, status, ts, 0.5, 50.0))
 out["points"] = n_host
 out["host_to_host_ms"] = best(lambda: ob.dewarp_frame(lut, rng, poses, status, ts, 0.5, 50.0, stream=st)) * 1e3
 out["device_inputs_ms"] = best(lambda: ob.dewarp_frame(lut, t_rng, t_pose, t_st, t_ts, 0.5, 50.0, stream=st)) * 1e3
+# asynchronous form: device outputs + device-side count, no host wait inside the call -> CUDA events over 50 calls
+t_out = torch.empty((H * W, 3), dtype=torch.float32, device=dev)
+t_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+for _ in range(5):
+    ob.dewarp_frame(lut, t_rng, t_pose, t_st, None, 0.5, 50.0, stream=st, out=t_out, out_count=t_cnt)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50):
+    ob.dewarp_frame(lut, t_rng, t_pose, t_st, None, 0.5, 50.0, stream=st, out=t_out, out_count=t_cnt)
+e1.record(); torch.cuda.synchronize()
+out["async_device_ms_per_call"] = e0.elapsed_time(e1) / 50
+out["async_count"] = int(t_cnt.item())
+out["launches_per_call"] = (lambda a: (ob.dewarp_frame(lut, t_rng, t_pose, t_st, None, 0.5, 50.0, stream=st, out=t_out, out_count=t_cnt), ob.kernel_launch_count() - a)[1])(ob.kernel_launch_count())
 t0 = time.perf_counter(); want = orc.dewarp_frame(rng, d, o, poses, status, ts, 0.5, 50.0)[0]; out["cpu_1thread_ms"] = (time.perf_counter() - t0) * 1e3
 out["matches_oracle"] = bool(np.array_equal(want, ob.dewarp_frame(lut, rng, poses, status, ts, 0.5, 50.0)))
 out["speedup_host_to_host"] = out["cpu_1thread_ms"] / out["host_to_host_ms"]

@@ -46,21 +46,23 @@ def two_pass():
 
 out = {}
 sweep = []
-for tw, stg, cta, th in ((256, 3, 6, 128), (256, 3, 4, 128), (256, 4, 4, 128), (256, 3, 6, 64), (512, 3, 3, 128),
-                         (512, 3, 3, 256), (128, 3, 8, 64)):
+for tw, stg, cta, th, rows in ((256, 4, 5, 64, 16), (256, 4, 6, 64, 16), (256, 5, 5, 64, 16), (256, 4, 5, 64, 8),
+                               (256, 4, 5, 96, 16), (256, 4, 5, 32, 16), (256, 5, 4, 64, 16), (256, 6, 4, 64, 32),
+                               (128, 4, 8, 32, 16), (512, 4, 3, 128, 16), (256, 4, 5, 64, 32), (384, 4, 4, 96, 16)):
     for k, v in (("cloud_pose_tw", tw), ("cloud_pose_stages", stg), ("cloud_pose_ctas_per_sm", cta),
-                 ("cloud_threads", th)):
+                 ("cloud_pose_threads", th), ("cloud_pose_rows", rows)):
         ob.set_tunable(k, v)
     try:
-        sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": timeit(fused, n=5)})
+        sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "rows": rows, "ms": timeit(fused, n=5)})
     except Exception as ex:
-        sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "error": str(ex)[:80]})
+        sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "rows": rows, "error": str(ex)[:80]})
 ok = sorted([r for r in sweep if "ms" in r], key=lambda r: r["ms"])
 out["sweep_best"] = ok[:6]
 out["sweep_worst"] = ok[-1]
 best = ok[0]
 for k, v in (("cloud_pose_tw", best["tw"]), ("cloud_pose_stages", best["stages"]),
-             ("cloud_pose_ctas_per_sm", best["ctas"]), ("cloud_threads", best["threads"])):
+             ("cloud_pose_ctas_per_sm", best["ctas"]), ("cloud_pose_threads", best["threads"]),
+             ("cloud_pose_rows", best["rows"])):
     ob.set_tunable(k, v)
 out["fused_tw_best_ms"] = timeit(fused)
 ob.set_tunable("cloud_threads", 128)
@@ -69,14 +71,6 @@ for lag in (0, 1):
     ob.set_tunable("cloud_store_lag", lag)
     out[f"plain_lag{lag}_ms"] = timeit(plain)
 ob.set_tunable("cloud_store_lag", 1)
-plain_sweep = []
-for tw, stg, cta, th in ((512, 4, 3, 256), (512, 2, 4, 256), (512, 3, 4, 128), (256, 3, 6, 128), (256, 3, 6, 64), (1024, 2, 2, 256), (1024, 3, 2, 256)):
-    for k, v in (("cloud_tw", tw), ("cloud_stages", stg), ("cloud_ctas_per_sm", cta), ("cloud_threads", th)):
-        ob.set_tunable(k, v)
-    plain_sweep.append({"tw": tw, "stages": stg, "ctas": cta, "threads": th, "ms": timeit(plain, n=5)})
-out["plain_sweep"] = plain_sweep
-for k, v in (("cloud_tw", 512), ("cloud_stages", 3), ("cloud_ctas_per_sm", 3), ("cloud_threads", 128)):
-    ob.set_tunable(k, v)
 try:
     out["two_pass_ms"] = timeit(two_pass, n=3)
     fused(); torch.cuda.synchronize()
