@@ -67,7 +67,10 @@ static Tunables& tunables_mut(int device) {
         t.decode_runtime_plans = env_int("OB_DECODE_RUNTIME_PLANS", 0);
         t.decode_pipe = env_int("OB_DECODE_PIPE", 1);
         t.decode_pipe_warps = std::min(24, std::max(6, env_int("OB_DECODE_PIPE_WARPS", 24)));
-        t.decode_pipe_dyn_rows = env_int("OB_DECODE_PIPE_DYN_ROWS", 1);
+        t.decode_pipe_dyn_rows = std::max(0, std::min(3, env_int("OB_DECODE_PIPE_DYN_ROWS", 3)));
+        t.decode_pipe_lane_arrive = env_int("OB_DECODE_PIPE_LANE_ARRIVE", 1);
+        t.decode_pipe_pk_split = std::min(16, std::max(1, env_int("OB_DECODE_PIPE_PK_SPLIT", 1)));
+        t.decode_pipe_lut_split = std::min(8, std::max(1, env_int("OB_DECODE_PIPE_LUT_SPLIT", 1)));
         t.decode_pipe_prefetch = env_int("OB_DECODE_PIPE_PREFETCH", 0);  // measured: the extra L2 fills are evicted again (+19 % DRAM reads)
         t.force_generic = env_int("OB_FORCE_GENERIC", 0);
         int sm = 148;
@@ -111,7 +114,10 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "decode_pipe") t.decode_pipe = value ? 1 : 0;
     else if (n == "decode_pipe_warps") t.decode_pipe_warps = std::min(24, std::max(6, value));
     else if (n == "decode_pipe_prefetch") t.decode_pipe_prefetch = value;
-    else if (n == "decode_pipe_dyn_rows") t.decode_pipe_dyn_rows = value ? 1 : 0;
+    else if (n == "decode_pipe_lane_arrive") t.decode_pipe_lane_arrive = value ? 1 : 0;
+    else if (n == "decode_pipe_pk_split") t.decode_pipe_pk_split = std::min(16, std::max(1, value));
+    else if (n == "decode_pipe_lut_split") t.decode_pipe_lut_split = std::min(8, std::max(1, value));
+    else if (n == "decode_pipe_dyn_rows") t.decode_pipe_dyn_rows = std::max(0, std::min(3, value));
     else if (n == "force_generic") t.force_generic = value;
     else return false;
     return true;

@@ -135,7 +135,7 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
     cudaStream_t st = stream_handle(s);
     Staging stg(st);
     std::vector<DecodeFrame> hf(n_frames);
-    bool vec_ok = true, frame_maps_ok = true;
+    bool vec_ok = true, frame_maps_ok = true, any_xyz = false;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     if (lut && (!al16(ldir) || !al16(loff))) vec_ok = false;
     for (size_t i = 0; i < n_frames; ++i) {
@@ -207,6 +207,7 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
                 e = stg.out(io.xyz[r], n_px * 3 * (ldtype == OB_F64 ? 8 : 4), &o);
                 if (e != cudaSuccess) return fail_cuda(e, "stage xyz");
                 f.xyz[r] = o;
+                any_xyz = true;
                 if (!al16(o)) vec_ok = false;
             }
             if (io.range_destaggered[r]) {
@@ -233,6 +234,7 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
     a.lut_maps = maps_for(L, device, ldir, loff, ldtype);
     a.lut_an = lut ? lut_analytic(lut) : nullptr;
     a.frame_luts_have_maps = frame_maps_ok;
+    a.any_xyz = any_xyz;
     e = launch_decode(a, device, st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     e = stg.flush();
@@ -370,6 +372,7 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
     a.lut_maps = maps_for(L, device, ldir, loff, ldtype);
     a.lut_an = lut ? lut_analytic(lut) : nullptr;
     a.frame_luts_have_maps = frame_maps_ok;
+    a.any_xyz = dxyz[0] != nullptr || dxyz[1] != nullptr;
     e = launch_decode(a, device, st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     e = stg.flush();
@@ -647,6 +650,7 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
     a.vec_ok = vec_ok;
     a.lut_maps = maps_for(L, j->device, ldir, loff, ldtype);
     a.lut_an = use_lut ? lut_analytic(use_lut) : nullptr;
+    a.any_xyz = xyz[0] != nullptr || xyz[1] != nullptr;
     e = launch_decode(a, j->device, j->st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     for (size_t k = 0; k < n_host;) {  // one D2H per run of outputs contiguous on both sides

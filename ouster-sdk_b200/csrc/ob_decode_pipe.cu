@@ -45,11 +45,14 @@ struct PipeParams {
     uint32_t RB;           // rows per LUT sub-tile (= ncw * 32 / cpr)
     uint32_t n_sub;        // sub-tiles per tile (ceil(H / RB))
     uint32_t slot_bytes;   // bytes of one LUT ring slot (direction + offset box)
-    uint32_t box_bytes;    // bytes of one box
+    uint32_t box_bytes;    // bytes of one table's rows of a sub-tile (lut_ops tensor copies of box_bytes / lut_ops each)
+    uint32_t lut_ops;      // tensor copies per table and sub-tile
+    uint32_t pk_chunk;     // bytes per bulk copy of a packet (multiple of 16; the last chunk takes the rest)
     uint32_t lut_off;      // byte offsets inside the dynamic shared memory
     uint32_t stage_off;
     uint32_t nl;           // LUT ring slots (3 or 4)
     uint32_t prefetch;     // L2 prefetch distance of the packet tiles (0 = off)
+    uint32_t lane_arrive;  // 1: every compute lane arrives on pk_done itself; 0: __syncwarp + one elected arrival per warp
     uint32_t dyn_rows;     // phase A rows handed out through a shared-memory counter (static layouts)
 };
 
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
             // every lane arrives for itself (its own generic-proxy writes / reads of the stage control block):
             // no ordering is borrowed from a __syncwarp in front of a single elected arrival
             mbar_init(&pk_full[s], 32);
-            mbar_init(&pk_done[s], pp.ncw * 32);
+            mbar_init(&pk_done[s], pp.lane_arrive ? pp.ncw * 32 : pp.ncw);
         }
         for (unsigned s = 0; s < NL; ++s) {
             mbar_init(&lut_full[s], 1);
@@ -208,10 +211,14 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                     c.regular = 1;
                     mbar_expect_tx(&pk_full[s], n_groups * L.packet_size);
                     const unsigned slot0 = j0 / L.cpp;
-                    for (unsigned g = 0; g < n_groups; ++g)
-                        bulk_g2s_hint(st + static_cast<size_t>(g) * p.pkt_stride_s,
-                                      fr.packets + static_cast<size_t>(slot0 + g) * fr.packet_stride, L.packet_size,
-                                      &pk_full[s], pol_stream);
+                    for (unsigned g = 0; g < n_groups; ++g) {
+                        uint8_t* dstp = st + static_cast<size_t>(g) * p.pkt_stride_s;
+                        const uint8_t* srcp = fr.packets + static_cast<size_t>(slot0 + g) * fr.packet_stride;
+                        // several copies per packet: a single bulk operation is served at a fraction of what the
+                        // SM can pull from DRAM; independent operations overlap
+                        for (unsigned o = 0; o < L.packet_size; o += pp.pk_chunk)
+                            bulk_g2s_hint(dstp + o, srcp + o, min(pp.pk_chunk, L.packet_size - o), &pk_full[s], pol_stream);
+                    }
                 }
                 continue;
             }
@@ -277,9 +284,10 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                 for (unsigned g = 0; g < n_groups; ++g) {
                     if (!c.group_fast[g]) continue;
                     const int slot = c.col_src[g * L.cpp] / static_cast<int>(L.cpp);
-                    bulk_g2s_hint(st + static_cast<size_t>(g) * p.pkt_stride_s,
-                                  fr.packets + static_cast<size_t>(slot) * fr.packet_stride, L.packet_size,
-                                  &pk_full[s], pol_stream);
+                    uint8_t* dstp = st + static_cast<size_t>(g) * p.pkt_stride_s;
+                    const uint8_t* srcp = fr.packets + static_cast<size_t>(slot) * fr.packet_stride;
+                    for (unsigned o = 0; o < L.packet_size; o += pp.pk_chunk)
+                        bulk_g2s_hint(dstp + o, srcp + o, min(pp.pk_chunk, L.packet_size - o), &pk_full[s], pol_stream);
                 }
             }
         }
@@ -322,10 +330,13 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                 if (g >= NL) mbar_wait(&lut_done[slot], (round - 1u) & 1u);
                 uint8_t* dst = lut0 + static_cast<size_t>(slot) * pp.slot_bytes;
                 mbar_expect_tx(&lut_full[slot], 2u * pp.box_bytes);
-                tma_load_2d_hint(dst, m, static_cast<int>(j0 * 3u), static_cast<int>(sub * pp.RB), &lut_full[slot],
-                                 pol_keep);
-                tma_load_2d_hint(dst + pp.box_bytes, m + 128, static_cast<int>(j0 * 3u),
-                                 static_cast<int>(sub * pp.RB), &lut_full[slot], pol_keep);
+                const unsigned op_bytes = pp.box_bytes / pp.lut_ops, op_rows = pp.RB / pp.lut_ops;
+                for (unsigned o = 0; o < pp.lut_ops; ++o) {
+                    const int y = static_cast<int>(sub * pp.RB + o * op_rows);
+                    tma_load_2d_hint(dst + o * op_bytes, m, static_cast<int>(j0 * 3u), y, &lut_full[slot], pol_keep);
+                    tma_load_2d_hint(dst + pp.box_bytes + o * op_bytes, m + 128, static_cast<int>(j0 * 3u), y,
+                                     &lut_full[slot], pol_keep);
+                }
             }
         }
         return;
@@ -359,26 +370,10 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
     const bool aligned = p.word_aligned != 0;
     constexpr int VN = 16 / sizeof(T);  // scalars per 16-byte chunk
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-    // phase-B invariants of this thread: chunk q of row (sub-tile row rsub)
-    const unsigned rsub = static_cast<unsigned>(tid) / pp.cpr;
-    const unsigned q = static_cast<unsigned>(tid) - rsub * pp.cpr;
-    const unsigned e0 = q * VN;
-    const unsigned p0 = e0 / 3u;       // first pixel touched by this chunk
-    const unsigned k0 = e0 - 3u * p0;  // component of element 0 inside pixel p0
-    const unsigned p1 = (p0 + 1 < tc) ? p0 + 1 : p0;
-    bool first_px[VN];                 // element e belongs to pixel p0 (else to p1)
-#pragma unroll
-    for (int e = 0; e < VN; ++e) first_px[e] = (k0 + e) < 3u;
     const DecodeParams::Plan& pl0 = p.plan[p.range_field[0]];
     const DecodeParams::Plan& pl1 = p.plan[p.range_field[n_ret > 1 ? 1 : 0]];
     const bool simple = (pl0.mb | pl1.mb | pl0.rs | pl1.rs) == 0 && pl0.d == 0 && pl1.d == 0;
     const uint32_t ma0 = pl0.ma, ma1 = pl1.ma;
-    // shared addresses of the two pixels' range words inside stage 0, row 0 (regular tiles)
-    const uint32_t stage_sa = smem_u32(stage0);
-    const uint32_t lut_sa = smem_u32(lut0) + static_cast<uint32_t>(tid) * 16u;
-    const uint32_t coa = static_cast<uint32_t>(col_offset(p0)) + rsub * cds;
-    const uint32_t cob = static_cast<uint32_t>(col_offset(p1)) + rsub * cds;
-    const uint32_t sub_step = pp.RB * cds;
     auto rng = [](const uint32_t* w, const DecodeParams::Plan& pl, bool valid, bool simple_) -> uint32_t {
         const uint32_t a = w[pl.wa] & pl.ma;
         if (simple_) return valid ? a : 0u;
@@ -387,22 +382,6 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
         return valid ? v : 0u;
     };
-    // one output chunk: element e = (e-th pixel's range) * dir + off, +0.0 for an empty return
-    auto chunk = [&](uint32_t ra, uint32_t rb, const V& dv, const V& ov) -> V {
-        const T fa = static_cast<T>(ra), fb = static_cast<T>(rb);
-        const T* de = reinterpret_cast<const T*>(&dv);
-        const T* oe = reinterpret_cast<const T*>(&ov);
-        V outv;
-        T* o2 = reinterpret_cast<T*>(&outv);
-#pragma unroll
-        for (int e = 0; e < VN; ++e) {
-            const bool fa_e = first_px[e];
-            const T v = project_nz(fa_e ? fa : fb, de[e], oe[e]);
-            o2[e] = (fa_e ? ra : rb) == 0 ? static_cast<T>(0) : v;
-        }
-        return outv;
-    };
-
     unsigned g = 0;  // running LUT sub-tile index (same sequence as the LUT producer)
     for (unsigned k = 0; k < n_my; ++k) {
         const int s = k % NS;
@@ -457,12 +436,15 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                                  p.n_returns > 0;
                 if (pp.dyn_rows) {
                     unsigned* ctr = &pc.row_ctr[cg];
+                    // dyn_rows 1: every row through the counter; 2: all but the last round of rows are static
+                    const unsigned n_static = pp.dyn_rows == 2u && re >= 2u * rstep ? re / rstep - 1u : 0u;
+                    const unsigned wrow0 = static_cast<unsigned>(warp);
                     switch (p.layout_id) {
-                        case 1: decode_static_tile_dyn<1>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
-                        case 2: decode_static_tile_dyn<2>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
-                        case 3: decode_static_tile_dyn<3>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
-                        case 4: decode_static_tile_dyn<4>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
-                        default: decode_static_tile_dyn<5>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, p); break;
+                        case 1: decode_static_tile_dyn<1>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, wrow0, rstep, n_static, p); break;
+                        case 2: decode_static_tile_dyn<2>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, wrow0, rstep, n_static, p); break;
+                        case 3: decode_static_tile_dyn<3>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, wrow0, rstep, n_static, p); break;
+                        case 4: decode_static_tile_dyn<4>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, wrow0, rstep, n_static, p); break;
+                        default: decode_static_tile_dyn<5>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, wrow0, rstep, n_static, p); break;
                     }
                     continue;
                 }
@@ -513,6 +495,45 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         }
         }
 
+        // Phase-B mapping of this thread (chunk q of sub-tile row rsub, the two pixels it touches, their shared
+        // addresses).  Derived per tile from an opaque copy of the thread index: kept live across phase A these
+        // ~12 loop invariants cost a spill at the kernel's register cap (864 threads -> 72 registers); the
+        // reload sat in front of every tile's first LUT wait.
+        unsigned tid_b = static_cast<unsigned>(tid);
+        asm volatile("" : "+r"(tid_b));
+        // phase-B invariants of this thread: chunk q of row (sub-tile row rsub)
+        const unsigned rsub = tid_b / pp.cpr;
+        const unsigned q = tid_b - rsub * pp.cpr;
+        const unsigned e0 = q * VN;
+        const unsigned p0 = e0 / 3u;       // first pixel touched by this chunk
+        const unsigned k0 = e0 - 3u * p0;  // component of element 0 inside pixel p0
+        const unsigned p1 = (p0 + 1 < tc) ? p0 + 1 : p0;
+        bool first_px[VN];                 // element e belongs to pixel p0 (else to p1)
+    #pragma unroll
+        for (int e = 0; e < VN; ++e) first_px[e] = (k0 + e) < 3u;
+        // shared addresses of the two pixels' range words inside stage 0, row 0 (regular tiles)
+        const uint32_t stage_sa = smem_u32(stage0);
+        const uint32_t lut_sa = smem_u32(lut0) + tid_b * 16u;
+        const uint32_t coa = static_cast<uint32_t>(col_offset(p0)) + rsub * cds;
+        const uint32_t cob = static_cast<uint32_t>(col_offset(p1)) + rsub * cds;
+        const uint32_t sub_step = pp.RB * cds;
+        // one output chunk: element e = (e-th pixel's range) * dir + off, +0.0 for an empty return
+        auto chunk = [&](uint32_t ra, uint32_t rb, const V& dv, const V& ov) -> V {
+            const T fa = static_cast<T>(ra), fb = static_cast<T>(rb);
+            const T* de = reinterpret_cast<const T*>(&dv);
+            const T* oe = reinterpret_cast<const T*>(&ov);
+            V outv;
+            T* o2 = reinterpret_cast<T*>(&outv);
+    #pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const bool fa_e = first_px[e];
+                const T v = project_nz(fa_e ? fa : fb, de[e], oe[e]);
+                o2[e] = (fa_e ? ra : rb) == 0 ? static_cast<T>(0) : v;
+            }
+            return outv;
+        };
+
+
         // ---- phase B: XYZ of the tile's sub-tiles from the LUT slices in shared memory.  All of them were
         //      prefetched into the ring while phase A ran (4 slots = a whole 128-row tile), so the waits
         //      below normally fall through ----
@@ -532,7 +553,62 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                 uint32_t aa0 = sst + coa + pl0.wa * 4u, ab0 = sst + cob + pl0.wa * 4u;
                 uint32_t aa1 = sst + coa + pl1.wa * 4u, ab1 = sst + cob + pl1.wa * 4u;
                 unsigned row = rsub;
-                for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g, row += pp.RB) {
+                unsigned sub = 0;
+                // two sub-tiles per step: both slots' waits first, then all shared-memory loads of both, so that the
+                // second half's load latency hides behind the first half's arithmetic (one chunk per thread and
+                // sub-tile leaves no other independent work between a wait and its stores)
+                for (; sub + 2 <= pp.n_sub; sub += 2, g += 2, row += 2 * pp.RB) {
+                    const unsigned slot_a = NL == 4u ? (g & 3u) : g % 3u;
+                    const unsigned round_a = NL == 4u ? (g >> 2) : g / 3u;
+                    const unsigned slot_b = NL == 4u ? ((g + 1) & 3u) : (g + 1) % 3u;
+                    const unsigned round_b = NL == 4u ? ((g + 1) >> 2) : (g + 1) / 3u;
+                    mbar_wait(&lut_full[slot_a], round_a & 1u);
+                    mbar_wait(&lut_full[slot_b], round_b & 1u);
+                    const bool on_a = row < L.H, on_b = row + pp.RB < L.H;
+                    const uint32_t la = lut_sa + slot_a * pp.slot_bytes, lb = lut_sa + slot_b * pp.slot_bytes;
+                    V dva{}, ova{}, dvb{}, ovb{};
+                    uint32_t ra0 = 0, rb0 = 0, ra1 = 0, rb1 = 0, rc0 = 0, rd0 = 0, rc1 = 0, rd1 = 0;
+                    if (on_a) {
+                        dva = lds_vec(la, static_cast<V*>(nullptr));
+                        ova = lds_vec(la + pp.box_bytes, static_cast<V*>(nullptr));
+                        ra0 = lds_u32(aa0);
+                        rb0 = lds_u32(ab0);
+                        if (x1 != nullptr) {
+                            ra1 = lds_u32(aa1);
+                            rb1 = lds_u32(ab1);
+                        }
+                    }
+                    if (on_b) {
+                        dvb = lds_vec(lb, static_cast<V*>(nullptr));
+                        ovb = lds_vec(lb + pp.box_bytes, static_cast<V*>(nullptr));
+                        rc0 = lds_u32(aa0 + sub_step);
+                        rd0 = lds_u32(ab0 + sub_step);
+                        if (x1 != nullptr) {
+                            rc1 = lds_u32(aa1 + sub_step);
+                            rd1 = lds_u32(ab1 + sub_step);
+                        }
+                    }
+                    if (on_a) {
+                        *reinterpret_cast<V*>(x0) = chunk(ra0 & ma0, rb0 & ma0, dva, ova);
+                        if (x1 != nullptr) *reinterpret_cast<V*>(x1) = chunk(ra1 & ma1, rb1 & ma1, dva, ova);
+                    }
+                    if (on_b) {
+                        *reinterpret_cast<V*>(x0 + row_step) = chunk(rc0 & ma0, rd0 & ma0, dvb, ovb);
+                        if (x1 != nullptr) *reinterpret_cast<V*>(x1 + row_step) = chunk(rc1 & ma1, rd1 & ma1, dvb, ovb);
+                    }
+                    aa0 += 2 * sub_step;
+                    ab0 += 2 * sub_step;
+                    aa1 += 2 * sub_step;
+                    ab1 += 2 * sub_step;
+                    x0 += 2 * row_step;
+                    if (x1 != nullptr) x1 += 2 * row_step;
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&lut_done[slot_a]);
+                        mbar_arrive(&lut_done[slot_b]);
+                    }
+                }
+                for (; sub < pp.n_sub; ++sub, ++g, row += pp.RB) {
                     const unsigned slot = NL == 4u ? (g & 3u) : g % 3u;
                     const unsigned round = NL == 4u ? (g >> 2) : g / 3u;
                     mbar_wait(&lut_full[slot], round & 1u);
@@ -643,7 +719,12 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                 }
             }
         }
-        mbar_arrive(&pk_done[s]);  // this lane is done with the stage and its control block
+        if (pp.lane_arrive) {
+            mbar_arrive(&pk_done[s]);  // this lane is done with the stage and its control block
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pk_done[s]);
+        }
     }
 }
 
@@ -754,6 +835,13 @@ static bool pipe_geometry(const DecodeLayout& L, uint32_t TC, int lut_dtype, uin
     return *RB <= 256;
 }
 
+// tensor copies per table and sub-tile: the tunable, reduced until it divides the sub-tile's rows
+static uint32_t pipe_lut_ops(const Tunables& tn, uint32_t RB) {
+    uint32_t n = static_cast<uint32_t>(std::max(1, tn.decode_pipe_lut_split));
+    while (n > 1 && RB % n != 0) --n;
+    return n;
+}
+
 static uint32_t pipe_tile_cols(const DecodeLayout& L, const Tunables& tn) {
     const uint32_t stride = (L.packet_size + 15) & ~15u;
     uint32_t P = 1;
@@ -771,7 +859,7 @@ bool decode_pipe_box(const DecodeLayout& L, int device, int lut_dtype, uint32_t*
     const uint32_t TC = pipe_tile_cols(L, tn);
     if (!pipe_geometry(L, TC, lut_dtype, static_cast<uint32_t>(tn.decode_pipe_warps), &cpr, &RB)) return false;
     *box_w = TC * 3;
-    *box_h = RB;
+    *box_h = RB / pipe_lut_ops(tn, RB);
     return true;
 }
 
@@ -827,7 +915,17 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
     pp.nl = pipe_ring_slots(p, pp.ncw);
     if (pp.nl == 0) return cudaErrorInvalidValue;
     const size_t smem = pipe_smem_bytes(p, pp.ncw, pp.nl, &pp.lut_off, &pp.stage_off);
-    pp.dyn_rows = tn.decode_pipe_dyn_rows ? 1u : 0u;
+    pp.lane_arrive = tn.decode_pipe_lane_arrive ? 1u : 0u;
+    pp.lut_ops = pipe_lut_ops(tn, pp.RB);
+    {
+        const uint32_t n = static_cast<uint32_t>(std::max(1, tn.decode_pipe_pk_split));
+        pp.pk_chunk = std::max<uint32_t>(16u, ((p.L.packet_size + n - 1) / n + 15u) & ~15u);
+    }
+    // row hand-out of phase A (tools/k2_parts.py): with the fused cloud the fully dynamic form is ~2 % ahead
+    // (the hand-out hides behind phase B's waits), decode-only launches are 6 % faster with fixed rows
+    pp.dyn_rows = tn.decode_pipe_dyn_rows >= 3
+                      ? (a.any_xyz ? 1u : 0u)
+                      : static_cast<uint32_t>(std::max(0, tn.decode_pipe_dyn_rows));
     pp.prefetch = static_cast<uint32_t>(std::max(0, std::min(8, tn.decode_pipe_prefetch)));
     const int threads = static_cast<int>(pp.ncw + 3) * 32;
     const int grid = static_cast<int>(std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count)));

@@ -399,24 +399,24 @@ __device__ __forceinline__ void decode_static(const uint8_t* px0, bool col_valid
     }
 }
 
-// The same row body with the rows handed out dynamically: every warp takes the next undecoded row of the
-// tile from a shared-memory counter (one atomic per row and warp), so the warps of a CTA finish a tile
-// together whatever H modulo the warp count is (128 rows over 24 warps is 5.33 rows each: with a fixed
-// stride the 6-row warps set the pace and the 5-row warps wait for the next tile's packets).
+// The same row body with the LAST rows handed out dynamically: every warp first decodes `n_static` rows of its
+// own residue class (row0 + i * rstep, no hand-out cost), then the warps share the remaining rows of the tile
+// through a shared-memory counter, so that they finish a tile together whatever H modulo the warp count is
+// (128 rows over 24 warps is 5.33 rows each: with a fixed stride the 6-row warps set the pace and the 5-row
+// warps wait for the next tile's packets).  Handing out ALL rows that way costs one same-address atomic per
+// row and warp -- 152 serialised shared-memory atomics per tile, a third of a tile's time when nothing else is
+// going on (tools/k2_parts.py).  The ticket of the next row is drawn while the current one is decoded.
 template <int L, bool FULL, bool ALL>
 __device__ __forceinline__ void decode_static_dyn(const uint8_t* px0, bool col_valid, bool lane_on,
                                                   uint8_t* const (&outp)[kMaxSlots], uint32_t* const (&rdp)[2],
                                                   unsigned col, unsigned W, unsigned H, unsigned* row_ctr,
+                                                  unsigned row0, unsigned rstep, unsigned n_static,
                                                   const DecodeParams& p) {
     constexpr int NW = PxLayout<L>::cds / 4;
     const bool has_rd = ALL || rdp[0] != nullptr || rdp[1] != nullptr;
     const bool has_shift = p.has_shift != 0;
     const unsigned lane = threadIdx.x & 31u;
-    for (;;) {
-        unsigned row = 0;
-        if (lane == 0) row = atomicAdd(row_ctr, 1u);
-        row = __shfl_sync(0xffffffffu, row, 0);
-        if (row >= H) break;
+    auto one_row = [&](unsigned row) {
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(px0) + row * NW;
         uint32_t w[NW];
 #pragma unroll
@@ -430,6 +430,17 @@ __device__ __forceinline__ void decode_static_dyn(const uint8_t* px0, bool col_v
         }
         store_all<L, FULL, ALL>(w, outp, rdp, pix, rdpix, col_valid, lane_on,
                                 std::make_integer_sequence<int, PxLayout<L>::n>{});
+    };
+    for (unsigned i = 0; i < n_static; ++i) one_row(row0 + i * rstep);
+    const unsigned base = n_static * rstep;  // first dynamically assigned row
+    if (base >= H) return;
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(row_ctr, 1u);
+    for (;;) {
+        const unsigned row = base + __shfl_sync(0xffffffffu, nxt, 0);
+        if (row >= H) break;
+        if (lane == 0) nxt = atomicAdd(row_ctr, 1u);
+        one_row(row);
     }
 }
 
@@ -437,10 +448,11 @@ template <int L>
 __device__ __forceinline__ void decode_static_tile_dyn(bool full, bool all, const uint8_t* px0, bool col_valid,
                                                        bool lane_on, uint8_t* const (&outp)[kMaxSlots],
                                                        uint32_t* const (&rdp)[2], unsigned col, unsigned W,
-                                                       unsigned H, unsigned* row_ctr, const DecodeParams& p) {
-    if (full && all) decode_static_dyn<L, true, true>(px0, true, true, outp, rdp, col, W, H, row_ctr, p);
-    else if (full) decode_static_dyn<L, true, false>(px0, true, true, outp, rdp, col, W, H, row_ctr, p);
-    else decode_static_dyn<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, row_ctr, p);
+                                                       unsigned H, unsigned* row_ctr, unsigned row0, unsigned rstep,
+                                                       unsigned n_static, const DecodeParams& p) {
+    if (full && all) decode_static_dyn<L, true, true>(px0, true, true, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
+    else if (full) decode_static_dyn<L, true, false>(px0, true, true, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
+    else decode_static_dyn<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
 }
 
 template <int L>

@@ -31,7 +31,10 @@ struct Tunables {
     int decode_prefetch;      // L2 prefetch of the next tile: 0 off, 1 at tile start (evict_last), 2 before phase B
     int decode_pipe;          // 1 (default): pipelined K2 (ob_decode_pipe.cu) whenever the launch is eligible
     int decode_pipe_warps;    // compute warps of the pipelined K2 (24)
-    int decode_pipe_dyn_rows; // 1 (default): phase A rows of the pipelined K2 are handed out dynamically
+    int decode_pipe_dyn_rows; // phase A rows of the pipelined K2: 0 fixed stride, 1 all through a counter, 2 last round through a counter, 3 (default) 1 with a fused cloud else 0
+    int decode_pipe_lane_arrive;  // 1 (default): per-lane arrivals on the stage-free barrier (racecheck-clean)
+    int decode_pipe_pk_split;  // bulk copies per packet (more TMA operations in flight per SM)
+    int decode_pipe_lut_split; // tensor copies per table and LUT sub-tile
     int decode_pipe_prefetch; // L2 prefetch distance (tiles) of the pipelined K2's packet loads, 0 = off
     int force_generic;     // 1: K1 takes the generic GPU kernel (any width / alignment) instead of the TMA one
     int sm_count;
@@ -154,6 +157,7 @@ struct DecodeLaunch {
     const void* lut_an{nullptr};    // launch-level LUT in LUT-free mode: device LutAnalyticT<T>
     bool all_regular{false};     // every frame: identity column map, bulk-copyable packets, all slots present
     bool frame_luts_have_maps{true};  // every per-frame LUT of the table carries lut_maps
+    bool any_xyz{true};          // some frame of the launch asks for the fused cloud (tuning hint only)
 };
 cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st);
 
