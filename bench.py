@@ -195,20 +195,21 @@ def measure_k1(args, ob, torch, dist, rank, local_rank, world, pcie):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = bc.ClockSampler(local_rank)   # NVML polling thread: warm-up and timed region, marked below
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = bc.ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
     l0 = ob.kernel_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    sampler.mark()
     ev[0].record(stream)
     for i in range(args.steps):
         step()
         ev[i + 1].record(stream)
     barrier()
+    sampler.mark()
     launches = ob.kernel_launch_count() - l0
     clocks = sampler.stop()
     ms_total = ev[0].elapsed_time(ev[-1])

@@ -5,6 +5,7 @@ import json
 import os
 import subprocess
 import threading
+import time
 
 import numpy as np
 
@@ -19,29 +20,89 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region: an NVML polling thread
+    (a timed region is a few milliseconds -- `nvidia-smi -lms` often delivers its first line after it),
+    with `nvidia-smi` as the fallback when NVML cannot be loaded.  `mark()` stamps the start / end of the
+    timed region; samples outside it (taken under the same load during the warm-up steps in front of it)
+    are only used when none fell inside, and the result says so."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.samples, self.marks, self._stop, self.t, self.nv = [], [], False, None, None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-i", str(self._visible_index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.0005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self._stop = True
+            self.t.join(timeout=1)
+            inside = self.samples
+            window = "timed_region"
+            if len(self.marks) >= 2:
+                inside = [x for x in self.samples if self.marks[0] <= x[0] <= self.marks[-1]]
+                if not inside:
+                    inside, window = self.samples, "warmup_and_timed_region"
+            bits = 0
+            for x in inside:
+                bits |= x[2]
+            sm = [x[1] for x in inside]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm,
+                    "reasons": [n for n, b in self.REASONS if bits & b], "samples": len(sm), "window": window,
+                    "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.proc.terminate()
@@ -56,7 +117,7 @@ class ClockSampler:
                    if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -129,20 +129,21 @@ def measure_k2(st, args, streams_per_gpu, pcie, with_e2e=True, with_cpu=True):
                                 pixel_shift_by_row=SHIFTS, xyz=st.xyz, range_destaggered=st.rd, timestamp=st.t_ts,
                                 measurement_id=st.t_mid, status=st.t_st, stream=st.obs, frame_luts=frame_luts)
 
+    sampler = bc.ClockSampler(st.local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     st.barrier()
-    sampler = bc.ClockSampler(st.local_rank)
-    sampler.start()
-    time.sleep(0.2)
     l0, lp0 = ob.kernel_launch_count(), ob.kernel_launch_count("decode_pipe")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     st.barrier()
+    sampler.mark()
     ev[0].record(st.stream)
     for i in range(args.steps):
         step()
         ev[i + 1].record(st.stream)
     st.barrier()
+    sampler.mark()
     launches = ob.kernel_launch_count() - l0
     pipe_launches = ob.kernel_launch_count("decode_pipe") - lp0
     clocks = sampler.stop()

@@ -52,6 +52,7 @@ struct PipeParams {
     uint32_t stage_off;
     uint32_t nl;           // LUT ring slots (3 or 4)
     uint32_t prefetch;     // L2 prefetch distance of the packet tiles (0 = off)
+    uint32_t helpers;      // extra warps that only run phase A (0: the third producer-side warp is the L2 prefetcher)
     uint32_t lane_arrive;  // 1: every compute lane arrives on pk_done itself; 0: __syncwarp + one elected arrival per warp
     uint32_t dyn_rows;     // phase A rows handed out through a shared-memory counter (static layouts)
 };
@@ -102,8 +103,9 @@ struct PipeCtl {
     uint32_t row_ctr[2];  // next undecoded row per 32-column group (dynamic row hand-out of phase A)
 };
 
-template <typename T>
-__global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
+// MAXT: 864 (24 compute + 3 producer-side warps, 72 registers) or 1024 (up to 6 phase-A helper warps, 64 registers)
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
     decode_pipe_kernel(const __grid_constant__ PipeParams pp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const DecodeParams& p = pp.d;
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int NCW = static_cast<int>(pp.ncw);
+    const int NA = NCW + static_cast<int>(pp.helpers);  // warps that run phase A
     constexpr int NS = kPipeStages;
     const unsigned NL = pp.nl;
 
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
             // every lane arrives for itself (its own generic-proxy writes / reads of the stage control block):
             // no ordering is borrowed from a __syncwarp in front of a single elected arrival
             mbar_init(&pk_full[s], 32);
-            mbar_init(&pk_done[s], pp.lane_arrive ? pp.ncw * 32 : pp.ncw);
+            mbar_init(&pk_done[s], pp.lane_arrive ? NA * 32 : NA);
         }
         for (unsigned s = 0; s < NL; ++s) {
             mbar_init(&lut_full[s], 1);
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         return;
     }
 
-    if (warp == NCW + 2) {
+    if (pp.helpers == 0 && warp == NCW + 2) {
         // =============================== L2 prefetcher ===============================
         // paced by the packet stages: when the packets of tile k have landed, warm L2 with those of tile
         // k + pf (pf = 2: its TMA load is issued one tile from now).  Regular tiles only.
@@ -382,6 +385,9 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         v = pl.d >= 0 ? (v << pl.d) : (v >> (-pl.d));
         return valid ? v : 0u;
     };
+    // helper warps (index >= NCW + 2) take rows of phase A like the compute warps and skip everything else
+    const bool helper = warp >= NCW;
+    const int aw = helper ? warp - 2 : warp;  // index among the phase-A warps
     unsigned g = 0;  // running LUT sub-tile index (same sequence as the LUT producer)
     for (unsigned k = 0; k < n_my; ++k) {
         const int s = k % NS;
@@ -389,7 +395,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         PipeTileCtl& c = pc.t;
         uint8_t* st = stage0 + static_cast<size_t>(s) * p.stage_bytes;
         // rows rotate over the warps from tile to tile so that H % NCW leftovers even out
-        const int wrot = (warp + static_cast<int>((k * 7u) % static_cast<unsigned>(NCW))) % NCW;
+        const int wrot = (aw + static_cast<int>((k * 7u) % static_cast<unsigned>(NA))) % NA;
 
         mbar_wait(&pk_full[s], (k / NS) & 1);
         const DecodeFrame& fr = pc.fr;  // shared-memory copy
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         const bool regular = c.regular != 0;
 
         // ---- column headers (timestamp / measurement_id / status) ----
-        if (fr.timestamp != nullptr || fr.measurement_id != nullptr || fr.status != nullptr) {
+        if (!helper && (fr.timestamp != nullptr || fr.measurement_id != nullptr || fr.status != nullptr)) {
             for (unsigned t = tid; t < tc; t += static_cast<unsigned>(NCW) * 32u) {
                 const int co = regular ? col_offset(t) : c.col_off[t];
                 uint64_t ts = 0, mid = 0, stt = 0;
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                     outp[i] = p.slot_field[i] >= 0 ? static_cast<uint8_t*>(fr.fields[p.slot_field[i]]) : nullptr;
                 uint32_t* rdp2[2] = {fr.rd[0], fr.rd[1]};
                 const unsigned col = static_cast<unsigned>(pix0);
-                const unsigned rstep = static_cast<unsigned>(NCW);
+                const unsigned rstep = static_cast<unsigned>(NA);
                 const bool all = p.layout_all != 0 && (p.n_returns < 1 || rdp2[0] != nullptr) &&
                                  (p.n_returns < 2 || rdp2[1] != nullptr) && fr.fields[0] != nullptr &&
                                  p.n_returns > 0;
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                     unsigned* ctr = &pc.row_ctr[cg];
                     // dyn_rows 1: every row through the counter; 2: all but the last round of rows are static
                     const unsigned n_static = pp.dyn_rows == 2u && re >= 2u * rstep ? re / rstep - 1u : 0u;
-                    const unsigned wrow0 = static_cast<unsigned>(warp);
+                    const unsigned wrow0 = static_cast<unsigned>(aw);
                     switch (p.layout_id) {
                         case 1: decode_static_tile_dyn<1>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, wrow0, rstep, n_static, p); break;
                         case 2: decode_static_tile_dyn<2>(regular, all, px0, col_valid, true, outp, rdp2, col, L.W, re, ctr, wrow0, rstep, n_static, p); break;
@@ -470,16 +476,16 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
                     const uint32_t zv = (fd.zero_pattern & 0xffffu) | ((fd.zero_pattern & 0xffffu) << 16);
                     const bool ho = out != nullptr, hr = rdp != nullptr;
                     if (regular) {
-                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
-                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
-                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
+                        if (es == 4) decode_rows_dispatch<4, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NA, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NA, rdp, p);
+                        else decode_rows_dispatch<1, true>(ho, hr, px0, cds, pl, true, zv, true, out, pix0, L.W, re, wf, NA, rdp, p);
                     } else {
-                        if (es == 4) decode_rows_dispatch<4, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
-                        else if (es == 2) decode_rows_dispatch<2, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
-                        else decode_rows_dispatch<1, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NCW, rdp, p);
+                        if (es == 4) decode_rows_dispatch<4, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NA, rdp, p);
+                        else if (es == 2) decode_rows_dispatch<2, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NA, rdp, p);
+                        else decode_rows_dispatch<1, false>(ho, hr, px0, cds, pl, col_valid, zv, true, out, pix0, L.W, re, wf, NA, rdp, p);
                     }
                 } else {  // wide or unaligned fields: generic 64-bit extraction
-                    for (unsigned row = wfirst; row < re; row += NCW) {
+                    for (unsigned row = wfirst; row < re; row += NA) {
                         const uint8_t* px = px0 + row * cds;
                         const uint64_t v = !col_valid ? zero_value(fd) : extract_smem(px, fd, aligned);
                         const size_t pix = static_cast<size_t>(row) * L.W + pix0;
@@ -537,7 +543,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         // ---- phase B: XYZ of the tile's sub-tiles from the LUT slices in shared memory.  All of them were
         //      prefetched into the ring while phase A ran (4 slots = a whole 128-row tile), so the waits
         //      below normally fall through ----
-        if (mode == 1u) {
+        if (mode == 1u && !helper) {
             T* xo0 = static_cast<T*>(fr.xyz[0]);
             T* xo1 = n_ret > 1 ? static_cast<T*>(fr.xyz[1]) : nullptr;
             const size_t ecol = static_cast<size_t>(j0) * 3 + static_cast<size_t>(q) * VN;
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__((kPipeMaxComputeWarps + 3) * 32, 1)
         }
 
         // ---- phase B, LUT-free: direction/offset rebuilt from the per-row / per-column tables ----
-        if (mode == 2u) {
+        if (mode == 2u && !helper) {
             const LutAnalyticT<T>& an =
                 *static_cast<const LutAnalyticT<T>*>(fr.lut_dir != nullptr ? fr.lut_an : pp.lut_an);
             const int co0 = regular ? col_offset(p0) : c.col_off[p0];
@@ -927,9 +933,18 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
                       ? (a.any_xyz ? 1u : 0u)
                       : static_cast<uint32_t>(std::max(0, tn.decode_pipe_dyn_rows));
     pp.prefetch = static_cast<uint32_t>(std::max(0, std::min(8, tn.decode_pipe_prefetch)));
-    const int threads = static_cast<int>(pp.ncw + 3) * 32;
+    // helper warps need the 1024-thread build (64 registers); static pixel layouts only (the plan-driven
+    // row loops are not tuned for the lower register cap)
+    pp.helpers = p.layout_id != 0 ? static_cast<uint32_t>(std::max(0, std::min(6, tn.decode_pipe_helpers))) : 0u;
+    if ((pp.ncw + 2 + pp.helpers) * 32u > 1024u) pp.helpers = 0;
+    const int threads = static_cast<int>(pp.ncw + 2 + std::max<uint32_t>(1u, pp.helpers)) * 32;
     const int grid = static_cast<int>(std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count)));
-    auto kern = a.lut_dtype == OB_F64 ? decode_pipe_kernel<double> : decode_pipe_kernel<float>;
+    void (*kern)(PipeParams);
+    if (threads > (kPipeMaxComputeWarps + 3) * 32)
+        kern = a.lut_dtype == OB_F64 ? decode_pipe_kernel<double, 1024> : decode_pipe_kernel<float, 1024>;
+    else
+        kern = a.lut_dtype == OB_F64 ? decode_pipe_kernel<double, (kPipeMaxComputeWarps + 3) * 32>
+                                     : decode_pipe_kernel<float, (kPipeMaxComputeWarps + 3) * 32>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     kern<<<std::max(grid, 1), threads, smem, st>>>(pp);

@@ -32,6 +32,7 @@ struct Tunables {
     int decode_pipe;          // 1 (default): pipelined K2 (ob_decode_pipe.cu) whenever the launch is eligible
     int decode_pipe_warps;    // compute warps of the pipelined K2 (24)
     int decode_pipe_dyn_rows; // phase A rows of the pipelined K2: 0 fixed stride, 1 all through a counter, 2 last round through a counter, 3 (default) 1 with a fused cloud else 0
+    int decode_pipe_helpers;      // extra phase-A-only warps of the pipelined K2 (0..6; > 0 selects the 64-register build)
     int decode_pipe_lane_arrive;  // 1 (default): per-lane arrivals on the stage-free barrier (racecheck-clean)
     int decode_pipe_pk_split;  // bulk copies per packet (more TMA operations in flight per SM)
     int decode_pipe_lut_split; // tensor copies per table and LUT sub-tile
