@@ -370,13 +370,15 @@ cudaError_t make_decode_params(const DecodeLaunch& a, int device, bool pipe, Dec
     // pipelined kernel packs the packets back to back (an over-read lands in the next packet's header, masked
     // off anyway) and keeps one 16-byte slack after the last stage -- that is what lets a 4-slot LUT ring fit
     p.pkt_stride_s = pipe ? ((L.packet_size + 15) & ~15u) : ((L.packet_size + 16 + 15) & ~15u);
-    if (tn.decode_tile_packets > 0) {
+    if (pipe) {
+        uint32_t ncw, ctas;
+        decode_pipe_shape(L, device, &p.P, &ncw, &ctas);
+    } else if (tn.decode_tile_packets > 0) {
         p.P = static_cast<uint32_t>(tn.decode_tile_packets);
     } else {
         // auto: as many packets as fit a ~68 KB stage (3 CTAs per SM), power of two, at least 32 columns
         p.P = 1;
-        const uint32_t max_cols = pipe ? 64u : static_cast<uint32_t>(kMaxTileCols);
-        while (p.P * 2 * p.pkt_stride_s <= 68u * 1024u && p.P * 2 * L.cpp <= max_cols) p.P *= 2;
+        while (p.P * 2 * p.pkt_stride_s <= 68u * 1024u && p.P * 2 * L.cpp <= static_cast<uint32_t>(kMaxTileCols)) p.P *= 2;
     }
     p.P = std::max<uint32_t>(1, std::min<uint32_t>(p.P, static_cast<uint32_t>(kMaxTileCols) / L.cpp));
     p.TC = p.P * L.cpp;

@@ -848,22 +848,55 @@ static uint32_t pipe_lut_ops(const Tunables& tn, uint32_t RB) {
     return n;
 }
 
-static uint32_t pipe_tile_cols(const DecodeLayout& L, const Tunables& tn) {
+// Launch shape of the pipelined kernel for a packet layout: packets per tile, compute warps per CTA, CTAs per SM.
+//   1 CTA/SM : `decode_pipe_warps` (24) compute warps, as many packets per tile as fit a ~68 KB stage pair
+//              (at most 64 columns: a LUT row segment is one TMA box), the 72-register build;
+//   2 CTAs/SM: half the warps each, stages of at most 28 KB (pair + 48 KB LUT ring < 113 KB), the 64-register build -- for short columns
+//              (<= 64-row sensors), whose tiles are too small to amortise the per-tile hand-offs of one
+//              CTA: two independent CTAs overlap each other's waits.  Falls back to 1 CTA/SM when a tile
+//              would shrink below 32 columns.
+void decode_pipe_shape(const DecodeLayout& L, int device, uint32_t* P_out, uint32_t* ncw_out, uint32_t* ctas_out) {
+    const Tunables& tn = tunables(device);
     const uint32_t stride = (L.packet_size + 15) & ~15u;
-    uint32_t P = 1;
-    if (tn.decode_tile_packets > 0) P = static_cast<uint32_t>(tn.decode_tile_packets);
-    else
-        while (P * 2 * stride <= 68u * 1024u && P * 2 * L.cpp <= 64u) P *= 2;
-    P = std::max<uint32_t>(1, std::min<uint32_t>(P, static_cast<uint32_t>(kMaxTileCols) / std::max<uint32_t>(L.cpp, 1)));
-    return P * L.cpp;
+    const uint32_t cpp = std::max<uint32_t>(L.cpp, 1);
+    auto fit = [&](uint32_t stage_budget) {  // packets per tile: power of two, one stage within the budget
+        uint32_t P = 1;
+        if (tn.decode_tile_packets > 0) P = static_cast<uint32_t>(tn.decode_tile_packets);
+        else
+            while (P * 2 * stride <= stage_budget && P * 2 * cpp <= 64u) P *= 2;
+        return std::max<uint32_t>(1, std::min<uint32_t>(P, static_cast<uint32_t>(kMaxTileCols) / cpp));
+    };
+    // auto: as many CTAs per SM (up to 3) as the layout allows -- a 128-row packet stage pair needs the whole SM.
+    // Measured over the sweep shapes (profiles/r02_sweep_k2_ctas.json): 32-row dual 0.58 -> 0.65 (2) -> 0.74-0.77 (3),
+    // 32-row single 0.39 -> 0.49, 64-row +2..6 %, 4 = 3 (the register file holds three 288-thread CTAs).
+    uint32_t ctas = tn.decode_pipe_ctas == 0 ? 3u : static_cast<uint32_t>(tn.decode_pipe_ctas);
+    uint32_t ncw = static_cast<uint32_t>(tn.decode_pipe_warps);
+    uint32_t P = fit(68u * 1024u);
+    for (; ctas > 1; --ctas) {
+        const uint32_t n = std::max<uint32_t>(3u, ncw / ctas / 3u * 3u);             // compute warps per CTA
+        const uint32_t lut = kPipeLutSlotsMax * 2u * n * 32u * 16u;                   // 4-slot LUT ring
+        const uint32_t per_cta = 228u * 1024u / ctas - 1024u;
+        if (per_cta < lut + 4096u) continue;
+        const uint32_t Pn = fit((per_cta - lut - 2048u) / 2u);
+        if ((n + 3u) * 32u * ctas * 64u > 65536u) continue;                           // registers of the 64-register build
+        if (Pn * cpp >= 32u && (Pn * cpp) % 32u == 0 && 2u * Pn * stride + lut + 2048u <= per_cta) {
+            P = Pn;
+            ncw = n;
+            break;
+        }
+    }
+    *P_out = P;
+    *ncw_out = ncw;
+    *ctas_out = ctas;
 }
 
 bool decode_pipe_box(const DecodeLayout& L, int device, int lut_dtype, uint32_t* box_w, uint32_t* box_h) {
     const Tunables& tn = tunables(device);
     if (!tn.decode_pipe || L.cpp == 0) return false;
-    uint32_t cpr, RB;
-    const uint32_t TC = pipe_tile_cols(L, tn);
-    if (!pipe_geometry(L, TC, lut_dtype, static_cast<uint32_t>(tn.decode_pipe_warps), &cpr, &RB)) return false;
+    uint32_t cpr, RB, P, ncw, ctas;
+    decode_pipe_shape(L, device, &P, &ncw, &ctas);
+    const uint32_t TC = P * L.cpp;
+    if (!pipe_geometry(L, TC, lut_dtype, ncw, &cpr, &RB)) return false;
     *box_w = TC * 3;
     *box_h = RB / pipe_lut_ops(tn, RB);
     return true;
@@ -879,10 +912,12 @@ static size_t pipe_smem_bytes(const DecodeParams& p, uint32_t ncw, uint32_t nl, 
     return off + static_cast<size_t>(kPipeStages) * p.stage_bytes + 16;  // + slack for trailing 8-byte field reads
 }
 // deepest LUT ring that fits: 4 slots hold the LUT of a whole 128-row tile (no refill is ever waited for)
-static uint32_t pipe_ring_slots(const DecodeParams& p, uint32_t ncw) {
+static uint32_t pipe_ring_slots(const DecodeParams& p, uint32_t ncw, uint32_t ctas) {
     uint32_t lo, so;
+    // per-CTA budget: 227 KB alone, half of the SM's 228 KB minus the 1 KB the runtime reserves per CTA otherwise
+    const size_t budget = ctas >= 2 ? (228u * 1024u / ctas - 1024u) : 227u * 1024u;
     for (uint32_t nl = kPipeLutSlotsMax; nl >= 3; --nl)
-        if (pipe_smem_bytes(p, ncw, nl, &lo, &so) <= 227 * 1024) return nl;
+        if (pipe_smem_bytes(p, ncw, nl, &lo, &so) <= budget) return nl;
     return 0;
 }
 
@@ -891,12 +926,13 @@ bool decode_pipe_eligible(const DecodeParams& p, const DecodeLaunch& a, int devi
     const Tunables& tn = tunables(device);
     if (!p.word_aligned || p.cpp_shift < 0 || L.W % 4 != 0 || (p.TC % L.cpp) != 0) return false;
     if (static_cast<uint64_t>(L.H) * L.W >= (1ull << 30)) return false;
-    uint32_t cpr, RB, lo, so;
-    if (!pipe_geometry(L, p.TC, a.lut_dtype, static_cast<uint32_t>(tn.decode_pipe_warps), &cpr, &RB)) return false;
-    (void)lo;
-    (void)so;
+    uint32_t cpr, RB, P, ncw, ctas;
+    decode_pipe_shape(L, device, &P, &ncw, &ctas);
+    if (P * L.cpp != p.TC) return false;  // make_decode_params(pipe) takes its tile from the same function
+    if (!pipe_geometry(L, p.TC, a.lut_dtype, ncw, &cpr, &RB)) return false;
     if (p.TC > static_cast<uint32_t>(kPipeTileCols) || p.TC / L.cpp > 16u) return false;
-    if (pipe_ring_slots(p, static_cast<uint32_t>(tn.decode_pipe_warps)) == 0) return false;
+    if (pipe_ring_slots(p, ncw, ctas) == 0) return false;
+    (void)tn;
     // XYZ path: 16-byte aligned rows, 32-bit range plans and TMA descriptors for every LUT in use
     if (p.n_returns > 0) {
         if (!p.vec_ok || !p.plan_ranges_fast) return false;
@@ -913,12 +949,13 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
     pp.d.stages = kPipeStages;
     pp.lut_maps = a.lut_maps;
     pp.lut_an = a.lut_an;
-    pp.ncw = static_cast<uint32_t>(tn.decode_pipe_warps);
+    uint32_t shape_p, ctas;
+    decode_pipe_shape(p.L, device, &shape_p, &pp.ncw, &ctas);
     if (!pipe_geometry(p.L, p.TC, a.lut_dtype, pp.ncw, &pp.cpr, &pp.RB)) return cudaErrorInvalidValue;
     pp.n_sub = (p.L.H + pp.RB - 1) / pp.RB;
     pp.box_bytes = pp.ncw * 32u * 16u;
     pp.slot_bytes = 2u * pp.box_bytes;
-    pp.nl = pipe_ring_slots(p, pp.ncw);
+    pp.nl = pipe_ring_slots(p, pp.ncw, ctas);
     if (pp.nl == 0) return cudaErrorInvalidValue;
     const size_t smem = pipe_smem_bytes(p, pp.ncw, pp.nl, &pp.lut_off, &pp.stage_off);
     pp.lane_arrive = tn.decode_pipe_lane_arrive ? 1u : 0u;
@@ -936,11 +973,11 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
     // helper warps need the 1024-thread build (64 registers); static pixel layouts only (the plan-driven
     // row loops are not tuned for the lower register cap)
     pp.helpers = p.layout_id != 0 ? static_cast<uint32_t>(std::max(0, std::min(6, tn.decode_pipe_helpers))) : 0u;
-    if ((pp.ncw + 2 + pp.helpers) * 32u > 1024u) pp.helpers = 0;
+    if ((pp.ncw + 2 + pp.helpers) * 32u > 1024u || ctas > 1) pp.helpers = 0;
     const int threads = static_cast<int>(pp.ncw + 2 + std::max<uint32_t>(1u, pp.helpers)) * 32;
-    const int grid = static_cast<int>(std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count)));
+    const int grid = static_cast<int>(std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count) * ctas));
     void (*kern)(PipeParams);
-    if (threads > (kPipeMaxComputeWarps + 3) * 32)
+    if (threads > (kPipeMaxComputeWarps + 3) * 32 || ctas > 1)  // 2 CTAs/SM: 2 x 480 threads x 64 registers
         kern = a.lut_dtype == OB_F64 ? decode_pipe_kernel<double, 1024> : decode_pipe_kernel<float, 1024>;
     else
         kern = a.lut_dtype == OB_F64 ? decode_pipe_kernel<double, (kPipeMaxComputeWarps + 3) * 32>

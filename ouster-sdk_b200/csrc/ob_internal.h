@@ -32,6 +32,7 @@ struct Tunables {
     int decode_pipe;          // 1 (default): pipelined K2 (ob_decode_pipe.cu) whenever the launch is eligible
     int decode_pipe_warps;    // compute warps of the pipelined K2 (24)
     int decode_pipe_dyn_rows; // phase A rows of the pipelined K2: 0 fixed stride, 1 all through a counter, 2 last round through a counter, 3 (default) 1 with a fused cloud else 0
+    int decode_pipe_ctas;         // CTAs per SM of the pipelined K2: 1, 2..4 (the warps split between them, 64-register build), 0 = auto (2 where the stages fit)
     int decode_pipe_helpers;      // extra phase-A-only warps of the pipelined K2 (0..6; > 0 selects the 64-register build)
     int decode_pipe_lane_arrive;  // 1 (default): per-lane arrivals on the stage-free barrier (racecheck-clean)
     int decode_pipe_pk_split;  // bulk copies per packet (more TMA operations in flight per SM)
@@ -171,6 +172,8 @@ bool decode_pipe_box(const DecodeLayout& L, int device, int lut_dtype, uint32_t*
 const void* lut_tensor_maps(const void* dir, const void* off, int dtype, size_t h, size_t w, uint32_t box_w,
                             uint32_t box_h, int device);
 void forget_lut_tensor_maps(const void* dir);
+// packets per tile, compute warps per CTA and CTAs per SM of the pipelined kernel for this layout
+void decode_pipe_shape(const DecodeLayout& L, int device, uint32_t* P, uint32_t* ncw, uint32_t* ctas);
 bool decode_pipe_eligible(const DecodeParams& p, const DecodeLaunch& a, int device);
 cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int device, cudaStream_t st);
 cudaError_t make_decode_params(const DecodeLaunch& a, int device, bool pipe, DecodeParams& p);
