@@ -70,17 +70,20 @@ class ClockSampler:
 
     def _poll(self):
         nv = self.nv
+        rs, i = 0, 0
         while not self._stop:
             try:
                 sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                except Exception:
-                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                if i % 4 == 0:  # the reasons bitmask is the slower query: every 4th sample (sticky bits are OR-ed)
+                    try:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
                 self.samples.append((time.perf_counter(), sm, rs))
+                i += 1
             except Exception:
                 pass
-            time.sleep(0.0005)
+            time.sleep(0.0002)
 
     def _read(self):
         for line in self.proc.stdout:
