@@ -650,7 +650,8 @@ cudaError_t launch_cloud(const CloudArgs<T>& a, int device, cudaStream_t st) {
     // Single-return frames move half the bytes per tile, so the per-tile fixed cost (mbarrier hand-offs,
     // TMA issue) weighs twice as much: 1024-pixel tiles, 4 stages, 2 CTAs per SM measured 0.91 of the copy
     // peak vs 0.73 with the dual-return geometry (profiles/r02_sweep_k1_single.md).
-    const bool wide = tn.cloud_auto && !pose && a.n_returns == 1 && sizeof(T) == 4;
+    // (rows of at least 1024 pixels: a 512-wide row is one 512-pixel tile either way, and 3 x 3 stages beat 2 x 4: 0.70 vs 0.63)
+    const bool wide = tn.cloud_auto && !pose && a.n_returns == 1 && sizeof(T) == 4 && a.W >= 1024;
     int TW = pose ? tn.cloud_pose_tw : (wide ? 1024 : tn.cloud_tw);
     if (sizeof(T) == 8) TW = std::max(4, TW / 2 / 4 * 4);
     TW = std::min(TW, a.W);

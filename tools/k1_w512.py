@@ -12,6 +12,7 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream()
 obs = ob.Stream(0, cuda_stream=stream.cuda_stream)
 peak, _ = bc.measured_peaks()
+cases = []
 for (h, w) in ((32, 512), (32, 1024), (64, 1024)):
     shifts = np.tile(np.array([3 * (w // 128), 2 * (w // 128), w // 128, 0], np.int32), h // 4)
     d, o = bench.synth_lut(seed=43, h=h, w=w)
@@ -23,7 +24,11 @@ for (h, w) in ((32, 512), (32, 1024), (64, 1024)):
     t_xyz = torch.empty((F, 1, h * w, 3), dtype=torch.float32, device=dev)
     t_rd = torch.empty((F, 1, h, w), dtype=torch.int32, device=dev)
     _, comp = bc.k1_bytes(h, w, 1, F)
-    for auto in (1, 0):
-        ob.set_tunable("cloud_auto", auto)
+    cases.append((h, w, shifts, lut, t_rng, t_xyz, t_rd, comp))
+for mode in ("auto", "tw512_s3_c3", "tw512_s4_c4", "tw256_s3_c6"):
+    if mode != "auto":
+        _, tw, st, ct = mode.replace("tw", "").replace("s", "").replace("c", "").split("_")[0], *[int(x) for x in mode.replace("tw", "").replace("s", "").replace("c", "").split("_")]
+        ob.set_tunable("cloud_tw", tw); ob.set_tunable("cloud_stages", st); ob.set_tunable("cloud_ctas_per_sm", ct)
+    for (h, w, shifts, lut, t_rng, t_xyz, t_rd, comp) in cases:
         s = bench_sweep._time(torch, stream, lambda: ob.scan_to_cloud(lut, shifts, t_rng, xyz=t_xyz, range_destaggered=t_rd, stream=obs), 10, 3)
-        print(f"{h}x{w} single auto={auto}: {s*1e3:.4f} ms frac {comp / s / 1e9 / peak:.3f}", flush=True)
+        print(f"{h}x{w} single {mode}: {s*1e3:.4f} ms frac {comp / s / 1e9 / peak:.3f}", flush=True)
