@@ -103,7 +103,8 @@ PROFILE_CASES = [
 ]
 
 
-@pytest.fixture(params=["pipe_static", "pipe_runtime", "static_layouts", "runtime_plans", "narrow_tiles"])
+@pytest.fixture(params=["pipe_static", "pipe_runtime", "pipe_one_cta", "pipe_helpers", "static_layouts", "runtime_plans",
+                        "narrow_tiles"])
 def plans(ob, request):
     """K2 has two kernels (the pipelined one, ob_decode_pipe.cu, and decode_kernel for the shapes it
     does not take) and two phase-A code paths in each: compile-time pixel layouts for the standard
@@ -116,7 +117,17 @@ def plans(ob, request):
     if request.param == "narrow_tiles":
         ob.set_tunable("decode_tile_packets", 1)
         ob.set_tunable("decode_stages", 2)
+    if request.param == "pipe_one_cta":
+        for k, v in (("decode_pipe_ctas", 1), ("decode_pipe_dyn_rows", 2), ("decode_pipe_lut_split", 4),
+                     ("decode_pipe_pk_split", 8), ("decode_pipe_lane_arrive", 0)):
+            ob.set_tunable(k, v)
+    if request.param == "pipe_helpers":
+        for k, v in (("decode_pipe_ctas", 1), ("decode_pipe_helpers", 5), ("decode_pipe_dyn_rows", 1)):
+            ob.set_tunable(k, v)
     yield request.param
+    for k, v in (("decode_pipe_ctas", 0), ("decode_pipe_helpers", 0), ("decode_pipe_dyn_rows", 3),
+                 ("decode_pipe_lut_split", 1), ("decode_pipe_pk_split", 1), ("decode_pipe_lane_arrive", 1)):
+        ob.set_tunable(k, v)
     ob.set_tunable("decode_pipe", 1)
     ob.set_tunable("decode_runtime_plans", 0)
     ob.set_tunable("decode_tile_packets", 0)
