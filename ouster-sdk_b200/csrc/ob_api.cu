@@ -68,6 +68,7 @@ static Tunables& tunables_mut(int device) {
         t.decode_pipe = env_int("OB_DECODE_PIPE", 1);
         t.decode_pipe_warps = std::min(24, std::max(6, env_int("OB_DECODE_PIPE_WARPS", 24)));
         t.decode_pipe_dyn_rows = std::max(0, std::min(3, env_int("OB_DECODE_PIPE_DYN_ROWS", 3)));
+        t.decode_pipe_tma_xyz = env_int("OB_DECODE_PIPE_TMA_XYZ", 0);  // measured: same time as the STG form
         t.decode_pipe_ctas = std::max(0, std::min(4, env_int("OB_DECODE_PIPE_CTAS", 0)));
         t.decode_pipe_helpers = std::max(0, std::min(6, env_int("OB_DECODE_PIPE_HELPERS", 0)));
         t.decode_pipe_lane_arrive = env_int("OB_DECODE_PIPE_LANE_ARRIVE", 1);
@@ -116,6 +117,7 @@ bool set_tunable(int device, const char* name, int value) {
     else if (n == "decode_pipe") t.decode_pipe = value ? 1 : 0;
     else if (n == "decode_pipe_warps") t.decode_pipe_warps = std::min(24, std::max(6, value));
     else if (n == "decode_pipe_prefetch") t.decode_pipe_prefetch = value;
+    else if (n == "decode_pipe_tma_xyz") t.decode_pipe_tma_xyz = value ? 1 : 0;
     else if (n == "decode_pipe_ctas") t.decode_pipe_ctas = std::max(0, std::min(4, value));
     else if (n == "decode_pipe_helpers") t.decode_pipe_helpers = std::max(0, std::min(6, value));
     else if (n == "decode_pipe_lane_arrive") t.decode_pipe_lane_arrive = value ? 1 : 0;

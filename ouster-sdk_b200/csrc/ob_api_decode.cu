@@ -373,6 +373,9 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
     a.lut_an = lut ? lut_analytic(lut) : nullptr;
     a.frame_luts_have_maps = frame_maps_ok;
     a.any_xyz = dxyz[0] != nullptr || dxyz[1] != nullptr;
+    a.xyz_base[0] = dxyz[0];
+    a.xyz_base[1] = dxyz[1];
+    a.xyz_frame_stride = b->xyz_frame_stride;
     e = launch_decode(a, device, st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     e = stg.flush();
@@ -651,6 +654,9 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
     a.lut_maps = maps_for(L, j->device, ldir, loff, ldtype);
     a.lut_an = use_lut ? lut_analytic(use_lut) : nullptr;
     a.any_xyz = xyz[0] != nullptr || xyz[1] != nullptr;
+    a.xyz_base[0] = xyz[0];  // a one-frame batch
+    a.xyz_base[1] = xyz[1];
+    a.xyz_frame_stride = static_cast<unsigned long long>(n_px) * 3 * (ldtype == OB_F64 ? 8 : 4);
     e = launch_decode(a, j->device, j->st);
     if (e != cudaSuccess) return fail_cuda(e, "decode launch");
     for (size_t k = 0; k < n_host;) {  // one D2H per run of outputs contiguous on both sides

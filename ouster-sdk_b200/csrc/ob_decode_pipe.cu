@@ -22,6 +22,7 @@
 // Reference behaviour replaced: see ob_decode.cu (parsing.cpp:628-675, lidar_frame.cpp:1422-1528,
 // impl/cartesian.h:36-66, impl/lidar_frame_impl.h:733-760).
 #include <cuda.h>
+#include <cstring>
 
 #include <mutex>
 #include <unordered_map>
@@ -52,9 +53,15 @@ struct PipeParams {
     uint32_t stage_off;
     uint32_t nl;           // LUT ring slots (3 or 4)
     uint32_t prefetch;     // L2 prefetch distance of the packet tiles (0 = off)
+    uint32_t tma_xyz;      // phase B writes its results over the LUT slices and bulk-stores the rows from shared memory
     uint32_t helpers;      // extra warps that only run phase A (0: the third producer-side warp is the L2 prefetcher)
     uint32_t lane_arrive;  // 1: every compute lane arrives on pk_done itself; 0: __syncwarp + one elected arrival per warp
     uint32_t dyn_rows;     // phase A rows handed out through a shared-memory counter (static layouts)
+    // store-warp mode (tma_xyz): the XYZ images of a uniformly strided batch as [frame][row][3 * column] tensors,
+    // one per return; the frame index of a tile is (its xyz pointer - xyz_base0) / xyz_fs
+    const uint8_t* xyz_base0;
+    unsigned long long xyz_fs;  // bytes between frames
+    alignas(64) CUtensorMap xyz_map[2];
 };
 
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar,
@@ -66,6 +73,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
         : "memory");
 }
 
+
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
+                 : "memory");
+}
 
 // explicit shared-memory accesses by 32-bit shared address: the compiler cannot always prove that a
 // pointer derived from the stage base is shared memory and then emits generic loads (measured: they were
@@ -84,6 +97,17 @@ __device__ __forceinline__ double2 lds_vec(uint32_t a, double2*) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
     return v;
+}
+
+__device__ __forceinline__ void sts_vec(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_vec(uint32_t a, const double2& v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+// one thread arrives for `count` participants
+__device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
 // per-stage bookkeeping of the pipelined kernel: the column tables of TileCtl plus a copy of the frame's
@@ -122,7 +146,8 @@ __global__ void __launch_bounds__(MAXT, 1)
     uint64_t* pk_done = pk_full + NS;                       // NS
     uint64_t* lut_full = pk_done + NS;                      // kPipeLutSlotsMax
     uint64_t* lut_done = lut_full + kPipeLutSlotsMax;       // kPipeLutSlotsMax
-    PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem + 96);   // NS entries
+    uint64_t* slot_free = lut_done + kPipeLutSlotsMax;      // kPipeLutSlotsMax (store-warp mode: slot read out by the bulk stores)
+    PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem + 128);  // NS entries
     uint8_t* lut0 = smem + pp.lut_off;
     uint8_t* stage0 = smem + pp.stage_off;
 
@@ -131,11 +156,13 @@ __global__ void __launch_bounds__(MAXT, 1)
             // every lane arrives for itself (its own generic-proxy writes / reads of the stage control block):
             // no ordering is borrowed from a __syncwarp in front of a single elected arrival
             mbar_init(&pk_full[s], 32);
-            mbar_init(&pk_done[s], pp.lane_arrive ? NA * 32 : NA);
+            // + the store warp, which reads the stage's control block too
+            mbar_init(&pk_done[s], (pp.lane_arrive ? NA * 32 : NA) + (pp.tma_xyz ? (pp.lane_arrive ? 32 : 1) : 0));
         }
         for (unsigned s = 0; s < NL; ++s) {
             mbar_init(&lut_full[s], 1);
             mbar_init(&lut_done[s], pp.ncw);
+            mbar_init(&slot_free[s], 1);
         }
         mbar_fence_init();
         fence_proxy_async();
@@ -330,7 +357,7 @@ __global__ void __launch_bounds__(MAXT, 1)
             for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g) {
                 const unsigned slot = NL == 4u ? (g & 3u) : g % 3u;
                 const unsigned round = NL == 4u ? (g >> 2) : g / 3u;
-                if (g >= NL) mbar_wait(&lut_done[slot], (round - 1u) & 1u);
+                if (g >= NL) mbar_wait(pp.tma_xyz ? &slot_free[slot] : &lut_done[slot], (round - 1u) & 1u);
                 uint8_t* dst = lut0 + static_cast<size_t>(slot) * pp.slot_bytes;
                 mbar_expect_tx(&lut_full[slot], 2u * pp.box_bytes);
                 const unsigned op_bytes = pp.box_bytes / pp.lut_ops, op_rows = pp.RB / pp.lut_ops;
@@ -342,6 +369,56 @@ __global__ void __launch_bounds__(MAXT, 1)
                 }
             }
         }
+        return;
+    }
+
+    if (pp.tma_xyz && warp == NCW + 2) {
+        // =============================== store warp ===============================
+        // XYZ of the LUT-ring tiles leaves through TMA bulk stores from the slot the compute warps have just
+        // overwritten with their results: wait until every compute warp is done with a sub-tile (lut_done), copy
+        // its rows out (lane = row, one copy per row and return), and release the slot to the LUT producer when
+        // the copies have read it.  Tiles that do not take that path (irregular columns, shifted range fields,
+        // one return) only have their slots forwarded.
+        const DecodeParams::Plan& q0 = p.plan[p.range_field[0]];
+        const DecodeParams::Plan& q1 = p.plan[p.range_field[n_ret > 1 ? 1 : 0]];
+        const bool simple_w = (q0.mb | q1.mb | q0.rs | q1.rs) == 0 && q0.d == 0 && q1.d == 0;
+        unsigned g = 0;
+        for (unsigned k = 0; k < n_my; ++k) {
+            const int s = k % NS;
+            mbar_wait(&pk_full[s], (k / NS) & 1);
+            const PipeCtl& pc = ctl[s];
+            const unsigned j0 = pc.j0, mode = pc.mode;
+            if (mode == 1u) {
+                T* xo0 = static_cast<T*>(pc.fr.xyz[0]);
+                T* xo1 = n_ret > 1 ? static_cast<T*>(pc.fr.xyz[1]) : nullptr;
+                const bool tma_tile = pc.t.regular != 0 && simple_w && xo0 != nullptr && xo1 != nullptr;
+                const int fi = tma_tile ? static_cast<int>((reinterpret_cast<const uint8_t*>(xo0) - pp.xyz_base0) / pp.xyz_fs) : 0;
+                for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g) {
+                    const unsigned slot = NL == 4u ? (g & 3u) : g % 3u;
+                    const unsigned round = NL == 4u ? (g >> 2) : g / 3u;
+                    mbar_wait(&lut_done[slot], round & 1u);
+                    if (tma_tile && lane == 0) {
+                        // one tensor copy per return: 32 rows x 96 scalars of the slot -> the frame's XYZ image
+                        // (rows past H are clipped by the descriptor's bounds)
+                        const uint8_t* sl = lut0 + static_cast<size_t>(slot) * pp.slot_bytes;
+                        tma_store_3d(&pp.xyz_map[0], sl, static_cast<int>(j0 * 3u), static_cast<int>(sub * pp.RB), fi);
+                        tma_store_3d(&pp.xyz_map[1], sl + pp.box_bytes, static_cast<int>(j0 * 3u),
+                                     static_cast<int>(sub * pp.RB), fi);
+                        bulk_commit();
+                        bulk_wait_read<0>();  // the copies have read the slot
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&slot_free[slot]);
+                }
+            }
+            if (pp.lane_arrive) {
+                mbar_arrive(&pk_done[s]);
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pk_done[s]);
+            }
+        }
+        bulk_wait<0>();  // every copy has reached global memory before the CTA retires
         return;
     }
 
@@ -553,7 +630,39 @@ __global__ void __launch_bounds__(MAXT, 1)
             T* x1 = xo1 != nullptr ? xo1 + static_cast<size_t>(rsub) * L.W * 3 + ecol : nullptr;
             if (x0 != nullptr) __builtin_assume(__isGlobal(x0));
             if (x1 != nullptr) __builtin_assume(__isGlobal(x1));
-            if (fast_b) {
+            if (fast_b && pp.tma_xyz && xo1 != nullptr) {
+                // Results leave through TMA: every thread overwrites the direction chunk it has just read with the
+                // first return's XYZ and the offset chunk with the second return's (in place, like K1); the store
+                // warp bulk-stores the sub-tile's rows (one 384-byte copy per row and return) straight from the slot
+                // once every compute warp has arrived on lut_done, and hands the slot back to the LUT producer when
+                // the copies have read it.  That takes the 192 STG.128 of a tile -- 3.3 k cycles of the SM's store
+                // port (tools/micro/stg_issue.cu) -- out of the compute warps' way.
+                const uint32_t sst = stage_sa + static_cast<uint32_t>(s) * p.stage_bytes;
+                uint32_t aa0 = sst + coa + pl0.wa * 4u, ab0 = sst + cob + pl0.wa * 4u;
+                uint32_t aa1 = sst + coa + pl1.wa * 4u, ab1 = sst + cob + pl1.wa * 4u;
+                unsigned row = rsub;
+                for (unsigned sub = 0; sub < pp.n_sub; ++sub, ++g, row += pp.RB) {
+                    const unsigned slot = NL == 4u ? (g & 3u) : g % 3u;
+                    const unsigned round = NL == 4u ? (g >> 2) : g / 3u;
+                    mbar_wait(&lut_full[slot], round & 1u);
+                    if (row < L.H) {
+                        const uint32_t la = lut_sa + slot * pp.slot_bytes;
+                        const V dv = lds_vec(la, static_cast<V*>(nullptr));
+                        const V ov = lds_vec(la + pp.box_bytes, static_cast<V*>(nullptr));
+                        const uint32_t ra0 = lds_u32(aa0) & ma0, rb0 = lds_u32(ab0) & ma0;
+                        const uint32_t ra1 = lds_u32(aa1) & ma1, rb1 = lds_u32(ab1) & ma1;
+                        sts_vec(la, chunk(ra0, rb0, dv, ov));
+                        sts_vec(la + pp.box_bytes, chunk(ra1, rb1, dv, ov));
+                    }
+                    aa0 += sub_step;
+                    ab0 += sub_step;
+                    aa1 += sub_step;
+                    ab1 += sub_step;
+                    fence_proxy_async();  // generic-proxy results -> visible to the store warp's bulk copies
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&lut_done[slot]);
+                }
+            } else if (fast_b) {
                 // lean path (the normal case): running 32-bit shared addresses and running global pointers
                 const uint32_t sst = stage_sa + static_cast<uint32_t>(s) * p.stage_bytes;
                 uint32_t aa0 = sst + coa + pl0.wa * 4u, ab0 = sst + cob + pl0.wa * 4u;
@@ -902,9 +1011,9 @@ bool decode_pipe_box(const DecodeLayout& L, int device, int lut_dtype, uint32_t*
     return true;
 }
 
-// dynamic shared memory layout: [mbarriers 96 B][PipeCtl x stages][LUT ring][packet stages][16 B slack]
+// dynamic shared memory layout: [mbarriers 128 B][PipeCtl x stages][LUT ring][packet stages][16 B slack]
 static size_t pipe_smem_bytes(const DecodeParams& p, uint32_t ncw, uint32_t nl, uint32_t* lut_off, uint32_t* stage_off) {
-    size_t off = 96 + static_cast<size_t>(kPipeStages) * sizeof(PipeCtl);
+    size_t off = 128 + static_cast<size_t>(kPipeStages) * sizeof(PipeCtl);
     off = (off + 127) & ~static_cast<size_t>(127);
     *lut_off = static_cast<uint32_t>(off);
     off += static_cast<size_t>(nl) * 2u * (ncw * 32u * 16u);
@@ -959,6 +1068,31 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
     if (pp.nl == 0) return cudaErrorInvalidValue;
     const size_t smem = pipe_smem_bytes(p, pp.ncw, pp.nl, &pp.lut_off, &pp.stage_off);
     pp.lane_arrive = tn.decode_pipe_lane_arrive ? 1u : 0u;
+    pp.tma_xyz = 0;
+    pp.xyz_base0 = nullptr;
+    pp.xyz_fs = 1;
+    std::memset(pp.xyz_map, 0, sizeof(pp.xyz_map));
+    if (tn.decode_pipe_tma_xyz && a.xyz_base[0] != nullptr && a.xyz_base[1] != nullptr && p.n_returns == 2 &&
+        a.xyz_frame_stride % 16 == 0 && a.n_frames > 0) {
+        // the batch's XYZ images as two [frame][row][3 * column] tensors; box = one LUT sub-tile
+        EncodeTiledFn enc = encode_tiled_fn();
+        const size_t es = a.lut_dtype == OB_F64 ? 8 : 4;
+        const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(p.L.W) * 3, p.L.H, a.n_frames};
+        const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(p.L.W) * 3 * es, a.xyz_frame_stride};
+        const cuuint32_t box[3] = {p.TC * 3, pp.RB, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUtensorMapDataType dt = a.lut_dtype == OB_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        bool ok = enc != nullptr && box[0] <= 256 && box[1] <= 256 && (p.L.W * 3 * es) % 16 == 0;
+        for (int r = 0; r < 2 && ok; ++r)
+            ok = enc(&pp.xyz_map[r], dt, 3, const_cast<void*>(a.xyz_base[r]), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        if (ok) {
+            pp.tma_xyz = 1;
+            pp.xyz_base0 = static_cast<const uint8_t*>(a.xyz_base[0]);
+            pp.xyz_fs = std::max<unsigned long long>(a.xyz_frame_stride, 1);
+        }
+    }
     pp.lut_ops = pipe_lut_ops(tn, pp.RB);
     {
         const uint32_t n = static_cast<uint32_t>(std::max(1, tn.decode_pipe_pk_split));
@@ -973,7 +1107,7 @@ cudaError_t launch_decode_pipe(DecodeParams& p, const DecodeLaunch& a, int devic
     // helper warps need the 1024-thread build (64 registers); static pixel layouts only (the plan-driven
     // row loops are not tuned for the lower register cap)
     pp.helpers = p.layout_id != 0 ? static_cast<uint32_t>(std::max(0, std::min(6, tn.decode_pipe_helpers))) : 0u;
-    if ((pp.ncw + 2 + pp.helpers) * 32u > 1024u || ctas > 1) pp.helpers = 0;
+    if ((pp.ncw + 2 + pp.helpers) * 32u > 1024u || ctas > 1 || pp.tma_xyz) pp.helpers = 0;
     const int threads = static_cast<int>(pp.ncw + 2 + std::max<uint32_t>(1u, pp.helpers)) * 32;
     const int grid = static_cast<int>(std::min<uint32_t>(p.n_tiles, static_cast<uint32_t>(tn.sm_count) * ctas));
     void (*kern)(PipeParams);

@@ -32,6 +32,7 @@ struct Tunables {
     int decode_pipe;          // 1 (default): pipelined K2 (ob_decode_pipe.cu) whenever the launch is eligible
     int decode_pipe_warps;    // compute warps of the pipelined K2 (24)
     int decode_pipe_dyn_rows; // phase A rows of the pipelined K2: 0 fixed stride, 1 all through a counter, 2 last round through a counter, 3 (default) 1 with a fused cloud else 0
+    int decode_pipe_tma_xyz;      // phase B of the pipelined K2 leaves XYZ in the LUT slot and a store warp writes it out with tensor copies (dual return, uniformly strided batch); default 0
     int decode_pipe_ctas;         // CTAs per SM of the pipelined K2: 1, 2..4 (the warps split between them, 64-register build), 0 = auto (2 where the stages fit)
     int decode_pipe_helpers;      // extra phase-A-only warps of the pipelined K2 (0..6; > 0 selects the 64-register build)
     int decode_pipe_lane_arrive;  // 1 (default): per-lane arrivals on the stage-free barrier (racecheck-clean)
@@ -159,6 +160,10 @@ struct DecodeLaunch {
     const void* lut_an{nullptr};    // launch-level LUT in LUT-free mode: device LutAnalyticT<T>
     bool all_regular{false};     // every frame: identity column map, bulk-copyable packets, all slots present
     bool frame_luts_have_maps{true};  // every per-frame LUT of the table carries lut_maps
+    // XYZ outputs of a uniformly strided batch (frame f at base + f * stride): lets the pipelined kernel store
+    // them with tensor copies; null when the frames' XYZ pointers are unrelated
+    const void* xyz_base[2]{nullptr, nullptr};
+    unsigned long long xyz_frame_stride{0};
     bool any_xyz{true};          // some frame of the launch asks for the fused cloud (tuning hint only)
 };
 cudaError_t launch_decode(const DecodeLaunch& a, int device, cudaStream_t st);

@@ -103,8 +103,8 @@ PROFILE_CASES = [
 ]
 
 
-@pytest.fixture(params=["pipe_static", "pipe_runtime", "pipe_one_cta", "pipe_helpers", "static_layouts", "runtime_plans",
-                        "narrow_tiles"])
+@pytest.fixture(params=["pipe_static", "pipe_runtime", "pipe_one_cta", "pipe_helpers", "pipe_tma_store", "static_layouts",
+                        "runtime_plans", "narrow_tiles"])
 def plans(ob, request):
     """K2 has two kernels (the pipelined one, ob_decode_pipe.cu, and decode_kernel for the shapes it
     does not take) and two phase-A code paths in each: compile-time pixel layouts for the standard
@@ -121,12 +121,15 @@ def plans(ob, request):
         for k, v in (("decode_pipe_ctas", 1), ("decode_pipe_dyn_rows", 2), ("decode_pipe_lut_split", 4),
                      ("decode_pipe_pk_split", 8), ("decode_pipe_lane_arrive", 0)):
             ob.set_tunable(k, v)
+    if request.param == "pipe_tma_store":   # XYZ through the store warp's tensor copies (batched / job launches)
+        ob.set_tunable("decode_pipe_tma_xyz", 1)
     if request.param == "pipe_helpers":
         for k, v in (("decode_pipe_ctas", 1), ("decode_pipe_helpers", 5), ("decode_pipe_dyn_rows", 1)):
             ob.set_tunable(k, v)
     yield request.param
     for k, v in (("decode_pipe_ctas", 0), ("decode_pipe_helpers", 0), ("decode_pipe_dyn_rows", 3),
-                 ("decode_pipe_lut_split", 1), ("decode_pipe_pk_split", 1), ("decode_pipe_lane_arrive", 1)):
+                 ("decode_pipe_lut_split", 1), ("decode_pipe_pk_split", 1), ("decode_pipe_lane_arrive", 1),
+                 ("decode_pipe_tma_xyz", 0)):
         ob.set_tunable(k, v)
     ob.set_tunable("decode_pipe", 1)
     ob.set_tunable("decode_runtime_plans", 0)

@@ -29,11 +29,13 @@ variants = {
 out = {}
 configs = [tuple(int(x) for x in c.split(",")) for c in os.environ.get("K2_SPLITS", "1,1").split(";")]
 only = os.environ.get("K2_VARIANTS")
-dyns = [int(x) for x in os.environ.get("K2_DYN", "2").split(",")]
+dyns = [int(x) for x in os.environ.get("K2_DYN", "3").split(",")]
 arrs = [int(x) for x in os.environ.get("K2_LANE_ARRIVE", "1").split(",")]
 helps = [int(x) for x in os.environ.get("K2_HELPERS", "0").split(",")]
-configs = [(a, b, d, la, h) for (a, b) in configs for d in dyns for la in arrs for h in helps]
-for pk_split, lut_split, dyn, la, nh in configs:
+tmas = [int(x) for x in os.environ.get("K2_TMA_XYZ", "1").split(",")]
+configs = [(a, b, d, la, h, tx) for (a, b) in configs for d in dyns for la in arrs for h in helps for tx in tmas]
+for pk_split, lut_split, dyn, la, nh, tx in configs:
+  ob.set_tunable("decode_pipe_tma_xyz", tx)
   ob.set_tunable("decode_pipe_helpers", nh)
   ob.set_tunable("decode_pipe_lane_arrive", la)
   ob.set_tunable("decode_pipe_pk_split", pk_split)
@@ -58,7 +60,7 @@ for pk_split, lut_split, dyn, la, nh in configs:
     ms = e0.elapsed_time(e1) / 20
     fb = sum(int(np.prod(t.shape[1:])) * t.element_size() for t in v["fields"].values())
     b = F * (wire + fb + (R * H * W * 12 if v["xyz"] else 0) + (R * H * W * 4 if v["rd"] else 0)) + (H * W * 24 if v["xyz"] else 0)
-    key = name if len(configs) == 1 else f"{name}@pk{pk_split},lut{lut_split},dyn{dyn},la{la},h{nh}"
+    key = name if len(configs) == 1 else f"{name}@pk{pk_split},lut{lut_split},dyn{dyn},la{la},h{nh},tma{tx}"
     out[key] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6, "frac": b / ms / 1e6 / peak}
     print("%-28s ms %.4f  %.0f GB/s  frac %.3f" % (key, ms, b / ms / 1e6, b / ms / 1e6 / peak), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
