@@ -170,6 +170,11 @@ ob_status ob_decode_frames(const ob_decoder* dec, const ob_decode_io* frames, si
             if (e != cudaSuccess) return fail_cuda(e, "stage field output");
             f.fields[k] = o;
         }
+        {
+            bool allf = L.n_fields > 0;
+            for (uint32_t k = 0; k < L.n_fields; ++k) allf = allf && f.fields[k] != nullptr;
+            if (allf) f.flags |= 4u;  // every decoder field has an output image
+        }
         if (io.timestamp) {
             e = stg.out(io.timestamp, static_cast<size_t>(L.W) * 8, &o);
             if (e != cudaSuccess) return fail_cuda(e, "stage timestamp");
@@ -339,8 +344,12 @@ ob_status ob_decode_batch_run(const ob_decoder* dec, const ob_decode_batch* b, c
         d.packet_stride = b->packet_stride;
         d.n_slots = static_cast<uint32_t>(b->n_slots);
         d.flags = 1u | (bulk_ok ? 2u : 0u);
-        for (uint32_t k = 0; k < L.n_fields; ++k)
+        bool allf = L.n_fields > 0;
+        for (uint32_t k = 0; k < L.n_fields; ++k) {
             if (dfields[k]) d.fields[k] = static_cast<uint8_t*>(dfields[k]) + f * b->field_frame_stride[k];
+            allf = allf && dfields[k] != nullptr;
+        }
+        if (allf) d.flags |= 4u;  // every decoder field has an output image
         if (dts) d.timestamp = reinterpret_cast<uint64_t*>(static_cast<uint8_t*>(dts) + f * b->timestamp_frame_stride);
         if (dmid) d.measurement_id = reinterpret_cast<uint16_t*>(static_cast<uint8_t*>(dmid) + f * b->measurement_id_frame_stride);
         if (dstat) d.status = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(dstat) + f * b->status_frame_stride);
@@ -630,7 +639,14 @@ ob_status ob_decode_job_submit(ob_decode_job* j, const ob_decode_io* io, const o
         if (e != cudaSuccess) return fail_cuda(e, "stage column map");
         f.col_src = j->d_colsrc;
     }
-    for (uint32_t k = 0; k < L.n_fields; ++k) f.fields[k] = fld[k];
+    {
+        bool allf = L.n_fields > 0;
+        for (uint32_t k = 0; k < L.n_fields; ++k) {
+            f.fields[k] = fld[k];
+            allf = allf && fld[k] != nullptr;
+        }
+        if (allf) f.flags |= 4u;  // every decoder field has an output image
+    }
     f.timestamp = static_cast<uint64_t*>(ts);
     f.measurement_id = static_cast<uint16_t*>(mid);
     f.status = static_cast<uint32_t*>(stt);

@@ -238,9 +238,7 @@ __global__ void __launch_bounds__(384, 3) decode_kernel(const __grid_constant__ 
                 const bool full = regular && (RW > 1 || (cg + 1) * 32u <= tc);
                 const unsigned col = static_cast<unsigned>(pix0);
                 const unsigned row0 = static_cast<unsigned>(warp) * RW + sub, rstep = static_cast<unsigned>(nwarps) * RW;
-                const bool all = p.layout_all != 0 && (p.n_returns < 1 || rdp2[0] != nullptr) &&
-                                 (p.n_returns < 2 || rdp2[1] != nullptr) && fr.fields[0] != nullptr &&
-                                 p.n_returns > 0;
+                const int all = static_output_mode(p, fr);
                 switch (p.layout_id) {
                     case 1: decode_static_tile<1>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;
                     case 2: decode_static_tile<2>(full, all, px0, col_valid, lane_on, outp, rdp2, col, L.W, L.H, row0, rstep, p); break;

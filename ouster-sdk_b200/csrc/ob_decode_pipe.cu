@@ -514,9 +514,7 @@ __global__ void __launch_bounds__(MAXT, 1)
                 uint32_t* rdp2[2] = {fr.rd[0], fr.rd[1]};
                 const unsigned col = static_cast<unsigned>(pix0);
                 const unsigned rstep = static_cast<unsigned>(NA);
-                const bool all = p.layout_all != 0 && (p.n_returns < 1 || rdp2[0] != nullptr) &&
-                                 (p.n_returns < 2 || rdp2[1] != nullptr) && fr.fields[0] != nullptr &&
-                                 p.n_returns > 0;
+                const int all = static_output_mode(p, fr);
                 if (pp.dyn_rows) {
                     unsigned* ctr = &pc.row_ctr[cg];
                     // dyn_rows 1: every row through the counter; 2: all but the last round of rows are static

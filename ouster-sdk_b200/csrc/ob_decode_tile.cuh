@@ -330,9 +330,12 @@ __device__ __forceinline__ uint32_t slot_value(const uint32_t (&w)[PxLayout<L>::
     return v;
 }
 
-// ALL: every slot of the layout has an output image and every range slot a destaggered image
+// ALL (output mode of a tile, uniform): 1 = every slot of the layout has an output image and every range slot a
+// destaggered image (the default LidarFrame of the profile with a fused cloud), 2 = every slot has an output
+// image and there is no destaggered range (the plain ScanBatcher result) -- no null tests in the row loop
+// either way; 0 = anything else, tested pointer by pointer.
 // (the default LidarFrame of the profile with a fused cloud) -> no null tests in the row loop.
-template <int L, int I, bool FULL, bool ALL>
+template <int L, int I, bool FULL, int ALL>
 __device__ __forceinline__ void slot_store(const uint32_t (&w)[PxLayout<L>::cds / 4], uint8_t* const (&outp)[kMaxSlots],
                                            uint32_t* const (&rdp)[2], unsigned pix, unsigned rdpix,
                                            bool col_valid, bool lane_on) {
@@ -340,18 +343,18 @@ __device__ __forceinline__ void slot_store(const uint32_t (&w)[PxLayout<L>::cds 
     uint8_t* o = outp[I];
     uint32_t* r = nullptr;
     if constexpr (sl.ret >= 0) r = rdp[sl.ret];
-    if (ALL || o != nullptr || r != nullptr) {  // uniform per tile
+    if (ALL != 0 || o != nullptr || r != nullptr) {  // uniform per tile
         uint32_t v = slot_value<L, I>(w);
         if (!FULL) v = col_valid ? v : 0u;
         if (FULL || lane_on) {
-            if (ALL || o != nullptr) {
+            if (ALL != 0 || o != nullptr) {
                 __builtin_assume(__isGlobal(o));
                 if constexpr (sl.es == 4) reinterpret_cast<uint32_t*>(o)[pix] = v;
                 else if constexpr (sl.es == 2) reinterpret_cast<uint16_t*>(o)[pix] = static_cast<uint16_t>(v);
                 else o[pix] = static_cast<uint8_t>(v);
             }
             if constexpr (sl.ret >= 0) {
-                if (ALL || r != nullptr) {
+                if (ALL == 1 || (ALL == 0 && r != nullptr)) {
                     __builtin_assume(__isGlobal(r));
                     r[rdpix] = v;
                 }
@@ -360,7 +363,7 @@ __device__ __forceinline__ void slot_store(const uint32_t (&w)[PxLayout<L>::cds 
     }
 }
 
-template <int L, bool FULL, bool ALL, int... I>
+template <int L, bool FULL, int ALL, int... I>
 __device__ __forceinline__ void store_all(const uint32_t (&w)[PxLayout<L>::cds / 4], uint8_t* const (&outp)[kMaxSlots],
                                           uint32_t* const (&rdp)[2], unsigned pix, unsigned rdpix, bool col_valid,
                                           bool lane_on, std::integer_sequence<int, I...>) {
@@ -369,13 +372,13 @@ __device__ __forceinline__ void store_all(const uint32_t (&w)[PxLayout<L>::cds /
 
 // Phase A with a compile-time layout: lane = frame column, warps stride the rows, all fields of a
 // pixel from registers.
-template <int L, bool FULL, bool ALL>
+template <int L, bool FULL, int ALL>
 __device__ __forceinline__ void decode_static(const uint8_t* px0, bool col_valid, bool lane_on,
                                               uint8_t* const (&outp)[kMaxSlots], uint32_t* const (&rdp)[2],
                                               unsigned col, unsigned W, unsigned H, unsigned row0, unsigned rstep,
                                               const DecodeParams& p) {
     constexpr int NW = PxLayout<L>::cds / 4;
-    const bool has_rd = ALL || rdp[0] != nullptr || rdp[1] != nullptr;
+    const bool has_rd = ALL == 1 || (ALL == 0 && (rdp[0] != nullptr || rdp[1] != nullptr));
     const bool has_shift = p.has_shift != 0;
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(px0) + row0 * NW;
     const unsigned wstep = rstep * NW;
@@ -406,14 +409,14 @@ __device__ __forceinline__ void decode_static(const uint8_t* px0, bool col_valid
 // warps wait for the next tile's packets).  Handing out ALL rows that way costs one same-address atomic per
 // row and warp -- 152 serialised shared-memory atomics per tile, a third of a tile's time when nothing else is
 // going on (tools/k2_parts.py).  The ticket of the next row is drawn while the current one is decoded.
-template <int L, bool FULL, bool ALL>
+template <int L, bool FULL, int ALL>
 __device__ __forceinline__ void decode_static_dyn(const uint8_t* px0, bool col_valid, bool lane_on,
                                                   uint8_t* const (&outp)[kMaxSlots], uint32_t* const (&rdp)[2],
                                                   unsigned col, unsigned W, unsigned H, unsigned* row_ctr,
                                                   unsigned row0, unsigned rstep, unsigned n_static,
                                                   const DecodeParams& p) {
     constexpr int NW = PxLayout<L>::cds / 4;
-    const bool has_rd = ALL || rdp[0] != nullptr || rdp[1] != nullptr;
+    const bool has_rd = ALL == 1 || (ALL == 0 && (rdp[0] != nullptr || rdp[1] != nullptr));
     const bool has_shift = p.has_shift != 0;
     const unsigned lane = threadIdx.x & 31u;
     auto one_row = [&](unsigned row) {
@@ -444,25 +447,37 @@ __device__ __forceinline__ void decode_static_dyn(const uint8_t* px0, bool col_v
     }
 }
 
+// output mode of a tile for the compile-time layouts (see slot_store): frame flag bit 2 = the host found an output
+// image for every field of the decoder
+__device__ __forceinline__ int static_output_mode(const DecodeParams& p, const DecodeFrame& fr) {
+    if (p.layout_all == 0 || (fr.flags & 4u) == 0 || p.n_returns == 0) return 0;
+    const bool rd0 = fr.rd[0] != nullptr, rd1 = p.n_returns > 1 ? fr.rd[1] != nullptr : rd0;
+    if (rd0 && rd1) return 1;
+    if (!rd0 && !(p.n_returns > 1 && fr.rd[1] != nullptr)) return 2;
+    return 0;
+}
+
 template <int L>
-__device__ __forceinline__ void decode_static_tile_dyn(bool full, bool all, const uint8_t* px0, bool col_valid,
+__device__ __forceinline__ void decode_static_tile_dyn(bool full, int all, const uint8_t* px0, bool col_valid,
                                                        bool lane_on, uint8_t* const (&outp)[kMaxSlots],
                                                        uint32_t* const (&rdp)[2], unsigned col, unsigned W,
                                                        unsigned H, unsigned* row_ctr, unsigned row0, unsigned rstep,
                                                        unsigned n_static, const DecodeParams& p) {
-    if (full && all) decode_static_dyn<L, true, true>(px0, true, true, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
-    else if (full) decode_static_dyn<L, true, false>(px0, true, true, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
-    else decode_static_dyn<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
+    if (full && all == 1) decode_static_dyn<L, true, 1>(px0, true, true, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
+    else if (full && all == 2) decode_static_dyn<L, true, 2>(px0, true, true, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
+    else if (full) decode_static_dyn<L, true, 0>(px0, true, true, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
+    else decode_static_dyn<L, false, 0>(px0, col_valid, lane_on, outp, rdp, col, W, H, row_ctr, row0, rstep, n_static, p);
 }
 
 template <int L>
-__device__ __forceinline__ void decode_static_tile(bool full, bool all, const uint8_t* px0, bool col_valid,
+__device__ __forceinline__ void decode_static_tile(bool full, int all, const uint8_t* px0, bool col_valid,
                                                    bool lane_on, uint8_t* const (&outp)[kMaxSlots],
                                                    uint32_t* const (&rdp)[2], unsigned col, unsigned W, unsigned H,
                                                    unsigned row0, unsigned rstep, const DecodeParams& p) {
-    if (full && all) decode_static<L, true, true>(px0, true, true, outp, rdp, col, W, H, row0, rstep, p);
-    else if (full) decode_static<L, true, false>(px0, true, true, outp, rdp, col, W, H, row0, rstep, p);
-    else decode_static<L, false, false>(px0, col_valid, lane_on, outp, rdp, col, W, H, row0, rstep, p);
+    if (full && all == 1) decode_static<L, true, 1>(px0, true, true, outp, rdp, col, W, H, row0, rstep, p);
+    else if (full && all == 2) decode_static<L, true, 2>(px0, true, true, outp, rdp, col, W, H, row0, rstep, p);
+    else if (full) decode_static<L, true, 0>(px0, true, true, outp, rdp, col, W, H, row0, rstep, p);
+    else decode_static<L, false, 0>(px0, col_valid, lane_on, outp, rdp, col, W, H, row0, rstep, p);
 }
 
 }  // namespace ob

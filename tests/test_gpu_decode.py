@@ -186,6 +186,37 @@ def test_subset_of_fields_other_images_untouched(ob, plans, keep):
             assert np.array_equal(io["xyz"][r], orc.cartesian(src.field(nm), d, o)), nm
 
 
+@pytest.mark.parametrize("missing", [("NEAR_IR",), ("RANGE2", "FLAGS2"), ("SIGNAL", "SIGNAL2", "REFLECTIVITY")])
+@pytest.mark.parametrize("with_rd", [True, False])
+def test_full_decoder_frame_without_some_fields(ob, plans, missing, with_rd):
+    """A decoder built for the whole profile, a frame that lacks some of its fields (LidarFrame without an
+    optional channel): the no-null-test row loops (all outputs present, with or without the destaggered range)
+    must not be chosen -- the fields that are there decode, the fused cloud and the destaggered range too."""
+    h, w = 64, 512
+    pf = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", h, w)
+    src = random_frame(pf, seed=77)
+    packets, _ = orc.frame_to_packets(src, pf)
+    layout, fields = decoder_desc_from_oracle(pf, src)
+    dec = ob.Decoder(layout, fields)
+    outs = {f["name"]: np.full((h, w), 0xAB, src.field(f["name"]).dtype) for f in fields if f["name"] not in missing}
+    d, o = random_lut(h * w, 6)
+    lut = ob.XYZLutT.from_arrays(d, o, h, w)
+    shifts = np.random.default_rng(2).integers(0, 40, h).astype(np.int32)
+    io = {"packets": np.ascontiguousarray(packets), "n_slots": len(packets), "packet_stride": packets.shape[1],
+          "col_src": None, "fields": outs, "xyz": [np.full((h * w, 3), 9, np.float32) for _ in range(2)]}
+    if with_rd:
+        io["range_destaggered"] = [np.full((h, w), 9, np.uint32) for _ in range(2)]
+    st = ob.Stream(0)
+    dec.decode([io], lut=lut, pixel_shift_by_row=shifts if with_rd else None, stream=st)
+    st.sync()
+    for name, a in outs.items():
+        assert np.array_equal(a, src.field(name)), name
+    for r, nm in enumerate(("RANGE", "RANGE2")):
+        assert np.array_equal(io["xyz"][r], orc.cartesian(src.field(nm), d, o)), nm
+        if with_rd:
+            assert np.array_equal(io["range_destaggered"][r], orc.destagger(src.field(nm), shifts)), nm
+
+
 def test_fault_injection_matches_oracle_batcher(ob, plans):
     """dropped packet, invalidated columns, swapped packets, duplicate packet
     (tests/frame_batcher_test.cpp:119-170, 208-259)."""
