@@ -195,6 +195,7 @@ def measure_k1(args, ob, torch, dist, rank, local_rank, world, pcie):
             dist.barrier()
         torch.cuda.synchronize()
 
+    bc.gpu_spin(torch, dev)                 # clocks up after the host-only set-up
     sampler = bc.ClockSampler(local_rank)   # NVML polling thread: warm-up and timed region, marked below
     sampler.start()
     for _ in range(args.warmup):
@@ -347,6 +348,7 @@ def measure_lut_free(args, ob, torch, dist, rank, local_rank, world):
     out = {}
 
     def timed(step, steps=10, warmup=3):
+        bc.gpu_spin(torch, dev)
         for _ in range(warmup):
             step()
         if dist is not None:

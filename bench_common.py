@@ -19,6 +19,30 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+_SPIN = {}
+
+
+def gpu_spin(torch, dev, ms=40.0):
+    """Part of the warm-up: keep the GPU busy for `ms` milliseconds right before a measurement.  The bench
+    alternates GPU measurements with seconds of host-only work (oracle parity checks, the CPU baseline legs);
+    after such a gap the first launches run while the clocks are still ramping, and three 60-microsecond warm-up
+    launches do not cover the ramp (the same K2 launch measured 0.058 ms back to back and 0.080 ms after a CPU
+    leg).  The spin kernel is a plain torch elementwise op on a private buffer; nothing of it is timed."""
+    key = str(dev)
+    if key not in _SPIN:
+        _SPIN[key] = torch.zeros(16 << 20, dtype=torch.float32, device=dev)
+    x = _SPIN[key]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(2000):
+        for _ in range(20):
+            x.add_(1.0)
+        e1.record()
+        e1.synchronize()
+        if e0.elapsed_time(e1) >= ms:
+            break
+
+
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled DURING the timed region: an NVML polling thread
     (a timed region is a few milliseconds -- `nvidia-smi -lms` often delivers its first line after it),

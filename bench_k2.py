@@ -129,6 +129,7 @@ def measure_k2(st, args, streams_per_gpu, pcie, with_e2e=True, with_cpu=True):
                                 pixel_shift_by_row=SHIFTS, xyz=st.xyz, range_destaggered=st.rd, timestamp=st.t_ts,
                                 measurement_id=st.t_mid, status=st.t_st, stream=st.obs, frame_luts=frame_luts)
 
+    bc.gpu_spin(torch, dev)
     sampler = bc.ClockSampler(st.local_rank)
     sampler.start()
     for _ in range(max(args.warmup, 3)):

@@ -18,6 +18,7 @@ TARGET_BYTES_K1 = 1.2e9   # K1: as many bytes per step as the headline's 128-fra
 
 
 def _time(torch, stream, step, steps, warmup):
+    bc.gpu_spin(torch, torch.device("cuda", torch.cuda.current_device()))   # clocks up after the host-only gap
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -42,7 +43,7 @@ def run_sweep(args, ob, torch, dist, rank, local_rank, world):
     orc = None
     if with_cpu:
         from oracle import oracle as orc   # CPU baseline leg only
-    steps, warmup = 5, 3
+    steps, warmup = 20, 5
     tdt = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
     out = []
     for (h, w) in SHAPES:
