@@ -12,3 +12,5 @@ for tool in memcheck racecheck synccheck; do
   echo "$tool rc=$?"; tail -2 gpurun_out/r02_sanitize_$tool.txt
 done
 timeout 600 python tools/k2_parts.py 2>&1 | tail -9
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:decode_pipe -s 4 -c 1 -o gpurun_out/k2_pipe_head -f python bench.py --only k2 --kernel-only --steps 3 --warmup 3 > gpurun_out/ncu_k2_head.log 2>&1; tail -1 gpurun_out/ncu_k2_head.log
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:cloud_tma -s 4 -c 1 -o gpurun_out/k1_head -f python bench.py --only k1 --kernel-only --steps 3 --warmup 3 > gpurun_out/ncu_k1_head.log 2>&1; tail -1 gpurun_out/ncu_k1_head.log
