@@ -188,6 +188,51 @@ ob.scan_to_cloud(al, shifts, rngs, xyz=xa, stream=st)
 st.sync()
 assert np.allclose(xa[0, 0], io["xyz"][0], rtol=1e-5, atol=1e-4)
 print("K2 pipelined (f32, f64, LUT-free) ok")
+# the pipelined kernel's other launch shapes: 3 CTAs per SM (32-row sensor), phase-A helper warps, store-warp tensor
+# copies for XYZ (batched launch), each against the oracle
+pf32 = oracle_pf("RNG19_RFL8_SIG16_NIR16_DUAL", 32, 128)
+src32 = random_frame(pf32, seed=9)
+pk32, _ = orc.frame_to_packets(src32, pf32)
+layout32, fields32 = decoder_desc_from_oracle(pf32, src32)
+dec32 = ob.Decoder(layout32, fields32)
+sh32 = (np.arange(32, dtype=np.int32) * 5) % 23
+d32, o32 = random_lut(32 * 128, 11, np.float32)
+lut32 = ob.XYZLutT.from_arrays(d32, o32, 32, 128)
+for tun in ({"decode_pipe_ctas": 3}, {"decode_pipe_ctas": 1, "decode_pipe_helpers": 5}, {"decode_pipe_ctas": 1, "decode_pipe_tma_xyz": 1}):
+    for k, v in tun.items():
+        ob.set_tunable(k, v)
+    n1 = ob.kernel_launch_count("decode_pipe")
+    io = {"packets": np.ascontiguousarray(pk32), "n_slots": len(pk32), "packet_stride": pk32.shape[1], "col_src": None,
+          "fields": {f["name"]: np.zeros(src32.field(f["name"]).shape, src32.field(f["name"]).dtype) for f in fields32},
+          "xyz": [np.zeros((32 * 128, 3), np.float32) for _ in range(2)],
+          "range_destaggered": [np.zeros((32, 128), np.uint32) for _ in range(2)]}
+    if "decode_pipe_tma_xyz" in tun:   # the store warp needs a uniformly strided batch: the batch entry point
+        import torch
+        dev0 = torch.device("cuda", 0)
+        F = 3
+        t_pk = torch.from_numpy(np.stack([pk32] * F)).to(dev0)
+        tf = {f["name"]: torch.zeros((F, 32, 128), dtype={1: torch.uint8, 2: torch.int16, 4: torch.int32}[f["elem_size"]], device=dev0)
+              for f in dec32.fields}
+        tx = [torch.zeros((F, 32 * 128, 3), dtype=torch.float32, device=dev0) for _ in range(2)]
+        trd = [torch.zeros((F, 32, 128), dtype=torch.int32, device=dev0) for _ in range(2)]
+        dec32.decode_batch(F, t_pk, pk32.shape[0], pk32.shape[1], pk32.shape[0] * pk32.shape[1], tf, lut=lut32,
+                           pixel_shift_by_row=sh32, xyz=tx, range_destaggered=trd, stream=st)
+        st.sync()
+        for r, nm in enumerate(("RANGE", "RANGE2")):
+            assert np.array_equal(tx[r][F - 1].cpu().numpy(), orc.cartesian(src32.field(nm), d32, o32))
+            assert np.array_equal(trd[r][F - 1].cpu().numpy().view(np.uint32), orc.destagger(src32.field(nm), sh32))
+    else:
+        dec32.decode([io], lut=lut32, pixel_shift_by_row=sh32, stream=st)
+        st.sync()
+        for n, a in io["fields"].items():
+            assert np.array_equal(a, src32.field(n)), n
+        for r, nm in enumerate(("RANGE", "RANGE2")):
+            assert np.array_equal(io["xyz"][r], orc.cartesian(src32.field(nm), d32, o32))
+            assert np.array_equal(io["range_destaggered"][r], orc.destagger(src32.field(nm), sh32))
+    assert ob.kernel_launch_count("decode_pipe") > n1, "the pipelined K2 did not run"
+    for k in tun:
+        ob.set_tunable(k, 0)
+print("K2 pipelined: 3 CTAs/SM, helper warps, store-warp XYZ ok")
 sih = ob.SensorInfo("RNG19_RFL8_SIG16_NIR16_DUAL", 16, 128, fw_rev="v3.2.1")
 fr = ob.LidarFrame(sih)
 rs = np.random.default_rng(12)
