@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
+    extra = os.environ.get("OB_EXTRA_NVCC_FLAGS", "").split()   # experiments only (e.g. -DOB_K2_STREAM_STORES)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
                                  "-I", os.path.join(PKG, "host"), "-o", LIB] + sources()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

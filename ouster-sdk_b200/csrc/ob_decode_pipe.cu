@@ -80,6 +80,14 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
                  : "memory");
 }
 
+#ifdef OB_K2_STREAM_STORES
+#define K2_STV(ptr, val) st_stream_vec(ptr, val)
+__device__ __forceinline__ void st_stream_vec(float* p, const float4& v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void st_stream_vec(double* p, const double2& v) { __stcs(reinterpret_cast<double2*>(p), v); }
+#else
+#define K2_STV(ptr, val) (*reinterpret_cast<V*>(ptr) = (val))
+#endif
+
 // explicit shared-memory accesses by 32-bit shared address: the compiler cannot always prove that a
 // pointer derived from the stage base is shared memory and then emits generic loads (measured: they were
 // the kernel's main long-scoreboard stall)
@@ -702,12 +710,12 @@ __global__ void __launch_bounds__(MAXT, 1)
                         }
                     }
                     if (on_a) {
-                        *reinterpret_cast<V*>(x0) = chunk(ra0 & ma0, rb0 & ma0, dva, ova);
-                        if (x1 != nullptr) *reinterpret_cast<V*>(x1) = chunk(ra1 & ma1, rb1 & ma1, dva, ova);
+                        K2_STV(x0, chunk(ra0 & ma0, rb0 & ma0, dva, ova));
+                        if (x1 != nullptr) K2_STV(x1, chunk(ra1 & ma1, rb1 & ma1, dva, ova));
                     }
                     if (on_b) {
-                        *reinterpret_cast<V*>(x0 + row_step) = chunk(rc0 & ma0, rd0 & ma0, dvb, ovb);
-                        if (x1 != nullptr) *reinterpret_cast<V*>(x1 + row_step) = chunk(rc1 & ma1, rd1 & ma1, dvb, ovb);
+                        K2_STV(x0 + row_step, chunk(rc0 & ma0, rd0 & ma0, dvb, ovb));
+                        if (x1 != nullptr) K2_STV(x1 + row_step, chunk(rc1 & ma1, rd1 & ma1, dvb, ovb));
                     }
                     aa0 += 2 * sub_step;
                     ab0 += 2 * sub_step;
@@ -730,10 +738,10 @@ __global__ void __launch_bounds__(MAXT, 1)
                         const V dv = lds_vec(la, static_cast<V*>(nullptr));
                         const V ov = lds_vec(la + pp.box_bytes, static_cast<V*>(nullptr));
                         const uint32_t ra0 = lds_u32(aa0) & ma0, rb0 = lds_u32(ab0) & ma0;
-                        *reinterpret_cast<V*>(x0) = chunk(ra0, rb0, dv, ov);
+                        K2_STV(x0, chunk(ra0, rb0, dv, ov));
                         if (x1 != nullptr) {
                             const uint32_t ra1 = lds_u32(aa1) & ma1, rb1 = lds_u32(ab1) & ma1;
-                            *reinterpret_cast<V*>(x1) = chunk(ra1, rb1, dv, ov);
+                            K2_STV(x1, chunk(ra1, rb1, dv, ov));
                         }
                     }
                     aa0 += sub_step;
@@ -764,8 +772,8 @@ __global__ void __launch_bounds__(MAXT, 1)
                         const V ov = lds_vec(la + pp.box_bytes, static_cast<V*>(nullptr));
                         const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa + static_cast<size_t>(row) * cds);
                         const uint32_t* wb = reinterpret_cast<const uint32_t*>(pb + static_cast<size_t>(row) * cds);
-                        if (x0 != nullptr) *reinterpret_cast<V*>(x0) = chunk(rng(wa, pl0, v0, simple), rng(wb, pl0, v1, simple), dv, ov);
-                        if (x1 != nullptr) *reinterpret_cast<V*>(x1) = chunk(rng(wa, pl1, v0, simple), rng(wb, pl1, v1, simple), dv, ov);
+                        if (x0 != nullptr) K2_STV(x0, chunk(rng(wa, pl0, v0, simple), rng(wb, pl0, v1, simple), dv, ov));
+                        if (x1 != nullptr) K2_STV(x1, chunk(rng(wa, pl1, v0, simple), rng(wb, pl1, v1, simple), dv, ov));
                     }
                     if (x0 != nullptr) x0 += row_step;
                     if (x1 != nullptr) x1 += row_step;

@@ -349,14 +349,24 @@ __device__ __forceinline__ void slot_store(const uint32_t (&w)[PxLayout<L>::cds 
         if (FULL || lane_on) {
             if (ALL != 0 || o != nullptr) {
                 __builtin_assume(__isGlobal(o));
+#ifdef OB_K2_STREAM_STORES  // experiment (measured slower, 0.130 vs 0.113 ms): evict-first stores for the write-once outputs
+                if constexpr (sl.es == 4) __stcs(reinterpret_cast<uint32_t*>(o) + pix, v);
+                else if constexpr (sl.es == 2) __stcs(reinterpret_cast<unsigned short*>(o) + pix, static_cast<unsigned short>(v));
+                else __stcs(reinterpret_cast<unsigned char*>(o) + pix, static_cast<unsigned char>(v));
+#else
                 if constexpr (sl.es == 4) reinterpret_cast<uint32_t*>(o)[pix] = v;
                 else if constexpr (sl.es == 2) reinterpret_cast<uint16_t*>(o)[pix] = static_cast<uint16_t>(v);
                 else o[pix] = static_cast<uint8_t>(v);
+#endif
             }
             if constexpr (sl.ret >= 0) {
                 if (ALL == 1 || (ALL == 0 && r != nullptr)) {
                     __builtin_assume(__isGlobal(r));
+#ifdef OB_K2_STREAM_STORES
+                    __stcs(r + rdpix, v);
+#else
                     r[rdpix] = v;
+#endif
                 }
             }
         }
