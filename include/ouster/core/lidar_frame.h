@@ -69,6 +69,10 @@ class OUSTER_API_CLASS HostBuffer {
     const uint8_t* data() const { return p_; }
     size_t size() const { return n_; }
     OUSTER_API_FUNCTION void resize(size_t bytes);  ///< contents are zeroed
+    /// Shares ownership of the memory block behind this buffer: an asynchronous writer (a decode job in
+    /// flight) holds it so that the block cannot return to the pool -- and be handed to another frame --
+    /// before the writer is done, even if the buffer's owner is destroyed, moved or resized meanwhile.
+    std::shared_ptr<void> keepalive() const { return arena_; }
     OUSTER_API_FUNCTION bool operator==(const HostBuffer& o) const;
     /// Zero-initialised buffers of the given sizes laid out back to back (256-byte aligned) in ONE
     /// block, so that a device->host transfer of all of them is a single copy (ob_decode_job_submit
@@ -81,7 +85,7 @@ class OUSTER_API_CLASS HostBuffer {
     size_t n_{0};
     size_t cap_{0};
     bool pinned_{false};
-    std::shared_ptr<void> arena_;  ///< set when p_ lies inside a block shared with other buffers
+    std::shared_ptr<void> arena_;  ///< owner of the block p_ lies in (shared with other buffers after carve())
 };
 
 /// Typed dense buffer (field.h:828+).  Zero-initialised like the reference's calloc (field.cpp:254).
@@ -98,6 +102,7 @@ class OUSTER_API_CLASS Field {
     size_t size() const { return element_size() ? buf_.size() / element_size() : 0; }
     void* get() { return buf_.data(); }
     const void* get() const { return buf_.data(); }
+    std::shared_ptr<void> keepalive() const { return buf_.keepalive(); }  ///< see HostBuffer::keepalive
     template <typename T>
     T* get() { return reinterpret_cast<T*>(buf_.data()); }
     template <typename T>
@@ -353,12 +358,11 @@ class OUSTER_API_CLASS FrameBatcher {
     /// reference.  n >= 2: batch() returns true as soon as the frame's GPU pass is *submitted*; the
     /// caller batches the next frame into another LidarFrame (and FusedCloud) meanwhile and calls
     /// wait(frame) before reading pixel fields / fused outputs.  Column and packet headers are
-    /// host-written and valid immediately.  A frame must outlive its wait(): the in-flight job holds
-    /// raw pointers into the frame's page-locked storage, so a LidarFrame (or FusedCloud) that is
-    /// destroyed, moved or resized before wait(frame) leaves a device->host copy aimed at memory that
-    /// may already belong to another frame.  FramePipeline owns its frames and does this correctly;
-    /// direct users of depth >= 2 must keep every submitted frame alive and unmoved until waited.  See FramePipeline
-    /// (frame_pipeline.h) for a ready-made ring of frames.
+    /// host-written and valid immediately.  The in-flight job shares ownership of the page-locked blocks
+    /// it writes (fields and fused outputs): a LidarFrame (or FusedCloud) that is destroyed, moved or resized
+    /// before wait(frame) does not send the device->host copy into memory of another frame -- its results
+    /// are simply lost with the old blocks.  See FramePipeline (frame_pipeline.h) for a ready-made ring of
+    /// frames.
     OUSTER_API_FUNCTION void set_pipeline_depth(size_t n);
     OUSTER_API_FUNCTION size_t pipeline_depth() const;
     /// Block until the GPU pass that fills lidar_frame has landed (no-op when none is pending).

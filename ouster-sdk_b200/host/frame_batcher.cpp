@@ -48,6 +48,7 @@ struct FrameBatcher::Staging {
         size_t bounce_cap{0};  // packets
         bool bounce_cuda{false};
         const LidarFrame* owner{nullptr};  // frame whose outputs the job is writing
+        std::vector<std::shared_ptr<void>> keep;  // the host blocks it writes, held until the job has landed
         bool user_uploads{false};          // uploads that read caller memory are in flight
     };
     // pending upload: `count` packets, src_stride apart, into slots [first, first+count)
@@ -184,6 +185,7 @@ void FrameBatcher::wait(const LidarFrame& f) {
         if (j.owner == &f && j.job) {
             j.owner = nullptr;
             b200::check(ob_decode_job_wait(j.job));
+            j.keep.clear();
         }
 }
 
@@ -193,6 +195,7 @@ void FrameBatcher::wait_all() {
         if (j.job) {
             j.owner = nullptr;
             b200::check(ob_decode_job_wait(j.job));
+            j.keep.clear();
         }
 }
 
@@ -250,6 +253,7 @@ void FrameBatcher::start_frame(int64_t f_id, const uint8_t* packet_buf, LidarFra
         ScopedNs t(stats_.ns_wait);
         s.job().owner = nullptr;
         b200::check(ob_decode_job_wait(s.job().job));
+        s.job().keep.clear();
     }
     s.n_slots = 0;
     s.runs.clear();
@@ -487,8 +491,13 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
     bool identity = s.n_slots * static_cast<size_t>(pf.columns_per_packet) >= f.w;
     for (size_t c = 0; c < f.w && identity; ++c) identity = s.col_src[c] == static_cast<int32_t>(c);
     io.col_src = identity ? nullptr : s.col_src.data();
+    j.keep.clear();
+    auto hold = [&j](std::shared_ptr<void> k) {
+        if (k && (j.keep.empty() || j.keep.back() != k)) j.keep.push_back(std::move(k));
+    };
     for (size_t i = 0; i < names.size(); ++i) {
         io.fields[i] = f.field(names[i]).get();
+        hold(f.field(names[i]).keepalive());
         if (dev_out_on_)
             for (const auto& df : dev_out_.fields)
                 if (df.first == names[i] && df.second) io.fields[i] = df.second;
@@ -502,9 +511,11 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
         fused_->reserve(f.h, f.w, n_returns_);
         for (int r = 0; r < n_returns_; ++r) {
             io.xyz[r] = fused_->xyz[r].data();
+            hold(fused_->xyz[r].keepalive());
             if (dev_out_on_ && dev_out_.xyz[r]) io.xyz[r] = dev_out_.xyz[r];
             if (!fused_->pixel_shift_by_row.empty()) {
                 io.range_destaggered[r] = reinterpret_cast<uint32_t*>(fused_->range_destaggered[r].data());
+                hold(fused_->range_destaggered[r].keepalive());
                 if (dev_out_on_ && dev_out_.range_destaggered[r]) io.range_destaggered[r] = dev_out_.range_destaggered[r];
             }
         }
@@ -523,6 +534,7 @@ void FrameBatcher::decode_staged(LidarFrame& f) {
         j.owner = nullptr;
         j.user_uploads = false;
         b200::check(ob_decode_job_wait(j.job));
+        j.keep.clear();
     }
 }
 

@@ -97,8 +97,7 @@ HostBuffer& HostBuffer::operator=(HostBuffer&& o) noexcept {
 }
 HostBuffer::~HostBuffer() { release(); }
 void HostBuffer::release() {
-    if (arena_) arena_.reset();  // the shared block goes back to the pool with its last user
-    else pool().give_back(p_, cap_, pinned_);
+    arena_.reset();  // the block goes back to the pool with its last user (buffers of a carve(), jobs in flight)
     p_ = nullptr;
     n_ = cap_ = 0;
 }
@@ -131,6 +130,9 @@ void HostBuffer::resize(size_t bytes) {
         release();
         if (bytes == 0) return;
         p_ = static_cast<uint8_t*>(pool().acquire(bytes, &cap_, &pinned_));
+        const size_t cap = cap_;
+        const bool pinned = pinned_;
+        arena_ = std::shared_ptr<void>(p_, [cap, pinned](void* p) { pool().give_back(p, cap, pinned); });
     }
     n_ = bytes;
     if (n_) std::memset(p_, 0, n_);

@@ -238,3 +238,27 @@ def test_decode_job_c_abi_device_outputs(ob):
     io.n_slots = pk.shape[0] + 1
     assert lib.ob_decode_job_submit(job, C.byref(io), None, None, 0) != 0
     check(lib.ob_decode_job_destroy(job))
+
+
+def test_frame_destroyed_before_wait_does_not_corrupt_the_next_frame(ob):
+    """depth 2: a LidarFrame dropped right after its GPU pass was submitted.  The job in flight shares ownership
+    of the frame's page-locked block, so the block cannot go back to the pool (and into the next LidarFrame that
+    is created) before the device->host copy has landed."""
+    opf = oracle_pf(PROFILE, H, W)
+    si = ob.SensorInfo(PROFILE, H, W, fw_rev="v3.2.1")
+    frames = _frames(opf, 6, seed=300)
+    b = ob.FrameBatcher(si)
+    b.set_pipeline_depth(2)
+    for k, (_, pk, ts) in enumerate(frames):
+        fr = ob.LidarFrame(si)
+        _, done = b.batch_burst(pk, ts, fr)
+        assert done
+        del fr                                   # destroyed with its GPU pass in flight
+        nxt = ob.LidarFrame(si)                  # would pick the freed block up from the pool
+        for name in nxt.fields:
+            nxt.field(name)[...] = 0x5A
+        b.wait()                                 # the orphaned job lands (somewhere else)
+        for name in nxt.fields:
+            a = nxt.field(name)
+            assert np.all(a == 0x5A), (k, name)
+        del nxt
