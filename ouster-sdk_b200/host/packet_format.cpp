@@ -201,6 +201,12 @@ PacketFormat::PacketFormat(const DataFormat& format)
     d.fields = parse_fields(spec.fields);
     const FieldDecodeInfo none = field_info(0, 0);
     if (legacy) {
+        // parsing.cpp:480-490: LEGACY lidar packets cannot be combined with the newer IMU / zone-monitor packet
+        // formats (their headers and footers differ); the reference rejects the configuration with this text
+        if (format.udp_profile_imu == UDPProfileIMU::ACCEL32_GYRO32_NMEA || format.zone_monitoring_enabled)
+            throw std::runtime_error(
+                "Invalid sensor configuration. Mixing LEGACY lidar packets and non-LEGACY IMU and ZONE packets is not "
+                "possible or supported by the SDK. Your udp_profile_lidar may be incorrect for this data.");
         d.packet_type = d.init_id = d.prod_sn = d.alert_flags = none;
         d.countdown_thermal = d.countdown_shot = d.thermal_shutdown = d.shot_limiting = none;
         d.frame_id = field_info(80, 16);  // inside the first column header

@@ -121,6 +121,15 @@ int main() {
     expect_throw<std::invalid_argument>(
         [&] { destagger<uint32_t>(ArrayRef<const uint32_t>(range), std::vector<int>(h - 1, 0)); },
         "image height does not match shifts size");
+    // LEGACY lidar packets with the newer IMU / zone-monitor packets: rejected like the reference (parsing.cpp:480-490)
+    expect_throw<std::runtime_error>(
+        [&] {
+            DataFormat bad = info->format;
+            bad.udp_profile_lidar = UDPProfileLidar::LEGACY;
+            bad.udp_profile_imu = UDPProfileIMU::ACCEL32_GYRO32_NMEA;
+            PacketFormat pf_bad(bad);
+        },
+        "Mixing LEGACY lidar packets");
     expect_throw<std::invalid_argument>(
         [&] {
             img_t<uint32_t> small(h, w / 2);
