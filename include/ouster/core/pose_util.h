@@ -102,7 +102,7 @@ PointCloudXYZ<T> dewarp(const LidarFrame& lidar_frame, const XYZLutT<T>& xyzlut,
 
 /// dewarp(frame_set, xyzluts, min_range, max_range) (pose_util.h:475, impl/dewarp_impl.h:84-117): the
 /// dewarped points of every frame of the set, frame after frame, each frame with its own LUT.  One batched
-/// GPU pass for the whole set (ob_dewarp_frames: three launches, one host round trip).  Optional per-point
+/// GPU pass for the whole set (ob_dewarp_frames: one launch).  Optional per-point
 /// provenance like impl::dewarp_impl: frame index, column index, column timestamp (appended).
 template <typename T>
 PointCloudXYZ<T> dewarp(const FrameSet& frame_set, const std::vector<XYZLutT<T>>& xyzluts, double min_range,
